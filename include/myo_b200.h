@@ -1,0 +1,228 @@
+/* myo_b200.h -- C ABI of the B200-native batched myo-simulator (libmyo_b200.so).
+ *
+ * The reference (amathislab/myochallenge) has no FFI of its own: its hot path crosses two Python
+ * seams.  Every entry point below names the reference interface it replaces:
+ *
+ *   myo_model_*      <- mujoco_py.load_model_from_mjb / sim.model.* views that MyoSuite's
+ *                       BaseV0.__init__ builds from the `model_path` kwarg
+ *                       (/root/reference/src/envs/__init__.py:17,29,44,62) and that
+ *                       /root/reference/src/envs/baoding.py:372-389,560-604 read and write.
+ *   myo_batch_create <- make_parallel_envs + SubprocVecEnv([...16 thunks])
+ *                       (/root/reference/src/main_baoding.py:56-65,74) and the env kwargs of
+ *                       /root/reference/src/envs/__init__.py:58-74 (Baoding P2), :137-150 (finger).
+ *   myo_batch_reset  <- CustomBaodingP2Env.reset (/root/reference/src/envs/baoding.py:494-647),
+ *                       CustomPoseEnv.reset (/root/reference/src/envs/pose.py:53-99).
+ *   myo_batch_step   <- VecEnv.step_async/step_wait -> env.step: BaodingEnvV1.step target update,
+ *                       BaseV0.step action remap, Robot.step (frame_skip x mj_step), get_obs,
+ *                       get_reward_dict (/root/reference/src/envs/baoding.py:403-467), TimeLimit and
+ *                       the SubprocVecEnv worker's auto-reset.
+ *   myo_batch_mj_step / myo_batch_forward <- MjSim.step() / MjSim.forward()
+ *                       (/root/reference/src/envs/baoding.py:183,206,625,632 reach them).
+ *   myo_batch_set_state / get_state <- MujocoEnv.set_state / sim.data.qpos,qvel,act
+ *                       (/root/reference/src/envs/baoding.py:206,632,645).
+ *   myo_batch_set_param / get_param <- in-place writes to sim.model.body_mass / geom_friction /
+ *                       geom_size / site_pos (/root/reference/src/envs/baoding.py:560-604).
+ *   myo_policy_*     <- sb3_contrib RecurrentActorCriticPolicy.forward as constructed by
+ *                       /root/reference/src/train/trainer.py:49-64.
+ *
+ * Conventions: every function returns 0 on success or a negative myo_status; the message for the
+ * calling thread's last failure is myo_last_error().  Nothing throws across the boundary.  Handles
+ * are opaque and owned by the library.  Pointers named *_dev are CUDA device pointers owned by the
+ * caller (e.g. torch tensors); `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * Calls on one handle are not thread-safe; different handles are independent (one per GPU).
+ * There is no CPU fallback: without a CUDA device every batch/policy call fails with MYO_E_CUDA.
+ */
+#ifndef MYO_B200_H
+#define MYO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct myo_model myo_model;
+typedef struct myo_batch myo_batch;
+typedef struct myo_policy myo_policy;
+
+typedef enum {
+  MYO_OK = 0,
+  MYO_E_ARG = -1,      /* bad argument */
+  MYO_E_IO = -2,       /* file could not be read */
+  MYO_E_FORMAT = -3,   /* not a MuJoCo 2.1.0 MJB */
+  MYO_E_UNSUPPORTED = -4, /* model uses a feature outside the supported subset */
+  MYO_E_CUDA = -5,     /* CUDA runtime error / no device */
+  MYO_E_LIMIT = -6     /* model exceeds a compiled-in capacity */
+} myo_status;
+
+typedef enum { MYO_TASK_NONE = 0, MYO_TASK_POSE = 1, MYO_TASK_BAODING = 2 } myo_task_kind;
+
+/* Baoding `Task` enum values (MyoSuite baoding_v1.Task; 0 = hold, see
+ * /root/reference/src/envs/baoding.py:287-294, /root/reference/src/models/classifier.py:116) */
+enum { MYO_BAODING_HOLD = 0, MYO_BAODING_CW = 1, MYO_BAODING_CCW = 2 };
+
+/* per-world overridable model parameters (the arrays the reference's reset() writes in place) */
+typedef enum {
+  MYO_PARAM_BODY_MASS = 0,     /* 1 float  */
+  MYO_PARAM_GEOM_SIZE = 1,     /* 3 floats */
+  MYO_PARAM_GEOM_FRICTION = 2, /* 3 floats */
+  MYO_PARAM_SITE_POS = 3       /* 3 floats */
+} myo_param_kind;
+
+#define MYO_MAX_OVERRIDE 4
+#define MYO_INFO_TERMS 8
+
+/* Task / env configuration: the kwargs of the gym registrations plus the curriculum knobs of
+ * CustomBaodingP2Env._setup (/root/reference/src/envs/baoding.py:300-401) and
+ * CustomPoseEnv._setup (/root/reference/src/envs/pose.py:7-51). */
+typedef struct myo_task_cfg {
+  int32_t kind;                 /* myo_task_kind */
+  int32_t frame_skip;           /* mj_steps per env step (10; die/pen 5) */
+  int32_t max_episode_steps;    /* gym TimeLimit horizon; <=0 disables truncation */
+  int32_t normalize_act;        /* BaseV0: ctrl = 1/(1+exp(-5(a-0.5))) for muscle actuators */
+  int32_t auto_reset;           /* SubprocVecEnv worker semantics: reset inside step on done */
+  int32_t solver_iterations;    /* Newton iteration cap per mj_step (<=0: model's opt.iterations) */
+  float solver_tolerance;       /* <=0: model's opt.tolerance */
+  /* reward weights, in the order written to info[]:
+   *  baoding: pos_dist_1 pos_dist_2 act_reg alive sparse solved done  (7 used)
+   *  pose   : pose bonus penalty act_reg sparse solved done           (7 used) */
+  float rwd_weight[MYO_INFO_TERMS];
+  /* ---- baoding ---- */
+  float drop_th, proximity_th;
+  float goal_time_period[2], goal_xrange[2], goal_yrange[2];
+  float obj_size_range[2], obj_mass_range[2], obj_friction_change[3];
+  int32_t task_choice_random;   /* 1: which_task ~ choice(Task) each reset; 0: fixed_task */
+  int32_t fixed_task;           /* used when !task_choice_random (WHICH_TASK = CCW) */
+  float overlap_probability, limit_init_angle; /* limit_init_angle <= 0: uniform 0..2pi */
+  float noise_fingers;
+  float center_pos[2];
+  int32_t randomize_physics;    /* 1: sample mass/size/friction per reset (P2); 0: nominal (P1) */
+  int32_t ball_body[2], ball_geom[2], ball_site[2], target_site[2];
+  int32_t ball_qposadr[2], ball_dofadr[2];
+  /* ---- pose ---- */
+  float pose_thd, far_th, target_distance;
+  int32_t reset_type;           /* 0 none, 1 init, 2 random */
+  int32_t target_type;          /* 0 fixed, 1 generate */
+  int32_t n_target_jnt;         /* <=0: target_jnt_value given for all nq */
+  int32_t target_jnt_ids[64];
+  float target_jnt_range[64][2];
+  float target_jnt_value[64];
+  /* ---- overrides (filled by the library for baoding; free for other tasks) ---- */
+  int32_t n_ovr_body, ovr_body[MYO_MAX_OVERRIDE];
+  int32_t n_ovr_geom, ovr_geom[MYO_MAX_OVERRIDE];
+  int32_t n_ovr_site, ovr_site[MYO_MAX_OVERRIDE];
+} myo_task_cfg;
+
+const char* myo_last_error(void);
+const char* myo_version(void);
+
+/* ---- model (host) -------------------------------------------------------------------------- */
+int myo_model_load_mjb(const char* path, myo_model** out);
+int myo_model_load_mjb_mem(const void* bytes, size_t len, myo_model** out);
+void myo_model_free(myo_model* m);
+/* integer size by mjModel name ("nq","nv","nu","na","nbody","njnt","ngeom","nsite","ntendon",...) */
+int myo_model_size(const myo_model* m, const char* name, int* out);
+/* option / statistic by name ("timestep","gravity2","tolerance","iterations","meaninertia",...) */
+int myo_model_opt(const myo_model* m, const char* name, double* out);
+/* host array by mjModel pointer name. dtype: 0 = float64, 1 = int32, 2 = uint8, 3 = float32, 4 = char.
+ * The pointer stays valid until myo_model_free and is writable (sim.model.* semantics): edits made
+ * before myo_batch_create are baked into the batch. */
+int myo_model_array(myo_model* m, const char* name, void** ptr, int* rows, int* cols, int* dtype);
+/* group: "body","jnt"/"joint","geom","site","tendon","actuator" */
+int myo_model_name2id(const myo_model* m, const char* group, const char* name);
+const char* myo_model_id2name(const myo_model* m, const char* group, int id);
+/* fills the baoding id fields of cfg (ball1/ball2 bodies, geoms, sites; target sites) by name */
+int myo_task_cfg_default(const myo_model* m, int kind, myo_task_cfg* cfg);
+
+/* ---- batch (device) ------------------------------------------------------------------------ */
+int myo_batch_create(const myo_model* m, int n_worlds, int device, const myo_task_cfg* cfg, uint64_t seed,
+                     myo_batch** out);
+void myo_batch_destroy(myo_batch* b);
+int myo_batch_dims(const myo_batch* b, int* n_worlds, int* nq, int* nv, int* na, int* nu, int* nobs, int* n_param);
+/* lanes per world the step kernel uses (8, 16 or 32), and its dynamic shared memory per CTA */
+int myo_batch_launch_info(const myo_batch* b, int* lanes_per_world, int* worlds_per_cta, int* smem_bytes,
+                          int* regs_per_thread);
+/* mask_dev: uint8[n_worlds] or NULL for all worlds. Samples the task's reset distribution on
+ * device with a counter-based RNG keyed by (seed, world, episode). obs_dev may be NULL. */
+int myo_batch_reset(myo_batch* b, const uint8_t* mask_dev, float* obs_dev, void* stream);
+int myo_batch_set_state(myo_batch* b, const float* qpos_dev, const float* qvel_dev, const float* act_dev,
+                        const float* time_dev, void* stream);
+int myo_batch_get_state(myo_batch* b, float* qpos_dev, float* qvel_dev, float* act_dev, float* time_dev,
+                        void* stream);
+/* values_dev: float[n_worlds][ncomp] for override slot (kind, id) declared in the task cfg */
+int myo_batch_set_param(myo_batch* b, int kind, int id, const float* values_dev, void* stream);
+int myo_batch_get_param(myo_batch* b, int kind, int id, float* values_dev, void* stream);
+/* one env step for every world. actions[n,nu] in [-1,1]; obs[n,nobs]; reward[n]; done[n] (env
+ * termination OR time limit, as SB3 sees it); truncated[n] (TimeLimit.truncated);
+ * terminal_obs[n,nobs] (written for worlds that finished; may be NULL); info[n,MYO_INFO_TERMS]
+ * reward terms + dense (may be NULL). */
+int myo_batch_step(myo_batch* b, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                   uint8_t* truncated_dev, float* terminal_obs_dev, float* info_dev, void* stream);
+/* raw physics: nsub x mj_step with ctrl[n,nu] applied as data.ctrl (no task logic) */
+int myo_batch_mj_step(myo_batch* b, const float* ctrl_dev, int nsub, void* stream);
+/* mj_forward at the current state (fills the stage buffers myo_batch_stage_dump reads) */
+int myo_batch_forward(myo_batch* b, const float* ctrl_dev, void* stream);
+/* current observation without stepping (env.get_obs()) */
+int myo_batch_get_obs(myo_batch* b, float* obs_dev, void* stream);
+
+/* per-component parity hooks: copies a stage result of the LAST myo_batch_forward / mj_step
+ * substep into out_dev (float or int32 [n_worlds][width]); *width may be queried with out_dev NULL */
+typedef enum {
+  MYO_STAGE_XPOS = 0,        /* [nbody*3] */
+  MYO_STAGE_XMAT = 1,        /* [nbody*9] */
+  MYO_STAGE_SITE_XPOS = 2,   /* [nsite*3] */
+  MYO_STAGE_TEN_LENGTH = 3,  /* [ntendon] */
+  MYO_STAGE_TEN_J = 4,       /* [ntendon*nv] dense */
+  MYO_STAGE_QM = 5,          /* [nv*nv] dense mass matrix */
+  MYO_STAGE_QFRC_BIAS = 6,   /* [nv] */
+  MYO_STAGE_QFRC_PASSIVE = 7,
+  MYO_STAGE_QFRC_ACTUATOR = 8,
+  MYO_STAGE_ACT_FORCE = 9,   /* [nu] */
+  MYO_STAGE_QACC_SMOOTH = 10,
+  MYO_STAGE_QACC = 11,
+  MYO_STAGE_NCON = 12,       /* int32 [1] */
+  MYO_STAGE_CONTACT_GEOMS = 13, /* int32 [ncon_max*2], -1 padded */
+  MYO_STAGE_CONTACT_DIST = 14,  /* [ncon_max] */
+  MYO_STAGE_NEFC = 15,       /* int32 [1] */
+  MYO_STAGE_EFC_TYPE_ID = 16,/* int32 [nefc_max*2] (type,id), -1 padded */
+  MYO_STAGE_EFC_J = 17,      /* [nefc_max*nv] dense */
+  MYO_STAGE_EFC_AREF = 18,   /* [nefc_max] */
+  MYO_STAGE_EFC_D = 19,      /* [nefc_max] */
+  MYO_STAGE_EFC_FORCE = 20,  /* [nefc_max] */
+  MYO_STAGE_QFRC_CONSTRAINT = 21,
+  MYO_STAGE_ACT_DOT = 22,    /* [na] */
+  MYO_STAGE_SOLVER_ITER = 23,/* int32 [1] */
+  MYO_STAGE_STATUS = 24,     /* int32 [1] bit flags: 1 unsupported pair in range, 2 contact overflow,
+                                4 constraint overflow, 8 non-finite state */
+  MYO_STAGE_COUNT = 25
+} myo_stage;
+int myo_batch_stage_dump(myo_batch* b, int stage, void* out_dev, int* width, void* stream);
+/* OR of the status flags over all worlds since the last call (host int) */
+int myo_batch_status(myo_batch* b, int* flags, void* stream);
+/* number of kernel launches issued on behalf of this batch since creation */
+int64_t myo_batch_launch_count(const myo_batch* b);
+
+/* ---- recurrent policy forward (sb3-contrib MlpLstmPolicy, separate actor/critic LSTMs) ------ */
+typedef struct myo_policy_cfg {
+  int32_t obs_dim, act_dim, lstm_hidden;
+  int32_t n_pi_layers, pi_layers[4];   /* mlp_extractor policy_net widths (ReLU) */
+  int32_t n_vf_layers, vf_layers[4];
+} myo_policy_cfg;
+int myo_policy_create(const myo_policy_cfg* cfg, int max_batch, int device, myo_policy** out);
+void myo_policy_destroy(myo_policy* p);
+/* name follows the SB3 state-dict key (e.g. "lstm_actor.weight_ih_l0", "action_net.bias", "log_std");
+ * data_dev: fp32 device tensor in torch layout */
+int myo_policy_set_weight(myo_policy* p, const char* name, const float* data_dev, int64_t numel, void* stream);
+/* obs[n,obs_dim] (already normalised); h/c: [2][n][H] (0 = actor, 1 = critic), updated in place;
+ * episode_start[n] (float 0/1) zeroes the state first; noise[n,act_dim] ~ N(0,1) or NULL for the
+ * deterministic mean; outputs: actions[n,act_dim] (unclipped), values[n], logp[n]. */
+int myo_policy_forward(myo_policy* p, int n, const float* obs_dev, float* h_dev, float* c_dev,
+                       const float* episode_start_dev, const float* noise_dev, float* actions_dev,
+                       float* values_dev, float* logp_dev, void* stream);
+int64_t myo_policy_launch_count(const myo_policy* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYO_B200_H */

@@ -1,0 +1,103 @@
+// Device-side model tables and per-world scratch layout shared by the host packer and the kernels.
+#pragma once
+#include <cstdint>
+
+#include "../../include/myo_b200.h"
+
+namespace myo {
+
+constexpr int KC = 8;    // max dofs on a body's ancestor chain (myoHand distal phalanx: 3 wrist + 4 finger)
+constexpr int KT = 8;    // max dofs a tendon's moment arm touches
+constexpr int KS = 16;   // max support of one contact block (chain A xor chain B)
+constexpr int LIM_WORDS = 28;   // scratch words per limit record
+constexpr int CON_WORDS = 104;  // scratch words per contact record
+constexpr int ROW_WORDS = 6;    // scratch words per constraint row
+
+enum { J_FREE = 0, J_BALL = 1, J_SLIDE = 2, J_HINGE = 3 };
+enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_ELLIPSOID = 4, G_CYLINDER = 5, G_BOX = 6 };
+enum { W_PULLEY = 2, W_SITE = 3, W_SPHERE = 4, W_CYLINDER = 5 };
+enum { ST_UNSUPPORTED = 1, ST_CON_OVERFLOW = 2, ST_EFC_OVERFLOW = 4, ST_NONFINITE = 8 };
+enum { EFC_LIMIT_JOINT = 3, EFC_LIMIT_TENDON = 4, EFC_CONTACT_FRICTIONLESS = 5, EFC_CONTACT_PYRAMIDAL = 6 };
+
+// limit record layout (floats/ints in scratch)
+enum { L_KIND = 0, L_ID = 1, L_NSUP = 2, L_POS = 3, L_MARGIN = 4, L_IDX = 8 /*KT ints*/, L_J = 16 /*KT floats*/ };
+// contact record layout
+enum { C_G1 = 0, C_G2 = 1, C_DIM = 2, C_NSUP = 3, C_DIST = 4, C_MARGIN = 5, C_MU = 6, C_ROW0 = 7, C_POS = 8 /*3*/,
+       C_FRAME = 11 /*9*/, C_SOLREF = 20 /*2*/, C_SOLIMP = 22 /*5*/, C_BA = 27, C_BB = 28, C_FRI = 29 /*3*/,
+       C_IDX = 32 /*KS ints*/, C_N = 48 /*3*KS floats*/ };
+// row record
+enum { R_D = 0, R_AREF = 1, R_JAR = 2, R_JP = 3, R_BLOCK = 4 /*int: block | coef<<16*/, R_AUX = 5 };
+
+struct DevModel {
+  // sizes
+  int nq, nv, nu, na, nbody, njnt, ngeom, nsite, ntendon, nwrap, nM, npair, nlevel, ndlevel;
+  int nq4, nv4, na4, nu4, nparam, nparam4, nobs, nobs4;
+  int nlim_max, ncon_max, nefc_max;
+  int solver_iter;
+  float solver_tol, timestep, gravity[3], inv_sqrt_impratio, meaninertia;
+  int any_damping, any_tendon_passive, any_joint_spring;
+  // body tables
+  const int *b_parent, *b_root, *b_jntadr, *b_jntnum, *b_dofadr, *b_dofnum, *b_nchain, *b_chain, *b_mass_slot,
+      *b_sameframe, *b_childadr, *b_child, *lvl_adr, *lvl_body;
+  const float *b_pos, *b_quat, *b_ipos, *b_iquat, *b_mass, *b_inertia, *b_invweight0;
+  // joints
+  const int *j_type, *j_qposadr, *j_dofadr, *j_body, *j_limited;
+  const float *j_pos, *j_axis, *j_qpos0, *j_range, *j_margin, *j_solref, *j_solimp, *j_stiffness, *j_qpos_spring;
+  // dofs
+  const int *d_body, *d_parent, *d_simple, *d_Madr, *d_depth, *d_descadr, *d_desc, *dlvl_adr, *dlvl_dof, *d_jnt,
+      *d_actadr, *d_actlist;
+  const float *d_armature, *d_damping, *d_invweight0, *d_M0;
+  // geoms
+  const int *g_type, *g_body, *g_condim, *g_priority, *g_size_slot, *g_fri_slot;
+  const float *g_pos, *g_mat, *g_size, *g_rbound, *g_friction, *g_solmix, *g_solref, *g_solimp, *g_margin, *g_gap;
+  // collision pair list (static filters applied on host), geom1.type <= geom2.type
+  const int *p_g1, *p_g2, *p_supported;
+  // sites
+  const int *s_body, *s_pos_slot;
+  const float* s_pos;
+  // tendons + wraps
+  const int *t_adr, *t_num, *t_limited, *t_ndof, *t_dof, *w_type, *w_obj, *w_side;
+  const float *t_range, *t_margin, *t_solref, *t_solimp, *t_invweight0, *t_stiffness, *t_damping, *t_lengthspring,
+      *w_prm;
+  // actuators
+  const int *a_tendon, *a_dyntype, *a_gaintype, *a_biastype, *a_ctrllimited, *a_forcelimited;
+  const float *a_dynprm, *a_gainprm, *a_biasprm, *a_ctrlrange, *a_forcerange, *a_gear, *a_acc0, *a_lengthrange;
+  // scratch offsets (words) inside one world's shared-memory block
+  int o_qpos, o_qvel, o_act, o_ctrl, o_warm, o_xpos, o_xquat, o_xmat, o_xipos, o_cdof, o_cinert, o_cvel, o_cdofdot,
+      o_cacc, o_cfrc, o_M, o_LD, o_tenL, o_tenV, o_tenJ, o_actF, o_bias, o_passive, o_qact, o_smooth, o_qaccs,
+      o_qacc, o_qcon, o_actdot, o_grad, o_p, o_Mp, o_Ma, o_H, o_lim, o_con, o_row, o_misc, o_obs, o_wparam,
+      scratch_words;
+  const float* init_qpos;   // [nq] state written by reset (MyoSuite init_qpos)
+  const float* param0;      // [nparam4] nominal values of the per-world override parameters
+  float frame_dt;           // frame_skip * timestep (MyoSuite env.dt)
+};
+
+// per-batch device pointers
+struct BatchPtrs {
+  int n_worlds;
+  float *qpos, *qvel, *act, *warm, *time, *wparam, *task_f, *pose_target;
+  int *task_i, *status;
+  float* dump;   // [n][scratch_words] written by forward / mj_step mode (may be null)
+  unsigned long long seed;
+};
+
+enum { TI_ELAPSED = 0, TI_EPISODE = 1, TI_TASK = 2, TI_FLAGS = 3, TI_WORDS = 4 };
+enum { TF_ANGLE1 = 0, TF_ANGLE2 = 1, TF_XR = 2, TF_YR = 3, TF_PERIOD = 4, TF_WORDS = 8 };
+// o_misc scratch words
+enum { MI_NLIM = 0, MI_NCON = 1, MI_NEFC = 2, MI_ITER = 3, MI_STATUS = 4, MI_WORDS = 8 };
+
+enum StepMode { MODE_ENV_STEP = 0, MODE_MJ_STEP = 1, MODE_FORWARD = 2, MODE_GET_OBS = 3, MODE_RESET = 4 };
+
+struct StepArgs {
+  int mode, nsub;
+  const float* in;        // actions or ctrl [n][nu]
+  float* obs;             // [n][nobs]
+  float* reward;          // [n]
+  uint8_t* done;          // [n]
+  uint8_t* truncated;     // [n]
+  float* terminal_obs;    // [n][nobs]
+  float* info;            // [n][MYO_INFO_TERMS]
+  const uint8_t* mask;    // reset mask
+};
+
+}  // namespace myo

@@ -1,0 +1,595 @@
+// World kernel + the device half of the C ABI (myo_batch_*).
+//
+// One world per tile of G lanes (G = 8 / 16 / 32 by model size); the world's whole mjData subset
+// lives in the tile's slice of shared memory for the duration of an env step: frame_skip mj_steps,
+// then kinematics at the new state, observation, reward, termination, TimeLimit and auto-reset,
+// all in one launch. HBM is touched once per env step: state + per-world parameters in (float4,
+// world-major rows so a tile reads one contiguous row), state + obs/reward/flags out.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "myo_pack.hpp"
+#include "myo_task.cuh"
+
+const myo::Model& myo_model_host(const myo_model* m);
+
+// kernel launch; tests/emul re-defines this to run the same kernels single-lane on the host
+#ifndef MYO_LAUNCH
+#define MYO_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+#ifndef MYO_LANES_CASES
+#define MYO_LANES_CASES(b, FN, ...)                 \
+  switch ((b)->pm.lanes) {                          \
+    case 8: rc = FN<8>(__VA_ARGS__); break;         \
+    case 16: rc = FN<16>(__VA_ARGS__); break;       \
+    default: rc = FN<32>(__VA_ARGS__); break;       \
+  }
+#endif
+
+namespace myo {
+
+constexpr int kThreads = 256;
+
+template <int G>
+__device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G>& c, int w) {
+  int status = 0;
+  int* ti = b.task_i + (size_t)w * TI_WORDS;
+  float* tf = b.task_f + (size_t)w * TF_WORDS;
+  float* ptarget = b.pose_target + (size_t)w * m.nq4;
+  int* misc = SI(o_misc);
+  if (a.mode == MODE_RESET) {
+    if (a.mask && !a.mask[w]) return;
+    load_world<G>(m, c, b, w);
+    task_reset<G>(m, t, c, b, w, ti, tf, ptarget);
+    if (c.lane == 0) b.time[w] = 0.f;
+    if (a.obs) {
+      phase_tree_forward<G>(m, c, false);
+      task_obs<G>(m, t, c, ptarget);
+      for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
+    }
+    store_world<G>(m, c, b, w, true);
+    return;
+  }
+  load_world<G>(m, c, b, w);
+  if (a.mode == MODE_GET_OBS) {
+    phase_tree_forward<G>(m, c, false);
+    task_obs<G>(m, t, c, ptarget);
+    for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
+    return;
+  }
+  if (a.mode == MODE_FORWARD || a.mode == MODE_MJ_STEP) {
+    for (int i = c.lane; i < m.nu; i += G) SF(o_ctrl)[i] = a.in ? a.in[(size_t)w * m.nu + i] : 0.f;
+    c.tile.sync();
+    if (a.mode == MODE_FORWARD) mj_forward_dev<G>(m, c, &status);
+    else {
+      for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(m, c, &status);
+      if (c.lane == 0) b.time[w] += (float)a.nsub * m.timestep;
+    }
+  } else {   // MODE_ENV_STEP
+    if (t.kind == MYO_TASK_BAODING) baoding_targets<G>(m, t, c, ti, tf);
+    task_action<G>(m, t, c, a.in + (size_t)w * m.nu);
+    c.tile.sync();
+    for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(m, c, &status);
+    // get_obs: kinematics at the post-step state (MyoSuite get_obs -> sim.forward)
+    phase_tree_forward<G>(m, c, false);
+    task_obs<G>(m, t, c, ptarget);
+    float info[MYO_INFO_TERMS], reward;
+    bool env_done;
+    task_reward<G>(m, t, c, info, &reward, &env_done);
+    const int elapsed = ti[TI_ELAPSED] + 1;
+    const bool limit = t.max_episode_steps > 0 && elapsed >= t.max_episode_steps;
+    const bool done = env_done || limit;
+    c.tile.sync();
+    if (c.lane == 0) {
+      ti[TI_ELAPSED] = elapsed;
+      b.time[w] += (float)a.nsub * m.timestep;
+      a.reward[w] = reward;
+      a.done[w] = done ? 1 : 0;
+      if (a.truncated) a.truncated[w] = (limit && !env_done) ? 1 : 0;
+    }
+    if (a.info) for (int k = c.lane; k < MYO_INFO_TERMS; k += G) a.info[(size_t)w * MYO_INFO_TERMS + k] = info[k];
+    if (done && t.auto_reset) {
+      if (a.terminal_obs) for (int i = c.lane; i < m.nobs; i += G) a.terminal_obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
+      task_reset<G>(m, t, c, b, w, ti, tf, ptarget);
+      if (c.lane == 0) b.time[w] = 0.f;
+      phase_tree_forward<G>(m, c, false);
+      task_obs<G>(m, t, c, ptarget);
+    }
+    for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
+  }
+  // status flags
+  for (int i = c.lane; i < m.nq; i += G) if (!isfinite(SF(o_qpos)[i])) status |= ST_NONFINITE;
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) status |= c.tile.shfl_xor(status, o);
+  if (c.lane == 0) {
+    misc[MI_STATUS] = status;
+    if (status) atomicOr(b.status, status);
+  }
+  store_world<G>(m, c, b, w, true);
+  if (b.dump && a.mode != MODE_ENV_STEP) {
+    c.tile.sync();
+    float* out = b.dump + (size_t)w * m.scratch_words;
+    for (int i = c.lane; i < m.scratch_words; i += G) out[i] = c.s[i];
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) world_kernel(const __grid_constant__ DevModel m, const __grid_constant__ myo_task_cfg t,
+                                                        const __grid_constant__ BatchPtrs b, const __grid_constant__ StepArgs a) {
+#ifdef MYO_EMUL
+  float* smem = reinterpret_cast<float*>(emul_smem);
+#else
+  extern __shared__ float4 smem4[];
+  float* smem = reinterpret_cast<float*>(smem4);
+#endif
+  cg::thread_block block = cg::this_thread_block();
+  cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
+  Ctx<G> c(tile);
+  const int wpc = blockDim.x / G;
+  const int tid = threadIdx.x / G;
+  c.s = smem + (size_t)tid * m.scratch_words;
+  c.wp = c.s + m.o_wparam;
+  for (int w = blockIdx.x * wpc + tid; w < b.n_worlds; w += gridDim.x * wpc) {
+    run_world<G>(m, t, b, a, c, w);
+    c.tile.sync();
+  }
+}
+
+// ---- stage extraction: factored scratch -> dense arrays, one thread per world ------------------
+__global__ void extract_kernel(const __grid_constant__ DevModel m, const float* dump, int n, int stage, void* outv, int width) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const float* s = dump + (size_t)w * m.scratch_words;
+  const int* si = reinterpret_cast<const int*>(s);
+  float* of = reinterpret_cast<float*>(outv) + (size_t)w * width;
+  int* oi = reinterpret_cast<int*>(outv) + (size_t)w * width;
+  const int* misc = si + m.o_misc;
+  const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON], nefc = misc[MI_NEFC];
+  auto copyf = [&](int off, int cnt) { for (int i = 0; i < cnt; i++) of[i] = s[off + i]; };
+  switch (stage) {
+    case MYO_STAGE_XPOS: copyf(m.o_xpos, 3 * m.nbody); break;
+    case MYO_STAGE_XMAT: copyf(m.o_xmat, 9 * m.nbody); break;
+    case MYO_STAGE_SITE_XPOS:
+      for (int k = 0; k < m.nsite; k++) site_world(m, s, s + m.o_wparam, k, of + 3 * k);
+      break;
+    case MYO_STAGE_TEN_LENGTH: copyf(m.o_tenL, m.ntendon); break;
+    case MYO_STAGE_TEN_J:
+      for (int i = 0; i < m.ntendon * m.nv; i++) of[i] = 0.f;
+      for (int t = 0; t < m.ntendon; t++)
+        for (int e = 0; e < m.t_ndof[t]; e++) of[t * m.nv + m.t_dof[t * KT + e]] = s[m.o_tenJ + t * KT + e];
+      break;
+    case MYO_STAGE_QM:
+      for (int i = 0; i < m.nv * m.nv; i++) of[i] = 0.f;
+      for (int i = 0; i < m.nv; i++) {
+        int adr = m.d_Madr[i], j = i;
+        while (j >= 0) { of[i * m.nv + j] = of[j * m.nv + i] = s[m.o_M + adr++]; j = m.d_parent[j]; }
+      }
+      break;
+    case MYO_STAGE_QFRC_BIAS: copyf(m.o_bias, m.nv); break;
+    case MYO_STAGE_QFRC_PASSIVE: copyf(m.o_passive, m.nv); break;
+    case MYO_STAGE_QFRC_ACTUATOR: copyf(m.o_qact, m.nv); break;
+    case MYO_STAGE_ACT_FORCE: copyf(m.o_actF, m.nu); break;
+    case MYO_STAGE_QACC_SMOOTH: copyf(m.o_qaccs, m.nv); break;
+    case MYO_STAGE_QACC: copyf(m.o_qacc, m.nv); break;
+    case MYO_STAGE_QFRC_CONSTRAINT: copyf(m.o_qcon, m.nv); break;
+    case MYO_STAGE_ACT_DOT: copyf(m.o_actdot, m.na); break;
+    case MYO_STAGE_NCON: oi[0] = ncon; break;
+    case MYO_STAGE_NEFC: oi[0] = nefc; break;
+    case MYO_STAGE_SOLVER_ITER: oi[0] = misc[MI_ITER]; break;
+    case MYO_STAGE_STATUS: oi[0] = misc[MI_STATUS]; break;
+    case MYO_STAGE_CONTACT_GEOMS:
+      for (int k = 0; k < m.ncon_max; k++) {
+        oi[2 * k] = k < ncon ? si[m.o_con + k * CON_WORDS + C_G1] : -1;
+        oi[2 * k + 1] = k < ncon ? si[m.o_con + k * CON_WORDS + C_G2] : -1;
+      }
+      break;
+    case MYO_STAGE_CONTACT_DIST:
+      for (int k = 0; k < m.ncon_max; k++) of[k] = k < ncon ? s[m.o_con + k * CON_WORDS + C_DIST] : 0.f;
+      break;
+    case MYO_STAGE_EFC_TYPE_ID:
+    case MYO_STAGE_EFC_J:
+    case MYO_STAGE_EFC_AREF:
+    case MYO_STAGE_EFC_D:
+    case MYO_STAGE_EFC_FORCE: {
+      const int per = stage == MYO_STAGE_EFC_J ? m.nv : (stage == MYO_STAGE_EFC_TYPE_ID ? 2 : 1);
+      for (int i = 0; i < m.nefc_max * per; i++) { if (stage == MYO_STAGE_EFC_TYPE_ID) oi[i] = -1; else of[i] = 0.f; }
+      for (int r = 0; r < nefc; r++) {
+        const float* row = s + m.o_row + r * ROW_WORDS;
+        if (stage == MYO_STAGE_EFC_AREF) of[r] = row[R_AREF];
+        else if (stage == MYO_STAGE_EFC_D) of[r] = row[R_D];
+        else if (stage == MYO_STAGE_EFC_FORCE) of[r] = row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] : 0.f;
+      }
+      if (stage == MYO_STAGE_EFC_TYPE_ID || stage == MYO_STAGE_EFC_J) {
+        for (int r = 0; r < nlim; r++) {
+          const float* lr = s + m.o_lim + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
+          if (stage == MYO_STAGE_EFC_TYPE_ID) { oi[2 * r] = li[L_KIND]; oi[2 * r + 1] = li[L_ID]; }
+          else for (int e = 0; e < li[L_NSUP]; e++) of[r * m.nv + li[L_IDX + e]] = lr[L_J + e];
+        }
+        for (int k = 0; k < ncon; k++) {
+          const float* cr = s + m.o_con + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+          const int row0 = ci[C_ROW0];
+          if (row0 < 0) continue;
+          const int nr = ci[C_DIM] == 1 ? 1 : 4;
+          for (int q = 0; q < nr; q++) {
+            const int r = row0 + q;
+            if (stage == MYO_STAGE_EFC_TYPE_ID) { oi[2 * r] = nr == 1 ? EFC_CONTACT_FRICTIONLESS : EFC_CONTACT_PYRAMIDAL; oi[2 * r + 1] = k; }
+            else {
+              const float mu = cr[C_MU];
+              for (int e = 0; e < ci[C_NSUP]; e++) {
+                float v = cr[C_N + e];
+                if (nr == 4) v += ((q & 1) ? -mu : mu) * ((q < 2) ? cr[C_N + KS + e] : cr[C_N + 2 * KS + e]);
+                of[r * m.nv + ci[C_IDX + e]] = v;
+              }
+            }
+          }
+        }
+      }
+    } break;
+    default: break;
+  }
+}
+
+__global__ void init_worlds_kernel(const __grid_constant__ DevModel m, BatchPtrs b, int fixed_task) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= b.n_worlds) return;
+  for (int i = 0; i < m.nq4; i++) { b.qpos[(size_t)w * m.nq4 + i] = i < m.nq ? m.init_qpos[i] : 0.f; b.pose_target[(size_t)w * m.nq4 + i] = 0.f; }
+  for (int i = 0; i < m.nv4; i++) { b.qvel[(size_t)w * m.nv4 + i] = 0.f; b.warm[(size_t)w * m.nv4 + i] = 0.f; }
+  for (int i = 0; i < m.na4; i++) b.act[(size_t)w * m.na4 + i] = 0.f;
+  for (int i = 0; i < m.nparam4; i++) b.wparam[(size_t)w * m.nparam4 + i] = m.param0[i];
+  b.time[w] = 0.f;
+  int* ti = b.task_i + (size_t)w * TI_WORDS;
+  ti[TI_ELAPSED] = 0; ti[TI_EPISODE] = 0; ti[TI_TASK] = fixed_task; ti[TI_FLAGS] = 0;
+  float* tf = b.task_f + (size_t)w * TF_WORDS;
+  for (int k = 0; k < TF_WORDS; k++) tf[k] = 0.f;
+  tf[TF_ANGLE1] = 0.25f * kPi; tf[TF_ANGLE2] = 0.25f * kPi - kPi; tf[TF_XR] = 0.025f; tf[TF_YR] = 0.028f; tf[TF_PERIOD] = 5.f;
+}
+
+// padded [n][w4] <-> packed [n][w] row copies for set_state / get_state / params
+__global__ void repack_kernel(float* dst, int dst_stride, int dst_off, const float* src, int src_stride, int src_off, int width, int n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * width) return;
+  const int w = (int)(i / width), k = (int)(i % width);
+  dst[(size_t)w * dst_stride + dst_off + k] = src[(size_t)w * src_stride + src_off + k];
+}
+
+}  // namespace myo
+
+// ------------------------------------------------------------------------------------------------
+struct myo_batch {
+  myo::PackedModel pm;
+  myo_task_cfg cfg;
+  myo::BatchPtrs p{};
+  int device = 0, n = 0;
+  int grid = 0, threads = myo::kThreads, smem = 0, regs = 0, wpc = 0;
+  int64_t launches = 0;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+using namespace myo;
+
+#define CK(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                               \
+      return MYO_E_CUDA;                                                                            \
+    }                                                                                               \
+  } while (0)
+
+template <class T> int dev_alloc(myo_batch* b, T** p, size_t count) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(count, 4) * sizeof(T)));
+  CK(cudaMemset(q, 0, std::max<size_t>(count, 4) * sizeof(T)));
+  b->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return MYO_OK;
+}
+
+template <int G> int launch_world(myo_batch* b, const StepArgs& a, cudaStream_t st) {
+  MYO_LAUNCH(world_kernel<G>, b->grid, b->threads, b->smem, st, b->pm.dm, b->cfg, b->p, a);
+  b->launches++;
+  CK(cudaGetLastError());
+  return MYO_OK;
+}
+int launch(myo_batch* b, const StepArgs& a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(b->device));
+  int rc = MYO_OK;
+  MYO_LANES_CASES(b, launch_world, b, a, st)
+  return rc;
+}
+template <int G> int configure(myo_batch* b) {
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, world_kernel<G>));
+  b->regs = fa.numRegs;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, b->device));
+  const size_t world_bytes = (size_t)b->pm.dm.scratch_words * sizeof(float);
+  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  // worlds per CTA: fill the SM's shared memory with as few CTAs as keep threads <= kThreads
+  int wpc = kThreads / G;
+  while (wpc > 1 && wpc * world_bytes > max_smem) wpc--;
+  if (wpc * world_bytes > max_smem) { set_error("one world's scratch exceeds shared memory per CTA"); return MYO_E_LIMIT; }
+  b->wpc = wpc;
+  b->threads = wpc * G;
+  b->smem = (int)(wpc * world_bytes);
+  CK(cudaFuncSetAttribute(world_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem));
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, world_kernel<G>, b->threads, b->smem));
+  if (per_sm < 1) per_sm = 1;
+  const int need = (b->n + wpc - 1) / wpc;
+  b->grid = std::max(1, std::min(need, prop.multiProcessorCount * per_sm));
+  return MYO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int myo_task_cfg_default(const myo_model* mh, int kind, myo_task_cfg* cfg) {
+  if (!mh || !cfg) { myo::set_error("null argument"); return MYO_E_ARG; }
+  const myo::Model& m = myo_model_host(mh);
+  memset(cfg, 0, sizeof *cfg);
+  cfg->kind = kind; cfg->frame_skip = 10; cfg->max_episode_steps = kind == MYO_TASK_BAODING ? 200 : 100;
+  cfg->normalize_act = 1; cfg->auto_reset = 1;
+  cfg->solver_iterations = 0; cfg->solver_tolerance = 0.f;
+  if (kind == MYO_TASK_BAODING) {
+    // BaodingEnvV1.DEFAULT_RWD_KEYS_AND_WEIGHTS (pos_dist 5/5, alive 0, act_reg 0), /root/reference/src/envs/baoding.py:16-22
+    cfg->rwd_weight[0] = 5.f; cfg->rwd_weight[1] = 5.f;
+    cfg->drop_th = 1.25f; cfg->proximity_th = 0.015f;
+    cfg->goal_time_period[0] = cfg->goal_time_period[1] = 5.f;
+    cfg->goal_xrange[0] = cfg->goal_xrange[1] = 0.025f; cfg->goal_yrange[0] = cfg->goal_yrange[1] = 0.028f;
+    cfg->obj_size_range[0] = 0.018f; cfg->obj_size_range[1] = 0.024f;
+    cfg->obj_mass_range[0] = 0.030f; cfg->obj_mass_range[1] = 0.300f;
+    cfg->obj_friction_change[0] = 0.2f; cfg->obj_friction_change[1] = 0.001f; cfg->obj_friction_change[2] = 0.00002f;
+    cfg->task_choice_random = 0; cfg->fixed_task = MYO_BAODING_CCW;
+    cfg->center_pos[0] = -0.0125f; cfg->center_pos[1] = -0.07f;
+    cfg->randomize_physics = 1;
+    const char* bn[2] = {"ball1", "ball2"}; const char* sn[2] = {"ball1_site", "ball2_site"};
+    const char* tn[2] = {"target1_site", "target2_site"};
+    for (int k = 0; k < 2; k++) {
+      cfg->ball_body[k] = m.name2id("body", bn[k]); cfg->ball_geom[k] = m.name2id("geom", bn[k]);
+      cfg->ball_site[k] = m.name2id("site", sn[k]); cfg->target_site[k] = m.name2id("site", tn[k]);
+      if (cfg->ball_body[k] < 0 || cfg->ball_geom[k] < 0 || cfg->ball_site[k] < 0 || cfg->target_site[k] < 0) {
+        myo::set_error("model lacks the baoding names ball{1,2}, ball{1,2}_site, target{1,2}_site");
+        return MYO_E_ARG;
+      }
+      const int j = m.i("body_jntadr")[cfg->ball_body[k]];
+      cfg->ball_qposadr[k] = m.i("jnt_qposadr")[j]; cfg->ball_dofadr[k] = m.i("jnt_dofadr")[j];
+    }
+    cfg->n_ovr_body = 2; cfg->ovr_body[0] = cfg->ball_body[0]; cfg->ovr_body[1] = cfg->ball_body[1];
+    cfg->n_ovr_geom = 2; cfg->ovr_geom[0] = cfg->ball_geom[0]; cfg->ovr_geom[1] = cfg->ball_geom[1];
+    cfg->n_ovr_site = 2; cfg->ovr_site[0] = cfg->target_site[0]; cfg->ovr_site[1] = cfg->target_site[1];
+  } else if (kind == MYO_TASK_POSE) {
+    // PoseEnvV0.DEFAULT_RWD_KEYS_AND_WEIGHTS: pose 1, bonus 4, penalty 50, act_reg 1 (order: pose bonus penalty act_reg)
+    cfg->rwd_weight[0] = 1.f; cfg->rwd_weight[1] = 4.f; cfg->rwd_weight[2] = 50.f; cfg->rwd_weight[3] = 1.f;
+    cfg->pose_thd = 0.35f; cfg->far_th = 4.f * 3.14159265358979f / 2.f; cfg->target_distance = 1.f;
+    cfg->reset_type = 1; cfg->target_type = 1;
+  }
+  return MYO_OK;
+}
+
+int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_task_cfg* cfg, uint64_t seed, myo_batch** out) {
+  if (!mh || !cfg || !out || n_worlds <= 0) { myo::set_error("bad argument to myo_batch_create"); return MYO_E_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    myo::set_error("no CUDA device available (this library has no CPU path)");
+    return MYO_E_CUDA;
+  }
+  myo_batch* b = new myo_batch();
+  b->cfg = *cfg; b->device = device; b->n = n_worlds;
+  int status = MYO_OK;
+  std::string err = myo::pack_model(myo_model_host(mh), *cfg, b->pm, status);
+  if (!err.empty()) { delete b; myo::set_error(err); return status; }
+  if (cfg->kind == MYO_TASK_POSE && cfg->n_target_jnt > 64) { delete b; myo::set_error("too many target joints"); return MYO_E_LIMIT; }
+  auto fail = [&](int code) { myo_batch_destroy(b); return code; };
+  if (cudaSetDevice(device) != cudaSuccess) { myo::set_error("cudaSetDevice failed"); return fail(MYO_E_CUDA); }
+  const myo::DevModel& dm = b->pm.dm;
+  int rc;
+  if ((rc = dev_alloc(b, &b->pm.d_ibuf, b->pm.ibuf.size()))) return fail(rc);
+  if ((rc = dev_alloc(b, &b->pm.d_fbuf, b->pm.fbuf.size()))) return fail(rc);
+  if (cudaMemcpy(b->pm.d_ibuf, b->pm.ibuf.data(), b->pm.ibuf.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(b->pm.d_fbuf, b->pm.fbuf.data(), b->pm.fbuf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    myo::set_error("model upload failed");
+    return fail(MYO_E_CUDA);
+  }
+  myo::resolve_pointers(b->pm, b->pm.d_ibuf, b->pm.d_fbuf);
+  const size_t n = (size_t)n_worlds;
+  b->p.n_worlds = n_worlds; b->p.seed = seed;
+  if ((rc = dev_alloc(b, &b->p.qpos, n * dm.nq4)) || (rc = dev_alloc(b, &b->p.qvel, n * dm.nv4)) ||
+      (rc = dev_alloc(b, &b->p.act, n * dm.na4)) || (rc = dev_alloc(b, &b->p.warm, n * dm.nv4)) ||
+      (rc = dev_alloc(b, &b->p.time, n)) || (rc = dev_alloc(b, &b->p.wparam, n * dm.nparam4)) ||
+      (rc = dev_alloc(b, &b->p.task_f, n * myo::TF_WORDS)) || (rc = dev_alloc(b, &b->p.pose_target, n * dm.nq4)) ||
+      (rc = dev_alloc(b, &b->p.task_i, n * myo::TI_WORDS)) || (rc = dev_alloc(b, &b->p.status, 4)))
+    return fail(rc);
+  b->p.dump = nullptr;
+  MYO_LANES_CASES(b, configure, b)
+  if (rc) return fail(rc);
+  MYO_LAUNCH(myo::init_worlds_kernel, (n_worlds + 127) / 128, 128, 0, (cudaStream_t)0, dm, b->p, cfg->fixed_task);
+  b->launches++;
+  if (cudaDeviceSynchronize() != cudaSuccess) { myo::set_error("world initialisation failed"); return fail(MYO_E_CUDA); }
+  *out = b;
+  return MYO_OK;
+}
+
+void myo_batch_destroy(myo_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  for (void* p : b->allocs) cudaFree(p);
+  delete b;
+}
+
+int myo_batch_dims(const myo_batch* b, int* n_worlds, int* nq, int* nv, int* na, int* nu, int* nobs, int* n_param) {
+  if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
+  const myo::DevModel& d = b->pm.dm;
+  if (n_worlds) *n_worlds = b->n;
+  if (nq) *nq = d.nq;
+  if (nv) *nv = d.nv;
+  if (na) *na = d.na;
+  if (nu) *nu = d.nu;
+  if (nobs) *nobs = d.nobs;
+  if (n_param) *n_param = d.nparam;
+  return MYO_OK;
+}
+
+int myo_batch_launch_info(const myo_batch* b, int* lanes_per_world, int* worlds_per_cta, int* smem_bytes, int* regs_per_thread) {
+  if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
+  if (lanes_per_world) *lanes_per_world = b->pm.lanes;
+  if (worlds_per_cta) *worlds_per_cta = b->wpc;
+  if (smem_bytes) *smem_bytes = b->smem;
+  if (regs_per_thread) *regs_per_thread = b->regs;
+  return MYO_OK;
+}
+
+int myo_batch_reset(myo_batch* b, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+  if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
+  myo::StepArgs a{};
+  a.mode = myo::MODE_RESET; a.mask = mask_dev; a.obs = obs_dev;
+  return launch(b, a, stream);
+}
+
+int myo_batch_step(myo_batch* b, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                   uint8_t* truncated_dev, float* terminal_obs_dev, float* info_dev, void* stream) {
+  if (!b || !actions_dev || !obs_dev || !reward_dev || !done_dev) { myo::set_error("null argument to myo_batch_step"); return MYO_E_ARG; }
+  myo::StepArgs a{};
+  a.mode = myo::MODE_ENV_STEP; a.nsub = b->cfg.frame_skip > 0 ? b->cfg.frame_skip : 1;
+  a.in = actions_dev; a.obs = obs_dev; a.reward = reward_dev; a.done = done_dev; a.truncated = truncated_dev;
+  a.terminal_obs = terminal_obs_dev; a.info = info_dev;
+  return launch(b, a, stream);
+}
+
+static int ensure_dump(myo_batch* b) {
+  if (b->p.dump) return MYO_OK;
+  return dev_alloc(b, &b->p.dump, (size_t)b->n * b->pm.dm.scratch_words);
+}
+
+int myo_batch_mj_step(myo_batch* b, const float* ctrl_dev, int nsub, void* stream) {
+  if (!b || nsub < 0) { myo::set_error("bad argument to myo_batch_mj_step"); return MYO_E_ARG; }
+  int rc = ensure_dump(b);
+  if (rc) return rc;
+  myo::StepArgs a{};
+  a.mode = myo::MODE_MJ_STEP; a.nsub = nsub; a.in = ctrl_dev;
+  return launch(b, a, stream);
+}
+
+int myo_batch_forward(myo_batch* b, const float* ctrl_dev, void* stream) {
+  if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
+  int rc = ensure_dump(b);
+  if (rc) return rc;
+  myo::StepArgs a{};
+  a.mode = myo::MODE_FORWARD; a.in = ctrl_dev;
+  return launch(b, a, stream);
+}
+
+int myo_batch_get_obs(myo_batch* b, float* obs_dev, void* stream) {
+  if (!b || !obs_dev) { myo::set_error("null argument"); return MYO_E_ARG; }
+  myo::StepArgs a{};
+  a.mode = myo::MODE_GET_OBS; a.obs = obs_dev;
+  return launch(b, a, stream);
+}
+
+static int repack(myo_batch* b, float* dst, int ds, int doff, const float* src, int ss, int soff, int width, void* stream) {
+  if (width <= 0) return MYO_OK;
+  const long long total = (long long)b->n * width;
+  MYO_LAUNCH(myo::repack_kernel, (unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), dst, ds, doff, src, ss, soff, width, b->n);
+  b->launches++;
+  CK(cudaGetLastError());
+  return MYO_OK;
+}
+
+int myo_batch_set_state(myo_batch* b, const float* qpos_dev, const float* qvel_dev, const float* act_dev, const float* time_dev, void* stream) {
+  if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
+  CK(cudaSetDevice(b->device));
+  const myo::DevModel& d = b->pm.dm;
+  int rc = MYO_OK;
+  if (qpos_dev && (rc = repack(b, b->p.qpos, d.nq4, 0, qpos_dev, d.nq, 0, d.nq, stream))) return rc;
+  if (qvel_dev && (rc = repack(b, b->p.qvel, d.nv4, 0, qvel_dev, d.nv, 0, d.nv, stream))) return rc;
+  if (act_dev && d.na && (rc = repack(b, b->p.act, d.na4, 0, act_dev, d.na, 0, d.na, stream))) return rc;
+  if (time_dev && (rc = repack(b, b->p.time, 1, 0, time_dev, 1, 0, 1, stream))) return rc;
+  return MYO_OK;
+}
+
+int myo_batch_get_state(myo_batch* b, float* qpos_dev, float* qvel_dev, float* act_dev, float* time_dev, void* stream) {
+  if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
+  CK(cudaSetDevice(b->device));
+  const myo::DevModel& d = b->pm.dm;
+  int rc = MYO_OK;
+  if (qpos_dev && (rc = repack(b, qpos_dev, d.nq, 0, b->p.qpos, d.nq4, 0, d.nq, stream))) return rc;
+  if (qvel_dev && (rc = repack(b, qvel_dev, d.nv, 0, b->p.qvel, d.nv4, 0, d.nv, stream))) return rc;
+  if (act_dev && d.na && (rc = repack(b, act_dev, d.na, 0, b->p.act, d.na4, 0, d.na, stream))) return rc;
+  if (time_dev && (rc = repack(b, time_dev, 1, 0, b->p.time, 1, 0, 1, stream))) return rc;
+  return MYO_OK;
+}
+
+static const myo::PackedModel::Slot* find_slot(const myo_batch* b, int kind, int id) {
+  for (const auto& s : b->pm.slots) if (s.kind == kind && s.id == id) return &s;
+  return nullptr;
+}
+int myo_batch_set_param(myo_batch* b, int kind, int id, const float* values_dev, void* stream) {
+  if (!b || !values_dev) { myo::set_error("null argument"); return MYO_E_ARG; }
+  const auto* s = find_slot(b, kind, id);
+  if (!s) { myo::set_error("parameter was not declared as a per-world override in the task cfg"); return MYO_E_ARG; }
+  CK(cudaSetDevice(b->device));
+  return repack(b, b->p.wparam, b->pm.dm.nparam4, s->slot, values_dev, s->ncomp, 0, s->ncomp, stream);
+}
+int myo_batch_get_param(myo_batch* b, int kind, int id, float* values_dev, void* stream) {
+  if (!b || !values_dev) { myo::set_error("null argument"); return MYO_E_ARG; }
+  const auto* s = find_slot(b, kind, id);
+  if (!s) { myo::set_error("parameter was not declared as a per-world override in the task cfg"); return MYO_E_ARG; }
+  CK(cudaSetDevice(b->device));
+  return repack(b, values_dev, s->ncomp, 0, b->p.wparam, b->pm.dm.nparam4, s->slot, s->ncomp, stream);
+}
+
+int myo_batch_stage_dump(myo_batch* b, int stage, void* out_dev, int* width, void* stream) {
+  if (!b || stage < 0 || stage >= MYO_STAGE_COUNT) { myo::set_error("bad stage"); return MYO_E_ARG; }
+  const myo::DevModel& d = b->pm.dm;
+  int w = 0;
+  switch (stage) {
+    case MYO_STAGE_XPOS: w = 3 * d.nbody; break;
+    case MYO_STAGE_XMAT: w = 9 * d.nbody; break;
+    case MYO_STAGE_SITE_XPOS: w = 3 * d.nsite; break;
+    case MYO_STAGE_TEN_LENGTH: w = d.ntendon; break;
+    case MYO_STAGE_TEN_J: w = d.ntendon * d.nv; break;
+    case MYO_STAGE_QM: w = d.nv * d.nv; break;
+    case MYO_STAGE_ACT_FORCE: w = d.nu; break;
+    case MYO_STAGE_ACT_DOT: w = d.na; break;
+    case MYO_STAGE_NCON: case MYO_STAGE_NEFC: case MYO_STAGE_SOLVER_ITER: case MYO_STAGE_STATUS: w = 1; break;
+    case MYO_STAGE_CONTACT_GEOMS: w = 2 * d.ncon_max; break;
+    case MYO_STAGE_CONTACT_DIST: w = d.ncon_max; break;
+    case MYO_STAGE_EFC_TYPE_ID: w = 2 * d.nefc_max; break;
+    case MYO_STAGE_EFC_J: w = d.nefc_max * d.nv; break;
+    case MYO_STAGE_EFC_AREF: case MYO_STAGE_EFC_D: case MYO_STAGE_EFC_FORCE: w = d.nefc_max; break;
+    default: w = d.nv; break;
+  }
+  if (width) *width = w;
+  if (!out_dev) return MYO_OK;
+  if (!b->p.dump) { myo::set_error("no stage data: call myo_batch_forward or myo_batch_mj_step first"); return MYO_E_ARG; }
+  CK(cudaSetDevice(b->device));
+  MYO_LAUNCH(myo::extract_kernel, (b->n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream), d, b->p.dump, b->n, stage, out_dev, w);
+  b->launches++;
+  CK(cudaGetLastError());
+  return MYO_OK;
+}
+
+int myo_batch_status(myo_batch* b, int* flags, void* stream) {
+  if (!b || !flags) { myo::set_error("null argument"); return MYO_E_ARG; }
+  CK(cudaSetDevice(b->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int h = 0;
+  CK(cudaMemcpyAsync(&h, b->p.status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemsetAsync(b->p.status, 0, sizeof(int), st));
+  *flags = h;
+  return MYO_OK;
+}
+
+int64_t myo_batch_launch_count(const myo_batch* b) { return b ? b->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// Host-side packer: turns the parsed MJB model (+ task configuration) into the flat device tables
+// the step kernel reads (DevModel) and derives the tree / sparsity metadata the kernel phases use.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "myo_dev.hpp"
+#include "myo_model.hpp"
+
+namespace myo {
+
+struct PackedModel {
+  DevModel dm{};                 // pointers are device pointers once upload() ran
+  std::vector<int> ibuf;         // all int tables, concatenated
+  std::vector<float> fbuf;       // all float tables, concatenated
+  std::vector<std::pair<size_t, size_t>> ifix, ffix;   // (byte offset of the pointer inside dm, element offset)
+  int* d_ibuf = nullptr;
+  float* d_fbuf = nullptr;
+  int lanes = 32;                // tile width G chosen for this model
+  // override slot bookkeeping: (kind, id) -> (slot, ncomp)
+  struct Slot { int kind, id, slot, ncomp; };
+  std::vector<Slot> slots;
+  std::vector<float> param0, init_qpos;
+};
+
+// returns "" on success; status gets a myo_status code on failure
+std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out, int& status);
+// rebuild fbuf-resident init_qpos / param0 after host edits (before upload)
+void resolve_pointers(PackedModel& pm, const int* ibase, const float* fbase);
+
+}  // namespace myo

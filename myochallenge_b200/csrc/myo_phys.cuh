@@ -1,0 +1,1377 @@
+// Physics phases of one mj_step for one world held in shared memory, executed by a tile of G lanes.
+// Each phase states the MuJoCo 2.1.0 stage it reproduces; the
+// reference reaches them through env.step -> Robot.step -> sim.step
+// (/root/reference/src/envs/baoding.py:183,625; /root/reference/src/envs/pose.py:102).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "myo_dev.hpp"
+#include "myo_math.cuh"
+
+namespace myo {
+namespace cg = cooperative_groups;
+
+template <int G>
+struct Ctx {
+  cg::thread_block_tile<G> tile;
+  int lane;
+  float* s;          // this world's scratch (shared memory)
+  float* wp;         // this world's override parameters (global memory)
+  __device__ Ctx(cg::thread_block_tile<G> t) : tile(t), lane(t.thread_rank()), s(nullptr), wp(nullptr) {}
+};
+
+#define SF(field) (c.s + m.field)
+#define SI(field) (reinterpret_cast<int*>(c.s + m.field))
+
+template <int G> MYO_DI float tile_sum(const Ctx<G>& c, float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += c.tile.shfl_xor(v, o);
+  return v;
+}
+template <int G> MYO_DI float tile_max(const Ctx<G>& c, float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, c.tile.shfl_xor(v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a10.1 kinematics + comPos (+ comVel + RNE forward when dyn): one level-synchronous sweep.
+// Reference point of every kinematic tree = xipos of its root body (MuJoCo uses the subtree COM;
+// the dynamics are invariant to that choice and a nearby point keeps fp32 cross products small).
+template <int G>
+__device__ void body_forward(const DevModel& m, Ctx<G>& c, int b, bool dyn) {
+  const float* qpos = SF(o_qpos);
+  const float* qvel = SF(o_qvel);
+  float* cdof = SF(o_cdof);
+  const int pid = m.b_parent[b], jadr = m.b_jntadr[b], jnum = m.b_jntnum[b];
+  float pos[3], q[4];
+  const bool is_free = (jnum == 1 && m.j_type[jadr] == J_FREE);
+  if (is_free) {
+    const int qa = m.j_qposadr[jadr];
+    pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
+    q[0] = qpos[qa + 3]; q[1] = qpos[qa + 4]; q[2] = qpos[qa + 5]; q[3] = qpos[qa + 6];
+    normalize4(q);
+  } else {
+    const float* pp = SF(o_xpos) + 3 * pid;
+    const float* pR = SF(o_xmat) + 9 * pid;
+    float v[3];
+    mulmatvec3(v, pR, m.b_pos + 3 * b);
+    add3(pos, v, pp);
+    mulquat(q, SF(o_xquat) + 4 * pid, m.b_quat + 4 * b);
+    for (int j = jadr; j < jadr + jnum; j++) {
+      const int qa = m.j_qposadr[j], da = m.j_dofadr[j];
+      const float dq = qpos[qa] - m.j_qpos0[j];
+      float ax[3];
+      rotvecquat(ax, m.j_axis + 3 * j, q);
+      if (m.j_type[j] == J_SLIDE) {
+        pos[0] += ax[0] * dq; pos[1] += ax[1] * dq; pos[2] += ax[2] * dq;
+        cdof[6 * da] = 0.f; cdof[6 * da + 1] = 0.f; cdof[6 * da + 2] = 0.f;
+        cdof[6 * da + 3] = ax[0]; cdof[6 * da + 4] = ax[1]; cdof[6 * da + 5] = ax[2];
+      } else {  // hinge: stash axis | anchor, finished below once the tree reference is known
+        float anchor[3], ql[4], vec[3];
+        rotvecquat(anchor, m.j_pos + 3 * j, q);
+        add3(anchor, anchor, pos);
+        float sn, cs;
+        sincosf(0.5f * dq, &sn, &cs);
+        ql[0] = cs; ql[1] = m.j_axis[3 * j] * sn; ql[2] = m.j_axis[3 * j + 1] * sn; ql[3] = m.j_axis[3 * j + 2] * sn;
+        mulquat(q, q, ql);
+        rotvecquat(vec, m.j_pos + 3 * j, q);
+        sub3(pos, anchor, vec);
+        cdof[6 * da] = ax[0]; cdof[6 * da + 1] = ax[1]; cdof[6 * da + 2] = ax[2];
+        cdof[6 * da + 3] = anchor[0]; cdof[6 * da + 4] = anchor[1]; cdof[6 * da + 5] = anchor[2];
+      }
+    }
+    normalize4(q);
+  }
+  float R[9];
+  quat2mat(R, q);
+  float* xp = SF(o_xpos) + 3 * b;
+  float* xq = SF(o_xquat) + 4 * b;
+  float* xm = SF(o_xmat) + 9 * b;
+  cpy3(xp, pos);
+  xq[0] = q[0]; xq[1] = q[1]; xq[2] = q[2]; xq[3] = q[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) xm[k] = R[k];
+  float ip[3];
+  mulmatvec3(ip, R, m.b_ipos + 3 * b);
+  add3(ip, ip, pos);
+  cpy3(SF(o_xipos) + 3 * b, ip);
+  const int root = m.b_root[b];
+  float cref[3];
+  if (root == b) cpy3(cref, ip); else cpy3(cref, SF(o_xipos) + 3 * root);
+
+  // finish cdof (mj_comPos)
+  if (is_free) {
+    const int da = m.j_dofadr[jadr];
+    float off[3];
+    sub3(off, cref, pos);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float* t = cdof + 6 * (da + k);
+      t[0] = t[1] = t[2] = 0.f; t[3] = (k == 0); t[4] = (k == 1); t[5] = (k == 2);
+      float* r = cdof + 6 * (da + 3 + k);
+      float ax[3] = {R[k], R[3 + k], R[6 + k]};
+      cpy3(r, ax);
+      cross3(r + 3, ax, off);
+    }
+  } else {
+    for (int j = jadr; j < jadr + jnum; j++) {
+      if (m.j_type[j] != J_HINGE) continue;
+      float* t = cdof + 6 * m.j_dofadr[j];
+      float off[3];
+      sub3(off, cref, t + 3);
+      cross3(t + 3, t, off);
+    }
+  }
+  if (!dyn) return;
+
+  // cinert
+  {
+    float off[3], mass = m.b_mass[b];
+    const int slot = m.b_mass_slot[b];
+    if (slot >= 0) mass = c.wp[slot];
+    sub3(off, ip, cref);
+    float* ci = SF(o_cinert) + 10 * b;
+    if (m.b_sameframe[b]) inert_com(ci, m.b_inertia + 3 * b, R, off, mass);
+    else {
+      float qi[4], Ri[9];
+      mulquat(qi, q, m.b_iquat + 4 * b);
+      quat2mat(Ri, qi);
+      inert_com(ci, m.b_inertia + 3 * b, Ri, off, mass);
+    }
+  }
+  // cvel, cdof_dot (mj_comVel) and cacc, cfrc (mj_rne forward, flg_acc = 0)
+  float cv[6], ca[6];
+  {
+    const float* pv = SF(o_cvel) + 6 * pid;
+    const float* pa = SF(o_cacc) + 6 * pid;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { cv[k] = pv[k]; ca[k] = pa[k]; }
+  }
+  float* cdd = SF(o_cdofdot);
+  const int d0 = m.b_dofadr[b], dn = m.b_dofnum[b];
+  if (is_free) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float* t = cdd + 6 * (d0 + k);
+      t[0] = t[1] = t[2] = t[3] = t[4] = t[5] = 0.f;
+      cv[3 + k] += qvel[d0 + k];
+    }
+    float add[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const float* cd = cdof + 6 * (d0 + 3 + k);
+      float t[6];
+      cross_motion(t, cv, cd);
+      const float w = qvel[d0 + 3 + k];
+#pragma unroll
+      for (int e = 0; e < 6; e++) { cdd[6 * (d0 + 3 + k) + e] = t[e]; ca[e] += t[e] * w; add[e] += cd[e] * w; }
+    }
+#pragma unroll
+    for (int e = 0; e < 6; e++) cv[e] += add[e];
+  } else {
+    for (int d = d0; d < d0 + dn; d++) {
+      const float* cd = cdof + 6 * d;
+      float t[6];
+      cross_motion(t, cv, cd);
+      const float w = qvel[d];
+#pragma unroll
+      for (int e = 0; e < 6; e++) { cdd[6 * d + e] = t[e]; ca[e] += t[e] * w; cv[e] += cd[e] * w; }
+    }
+  }
+  float* ov = SF(o_cvel) + 6 * b;
+  float* oa = SF(o_cacc) + 6 * b;
+#pragma unroll
+  for (int k = 0; k < 6; k++) { ov[k] = cv[k]; oa[k] = ca[k]; }
+  {
+    const float* ci = SF(o_cinert) + 10 * b;
+    float f[6], t[6], t1[6];
+    mul_inert_vec(f, ci, ca);
+    mul_inert_vec(t, ci, cv);
+    cross_force(t1, cv, t);
+    float* of = SF(o_cfrc) + 6 * b;
+#pragma unroll
+    for (int k = 0; k < 6; k++) of[k] = f[k] + t1[k];
+  }
+}
+
+template <int G>
+__device__ void phase_tree_forward(const DevModel& m, Ctx<G>& c, bool dyn) {
+  if (c.lane == 0) {
+    float* xp = SF(o_xpos); float* xq = SF(o_xquat); float* xm = SF(o_xmat); float* xi = SF(o_xipos);
+    xp[0] = xp[1] = xp[2] = 0.f; xi[0] = xi[1] = xi[2] = 0.f;
+    xq[0] = 1.f; xq[1] = xq[2] = xq[3] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; k++) xm[k] = (k % 4 == 0) ? 1.f : 0.f;
+    if (dyn) {
+      float* cv = SF(o_cvel); float* ca = SF(o_cacc); float* cf = SF(o_cfrc); float* ci = SF(o_cinert);
+#pragma unroll
+      for (int k = 0; k < 6; k++) { cv[k] = 0.f; cf[k] = 0.f; }
+      ca[0] = ca[1] = ca[2] = 0.f; ca[3] = -m.gravity[0]; ca[4] = -m.gravity[1]; ca[5] = -m.gravity[2];
+#pragma unroll
+      for (int k = 0; k < 10; k++) ci[k] = 0.f;
+    }
+  }
+  c.tile.sync();
+  for (int L = 0; L < m.nlevel; L++) {
+    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) body_forward<G>(m, c, m.lvl_body[i], dyn);
+    c.tile.sync();
+  }
+}
+
+// mj_crb backward accumulation + mj_rne backward pass, children gathered in a fixed order
+template <int G>
+__device__ void phase_tree_backward(const DevModel& m, Ctx<G>& c) {
+  float* ci = SF(o_cinert); float* cf = SF(o_cfrc);
+  for (int L = m.nlevel - 2; L >= 0; L--) {
+    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) {
+      const int b = m.lvl_body[i];
+      for (int k = m.b_childadr[b]; k < m.b_childadr[b + 1]; k++) {
+        const int ch = m.b_child[k];
+#pragma unroll
+        for (int e = 0; e < 10; e++) ci[10 * b + e] += ci[10 * ch + e];
+#pragma unroll
+        for (int e = 0; e < 6; e++) cf[6 * b + e] += cf[6 * ch + e];
+      }
+    }
+    c.tile.sync();
+  }
+}
+
+// a10.4 mass matrix in MuJoCo's sparse dof_Madr layout (row i: i, parent(i), ...) + qfrc_bias
+template <int G>
+__device__ void phase_mass_bias(const DevModel& m, Ctx<G>& c) {
+  const float* cdof = SF(o_cdof); const float* crb = SF(o_cinert); const float* cf = SF(o_cfrc);
+  float* M = SF(o_M); float* bias = SF(o_bias);
+  for (int i = c.lane; i < m.nv; i += G) {
+    const int body = m.d_body[i];
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 6; e++) s += cdof[6 * i + e] * cf[6 * body + e];
+    bias[i] = s;
+    int adr = m.d_Madr[i];
+    if (m.d_simple[i]) {   // mj_crb: simple dofs take the stored dof_M0, off-diagonals stay zero
+      M[adr] = m.d_M0[i];
+      for (int s = 1; s <= m.d_depth[i]; s++) M[adr + s] = 0.f;
+      continue;
+    }
+    float buf[6];
+    mul_inert_vec(buf, crb + 10 * body, cdof + 6 * i);
+    int j = i;
+    bool first = true;
+    while (j >= 0) {
+      float v = 0.f;
+#pragma unroll
+      for (int e = 0; e < 6; e++) v += cdof[6 * j + e] * buf[e];
+      if (first) { v += m.d_armature[i]; first = false; }
+      M[adr++] = v;
+      j = m.d_parent[j];
+    }
+  }
+  c.tile.sync();
+}
+
+// mj_factorM restated in gather form so dofs of one depth factor in parallel without atomics:
+//   D(i)   = M(i,i) - sum_{k in desc(i)} L(k,i)^2 D(k)
+//   L(i,j) = (M(i,j) - sum_k L(k,i) L(k,j) D(k)) / D(i)      j ancestor of i
+// LD holds D on the diagonal slot and L on the ancestor slots. hdamp adds h*damping (mj_Euler).
+template <int G>
+__device__ void factor_sparse(const DevModel& m, Ctx<G>& c, float* LD, const float* M, float hdamp) {
+  for (int L = m.ndlevel - 1; L >= 0; L--) {
+    for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
+      const int i = m.dlvl_dof[idx];
+      const int adr = m.d_Madr[i], dep = m.d_depth[i];
+      if (m.d_simple[i]) {
+        LD[adr] = fmaxf(M[adr] + hdamp * m.d_damping[i], kMinVal);
+        for (int s = 1; s <= dep; s++) LD[adr + s] = 0.f;
+        continue;
+      }
+      float acc[KC];
+#pragma unroll
+      for (int s = 0; s < KC; s++) acc[s] = (s <= dep) ? M[adr + s] : 0.f;
+      acc[0] += hdamp * m.d_damping[i];
+      for (int kk = m.d_descadr[i]; kk < m.d_descadr[i + 1]; kk++) {
+        const int k = m.d_desc[kk];
+        const int ka = m.d_Madr[k], t = m.d_depth[k] - dep;
+        const float w = LD[ka + t] * LD[ka];
+#pragma unroll
+        for (int s = 0; s < KC; s++) if (s <= dep) acc[s] -= w * LD[ka + t + s];
+      }
+      const float d = fmaxf(acc[0], kMinVal);
+      const float inv = 1.f / d;
+      LD[adr] = d;
+#pragma unroll
+      for (int s = 1; s < KC; s++) if (s <= dep) LD[adr + s] = acc[s] * inv;
+    }
+    c.tile.sync();
+  }
+}
+// x <- (L' D L)^-1 x   (mj_solveLD, gather form)
+template <int G>
+__device__ void solve_sparse(const DevModel& m, Ctx<G>& c, const float* LD, float* x) {
+  for (int L = m.ndlevel - 1; L >= 0; L--) {     // x <- L^-T x, deepest first
+    for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
+      const int i = m.dlvl_dof[idx];
+      const int dep = m.d_depth[i];
+      float v = x[i];
+      for (int kk = m.d_descadr[i]; kk < m.d_descadr[i + 1]; kk++) {
+        const int k = m.d_desc[kk];
+        v -= LD[m.d_Madr[k] + m.d_depth[k] - dep] * x[k];
+      }
+      x[i] = v;
+    }
+    c.tile.sync();
+  }
+  for (int i = c.lane; i < m.nv; i += G) x[i] /= LD[m.d_Madr[i]];
+  c.tile.sync();
+  for (int L = 1; L < m.ndlevel; L++) {          // x <- L^-1 x, shallowest first
+    for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
+      const int i = m.dlvl_dof[idx];
+      int adr = m.d_Madr[i] + 1, j = m.d_parent[i];
+      float v = x[i];
+      while (j >= 0) { v -= LD[adr++] * x[j]; j = m.d_parent[j]; }
+      x[i] = v;
+    }
+    c.tile.sync();
+  }
+}
+// y = M x using the sparse symmetric layout (mj_mulM)
+template <int G>
+__device__ void mul_M(const DevModel& m, Ctx<G>& c, const float* M, const float* x, float* y) {
+  for (int i = c.lane; i < m.nv; i += G) {
+    const int dep = m.d_depth[i];
+    int adr = m.d_Madr[i], j = i;
+    float v = 0.f;
+    while (j >= 0) { v += M[adr++] * x[j]; j = m.d_parent[j]; }
+    if (!m.d_simple[i])
+      for (int kk = m.d_descadr[i]; kk < m.d_descadr[i + 1]; kk++) {
+        const int k = m.d_desc[kk];
+        v += M[m.d_Madr[k] + m.d_depth[k] - dep] * x[k];
+      }
+    y[i] = v;
+  }
+  c.tile.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// a10.2 tendon length + moment arms (mj_tendon + mju_wrap), one lane per tendon.
+MYO_DI void site_world(const DevModel& m, const float* s, const float* wp, int sid, float* out) {
+  const int b = m.s_body[sid];
+  const int slot = m.s_pos_slot[sid];
+  float lp[3];
+  if (slot >= 0) { lp[0] = wp[slot]; lp[1] = wp[slot + 1]; lp[2] = wp[slot + 2]; }
+  else cpy3(lp, m.s_pos + 3 * sid);
+  mulmatvec3(out, s + m.o_xmat + 9 * b, lp);
+  add3(out, out, s + m.o_xpos + 3 * b);
+}
+MYO_DI bool seg_intersect(const float* p1, const float* p2, const float* p3, const float* p4) {
+  const float det = (p4[1] - p3[1]) * (p2[0] - p1[0]) - (p4[0] - p3[0]) * (p2[1] - p1[1]);
+  if (fabsf(det) < kMinVal) return false;
+  const float a = ((p4[0] - p3[0]) * (p1[1] - p3[1]) - (p4[1] - p3[1]) * (p1[0] - p3[0])) / det;
+  const float b = ((p2[0] - p1[0]) * (p1[1] - p3[1]) - (p2[1] - p1[1]) * (p1[0] - p3[0])) / det;
+  return a >= 0.f && a <= 1.f && b >= 0.f && b <= 1.f;
+}
+// 2-D wrap around a circle (MuJoCo wrap_circle). Arc angle via atan2(|cross|, dot): same value as
+// MuJoCo's acos(dot) but well conditioned in fp32 for small arcs.
+__device__ float wrap_circle(float* pnt, const float* d, const float* sd, float rad) {
+  const float sqlen0 = d[0] * d[0] + d[1] * d[1], sqlen1 = d[2] * d[2] + d[3] * d[3], sqrad = rad * rad;
+  const float dif[2] = {d[2] - d[0], d[3] - d[1]};
+  const float dd = dif[0] * dif[0] + dif[1] * dif[1];
+  if (sqlen0 < sqrad || sqlen1 < sqrad || rad < kMinVal) return -1.f;
+  if (dd < kMinVal) return -1.f;
+  float a = clipf(-(dif[0] * d[0] + dif[1] * d[1]) / dd, 0.f, 1.f);
+  const float tmp[2] = {a * dif[0] + d[0], a * dif[1] + d[1]};
+  if (tmp[0] * tmp[0] + tmp[1] * tmp[1] > sqrad && (!sd || sd[0] * tmp[0] + sd[1] * tmp[1] >= 0.f)) return -1.f;
+  const float sqrt0 = sqrtf(sqlen0 - sqrad), sqrt1 = sqrtf(sqlen1 - sqrad);
+  float sol[2][4], good[2];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float sgn = (i == 0) ? 1.f : -1.f;
+    sol[i][0] = (d[0] * sqrad + sgn * rad * d[1] * sqrt0) / sqlen0;
+    sol[i][1] = (d[1] * sqrad - sgn * rad * d[0] * sqrt0) / sqlen0;
+    sol[i][2] = (d[2] * sqrad - sgn * rad * d[3] * sqrt1) / sqlen1;
+    sol[i][3] = (d[3] * sqrad + sgn * rad * d[2] * sqrt1) / sqlen1;
+    if (sd) {
+      float t[2] = {sol[i][0] + sol[i][2], sol[i][1] + sol[i][3]};
+      const float n = sqrtf(t[0] * t[0] + t[1] * t[1]);
+      if (n < kMinVal) { t[0] = 1.f; t[1] = 0.f; } else { t[0] /= n; t[1] /= n; }
+      good[i] = t[0] * sd[0] + t[1] * sd[1];
+    } else {
+      const float t[2] = {sol[i][0] - sol[i][2], sol[i][1] - sol[i][3]};
+      good[i] = -(t[0] * t[0] + t[1] * t[1]);
+    }
+    if (seg_intersect(d, sol[i], d + 2, sol[i] + 2)) good[i] = -10000.f;
+  }
+  const int i = (good[0] > good[1]) ? 0 : 1;
+  const float* sl = (i == 0) ? sol[0] : sol[1];
+  pnt[0] = sl[0]; pnt[1] = sl[1]; pnt[2] = sl[2]; pnt[3] = sl[3];
+  if (seg_intersect(d, pnt, d + 2, pnt + 2)) return -1.f;
+  const float dt = pnt[0] * pnt[2] + pnt[1] * pnt[3];
+  const float cr = pnt[1] * pnt[2] - pnt[0] * pnt[3];
+  float angle = atan2f(fabsf(cr), dt);
+  if ((cr > 0.f && i) || (cr < 0.f && !i)) angle = 2.f * kPi - angle;
+  return rad * angle;
+}
+// returns curved length (>= 0) and two world points in wpnt[0..5]; -1 no wrap; -2 unsupported (inside wrap)
+__device__ float wrap_geom(float* wpnt, const float* x0, const float* x1, const float* gpos, const float* gmat, float radius,
+                           int type, const float* side) {
+  float p0[3], p1[3], dif[3], axis0[3], axis1[3], normal[3];
+  sub3(dif, x0, gpos); mulmatTvec3(p0, gmat, dif);
+  sub3(dif, x1, gpos); mulmatTvec3(p1, gmat, dif);
+  if (norm3(p0) < kMinVal || norm3(p1) < kMinVal) return -1.f;
+  if (type == W_SPHERE) {
+    cpy3(axis0, p0); normalize3(axis0);
+    cross3(normal, p0, p1);
+    if (norm3(normal) < kMinVal) {
+      int im = 0;
+      if (fabsf(axis0[1]) > fabsf(axis0[im])) im = 1;
+      if (fabsf(axis0[2]) > fabsf(axis0[im])) im = 2;
+      float a1[3] = {1.f, 1.f, 1.f};
+      a1[im] = 0.f;
+      cross3(normal, axis0, a1);
+    }
+    normalize3(normal);
+    cross3(axis1, normal, axis0); normalize3(axis1);
+  } else {
+    axis0[0] = 1.f; axis0[1] = 0.f; axis0[2] = 0.f; axis1[0] = 0.f; axis1[1] = 1.f; axis1[2] = 0.f;
+  }
+  const float dd[4] = {dot3(p0, axis0), dot3(p0, axis1), dot3(p1, axis0), dot3(p1, axis1)};
+  float sd[2];
+  const float* sdp = nullptr;
+  if (side) {
+    float sv[3];
+    sub3(dif, side, gpos); mulmatTvec3(sv, gmat, dif);
+    const float in_norm = (type == W_SPHERE) ? norm3(sv) : sqrtf(sv[0] * sv[0] + sv[1] * sv[1]);
+    if (in_norm < radius) return -2.f;
+    sd[0] = dot3(sv, axis0); sd[1] = dot3(sv, axis1);
+    const float n = sqrtf(sd[0] * sd[0] + sd[1] * sd[1]);
+    if (n < kMinVal) { sd[0] = 1.f; sd[1] = 0.f; } else { sd[0] /= n; sd[1] /= n; }
+    sd[0] *= radius; sd[1] *= radius;
+    sdp = sd;
+  }
+  float pnt[4];
+  float wlen = wrap_circle(pnt, dd, sdp, radius);
+  if (wlen < 0.f) return -1.f;
+  float res[6];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    res[k] = axis0[k] * pnt[0] + axis1[k] * pnt[1];
+    res[3 + k] = axis0[k] * pnt[2] + axis1[k] * pnt[3];
+  }
+  if (type == W_CYLINDER) {
+    const float L0 = sqrtf((p0[0] - res[0]) * (p0[0] - res[0]) + (p0[1] - res[1]) * (p0[1] - res[1]));
+    const float L1 = sqrtf((p1[0] - res[3]) * (p1[0] - res[3]) + (p1[1] - res[4]) * (p1[1] - res[4]));
+    res[2] = p0[2] + (p1[2] - p0[2]) * L0 / (L0 + wlen + L1);
+    res[5] = p0[2] + (p1[2] - p0[2]) * (L0 + wlen) / (L0 + wlen + L1);
+    const float h = fabsf(res[5] - res[2]);
+    wlen = sqrtf(wlen * wlen + h * h);
+  }
+  mulmatvec3(wpnt, gmat, res); add3(wpnt, wpnt, gpos);
+  mulmatvec3(wpnt + 3, gmat, res + 3); add3(wpnt + 3, wpnt + 3, gpos);
+  return wlen;
+}
+// d(point on body)/dq . dir for every dof on `body`'s chain past the common prefix `cp`
+MYO_DI void moment_half(const DevModel& m, const float* s, int body, int cp, const float* pnt, const float* dir, float scale,
+                        const int* tdof, int ntd, float* J) {
+  const int n = m.b_nchain[body];
+  if (n <= cp) return;
+  float off[3];
+  sub3(off, pnt, s + m.o_xipos + 3 * m.b_root[body]);
+  const float* cdof = s + m.o_cdof;
+  for (int k = cp; k < n; k++) {
+    const int d = m.b_chain[body * KC + k];
+    const float* cd = cdof + 6 * d;
+    float t[3];
+    cross3(t, cd, off);
+    const float v = ((cd[3] + t[0]) * dir[0] + (cd[4] + t[1]) * dir[1] + (cd[5] + t[2]) * dir[2]) * scale;
+#pragma unroll
+    for (int e = 0; e < KT; e++) if (e < ntd && tdof[e] == d) J[e] += v;
+  }
+}
+MYO_DI int common_prefix(const DevModel& m, int ba, int bb) {
+  if (m.b_root[ba] != m.b_root[bb]) return 0;
+  const int na = m.b_nchain[ba], nb = m.b_nchain[bb];
+  int cp = 0;
+  while (cp < na && cp < nb && m.b_chain[ba * KC + cp] == m.b_chain[bb * KC + cp]) cp++;
+  return cp;
+}
+MYO_DI void segment_moment(const DevModel& m, const float* s, int ba, const float* pa, int bb, const float* pb, float inv_div,
+                           const int* tdof, int ntd, float* J) {
+  if (ba == bb) return;
+  float dir[3];
+  sub3(dir, pb, pa);
+  normalize3(dir);
+  const int cp = common_prefix(m, ba, bb);
+  moment_half(m, s, ba, cp, pa, dir, -inv_div, tdof, ntd, J);
+  moment_half(m, s, bb, cp, pb, dir, inv_div, tdof, ntd, J);
+}
+
+template <int G>
+__device__ void phase_tendon(const DevModel& m, Ctx<G>& c, int* status) {
+  const float* qvel = SF(o_qvel);
+  for (int t = c.lane; t < m.ntendon; t += G) {
+    const int adr = m.t_adr[t], num = m.t_num[t], ntd = m.t_ndof[t];
+    const int* tdof = m.t_dof + t * KT;
+    float J[KT];
+#pragma unroll
+    for (int e = 0; e < KT; e++) J[e] = 0.f;
+    float len = 0.f, inv_div = 1.f;
+    int j = 0;
+    while (j < num - 1) {
+      const int tp0 = m.w_type[adr + j], tp1 = m.w_type[adr + j + 1];
+      if (tp0 == W_PULLEY || tp1 == W_PULLEY) {
+        if (tp0 == W_PULLEY) inv_div = 1.f / m.w_prm[adr + j];
+        j++;
+        continue;
+      }
+      const int id0 = m.w_obj[adr + j];
+      int id1 = m.w_obj[adr + j + 1];
+      float x0[3], x1[3];
+      site_world(m, c.s, c.wp, id0, x0);
+      const int b0 = m.s_body[id0];
+      const bool isgeom = (tp1 == W_SPHERE || tp1 == W_CYLINDER);
+      float wlen = -1.f, wp2[6];
+      int bw = -1;
+      if (isgeom) {
+        const int g = id1;
+        id1 = m.w_obj[adr + j + 2];
+        site_world(m, c.s, c.wp, id1, x1);
+        bw = m.g_body[g];
+        float gpos[3], gmat[9];
+        mulmatvec3(gpos, SF(o_xmat) + 9 * bw, m.g_pos + 3 * g);
+        add3(gpos, gpos, SF(o_xpos) + 3 * bw);
+        mulmat3(gmat, SF(o_xmat) + 9 * bw, m.g_mat + 9 * g);
+        const int side = m.w_side[adr + j + 1];
+        float sp[3];
+        if (side >= 0) site_world(m, c.s, c.wp, side, sp);
+        float radius = m.g_size[3 * g];
+        if (m.g_size_slot[g] >= 0) radius = c.wp[m.g_size_slot[g]];
+        wlen = wrap_geom(wp2, x0, x1, gpos, gmat, radius, tp1, side >= 0 ? sp : nullptr);
+        if (wlen == -2.f) { *status |= ST_UNSUPPORTED; wlen = -1.f; }
+      } else {
+        site_world(m, c.s, c.wp, id1, x1);
+      }
+      const int b1 = m.s_body[id1];
+      if (wlen < 0.f) {
+        float d[3];
+        sub3(d, x1, x0);
+        len += norm3(d) * inv_div;
+        segment_moment(m, c.s, b0, x0, b1, x1, inv_div, tdof, ntd, J);
+      } else {
+        float d0[3], d1[3];
+        sub3(d0, wp2, x0); sub3(d1, x1, wp2 + 3);
+        len += (norm3(d0) + wlen + norm3(d1)) * inv_div;
+        segment_moment(m, c.s, b0, x0, bw, wp2, inv_div, tdof, ntd, J);
+        segment_moment(m, c.s, bw, wp2 + 3, b1, x1, inv_div, tdof, ntd, J);
+      }
+      j += isgeom ? 2 : 1;
+    }
+    float vel = 0.f;
+    float* Jo = SF(o_tenJ) + t * KT;
+#pragma unroll
+    for (int e = 0; e < KT; e++) { Jo[e] = J[e]; if (e < ntd) vel += J[e] * qvel[tdof[e]]; }
+    SF(o_tenL)[t] = len;
+    SF(o_tenV)[t] = vel;
+  }
+  c.tile.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// a10.7 muscle model (mju_muscleGain / Bias / Dynamics), passive forces, actuator forces
+MYO_DI float muscle_FL(float L, float lmin, float lmax) {
+  if (L < lmin || L > lmax) return 0.f;
+  const float a = 0.5f * (lmin + 1.f), b = 0.5f * (1.f + lmax);
+  float x;
+  if (L <= a) { x = (L - lmin) / fmaxf(kMinVal, a - lmin); return 0.5f * x * x; }
+  if (L <= 1.f) { x = (1.f - L) / fmaxf(kMinVal, 1.f - a); return 1.f - 0.5f * x * x; }
+  if (L <= b) { x = (L - 1.f) / fmaxf(kMinVal, b - 1.f); return 1.f - 0.5f * x * x; }
+  x = (lmax - L) / fmaxf(kMinVal, lmax - b);
+  return 0.5f * x * x;
+}
+template <int G>
+__device__ void phase_actuation(const DevModel& m, Ctx<G>& c) {
+  const float* ctrl = SF(o_ctrl); const float* act = SF(o_act);
+  for (int i = c.lane; i < m.nu; i += G) {
+    const int t = m.a_tendon[i];
+    const float gear = m.a_gear[i];
+    const float len = gear * SF(o_tenL)[t], vel = gear * SF(o_tenV)[t];
+    float u = ctrl[i];
+    if (m.a_ctrllimited[i]) u = clipf(u, m.a_ctrlrange[2 * i], m.a_ctrlrange[2 * i + 1]);
+    const int ai = i - (m.nu - m.na);
+    const float* dp = m.a_dynprm + 3 * i;
+    const float* gp = m.a_gainprm + 9 * i;
+    const float* bp = m.a_biasprm + 9 * i;
+    const float lr0 = m.a_lengthrange[2 * i], lr1 = m.a_lengthrange[2 * i + 1], acc0 = m.a_acc0[i];
+    const int dyn = m.a_dyntype[i];
+    float a_cur = (ai >= 0 && dyn != 0) ? act[ai] : 0.f;
+    if (dyn == 3) {          // muscle
+      const float uc = clipf(u, 0.f, 1.f), ac = clipf(a_cur, 0.f, 1.f);
+      const float tau = (uc > a_cur) ? dp[0] * (0.5f + 1.5f * ac) : dp[1] / (0.5f + 1.5f * ac);
+      SF(o_actdot)[ai] = (uc - a_cur) / fmaxf(kMinVal, tau);
+    } else if (dyn == 1) SF(o_actdot)[ai] = u;                                   // integrator
+    else if (dyn == 2) SF(o_actdot)[ai] = (u - a_cur) / fmaxf(kMinVal, dp[0]);     // filter
+    float gain, bias = 0.f;
+    if (m.a_gaintype[i] == 1) {
+      float F0 = gp[2];
+      if (F0 < 0.f) F0 = gp[3] / fmaxf(kMinVal, acc0);
+      const float L0 = (lr1 - lr0) / fmaxf(kMinVal, gp[1] - gp[0]);
+      const float L = gp[0] + (len - lr0) / fmaxf(kMinVal, L0);
+      const float V = vel / fmaxf(kMinVal, L0 * gp[6]);
+      const float FL = muscle_FL(L, gp[4], gp[5]);
+      const float y = gp[8] - 1.f;
+      float FV;
+      if (V <= -1.f) FV = 0.f;
+      else if (V <= 0.f) FV = (V + 1.f) * (V + 1.f);
+      else if (V <= y) FV = gp[8] - (y - V) * (y - V) / fmaxf(kMinVal, y);
+      else FV = gp[8];
+      gain = -F0 * FL * FV;
+    } else gain = gp[0];
+    if (m.a_biastype[i] == 1) bias = bp[0] + bp[1] * len + bp[2] * vel;
+    else if (m.a_biastype[i] == 2) {
+      float F0 = bp[2];
+      if (F0 < 0.f) F0 = bp[3] / fmaxf(kMinVal, acc0);
+      const float L0 = (lr1 - lr0) / fmaxf(kMinVal, bp[1] - bp[0]);
+      const float L = bp[0] + (len - lr0) / fmaxf(kMinVal, L0);
+      const float b = 0.5f * (1.f + bp[5]);
+      if (L <= 1.f) bias = 0.f;
+      else if (L <= b) { const float x = (L - 1.f) / fmaxf(kMinVal, b - 1.f); bias = -F0 * bp[7] * 0.5f * x * x; }
+      else { const float x = (L - b) / fmaxf(kMinVal, b - 1.f); bias = -F0 * bp[7] * (0.5f + x); }
+    }
+    float force = (dyn == 0 ? gain * u : gain * a_cur) + bias;
+    if (m.a_forcelimited[i]) force = clipf(force, m.a_forcerange[2 * i], m.a_forcerange[2 * i + 1]);
+    SF(o_actF)[i] = force;
+  }
+  c.tile.sync();
+  // qfrc_actuator = moment' * force and mj_passive, gathered per dof in a fixed order
+  const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel);
+  for (int d = c.lane; d < m.nv; d += G) {
+    float s = 0.f;
+    for (int k = m.d_actadr[d]; k < m.d_actadr[d + 1]; k++) {
+      const int code = m.d_actlist[k];
+      const int a = code >> 8, slot = code & 255;
+      s += m.a_gear[a] * SF(o_tenJ)[m.a_tendon[a] * KT + slot] * SF(o_actF)[a];
+    }
+    SF(o_qact)[d] = s;
+    float p = -m.d_damping[d] * qvel[d];
+    if (m.any_joint_spring) {
+      const int j = m.d_jnt[d];
+      const int jt = m.j_type[j];
+      if ((jt == J_HINGE || jt == J_SLIDE) && m.j_stiffness[j] != 0.f) {
+        const int qa = m.j_qposadr[j];
+        p -= m.j_stiffness[j] * (qpos[qa] - m.j_qpos_spring[j]);
+      }
+    }
+    if (m.any_tendon_passive) {
+      for (int t = 0; t < m.ntendon; t++) {
+        const float k = m.t_stiffness[t], bd = m.t_damping[t];
+        if (k == 0.f && bd == 0.f) continue;
+        const float frc = -k * (SF(o_tenL)[t] - m.t_lengthspring[t]) - bd * SF(o_tenV)[t];
+        for (int e = 0; e < m.t_ndof[t]; e++) if (m.t_dof[t * KT + e] == d) p += SF(o_tenJ)[t * KT + e] * frc;
+      }
+    }
+    SF(o_passive)[d] = p;
+    SF(o_smooth)[d] = p - SF(o_bias)[d] + s;
+    SF(o_qaccs)[d] = SF(o_smooth)[d];
+  }
+  c.tile.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// a10.5 collision: static candidate pair list, bounding-sphere cull with the *model's* rbound (stale
+// after size randomisation, as in the reference), primitive narrow phase with per-world sizes.
+MYO_DI void geom_world_pos(const DevModel& m, const float* s, int g, float* out) {
+  const int b = m.g_body[g];
+  mulmatvec3(out, s + m.o_xmat + 9 * b, m.g_pos + 3 * g);
+  add3(out, out, s + m.o_xpos + 3 * b);
+}
+MYO_DI void geom_world_zaxis(const DevModel& m, const float* s, int g, float* out) {
+  const float lz[3] = {m.g_mat[9 * g + 2], m.g_mat[9 * g + 5], m.g_mat[9 * g + 8]};
+  mulmatvec3(out, s + m.o_xmat + 9 * m.g_body[g], lz);
+}
+MYO_DI void make_frame(float* f) {
+  normalize3(f);
+  f[3] = 0.f; f[4] = 0.f; f[5] = 0.f;
+  if (f[1] < 0.5f && f[1] > -0.5f) f[4] = 1.f; else f[5] = 1.f;
+  const float t = dot3(f, f + 3);
+  f[3] -= t * f[0]; f[4] -= t * f[1]; f[5] -= t * f[2];
+  normalize3(f + 3);
+  cross3(f + 6, f, f + 3);
+}
+MYO_DI bool sphere_sphere(float margin, const float* p1, float r1, const float* p2, float r2, float* dist, float* pos, float* nrm) {
+  float dif[3];
+  sub3(dif, p2, p1);
+  const float cd2 = dot3(dif, dif), mind = margin + r1 + r2;
+  if (cd2 > mind * mind) return false;
+  const float n = normalize3(dif);
+  *dist = n - r1 - r2;
+  cpy3(nrm, dif);
+  const float k = r1 + 0.5f * (*dist);
+  pos[0] = p1[0] + dif[0] * k; pos[1] = p1[1] + dif[1] * k; pos[2] = p1[2] + dif[2] * k;
+  return true;
+}
+
+template <int G>
+__device__ void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
+  int* misc = SI(o_misc);
+  int ncon = 0;
+  for (int base = 0; base < m.npair; base += G) {
+    const int p = base + c.lane;
+    bool hit = false;
+    float dist = 0.f, pos[3] = {0, 0, 0}, nrm[3] = {1, 0, 0};
+    int g1 = 0, g2 = 0;
+    if (p < m.npair) {
+      g1 = m.p_g1[p]; g2 = m.p_g2[p];
+      const float margin = fmaxf(m.g_margin[g1], m.g_margin[g2]);
+      float p1[3], p2[3];
+      geom_world_pos(m, c.s, g1, p1);
+      geom_world_pos(m, c.s, g2, p2);
+      const float rb1 = m.g_rbound[g1], rb2 = m.g_rbound[g2];
+      bool pass = true;
+      const int t1 = m.g_type[g1], t2 = m.g_type[g2];
+      float z1[3] = {0.f, 0.f, 1.f};
+      if (rb1 > 0.f && rb2 > 0.f) {
+        float d[3];
+        sub3(d, p1, p2);
+        const float bound = rb1 + rb2 + margin;
+        pass = dot3(d, d) <= bound * bound;
+      } else if (t1 == G_PLANE && rb2 > 0.f) {
+        geom_world_zaxis(m, c.s, g1, z1);
+        float d[3];
+        sub3(d, p2, p1);
+        pass = dot3(d, z1) <= margin + rb2;
+      }
+      if (pass) {
+        if (!m.p_supported[p]) *status |= ST_UNSUPPORTED;
+        else {
+          float s1 = m.g_size[3 * g1], s2 = m.g_size[3 * g2];
+          if (m.g_size_slot[g1] >= 0) s1 = c.wp[m.g_size_slot[g1]];
+          if (m.g_size_slot[g2] >= 0) s2 = c.wp[m.g_size_slot[g2]];
+          if (t1 == G_SPHERE && t2 == G_SPHERE) hit = sphere_sphere(margin, p1, s1, p2, s2, &dist, pos, nrm);
+          else if (t1 == G_SPHERE && t2 == G_CAPSULE) {
+            float ax[3], v[3];
+            geom_world_zaxis(m, c.s, g2, ax);
+            sub3(v, p1, p2);
+            float half = m.g_size[3 * g2 + 1];
+            if (m.g_size_slot[g2] >= 0) half = c.wp[m.g_size_slot[g2] + 1];
+            const float x = clipf(dot3(ax, v), -half, half);
+            v[0] = p2[0] + ax[0] * x; v[1] = p2[1] + ax[1] * x; v[2] = p2[2] + ax[2] * x;
+            hit = sphere_sphere(margin, p1, s1, v, s2, &dist, pos, nrm);
+          } else {  // plane - sphere
+            float d[3];
+            sub3(d, p2, p1);
+            const float cd = dot3(d, z1);
+            if (cd <= margin + s2) {
+              hit = true;
+              dist = cd - s2;
+              cpy3(nrm, z1);
+              const float k = -0.5f * dist - s2;
+              pos[0] = p2[0] + z1[0] * k; pos[1] = p2[1] + z1[1] * k; pos[2] = p2[2] + z1[2] * k;
+            }
+          }
+          if (hit && dist >= margin) hit = false;
+        }
+      }
+    }
+    const unsigned ball = c.tile.ballot(hit);
+    if (hit) {
+      const int slot = ncon + __popc(ball & ((1u << c.lane) - 1u));
+      if (slot < m.ncon_max) {
+        float* cr = SF(o_con) + slot * CON_WORDS;
+        int* ci = reinterpret_cast<int*>(cr);
+        ci[C_G1] = g1; ci[C_G2] = g2;
+        cr[C_DIST] = dist;
+        cpy3(cr + C_POS, pos);
+        cpy3(cr + C_FRAME, nrm);
+      } else *status |= ST_CON_OVERFLOW;
+    }
+    ncon += __popc(ball);
+  }
+  if (ncon > m.ncon_max) ncon = m.ncon_max;
+  if (c.lane == 0) misc[MI_NCON] = ncon;
+  c.tile.sync();
+}
+
+// impedance, regularisation and reference-acceleration coefficients of one row (mj_makeImpedance)
+MYO_DI void row_params(const DevModel& m, const float* solref, const float* solimp, float pos, float margin, float diag,
+                       float* R, float* K, float* B, float* imp) {
+  const float s0 = clipf(solimp[0], 0.0001f, 0.9999f), s1 = clipf(solimp[1], 0.0001f, 0.9999f);
+  const float s2 = fmaxf(0.f, solimp[2]), s3 = clipf(solimp[3], 0.0001f, 0.9999f), s4 = fmaxf(1.f, solimp[4]);
+  float im;
+  if (s0 == s1 || s2 <= kMinVal) im = 0.5f * (s0 + s1);
+  else {
+    const float x = fabsf((pos - margin) / s2);
+    if (x >= 1.f) im = s1;
+    else if (x <= 0.f) im = s0;
+    else {
+      float y;
+      if (s4 == 1.f) y = x;
+      else if (x <= s3) y = (s4 == 2.f) ? x * x / s3 : powf(x, s4) / powf(s3, s4 - 1.f);
+      else y = (s4 == 2.f) ? 1.f - (1.f - x) * (1.f - x) / (1.f - s3) : 1.f - powf(1.f - x, s4) / powf(1.f - s3, s4 - 1.f);
+      im = s0 + y * (s1 - s0);
+    }
+  }
+  *imp = im;
+  *R = fmaxf(kMinVal, (1.f - im) * diag / im);
+  if (solref[0] > 0.f) {
+    const float tc = fmaxf(solref[0], 2.f * m.timestep), dr = solref[1];
+    *K = 1.f / fmaxf(kMinVal, s1 * s1 * tc * tc * dr * dr);
+    *B = 2.f / fmaxf(kMinVal, s1 * tc);
+  } else {
+    *K = -solref[0] / fmaxf(kMinVal, s1 * s1);
+    *B = -solref[1] / fmaxf(kMinVal, s1);
+  }
+}
+
+// a10.6 constraint assembly. Limits first (joints then tendons, MuJoCo order), then contacts with
+// 2*(condim-1) pyramid rows each. Rows keep (D, aref); Jacobians stay factored per block:
+// a limit has one basis vector over <= KT dofs, a contact has (normal, tangent1, tangent2) over
+// the <= KS dofs in chain(body1) xor chain(body2).
+template <int G>
+__device__ void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
+  int* misc = SI(o_misc);
+  const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel);
+  int nlim = 0;
+  // joint limits: row order joint-major, lower side before upper side
+  for (int base = 0; base < m.njnt; base += G) {
+    const int j = base + c.lane;
+    bool lo = false, hi = false;
+    float dlo = 0.f, dhi = 0.f, margin = 0.f;
+    if (j < m.njnt && m.j_limited[j] && (m.j_type[j] == J_HINGE || m.j_type[j] == J_SLIDE)) {
+      const float v = qpos[m.j_qposadr[j]];
+      margin = m.j_margin[j];
+      dlo = v - m.j_range[2 * j]; dhi = m.j_range[2 * j + 1] - v;
+      lo = dlo < margin; hi = dhi < margin;
+    }
+    const unsigned blo = c.tile.ballot(lo), bhi = c.tile.ballot(hi);
+    const unsigned lt = (1u << c.lane) - 1u;
+    int slot = nlim + __popc(blo & lt) + __popc(bhi & lt);
+    if (lo) {
+      if (slot < m.nlim_max) {
+        float* r = SF(o_lim) + slot * LIM_WORDS; int* ri = reinterpret_cast<int*>(r);
+        ri[L_KIND] = EFC_LIMIT_JOINT; ri[L_ID] = j; ri[L_NSUP] = 1; r[L_POS] = dlo; r[L_MARGIN] = margin;
+        ri[L_IDX] = m.j_dofadr[j]; r[L_J] = 1.f;
+      } else *status |= ST_EFC_OVERFLOW;
+      slot++;
+    }
+    if (hi) {
+      if (slot < m.nlim_max) {
+        float* r = SF(o_lim) + slot * LIM_WORDS; int* ri = reinterpret_cast<int*>(r);
+        ri[L_KIND] = EFC_LIMIT_JOINT; ri[L_ID] = j; ri[L_NSUP] = 1; r[L_POS] = dhi; r[L_MARGIN] = margin;
+        ri[L_IDX] = m.j_dofadr[j]; r[L_J] = -1.f;
+      } else *status |= ST_EFC_OVERFLOW;
+    }
+    nlim += __popc(blo) + __popc(bhi);
+  }
+  for (int base = 0; base < m.ntendon; base += G) {
+    const int t = base + c.lane;
+    bool lo = false, hi = false;
+    float dlo = 0.f, dhi = 0.f, margin = 0.f;
+    if (t < m.ntendon && m.t_limited[t]) {
+      const float v = SF(o_tenL)[t];
+      margin = m.t_margin[t];
+      dlo = v - m.t_range[2 * t]; dhi = m.t_range[2 * t + 1] - v;
+      lo = dlo < margin; hi = dhi < margin;
+    }
+    const unsigned blo = c.tile.ballot(lo), bhi = c.tile.ballot(hi);
+    const unsigned lt = (1u << c.lane) - 1u;
+    int slot = nlim + __popc(blo & lt) + __popc(bhi & lt);
+    for (int side = 0; side < 2; side++) {
+      if (!(side ? hi : lo)) continue;
+      if (slot < m.nlim_max) {
+        float* r = SF(o_lim) + slot * LIM_WORDS; int* ri = reinterpret_cast<int*>(r);
+        ri[L_KIND] = EFC_LIMIT_TENDON; ri[L_ID] = t; ri[L_NSUP] = m.t_ndof[t];
+        r[L_POS] = side ? dhi : dlo; r[L_MARGIN] = margin;
+        for (int e = 0; e < m.t_ndof[t]; e++) {
+          ri[L_IDX + e] = m.t_dof[t * KT + e];
+          r[L_J + e] = (side ? -1.f : 1.f) * SF(o_tenJ)[t * KT + e];
+        }
+      } else *status |= ST_EFC_OVERFLOW;
+      slot++;
+    }
+    nlim += __popc(blo) + __popc(bhi);
+  }
+  if (nlim > m.nlim_max) nlim = m.nlim_max;
+  const int ncon = misc[MI_NCON];
+  c.tile.sync();
+
+  // limit rows: parameters + reference acceleration
+  float* rows = SF(o_row);
+  for (int r = c.lane; r < nlim; r += G) {
+    const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
+    const int id = li[L_ID];
+    float R, K, B, imp, vel = 0.f;
+    if (li[L_KIND] == EFC_LIMIT_JOINT) {
+      row_params(m, m.j_solref + 2 * id, m.j_solimp + 5 * id, lr[L_POS], lr[L_MARGIN], m.d_invweight0[m.j_dofadr[id]], &R, &K, &B, &imp);
+      vel = lr[L_J] * qvel[li[L_IDX]];
+    } else {
+      row_params(m, m.t_solref + 2 * id, m.t_solimp + 5 * id, lr[L_POS], lr[L_MARGIN], m.t_invweight0[id], &R, &K, &B, &imp);
+      for (int e = 0; e < li[L_NSUP]; e++) vel += lr[L_J + e] * qvel[li[L_IDX + e]];
+    }
+    float* row = rows + r * ROW_WORDS;
+    row[R_D] = 1.f / R;
+    row[R_AREF] = -B * vel - K * imp * (lr[L_POS] - lr[L_MARGIN]);
+    reinterpret_cast<int*>(row)[R_BLOCK] = r;   // block = limit index, coef 0
+  }
+  // contacts: mixing (mj_contactParam), frame, support and basis Jacobians, rows
+  int nrow_con = 0, nrow_valid = 0;
+  for (int base = 0; base < ncon; base += G) {
+    const int k = base + c.lane;
+    int nr = 0;
+    if (k < ncon) {
+      float* cr = SF(o_con) + k * CON_WORDS; int* ci = reinterpret_cast<int*>(cr);
+      const int g1 = ci[C_G1], g2 = ci[C_G2];
+      float fri[3], solref[2], solimp[5];
+      int dim;
+      float f1[3], f2[3];
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+        f1[e] = (m.g_fri_slot[g1] >= 0) ? c.wp[m.g_fri_slot[g1] + e] : m.g_friction[3 * g1 + e];
+        f2[e] = (m.g_fri_slot[g2] >= 0) ? c.wp[m.g_fri_slot[g2] + e] : m.g_friction[3 * g2 + e];
+      }
+      const int pr1 = m.g_priority[g1], pr2 = m.g_priority[g2];
+      if (pr1 != pr2) {
+        const int g = pr1 > pr2 ? g1 : g2;
+        dim = m.g_condim[g];
+        solref[0] = m.g_solref[2 * g]; solref[1] = m.g_solref[2 * g + 1];
+#pragma unroll
+        for (int e = 0; e < 5; e++) solimp[e] = m.g_solimp[5 * g + e];
+#pragma unroll
+        for (int e = 0; e < 3; e++) fri[e] = pr1 > pr2 ? f1[e] : f2[e];
+      } else {
+        dim = max(m.g_condim[g1], m.g_condim[g2]);
+        const float sm1 = m.g_solmix[g1], sm2 = m.g_solmix[g2];
+        float mix;
+        if (sm1 >= kMinVal && sm2 >= kMinVal) mix = sm1 / (sm1 + sm2);
+        else if (sm1 < kMinVal && sm2 < kMinVal) mix = 0.5f;
+        else mix = (sm1 < kMinVal) ? 0.f : 1.f;
+        const float* r1 = m.g_solref + 2 * g1; const float* r2 = m.g_solref + 2 * g2;
+        if (r1[0] > 0.f && r2[0] > 0.f) { solref[0] = mix * r1[0] + (1.f - mix) * r2[0]; solref[1] = mix * r1[1] + (1.f - mix) * r2[1]; }
+        else { solref[0] = fminf(r1[0], r2[0]); solref[1] = fminf(r1[1], r2[1]); }
+#pragma unroll
+        for (int e = 0; e < 5; e++) solimp[e] = mix * m.g_solimp[5 * g1 + e] + (1.f - mix) * m.g_solimp[5 * g2 + e];
+#pragma unroll
+        for (int e = 0; e < 3; e++) fri[e] = fmaxf(f1[e], f2[e]);
+      }
+      const float margin = fmaxf(m.g_margin[g1], m.g_margin[g2]) - fmaxf(m.g_gap[g1], m.g_gap[g2]);
+      ci[C_DIM] = dim; cr[C_MARGIN] = margin; cr[C_MU] = fri[0];
+      cr[C_SOLREF] = solref[0]; cr[C_SOLREF + 1] = solref[1];
+#pragma unroll
+      for (int e = 0; e < 5; e++) cr[C_SOLIMP + e] = solimp[e];
+#pragma unroll
+      for (int e = 0; e < 3; e++) cr[C_FRI + e] = fri[e];
+      float fr[9];
+      cpy3(fr, cr + C_FRAME);
+      make_frame(fr);
+#pragma unroll
+      for (int e = 0; e < 9; e++) cr[C_FRAME + e] = fr[e];
+      const int ba = m.g_body[g1], bb = m.g_body[g2];
+      ci[C_BA] = ba; ci[C_BB] = bb;
+      // support + basis
+      const int cp = common_prefix(m, ba, bb);
+      int ns = 0;
+      const float* cdof = SF(o_cdof);
+      for (int half = 0; half < 2; half++) {
+        const int body = half ? bb : ba;
+        const float sgn = half ? 1.f : -1.f;
+        const int n = m.b_nchain[body];
+        if (n <= cp) continue;
+        float off[3];
+        sub3(off, cr + C_POS, SF(o_xipos) + 3 * m.b_root[body]);
+        for (int q = cp; q < n; q++) {
+          const int d = m.b_chain[body * KC + q];
+          const float* cd = cdof + 6 * d;
+          float t[3];
+          cross3(t, cd, off);
+          const float v[3] = {cd[3] + t[0], cd[4] + t[1], cd[5] + t[2]};
+          if (ns < KS) {
+            ci[C_IDX + ns] = d;
+            cr[C_N + ns] = sgn * dot3(fr, v);
+            cr[C_N + KS + ns] = sgn * dot3(fr + 3, v);
+            cr[C_N + 2 * KS + ns] = sgn * dot3(fr + 6, v);
+            ns++;
+          } else *status |= ST_UNSUPPORTED;
+        }
+      }
+      ci[C_NSUP] = ns;
+      if (cr[C_DIST] < margin) {
+        if (dim == 1) nr = 1;
+        else if (dim == 3) nr = 4;
+        else *status |= ST_UNSUPPORTED;
+      }
+      ci[C_ROW0] = nr;  // temporarily the row count; replaced by the first row index below
+    }
+    // exclusive scan of row counts inside the tile (fixed contact order)
+    int incl = nr;
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) { const int t = c.tile.shfl_up(incl, o); if (c.lane >= o) incl += t; }
+    const int excl = incl - nr;
+    const int total = c.tile.shfl(incl, G - 1);
+    if (k < ncon) {
+      int* ci = SI(o_con) + k * CON_WORDS;
+      int row0 = nlim + nrow_con + excl;
+      if (nr && row0 + nr > m.nefc_max) { *status |= ST_EFC_OVERFLOW; nr = 0; }
+      ci[C_ROW0] = nr ? row0 : -1;
+    }
+    int valid = nr;   // rows are dropped only at the tail, so valid rows stay contiguous
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) valid += c.tile.shfl_xor(valid, o);
+    nrow_valid += valid;
+    nrow_con += total;
+  }
+  const int nefc = nlim + nrow_valid;
+  c.tile.sync();
+  // contact rows: one lane per contact fills its rows
+  for (int k = c.lane; k < ncon; k += G) {
+    const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+    const int row0 = ci[C_ROW0];
+    if (row0 < 0) continue;
+    const int dim = ci[C_DIM], ns = ci[C_NSUP];
+    const float tran = m.b_invweight0[2 * ci[C_BA]] + m.b_invweight0[2 * ci[C_BB]];
+    float vn = 0.f, vt1 = 0.f, vt2 = 0.f;
+    for (int e = 0; e < ns; e++) {
+      const float w = qvel[ci[C_IDX + e]];
+      vn += cr[C_N + e] * w; vt1 += cr[C_N + KS + e] * w; vt2 += cr[C_N + 2 * KS + e] * w;
+    }
+    const float mu = cr[C_MU];
+    float R, K, B, imp;
+    // diagApprox of the first row: tran + mu^2 * tran (pyramidal) or tran (frictionless)
+    row_params(m, cr + C_SOLREF, cr + C_SOLIMP, cr[C_DIST], cr[C_MARGIN], dim == 1 ? tran : tran + mu * mu * tran, &R, &K, &B, &imp);
+    if (dim == 3) { const float mu_r = mu * m.inv_sqrt_impratio; R = 2.f * mu_r * mu_r * R; }
+    const float D = 1.f / R, ref = -K * imp * (cr[C_DIST] - cr[C_MARGIN]);
+    const int nr = dim == 1 ? 1 : 4;
+    for (int q = 0; q < nr; q++) {
+      float vel = vn;
+      if (dim == 3) vel += ((q & 1) ? -mu : mu) * ((q < 2) ? vt1 : vt2);
+      float* row = rows + (row0 + q) * ROW_WORDS;
+      row[R_D] = D;
+      row[R_AREF] = -B * vel + ref;
+      reinterpret_cast<int*>(row)[R_BLOCK] = (m.nlim_max + k) | ((dim == 3 ? q + 1 : 0) << 16);
+    }
+  }
+  if (c.lane == 0) { misc[MI_NLIM] = nlim; misc[MI_NEFC] = nefc; }
+  c.tile.sync();
+}
+
+// ------------------------------------------------------------------------------------------------
+// row helper: J_r . x for every row -> rows[r][field]; optionally subtract aref (jar = J a - aref)
+template <int G>
+__device__ void rows_dot(const DevModel& m, Ctx<G>& c, const float* x, int field, bool sub_aref) {
+  const int* misc = SI(o_misc);
+  const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
+  float* rows = SF(o_row);
+  for (int r = c.lane; r < nlim; r += G) {
+    const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
+    float v = 0.f;
+    for (int e = 0; e < li[L_NSUP]; e++) v += lr[L_J + e] * x[li[L_IDX + e]];
+    float* row = rows + r * ROW_WORDS;
+    row[field] = sub_aref ? v - row[R_AREF] : v;
+  }
+  for (int k = c.lane; k < ncon; k += G) {
+    const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+    const int row0 = ci[C_ROW0];
+    if (row0 < 0) continue;
+    float vn = 0.f, vt1 = 0.f, vt2 = 0.f;
+    for (int e = 0; e < ci[C_NSUP]; e++) {
+      const float w = x[ci[C_IDX + e]];
+      vn += cr[C_N + e] * w; vt1 += cr[C_N + KS + e] * w; vt2 += cr[C_N + 2 * KS + e] * w;
+    }
+    const float mu = cr[C_MU];
+    const int nr = ci[C_DIM] == 1 ? 1 : 4;
+    for (int q = 0; q < nr; q++) {
+      float v = vn;
+      if (nr == 4) v += ((q & 1) ? -mu : mu) * ((q < 2) ? vt1 : vt2);
+      float* row = rows + (row0 + q) * ROW_WORDS;
+      row[field] = sub_aref ? v - row[R_AREF] : v;
+    }
+  }
+  c.tile.sync();
+}
+
+// out[dof] += sum_r J_r[dof] * w_r  with w_r = (jar_r < 0 ? -D_r jar_r : 0) * scale  (forces)
+// blocks applied one after the other, lanes across the block's support: no atomics, fixed order.
+template <int G>
+__device__ void rows_JT_force(const DevModel& m, Ctx<G>& c, float* out, float scale) {
+  const int* misc = SI(o_misc);
+  const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
+  const float* rows = SF(o_row);
+  for (int r = 0; r < nlim; r++) {
+    const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
+    const float* row = rows + r * ROW_WORDS;
+    const float f = row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] * scale : 0.f;
+    if (f != 0.f && c.lane < li[L_NSUP]) out[li[L_IDX + c.lane]] += lr[L_J + c.lane] * f;
+    c.tile.sync();
+  }
+  for (int k = 0; k < ncon; k++) {
+    const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+    const int row0 = ci[C_ROW0];
+    if (row0 < 0) continue;
+    const int nr = ci[C_DIM] == 1 ? 1 : 4;
+    const float mu = cr[C_MU];
+    float fn = 0.f, ft1 = 0.f, ft2 = 0.f;
+    for (int q = 0; q < nr; q++) {
+      const float* row = rows + (row0 + q) * ROW_WORDS;
+      const float f = row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] * scale : 0.f;
+      fn += f;
+      if (nr == 4) { const float t = ((q & 1) ? -mu : mu) * f; if (q < 2) ft1 += t; else ft2 += t; }
+    }
+    for (int e = c.lane; e < ci[C_NSUP]; e += G)
+      out[ci[C_IDX + e]] += cr[C_N + e] * fn + cr[C_N + KS + e] * ft1 + cr[C_N + 2 * KS + e] * ft2;
+    c.tile.sync();
+  }
+}
+
+MYO_DI int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, i >= j
+
+// H = M + sum_{active rows} D_r J_r' J_r  (packed lower triangle)
+template <int G>
+__device__ void build_hessian(const DevModel& m, Ctx<G>& c) {
+  float* H = SF(o_H); const float* M = SF(o_M);
+  const int nv = m.nv;
+  for (int e = c.lane; e < nv * (nv + 1) / 2; e += G) H[e] = 0.f;
+  c.tile.sync();
+  for (int i = c.lane; i < nv; i += G) {
+    int adr = m.d_Madr[i], j = i;
+    while (j >= 0) { H[tri(i, j)] = M[adr++]; j = m.d_parent[j]; }
+  }
+  c.tile.sync();
+  const int* misc = SI(o_misc);
+  const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
+  const float* rows = SF(o_row);
+  for (int r = 0; r < nlim; r++) {
+    const float* row = rows + r * ROW_WORDS;
+    if (row[R_JAR] < 0.f) {
+      const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
+      const int ns = li[L_NSUP];
+      const float D = row[R_D];
+      for (int e = c.lane; e < ns * ns; e += G) {
+        const int a = e / ns, b = e - a * ns;
+        const int ia = li[L_IDX + a], ib = li[L_IDX + b];
+        if (ia >= ib) H[tri(ia, ib)] += D * lr[L_J + a] * lr[L_J + b];
+      }
+    }
+    c.tile.sync();
+  }
+  for (int k = 0; k < ncon; k++) {
+    const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+    const int row0 = ci[C_ROW0];
+    if (row0 < 0) continue;
+    const int nr = ci[C_DIM] == 1 ? 1 : 4, ns = ci[C_NSUP];
+    const float mu = cr[C_MU];
+    // W = sum_active D c c', c = (1, +-mu, 0) / (1, 0, +-mu)
+    float w00 = 0.f, w01 = 0.f, w02 = 0.f, w11 = 0.f, w22 = 0.f;
+    for (int q = 0; q < nr; q++) {
+      const float* row = rows + (row0 + q) * ROW_WORDS;
+      if (row[R_JAR] < 0.f) {
+        const float D = row[R_D];
+        w00 += D;
+        if (nr == 4) {
+          const float s = (q & 1) ? -mu : mu;
+          if (q < 2) { w01 += D * s; w11 += D * s * s; } else { w02 += D * s; w22 += D * s * s; }
+        }
+      }
+    }
+    if (w00 != 0.f) {
+      for (int e = c.lane; e < ns * ns; e += G) {
+        const int a = e / ns, b = e - a * ns;
+        const int ia = ci[C_IDX + a], ib = ci[C_IDX + b];
+        if (ia >= ib) {
+          const float na = cr[C_N + a], ta = cr[C_N + KS + a], ua = cr[C_N + 2 * KS + a];
+          const float nb = cr[C_N + b], tb = cr[C_N + KS + b], ub = cr[C_N + 2 * KS + b];
+          H[tri(ia, ib)] += w00 * na * nb + w01 * (na * tb + ta * nb) + w02 * (na * ub + ua * nb) + w11 * ta * tb + w22 * ua * ub;
+        }
+      }
+    }
+    c.tile.sync();
+  }
+}
+
+// in-place dense Cholesky (left-looking, lane per row) and solve; n <= 2*G
+template <int G>
+__device__ void chol_factor(Ctx<G>& c, float* H, int n) {
+  for (int j = 0; j < n; j++) {
+    const float* Lj = H + tri(j, 0);
+    for (int i = j + c.lane; i < n; i += G) {
+      float* Li = H + tri(i, 0);
+      float s = Li[j];
+      for (int k = 0; k < j; k++) s -= Li[k] * Lj[k];
+      Li[j] = s;                        // unscaled column; diagonal holds the pivot
+    }
+    c.tile.sync();
+    // the diagonal keeps the pivot L_jj^2 (never rewritten, so no read/write race on it)
+    const float inv = 1.f / sqrtf(fmaxf(H[tri(j, j)], kMinVal));
+    for (int i = j + 1 + c.lane; i < n; i += G) H[tri(i, j)] *= inv;
+    c.tile.sync();
+  }
+}
+template <int G>
+__device__ void chol_solve(Ctx<G>& c, const float* H, float* x, int n) {
+  for (int j = 0; j < n; j++) {          // forward: column oriented
+    if (c.lane == 0) x[j] = x[j] / sqrtf(fmaxf(H[tri(j, j)], kMinVal));
+    c.tile.sync();
+    const float xj = x[j];
+    for (int i = j + 1 + c.lane; i < n; i += G) x[i] -= H[tri(i, j)] * xj;
+    c.tile.sync();
+  }
+  for (int j = n - 1; j >= 0; j--) {     // backward with L'
+    if (c.lane == 0) x[j] = x[j] / sqrtf(fmaxf(H[tri(j, j)], kMinVal));
+    c.tile.sync();
+    const float xj = x[j];
+    for (int i = c.lane; i < j; i += G) x[i] -= H[tri(j, i)] * xj;
+    c.tile.sync();
+  }
+}
+
+// a10.8 constraint solve: primal Newton with exact line search on
+//   cost(a) = 1/2 (a - a_s)' M (a - a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
+// warm-started from the better of (qacc_warmstart, qacc_smooth) as MuJoCo's warmstart() does.
+template <int G>
+__device__ void phase_solve(const DevModel& m, Ctx<G>& c) {
+  int* misc = SI(o_misc);
+  const int nv = m.nv, nefc = misc[MI_NEFC];
+  float* a = SF(o_qacc); float* qcon = SF(o_qcon);
+  const float* as = SF(o_qaccs); const float* fs = SF(o_smooth);
+  float* rows = SF(o_row);
+  if (nefc == 0) {
+    for (int i = c.lane; i < nv; i += G) { a[i] = as[i]; SF(o_warm)[i] = as[i]; qcon[i] = 0.f; }
+    if (c.lane == 0) misc[MI_ITER] = 0;
+    c.tile.sync();
+    return;
+  }
+  float* Ma = SF(o_Ma); float* grad = SF(o_grad); float* p = SF(o_p); float* Mp = SF(o_Mp);
+  const float* M = SF(o_M);
+  // warm start selection
+  float cost_w, cost_s;
+  {
+    const float* w = SF(o_warm);
+    rows_dot<G>(m, c, w, R_JAR, true);
+    mul_M<G>(m, c, M, w, Ma);
+    float part = 0.f;
+    for (int r = c.lane; r < nefc; r += G) { const float* row = rows + r * ROW_WORDS; if (row[R_JAR] < 0.f) part += 0.5f * row[R_D] * row[R_JAR] * row[R_JAR]; }
+    for (int i = c.lane; i < nv; i += G) part += 0.5f * (Ma[i] - fs[i]) * (w[i] - as[i]);
+    cost_w = tile_sum<G>(c, part);
+    rows_dot<G>(m, c, as, R_JAR, true);
+    part = 0.f;
+    for (int r = c.lane; r < nefc; r += G) { const float* row = rows + r * ROW_WORDS; if (row[R_JAR] < 0.f) part += 0.5f * row[R_D] * row[R_JAR] * row[R_JAR]; }
+    cost_s = tile_sum<G>(c, part);
+    const bool use_smooth = !(cost_w <= cost_s);   // also catches NaN in the warm start
+    for (int i = c.lane; i < nv; i += G) a[i] = use_smooth ? as[i] : w[i];
+    c.tile.sync();
+  }
+  const float scale = 1.f / (m.meaninertia * (float)max(1, nv));
+  int iter = 0;
+  for (; iter < m.solver_iter; iter++) {
+    rows_dot<G>(m, c, a, R_JAR, true);
+    mul_M<G>(m, c, M, a, Ma);
+    for (int i = c.lane; i < nv; i += G) grad[i] = Ma[i] - fs[i];
+    c.tile.sync();
+    rows_JT_force<G>(m, c, grad, -1.f);
+    float g2 = 0.f, amax = 0.f;
+    for (int i = c.lane; i < nv; i += G) { g2 += grad[i] * grad[i]; amax = fmaxf(amax, fabsf(a[i])); }
+    g2 = tile_sum<G>(c, g2);
+    amax = tile_max<G>(c, amax);
+    if (sqrtf(g2) * scale < m.solver_tol) break;
+    build_hessian<G>(m, c);
+    chol_factor<G>(c, SF(o_H), nv);
+    for (int i = c.lane; i < nv; i += G) p[i] = -grad[i];
+    c.tile.sync();
+    chol_solve<G>(c, SF(o_H), p, nv);
+    rows_dot<G>(m, c, p, R_JP, false);
+    mul_M<G>(m, c, M, p, Mp);
+    float pMp = 0.f, gp = 0.f, pmax = 0.f;
+    for (int i = c.lane; i < nv; i += G) { pMp += p[i] * Mp[i]; gp += (Ma[i] - fs[i]) * p[i]; pmax = fmaxf(pmax, fabsf(p[i])); }
+    pMp = tile_sum<G>(c, pMp); gp = tile_sum<G>(c, gp); pmax = tile_max<G>(c, pmax);
+    // exact line search on the piecewise-quadratic phi(alpha): safeguarded Newton on phi'
+    float alpha = 0.f, lo = 0.f, hi = -1.f, d1_0 = 0.f;
+    for (int ls = 0; ls < 12; ls++) {
+      float d1 = 0.f, d2 = 0.f;
+      for (int r = c.lane; r < nefc; r += G) {
+        const float* row = rows + r * ROW_WORDS;
+        const float x = row[R_JAR] + alpha * row[R_JP];
+        if (x < 0.f) { d1 += row[R_D] * x * row[R_JP]; d2 += row[R_D] * row[R_JP] * row[R_JP]; }
+      }
+      d1 = tile_sum<G>(c, d1) + gp + alpha * pMp;
+      d2 = tile_sum<G>(c, d2) + pMp;
+      if (ls == 0) d1_0 = fabsf(d1);
+      if (fabsf(d1) <= 1e-6f * d1_0) break;
+      if (d1 < 0.f) lo = alpha; else hi = alpha;
+      float nxt = alpha - d1 / fmaxf(d2, kMinVal);
+      if (hi >= 0.f && (nxt <= lo || nxt >= hi)) nxt = 0.5f * (lo + hi);
+      if (nxt < lo) nxt = lo;
+      if (nxt == alpha) break;
+      alpha = nxt;
+    }
+    for (int i = c.lane; i < nv; i += G) a[i] += alpha * p[i];
+    c.tile.sync();
+    if (alpha * pmax <= 1e-6f * fmaxf(1.f, amax)) { iter++; break; }
+  }
+  // final forces at the solution
+  rows_dot<G>(m, c, a, R_JAR, true);
+  for (int i = c.lane; i < nv; i += G) { qcon[i] = 0.f; SF(o_warm)[i] = a[i]; }
+  c.tile.sync();
+  rows_JT_force<G>(m, c, qcon, 1.f);
+  if (c.lane == 0) misc[MI_ITER] = iter;
+  c.tile.sync();
+}
+
+// a10.9 mj_Euler (implicit in joint damping) + mj_advance
+template <int G>
+__device__ void phase_integrate(const DevModel& m, Ctx<G>& c) {
+  const float h = m.timestep;
+  float* qacc = SF(o_qacc); float* qvel = SF(o_qvel); float* qpos = SF(o_qpos); float* act = SF(o_act);
+  float* x = SF(o_grad);
+  if (m.any_damping) {
+    factor_sparse<G>(m, c, SF(o_LD), SF(o_M), h);
+    for (int i = c.lane; i < m.nv; i += G) x[i] = SF(o_smooth)[i] + SF(o_qcon)[i];
+    c.tile.sync();
+    solve_sparse<G>(m, c, SF(o_LD), x);
+  } else {
+    for (int i = c.lane; i < m.nv; i += G) x[i] = qacc[i];
+    c.tile.sync();
+  }
+  for (int i = c.lane; i < m.na; i += G) {
+    const int u = i + (m.nu - m.na);
+    float v = act[i] + h * SF(o_actdot)[i];
+    if (m.a_dyntype[u] == 3) v = clipf(v, 0.f, 1.f);
+    act[i] = v;
+  }
+  for (int i = c.lane; i < m.nv; i += G) qvel[i] += h * x[i];
+  c.tile.sync();
+  for (int j = c.lane; j < m.njnt; j += G) {
+    const int qa = m.j_qposadr[j], da = m.j_dofadr[j];
+    if (m.j_type[j] == J_FREE) {
+      qpos[qa] += h * qvel[da]; qpos[qa + 1] += h * qvel[da + 1]; qpos[qa + 2] += h * qvel[da + 2];
+      float w[3] = {qvel[da + 3], qvel[da + 4], qvel[da + 5]};
+      const float ang = h * normalize3(w);
+      float sn, cs;
+      sincosf(0.5f * ang, &sn, &cs);
+      const float ql[4] = {cs, w[0] * sn, w[1] * sn, w[2] * sn};
+      float q[4] = {qpos[qa + 3], qpos[qa + 4], qpos[qa + 5], qpos[qa + 6]};
+      if (ang != 0.f) mulquat(q, q, ql);
+      normalize4(q);
+      qpos[qa + 3] = q[0]; qpos[qa + 4] = q[1]; qpos[qa + 5] = q[2]; qpos[qa + 6] = q[3];
+    } else qpos[qa] += h * qvel[da];
+  }
+  c.tile.sync();
+}
+
+// one full mj_step on the world in scratch
+template <int G>
+__device__ void mj_forward_dev(const DevModel& m, Ctx<G>& c, int* status) {
+  phase_tree_forward<G>(m, c, true);
+  phase_tendon<G>(m, c, status);
+  phase_tree_backward<G>(m, c);
+  phase_mass_bias<G>(m, c);
+  factor_sparse<G>(m, c, SF(o_LD), SF(o_M), 0.f);
+  phase_collision<G>(m, c, status);
+  phase_constraints<G>(m, c, status);
+  phase_actuation<G>(m, c);
+  solve_sparse<G>(m, c, SF(o_LD), SF(o_qaccs));
+  phase_solve<G>(m, c);
+}
+template <int G>
+__device__ void mj_step_dev(const DevModel& m, Ctx<G>& c, int* status) {
+  mj_forward_dev<G>(m, c, status);
+  phase_integrate<G>(m, c);
+}
+
+}  // namespace myo

@@ -1,0 +1,241 @@
+// Task layer fused around the physics substeps: what the reference does in Python per env.step.
+//   baoding: BaodingEnvV1.step target update + CustomBaodingP2Env.get_reward_dict / reset
+//            (/root/reference/src/envs/baoding.py:403-467, 494-647), obs layout pinned by
+//            /root/reference/src/envs/baoding.py:186-190,627-631
+//   pose   : CustomPoseEnv.reset / get_target_pose (/root/reference/src/envs/pose.py:53-113) on
+//            MyoSuite PoseEnvV0 obs / reward keys
+//   both   : BaseV0.step muscle action remap, gym TimeLimit, SubprocVecEnv worker auto-reset.
+#pragma once
+#include "myo_phys.cuh"
+
+namespace myo {
+
+template <int G>
+__device__ void copy_words(Ctx<G>& c, float* dst, const float* src, int n4) {   // n4: multiple of 4 words
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = c.lane; i < n4 / 4; i += G) d4[i] = s4[i];
+}
+
+template <int G>
+__device__ void load_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int w) {
+  copy_words<G>(c, SF(o_qpos), b.qpos + (size_t)w * m.nq4, m.nq4);
+  copy_words<G>(c, SF(o_qvel), b.qvel + (size_t)w * m.nv4, m.nv4);
+  copy_words<G>(c, SF(o_warm), b.warm + (size_t)w * m.nv4, m.nv4);
+  if (m.na) copy_words<G>(c, SF(o_act), b.act + (size_t)w * m.na4, m.na4);
+  copy_words<G>(c, SF(o_wparam), b.wparam + (size_t)w * m.nparam4, m.nparam4);
+  c.tile.sync();
+}
+template <int G>
+__device__ void store_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int w, bool params) {
+  c.tile.sync();
+  copy_words<G>(c, b.qpos + (size_t)w * m.nq4, SF(o_qpos), m.nq4);
+  copy_words<G>(c, b.qvel + (size_t)w * m.nv4, SF(o_qvel), m.nv4);
+  copy_words<G>(c, b.warm + (size_t)w * m.nv4, SF(o_warm), m.nv4);
+  if (m.na) copy_words<G>(c, b.act + (size_t)w * m.na4, SF(o_act), m.na4);
+  if (params) copy_words<G>(c, b.wparam + (size_t)w * m.nparam4, SF(o_wparam), m.nparam4);
+}
+
+// BaseV0.step: muscle actuators with normalize_act get ctrl = 1/(1+exp(-5(a-0.5))); other actuators
+// are de-normalised linearly into ctrlrange (MyoSuite Robot.normalize_actions).
+template <int G>
+__device__ void task_action(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const float* a) {
+  float* ctrl = SF(o_ctrl);
+  for (int i = c.lane; i < m.nu; i += G) {
+    float u = a[i];
+    if (t.normalize_act) {
+      if (m.a_dyntype[i] == 3) u = 1.f / (1.f + expf(-5.f * (u - 0.5f)));
+      else {
+        const float lo = m.a_ctrlrange[2 * i], hi = m.a_ctrlrange[2 * i + 1];
+        u = 0.5f * (lo + hi) + clipf(u, -1.f, 1.f) * 0.5f * (hi - lo);
+      }
+    }
+    ctrl[i] = u;
+  }
+}
+
+// BaodingEnvV1.step: target sites follow goal[counter] = sign*2*pi*counter*dt/period (a6, a7)
+template <int G>
+__device__ void baoding_targets(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const int* ti, const float* tf) {
+  if (c.lane == 0) {
+    const int task = ti[TI_TASK], counter = ti[TI_ELAPSED];
+    const float sign = task == MYO_BAODING_CW ? -1.f : (task == MYO_BAODING_CCW ? 1.f : 0.f);
+    const float ang = sign * 2.f * kPi * ((float)counter * m.frame_dt / tf[TF_PERIOD]);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      const float th = ang + tf[TF_ANGLE1 + k];
+      float sn, cs;
+      sincosf(th, &sn, &cs);
+      const int slot = m.s_pos_slot[t.target_site[k]];
+      if (slot >= 0) {
+        c.wp[slot] = tf[TF_XR] * cs + t.center_pos[0];
+        c.wp[slot + 1] = tf[TF_YR] * sn + t.center_pos[1];
+      }
+    }
+  }
+  c.tile.sync();
+}
+
+// observation vector into scratch o_obs (kinematics must be current)
+template <int G>
+__device__ void task_obs(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const float* pose_target) {
+  float* obs = SF(o_obs);
+  const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel); const float* act = SF(o_act);
+  if (t.kind == MYO_TASK_BAODING) {
+    const int nh = m.nq - 14;
+    for (int i = c.lane; i < nh; i += G) obs[i] = qpos[i];
+    for (int i = c.lane; i < m.na; i += G) obs[nh + 24 + i] = act[i];
+    if (c.lane < 2) {
+      const int k = c.lane;
+      float o[3], g[3];
+      site_world(m, c.s, c.wp, t.ball_site[k], o);
+      site_world(m, c.s, c.wp, t.target_site[k], g);
+      const int da = t.ball_dofadr[k];
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+        obs[nh + 6 * k + e] = o[e];                          // object{k}_pos
+        obs[nh + 6 * k + 3 + e] = qvel[da + e] * m.frame_dt;   // object{k}_velp
+        obs[nh + 12 + 3 * k + e] = g[e];                     // target{k}_pos
+        obs[nh + 18 + 3 * k + e] = g[e] - o[e];              // target{k}_err
+      }
+    }
+  } else if (t.kind == MYO_TASK_POSE) {
+    for (int i = c.lane; i < m.nq; i += G) { obs[i] = qpos[i]; obs[m.nq + m.nv + i] = pose_target[i] - qpos[i]; }
+    for (int i = c.lane; i < m.nv; i += G) obs[m.nq + i] = qvel[i] * m.frame_dt;
+    for (int i = c.lane; i < m.na; i += G) obs[2 * m.nq + m.nv + i] = act[i];
+  } else {
+    for (int i = c.lane; i < m.nq; i += G) obs[i] = qpos[i];
+    for (int i = c.lane; i < m.nv; i += G) obs[m.nq + i] = qvel[i];
+    for (int i = c.lane; i < m.na; i += G) obs[m.nq + m.nv + i] = act[i];
+  }
+  c.tile.sync();
+}
+
+// reward terms + dense reward + termination from the observation in scratch. info: MYO_INFO_TERMS floats.
+template <int G>
+__device__ void task_reward(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, float* info, float* reward, bool* done) {
+  const float* obs = SF(o_obs); const float* act = SF(o_act);
+  float a2 = 0.f;
+  for (int i = c.lane; i < m.na; i += G) a2 += act[i] * act[i];
+  a2 = tile_sum<G>(c, a2);
+  const float act_mag = m.na ? sqrtf(a2) / (float)m.na : 0.f;
+  float term[MYO_INFO_TERMS];
+#pragma unroll
+  for (int k = 0; k < MYO_INFO_TERMS; k++) term[k] = 0.f;
+  bool dn = false;
+  if (t.kind == MYO_TASK_BAODING) {
+    const int nh = m.nq - 14;
+    const float* e1 = obs + nh + 18; const float* e2 = obs + nh + 21;
+    const float d1 = norm3(e1), d2 = norm3(e2);
+    const bool fall = obs[nh + 2] < t.drop_th || obs[nh + 8] < t.drop_th;
+    term[0] = -d1; term[1] = -d2; term[2] = -act_mag; term[3] = fall ? 0.f : 1.f; term[4] = -(d1 + d2);
+    term[5] = (d1 < t.proximity_th && d2 < t.proximity_th && !fall) ? 1.f : 0.f;
+    term[6] = fall ? 1.f : 0.f;
+    dn = fall;
+  } else if (t.kind == MYO_TASK_POSE) {
+    float e2 = 0.f;
+    for (int i = c.lane; i < m.nq; i += G) { const float e = obs[m.nq + m.nv + i]; e2 += e * e; }
+    const float dist = sqrtf(tile_sum<G>(c, e2));
+    term[0] = -dist;
+    term[1] = (dist < t.pose_thd ? 1.f : 0.f) + (dist < 1.5f * t.pose_thd ? 1.f : 0.f);
+    term[2] = dist > t.far_th ? -1.f : 0.f;
+    term[3] = -act_mag; term[4] = -dist; term[5] = dist < t.pose_thd ? 1.f : 0.f;
+    term[6] = dist > t.far_th ? 1.f : 0.f;
+    dn = dist > t.far_th;
+  }
+  float dense = 0.f;
+#pragma unroll
+  for (int k = 0; k < 7; k++) dense += t.rwd_weight[k] * term[k];
+  term[7] = dense;
+#pragma unroll
+  for (int k = 0; k < MYO_INFO_TERMS; k++) info[k] = term[k];
+  *reward = dense; *done = dn;
+}
+
+// env.reset(): sample the task's reset distribution with a counter-based RNG keyed by
+// (seed, world, episode) and write the initial state into scratch.
+template <int G>
+__device__ void task_reset(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const BatchPtrs& b, int w, int* ti,
+                           float* tf, float* pose_target) {
+  float* qpos = SF(o_qpos);
+  const int episode = ti[TI_EPISODE] + 1;
+  c.tile.sync();
+  if (!(t.kind == MYO_TASK_POSE && t.reset_type == 0)) {   // reset_type "none" keeps the last state
+    for (int i = c.lane; i < m.nq; i += G) qpos[i] = m.init_qpos[i];
+    for (int i = c.lane; i < m.nv; i += G) { SF(o_qvel)[i] = 0.f; SF(o_warm)[i] = 0.f; }
+    for (int i = c.lane; i < m.na; i += G) SF(o_act)[i] = 0.f;
+  }
+  c.tile.sync();
+  if (c.lane == 0) {
+    Philox rng;
+    rng.init(b.seed, (uint32_t)w, (uint32_t)episode);
+    ti[TI_EPISODE] = episode; ti[TI_ELAPSED] = 0;
+    if (t.kind == MYO_TASK_BAODING) {
+      float a1;
+      if (t.task_choice_random) {
+        ti[TI_TASK] = min(2, (int)(rng.uniform() * 3.f));
+        const float u = rng.uniform();
+        if (u < t.overlap_probability) a1 = 0.75f * kPi;
+        else if (t.limit_init_angle > 0.f) a1 = 0.75f * kPi + rng.uniform(-t.limit_init_angle, t.limit_init_angle);
+        else a1 = rng.uniform(0.f, 2.f * kPi);
+      } else {
+        ti[TI_TASK] = t.fixed_task;
+        a1 = (rng.uniform() < t.overlap_probability) ? 0.75f * kPi : 0.25f * kPi;
+      }
+      tf[TF_ANGLE1] = a1; tf[TF_ANGLE2] = a1 - kPi;
+      tf[TF_XR] = rng.uniform(t.goal_xrange[0], t.goal_xrange[1]);
+      tf[TF_YR] = rng.uniform(t.goal_yrange[0], t.goal_yrange[1]);
+      tf[TF_PERIOD] = rng.uniform(t.goal_time_period[0], t.goal_time_period[1]);
+      if (t.randomize_physics) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int ms = m.b_mass_slot[t.ball_body[k]];
+          if (ms >= 0) c.wp[ms] = rng.uniform(t.obj_mass_range[0], t.obj_mass_range[1]);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int fs = m.g_fri_slot[t.ball_geom[k]];
+          for (int e = 0; e < 3; e++) {
+            const float nominal = m.g_friction[3 * t.ball_geom[0] + e];
+            const float v = rng.uniform(nominal - t.obj_friction_change[e], nominal + t.obj_friction_change[e]);
+            if (fs >= 0) c.wp[fs + e] = v;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const int ss = m.g_size_slot[t.ball_geom[k]];
+          const float v = rng.uniform(t.obj_size_range[0], t.obj_size_range[1]);
+          if (ss >= 0) { c.wp[ss] = v; c.wp[ss + 1] = v; c.wp[ss + 2] = v; }
+        }
+      }
+      if (t.noise_fingers > 0.f && m.nq - 14 >= 23) {   // _add_noise_to_finger_positions: one draw per group
+        const float th = rng.uniform(-kPi / 18.f * t.noise_fingers, kPi / 18.f * t.noise_fingers);
+        qpos[4] = th; qpos[5] = th; qpos[6] = th;
+        const float fl = rng.uniform(0.f, kPi / 6.f * t.noise_fingers);
+        const int idx[12] = {7, 9, 10, 11, 13, 14, 15, 17, 18, 19, 21, 22};
+#pragma unroll
+        for (int k = 0; k < 12; k++) qpos[idx[k]] = fl;
+      }
+    } else if (t.kind == MYO_TASK_POSE) {
+      // update_target: sample target_jnt_value inside target_jnt_range, then get_target_pose scales the
+      // distance from init_qpos by target_distance
+      for (int i = 0; i < m.nq; i++) pose_target[i] = (t.n_target_jnt > 0) ? 0.f : t.target_jnt_value[i];
+      if (t.n_target_jnt > 0) {
+        for (int k = 0; k < t.n_target_jnt; k++) {
+          const float lo = t.target_jnt_range[k][0], hi = t.target_jnt_range[k][1];
+          const float v = (t.target_type == 1) ? rng.uniform(lo, hi) : 0.5f * (lo + hi);
+          pose_target[m.j_qposadr[t.target_jnt_ids[k]]] = v;
+        }
+      }
+      for (int i = 0; i < m.nq; i++) pose_target[i] = m.init_qpos[i] + t.target_distance * (pose_target[i] - m.init_qpos[i]);
+      if (t.reset_type == 2) {   // "random": uniform inside jnt_range for every joint
+        for (int j = 0; j < m.njnt; j++)
+          if (m.j_type[j] == J_HINGE || m.j_type[j] == J_SLIDE)
+            qpos[m.j_qposadr[j]] = rng.uniform(m.j_range[2 * j], m.j_range[2 * j + 1]);
+      }
+    }
+  }
+  c.tile.sync();
+}
+
+}  // namespace myo
