@@ -28,6 +28,33 @@ enum { C_G1 = 0, C_G2 = 1, C_DIM = 2, C_NSUP = 3, C_DIST = 4, C_MARGIN = 5, C_MU
 // row record
 enum { R_D = 0, R_AREF = 1, R_JAR = 2, R_JP = 3, R_BLOCK = 4 /*int: block | coef<<16*/, R_AUX = 5 };
 
+// Model tables live in shared memory: every kernel stages the packed table block (ints, then floats)
+// at the start of its dynamic shared memory, and a table is just a word offset into that block.
+#if defined(__CUDACC__) || defined(MYO_EMUL)
+#ifdef MYO_EMUL
+#define MYO_SMEM_WORDS (reinterpret_cast<float*>(emul_smem))
+#else
+extern __shared__ float4 myo_smem4[];
+#define MYO_SMEM_WORDS (reinterpret_cast<float*>(myo_smem4))
+#endif
+#define MYO_TAB_DI __device__ __forceinline__
+struct TabI {
+  int off;
+  MYO_TAB_DI const int* ptr() const { return reinterpret_cast<const int*>(MYO_SMEM_WORDS) + off; }
+  MYO_TAB_DI int operator[](int i) const { return ptr()[i]; }
+  MYO_TAB_DI const int* operator+(int i) const { return ptr() + i; }
+};
+struct TabF {
+  int off;
+  MYO_TAB_DI const float* ptr() const { return MYO_SMEM_WORDS + off; }
+  MYO_TAB_DI float operator[](int i) const { return ptr()[i]; }
+  MYO_TAB_DI const float* operator+(int i) const { return ptr() + i; }
+};
+#else
+struct TabI { int off; };
+struct TabF { int off; };
+#endif
+
 struct DevModel {
   // sizes
   int nq, nv, nu, na, nbody, njnt, ngeom, nsite, ntendon, nwrap, nM, npair, nlevel, ndlevel;
@@ -37,38 +64,40 @@ struct DevModel {
   float solver_tol, timestep, gravity[3], inv_sqrt_impratio, meaninertia;
   int any_damping, any_tendon_passive, any_joint_spring;
   // body tables
-  const int *b_parent, *b_root, *b_jntadr, *b_jntnum, *b_dofadr, *b_dofnum, *b_nchain, *b_chain, *b_mass_slot,
-      *b_sameframe, *b_childadr, *b_child, *lvl_adr, *lvl_body;
-  const float *b_pos, *b_quat, *b_ipos, *b_iquat, *b_mass, *b_inertia, *b_invweight0;
+  TabI b_parent, b_root, b_jntadr, b_jntnum, b_dofadr, b_dofnum, b_nchain, b_chain, b_mass_slot,
+      b_sameframe, b_childadr, b_child, lvl_adr, lvl_body;
+  TabF b_pos, b_quat, b_ipos, b_iquat, b_mass, b_inertia, b_invweight0;
   // joints
-  const int *j_type, *j_qposadr, *j_dofadr, *j_body, *j_limited;
-  const float *j_pos, *j_axis, *j_qpos0, *j_range, *j_margin, *j_solref, *j_solimp, *j_stiffness, *j_qpos_spring;
+  TabI j_type, j_qposadr, j_dofadr, j_body, j_limited;
+  TabF j_pos, j_axis, j_qpos0, j_range, j_margin, j_solref, j_solimp, j_stiffness, j_qpos_spring;
   // dofs
-  const int *d_body, *d_parent, *d_simple, *d_Madr, *d_depth, *d_descadr, *d_desc, *dlvl_adr, *dlvl_dof, *d_jnt,
-      *d_actadr, *d_actlist;
-  const float *d_armature, *d_damping, *d_invweight0, *d_M0;
+  TabI d_body, d_parent, d_simple, d_Madr, d_depth, d_descadr, d_desc, dlvl_adr, dlvl_dof, d_jnt,
+      d_actadr, d_actlist;
+  TabF d_armature, d_damping, d_invweight0, d_M0;
   // geoms
-  const int *g_type, *g_body, *g_condim, *g_priority, *g_size_slot, *g_fri_slot;
-  const float *g_pos, *g_mat, *g_size, *g_rbound, *g_friction, *g_solmix, *g_solref, *g_solimp, *g_margin, *g_gap;
+  TabI g_type, g_body, g_condim, g_priority, g_size_slot, g_fri_slot;
+  TabF g_pos, g_mat, g_size, g_rbound, g_friction, g_solmix, g_solref, g_solimp, g_margin, g_gap;
   // collision pair list (static filters applied on host), geom1.type <= geom2.type
-  const int *p_g1, *p_g2, *p_supported;
+  TabI p_g1, p_g2, p_supported;
   // sites
-  const int *s_body, *s_pos_slot;
-  const float* s_pos;
+  TabI s_body, s_pos_slot;
+  TabF s_pos;
   // tendons + wraps
-  const int *t_adr, *t_num, *t_limited, *t_ndof, *t_dof, *w_type, *w_obj, *w_side;
-  const float *t_range, *t_margin, *t_solref, *t_solimp, *t_invweight0, *t_stiffness, *t_damping, *t_lengthspring,
-      *w_prm;
+  TabI t_adr, t_num, t_limited, t_ndof, t_dof, w_type, w_obj, w_side;
+  TabF t_range, t_margin, t_solref, t_solimp, t_invweight0, t_stiffness, t_damping, t_lengthspring,
+      w_prm;
   // actuators
-  const int *a_tendon, *a_dyntype, *a_gaintype, *a_biastype, *a_ctrllimited, *a_forcelimited;
-  const float *a_dynprm, *a_gainprm, *a_biasprm, *a_ctrlrange, *a_forcerange, *a_gear, *a_acc0, *a_lengthrange;
+  TabI a_tendon, a_dyntype, a_gaintype, a_biastype, a_ctrllimited, a_forcelimited;
+  TabF a_dynprm, a_gainprm, a_biasprm, a_ctrlrange, a_forcerange, a_gear, a_acc0, a_lengthrange;
   // scratch offsets (words) inside one world's shared-memory block
   int o_qpos, o_qvel, o_act, o_ctrl, o_warm, o_xpos, o_xquat, o_xmat, o_xipos, o_cdof, o_cinert, o_cvel, o_cdofdot,
       o_cacc, o_cfrc, o_M, o_LD, o_tenL, o_tenV, o_tenJ, o_actF, o_bias, o_passive, o_qact, o_smooth, o_qaccs,
       o_qacc, o_qcon, o_actdot, o_grad, o_p, o_Mp, o_Ma, o_H, o_lim, o_con, o_row, o_misc, o_obs, o_wparam,
       scratch_words;
-  const float* init_qpos;   // [nq] state written by reset (MyoSuite init_qpos)
-  const float* param0;      // [nparam4] nominal values of the per-world override parameters
+  const float* g_tables;     // global copy of the table block
+  int tab_words;             // its size in words (multiple of 4); world scratch starts right after it
+  TabF init_qpos;   // [nq] state written by reset (MyoSuite init_qpos)
+  TabF param0;      // [nparam4] nominal values of the per-world override parameters
   float frame_dt;           // frame_skip * timestep (MyoSuite env.dt)
 };
 

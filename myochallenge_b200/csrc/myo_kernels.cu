@@ -118,15 +118,23 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
   }
 }
 
+// every kernel begins by staging the model's table block into shared memory (see myo_dev.hpp)
+__device__ void stage_tables(const DevModel& m) {
+  float4* dst = reinterpret_cast<float4*>(MYO_SMEM_WORDS);
+  const float4* src = reinterpret_cast<const float4*>(m.g_tables);
+#ifdef MYO_EMUL   // emulated threads run one after the other: each one stages the whole block
+  for (int i = 0; i < m.tab_words / 4; i++) dst[i] = src[i];
+#else
+  for (int i = threadIdx.x; i < m.tab_words / 4; i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+#endif
+}
+
 template <int G>
 __global__ void __launch_bounds__(kThreads) world_kernel(const __grid_constant__ DevModel m, const __grid_constant__ myo_task_cfg t,
                                                         const __grid_constant__ BatchPtrs b, const __grid_constant__ StepArgs a) {
-#ifdef MYO_EMUL
-  float* smem = reinterpret_cast<float*>(emul_smem);
-#else
-  extern __shared__ float4 smem4[];
-  float* smem = reinterpret_cast<float*>(smem4);
-#endif
+  stage_tables(m);
+  float* smem = MYO_SMEM_WORDS + m.tab_words;
   cg::thread_block block = cg::this_thread_block();
   cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
   Ctx<G> c(tile);
@@ -142,6 +150,7 @@ __global__ void __launch_bounds__(kThreads) world_kernel(const __grid_constant__
 
 // ---- stage extraction: factored scratch -> dense arrays, one thread per world ------------------
 __global__ void extract_kernel(const __grid_constant__ DevModel m, const float* dump, int n, int stage, void* outv, int width) {
+  stage_tables(m);
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n) return;
   const float* s = dump + (size_t)w * m.scratch_words;
@@ -235,6 +244,7 @@ __global__ void extract_kernel(const __grid_constant__ DevModel m, const float* 
 }
 
 __global__ void init_worlds_kernel(const __grid_constant__ DevModel m, BatchPtrs b, int fixed_task) {
+  stage_tables(m);
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= b.n_worlds) return;
   for (int i = 0; i < m.nq4; i++) { b.qpos[(size_t)w * m.nq4 + i] = i < m.nq ? m.init_qpos[i] : 0.f; b.pose_target[(size_t)w * m.nq4 + i] = 0.f; }
@@ -265,7 +275,7 @@ struct myo_batch {
   myo_task_cfg cfg;
   myo::BatchPtrs p{};
   int device = 0, n = 0;
-  int grid = 0, threads = myo::kThreads, smem = 0, regs = 0, wpc = 0;
+  int grid = 0, threads = myo::kThreads, smem = 0, regs = 0, wpc = 0, tab_bytes = 0;
   int64_t launches = 0;
   std::vector<void*> allocs;
 };
@@ -312,14 +322,19 @@ template <int G> int configure(myo_batch* b) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, b->device));
   const size_t world_bytes = (size_t)b->pm.dm.scratch_words * sizeof(float);
-  const size_t max_smem = prop.sharedMemPerBlockOptin;
+  const size_t tab_bytes = (size_t)b->pm.dm.tab_words * sizeof(float);
+  if (tab_bytes + world_bytes > prop.sharedMemPerBlockOptin) { set_error("model tables + one world exceed shared memory per CTA"); return MYO_E_LIMIT; }
+  const size_t max_smem = prop.sharedMemPerBlockOptin - tab_bytes;
   // worlds per CTA: fill the SM's shared memory with as few CTAs as keep threads <= kThreads
   int wpc = kThreads / G;
   while (wpc > 1 && wpc * world_bytes > max_smem) wpc--;
   if (wpc * world_bytes > max_smem) { set_error("one world's scratch exceeds shared memory per CTA"); return MYO_E_LIMIT; }
   b->wpc = wpc;
+  b->tab_bytes = (int)tab_bytes;
+  CK(cudaFuncSetAttribute(init_worlds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+  CK(cudaFuncSetAttribute(extract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
   b->threads = wpc * G;
-  b->smem = (int)(wpc * world_bytes);
+  b->smem = (int)(tab_bytes + wpc * world_bytes);
   CK(cudaFuncSetAttribute(world_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->smem));
   int per_sm = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, world_kernel<G>, b->threads, b->smem));
@@ -393,14 +408,12 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
   if (cudaSetDevice(device) != cudaSuccess) { myo::set_error("cudaSetDevice failed"); return fail(MYO_E_CUDA); }
   const myo::DevModel& dm = b->pm.dm;
   int rc;
-  if ((rc = dev_alloc(b, &b->pm.d_ibuf, b->pm.ibuf.size()))) return fail(rc);
-  if ((rc = dev_alloc(b, &b->pm.d_fbuf, b->pm.fbuf.size()))) return fail(rc);
-  if (cudaMemcpy(b->pm.d_ibuf, b->pm.ibuf.data(), b->pm.ibuf.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(b->pm.d_fbuf, b->pm.fbuf.data(), b->pm.fbuf.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+  if ((rc = dev_alloc(b, &b->pm.d_tables, b->pm.tables.size()))) return fail(rc);
+  if (cudaMemcpy(b->pm.d_tables, b->pm.tables.data(), b->pm.tables.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
     myo::set_error("model upload failed");
     return fail(MYO_E_CUDA);
   }
-  myo::resolve_pointers(b->pm, b->pm.d_ibuf, b->pm.d_fbuf);
+  b->pm.dm.g_tables = b->pm.d_tables;
   const size_t n = (size_t)n_worlds;
   b->p.n_worlds = n_worlds; b->p.seed = seed;
   if ((rc = dev_alloc(b, &b->p.qpos, n * dm.nq4)) || (rc = dev_alloc(b, &b->p.qvel, n * dm.nv4)) ||
@@ -412,7 +425,7 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
   b->p.dump = nullptr;
   MYO_LANES_CASES(b, configure, b)
   if (rc) return fail(rc);
-  MYO_LAUNCH(myo::init_worlds_kernel, (n_worlds + 127) / 128, 128, 0, (cudaStream_t)0, dm, b->p, cfg->fixed_task);
+  MYO_LAUNCH(myo::init_worlds_kernel, (n_worlds + 127) / 128, 128, b->tab_bytes, (cudaStream_t)0, dm, b->p, cfg->fixed_task);
   b->launches++;
   if (cudaDeviceSynchronize() != cudaSuccess) { myo::set_error("world initialisation failed"); return fail(MYO_E_CUDA); }
   *out = b;
@@ -572,7 +585,7 @@ int myo_batch_stage_dump(myo_batch* b, int stage, void* out_dev, int* width, voi
   if (!out_dev) return MYO_OK;
   if (!b->p.dump) { myo::set_error("no stage data: call myo_batch_forward or myo_batch_mj_step first"); return MYO_E_ARG; }
   CK(cudaSetDevice(b->device));
-  MYO_LAUNCH(myo::extract_kernel, (b->n + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream), d, b->p.dump, b->n, stage, out_dev, w);
+  MYO_LAUNCH(myo::extract_kernel, (b->n + 63) / 64, 64, b->tab_bytes, static_cast<cudaStream_t>(stream), d, b->p.dump, b->n, stage, out_dev, w);
   b->launches++;
   CK(cudaGetLastError());
   return MYO_OK;
@@ -591,5 +604,16 @@ int myo_batch_status(myo_batch* b, int* flags, void* stream) {
 }
 
 int64_t myo_batch_launch_count(const myo_batch* b) { return b ? b->launches : 0; }
+
+#ifdef MYO_PROFILE
+// development builds only: cumulative per-phase cycles (lane 0 of every world), then cleared
+int myo_debug_profile(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out16, myo::g_prof, sizeof(unsigned long long) * 16);
+  unsigned long long z[16] = {0};
+  cudaMemcpyToSymbol(myo::g_prof, z, sizeof z);
+  return 0;
+}
+#endif
 
 }  // extern "C"

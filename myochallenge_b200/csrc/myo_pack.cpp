@@ -17,20 +17,26 @@ namespace {
 struct Builder {
   PackedModel& pm;
   explicit Builder(PackedModel& p) : pm(p) {}
-  template <class T> size_t field_off(T* const* field) const {
-    return (size_t)((const char*)field - (const char*)&pm.dm);
-  }
-  void I(const int*& field, const std::vector<int>& v) {
-    pm.ifix.push_back({field_off(&field), pm.ibuf.size()});
+  void I(TabI& field, const std::vector<int>& v) {
+    field.off = (int)pm.ibuf.size();
     pm.ibuf.insert(pm.ibuf.end(), v.begin(), v.end());
+    if (v.empty()) pm.ibuf.push_back(0);
     while (pm.ibuf.size() % 4) pm.ibuf.push_back(0);
-    if (v.empty()) { pm.ibuf.insert(pm.ibuf.end(), 4, 0); }
   }
-  void F(const float*& field, const std::vector<float>& v) {
-    pm.ffix.push_back({field_off(&field), pm.fbuf.size()});
+  void F(TabF& field, const std::vector<float>& v) {
+    field.off = (int)pm.fbuf.size();
+    pm.ffix.push_back(&field);
     pm.fbuf.insert(pm.fbuf.end(), v.begin(), v.end());
+    if (v.empty()) pm.fbuf.push_back(0.f);
     while (pm.fbuf.size() % 4) pm.fbuf.push_back(0.f);
-    if (v.empty()) { pm.fbuf.insert(pm.fbuf.end(), 4, 0.f); }
+  }
+  void finish() {
+    const int ni = (int)pm.ibuf.size();
+    for (TabF* f : pm.ffix) f->off += ni;
+    pm.tables.resize(pm.ibuf.size() + pm.fbuf.size());
+    memcpy(pm.tables.data(), pm.ibuf.data(), pm.ibuf.size() * sizeof(int));
+    memcpy(pm.tables.data() + ni, pm.fbuf.data(), pm.fbuf.size() * sizeof(float));
+    pm.dm.tab_words = (int)pm.tables.size();
   }
 };
 
@@ -64,12 +70,6 @@ void quat2mat_h(const double* q, float* R) {
 int pad4(int n) { return (n + 3) / 4 * 4; }
 
 }  // namespace
-
-void resolve_pointers(PackedModel& pm, const int* ibase, const float* fbase) {
-  char* base = reinterpret_cast<char*>(&pm.dm);
-  for (auto& f : pm.ifix) { const int* p = ibase + f.second; memcpy(base + f.first, &p, sizeof p); }
-  for (auto& f : pm.ffix) { const float* p = fbase + f.second; memcpy(base + f.first, &p, sizeof p); }
-}
 
 std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out, int& status) {
   status = MYO_E_UNSUPPORTED;
@@ -414,6 +414,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   if (out.lanes < 32) { while (off % 32 != out.lanes) off += 4; }
   else if (off % 32 == 0) off += 4;
   d.scratch_words = off;
+  B.finish();
   status = MYO_OK;
   return "";
 }

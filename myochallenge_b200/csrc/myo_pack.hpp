@@ -10,12 +10,12 @@
 namespace myo {
 
 struct PackedModel {
-  DevModel dm{};                 // pointers are device pointers once upload() ran
+  DevModel dm{};                 // tables are word offsets into the table block
   std::vector<int> ibuf;         // all int tables, concatenated
   std::vector<float> fbuf;       // all float tables, concatenated
-  std::vector<std::pair<size_t, size_t>> ifix, ffix;   // (byte offset of the pointer inside dm, element offset)
-  int* d_ibuf = nullptr;
-  float* d_fbuf = nullptr;
+  std::vector<TabF*> ffix;       // float tables: offsets get shifted by ibuf.size() once packing is done
+  std::vector<float> tables;     // ibuf (bit-cast) followed by fbuf: the block staged into shared memory
+  float* d_tables = nullptr;
   int lanes = 32;                // tile width G chosen for this model
   // override slot bookkeeping: (kind, id) -> (slot, ncomp)
   struct Slot { int kind, id, slot, ncomp; };
@@ -25,7 +25,5 @@ struct PackedModel {
 
 // returns "" on success; status gets a myo_status code on failure
 std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out, int& status);
-// rebuild fbuf-resident init_qpos / param0 after host edits (before upload)
-void resolve_pointers(PackedModel& pm, const int* ibase, const float* fbase);
 
 }  // namespace myo

@@ -409,7 +409,9 @@ __device__ float wrap_circle(float* pnt, const float* d, const float* sd, float 
   const float dt = pnt[0] * pnt[2] + pnt[1] * pnt[3];
   const float cr = pnt[1] * pnt[2] - pnt[0] * pnt[3];
   float angle = atan2f(fabsf(cr), dt);
-  if ((cr > 0.f && i) || (cr < 0.f && !i)) angle = 2.f * kPi - angle;
+  // a grazing contact has cr ~ 0 with a rounding-noise sign; the reflex branch (arc > pi) is only
+  // taken when the sign is resolved, otherwise a zero-length arc would flip to a full 2*pi turn
+  if (fabsf(cr) > 1e-5f * sqrad && ((cr > 0.f && i) || (cr < 0.f && !i))) angle = 2.f * kPi - angle;
   return rad * angle;
 }
 // returns curved length (>= 0) and two world points in wpnt[0..5]; -1 no wrap; -2 unsupported (inside wrap)
@@ -1259,6 +1261,7 @@ __device__ void phase_solve(const DevModel& m, Ctx<G>& c) {
   }
   const float scale = 1.f / (m.meaninertia * (float)max(1, nv));
   int iter = 0;
+  float prev_step = 3.0e38f;
   for (; iter < m.solver_iter; iter++) {
     rows_dot<G>(m, c, a, R_JAR, true);
     mul_M<G>(m, c, M, a, Ma);
@@ -1302,7 +1305,14 @@ __device__ void phase_solve(const DevModel& m, Ctx<G>& c) {
     }
     for (int i = c.lane; i < nv; i += G) a[i] += alpha * p[i];
     c.tile.sync();
-    if (alpha * pmax <= 1e-6f * fmaxf(1.f, amax)) { iter++; break; }
+#ifdef MYO_SOLVER_DEBUG
+    if (iter > 8) printf("it %d gnorm*scale %.3e alpha %.6f pmax %.3e amax %.3e gp %.3e pMp %.3e nefc %d\n", iter, sqrtf(g2) * scale, alpha, pmax, amax, gp, pMp, nefc);
+#endif
+    // fp32 termination: the Newton step is at the rounding floor of qacc (quadratic convergence makes
+    // the remaining error far smaller than the last step), or it stopped shrinking (noise-level cycling)
+    const float step = alpha * pmax, aref_mag = fmaxf(1.f, amax);
+    if (step <= 2e-5f * aref_mag || (iter > 0 && step >= 0.5f * prev_step && step <= 1e-3f * aref_mag)) { iter++; break; }
+    prev_step = step;
   }
   // final forces at the solution
   rows_dot<G>(m, c, a, R_JAR, true);
@@ -1354,24 +1364,36 @@ __device__ void phase_integrate(const DevModel& m, Ctx<G>& c) {
   c.tile.sync();
 }
 
+// optional per-phase cycle counters (development builds: -DMYO_PROFILE)
+#ifdef MYO_PROFILE
+__device__ unsigned long long g_prof[16];
+#define MYO_PH_BEGIN long long ph_t0 = clock64();
+#define MYO_PH(i) { long long ph_t = clock64(); if (c.lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(ph_t - ph_t0)); ph_t0 = clock64(); }
+#else
+#define MYO_PH_BEGIN
+#define MYO_PH(i)
+#endif
+
 // one full mj_step on the world in scratch
 template <int G>
 __device__ void mj_forward_dev(const DevModel& m, Ctx<G>& c, int* status) {
-  phase_tree_forward<G>(m, c, true);
-  phase_tendon<G>(m, c, status);
-  phase_tree_backward<G>(m, c);
-  phase_mass_bias<G>(m, c);
-  factor_sparse<G>(m, c, SF(o_LD), SF(o_M), 0.f);
-  phase_collision<G>(m, c, status);
-  phase_constraints<G>(m, c, status);
-  phase_actuation<G>(m, c);
-  solve_sparse<G>(m, c, SF(o_LD), SF(o_qaccs));
-  phase_solve<G>(m, c);
+  MYO_PH_BEGIN
+  phase_tree_forward<G>(m, c, true); MYO_PH(0)
+  phase_tendon<G>(m, c, status); MYO_PH(1)
+  phase_tree_backward<G>(m, c); MYO_PH(2)
+  phase_mass_bias<G>(m, c); MYO_PH(3)
+  factor_sparse<G>(m, c, SF(o_LD), SF(o_M), 0.f); MYO_PH(4)
+  phase_collision<G>(m, c, status); MYO_PH(5)
+  phase_constraints<G>(m, c, status); MYO_PH(6)
+  phase_actuation<G>(m, c); MYO_PH(7)
+  solve_sparse<G>(m, c, SF(o_LD), SF(o_qaccs)); MYO_PH(8)
+  phase_solve<G>(m, c); MYO_PH(9)
 }
 template <int G>
 __device__ void mj_step_dev(const DevModel& m, Ctx<G>& c, int* status) {
   mj_forward_dev<G>(m, c, status);
-  phase_integrate<G>(m, c);
+  MYO_PH_BEGIN
+  phase_integrate<G>(m, c); MYO_PH(10)
 }
 
 }  // namespace myo

@@ -46,6 +46,7 @@ template <class F> cudaError_t cudaFuncGetAttributes(cudaFuncAttributes* a, F) {
 template <class F> cudaError_t cudaFuncSetAttribute(F, int, int) { return 0; }
 template <class F> cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, int) { *n = 1; return 0; }
 
+inline void __syncthreads() {}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }
