@@ -103,7 +103,8 @@ struct DevModel {
 
 // per-batch device pointers
 struct BatchPtrs {
-  int n_worlds;
+  int n_worlds;   // worlds the caller sees
+  int n_alloc;    // worlds allocated and stepped (n_worlds rounded up to a multiple of worlds per CTA)
   float *qpos, *qvel, *act, *warm, *time, *wparam, *task_f, *pose_target;
   int *task_i, *status;
   float* dump;   // [n][scratch_words] written by forward / mj_step mode (may be null)

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,12 +43,14 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
   float* tf = b.task_f + (size_t)w * TF_WORDS;
   float* ptarget = b.pose_target + (size_t)w * m.nq4;
   int* misc = SI(o_misc);
+  const bool io = w < b.n_worlds;                    // padding worlds never touch caller buffers
+  const int wi = io ? w : b.n_worlds - 1;
   if (a.mode == MODE_RESET) {
-    if (a.mask && !a.mask[w]) return;
+    if (a.mask && !a.mask[wi]) return;
     load_world<G>(m, c, b, w);
     task_reset<G>(m, t, c, b, w, ti, tf, ptarget);
     if (c.lane == 0) b.time[w] = 0.f;
-    if (a.obs) {
+    if (a.obs && io) {
       phase_tree_forward<G>(m, c, false);
       task_obs<G>(m, t, c, ptarget);
       for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
@@ -57,13 +60,14 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
   }
   load_world<G>(m, c, b, w);
   if (a.mode == MODE_GET_OBS) {
+    if (!io) return;
     phase_tree_forward<G>(m, c, false);
     task_obs<G>(m, t, c, ptarget);
     for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
     return;
   }
   if (a.mode == MODE_FORWARD || a.mode == MODE_MJ_STEP) {
-    for (int i = c.lane; i < m.nu; i += G) SF(o_ctrl)[i] = a.in ? a.in[(size_t)w * m.nu + i] : 0.f;
+    for (int i = c.lane; i < m.nu; i += G) SF(o_ctrl)[i] = a.in ? a.in[(size_t)wi * m.nu + i] : 0.f;
     c.tile.sync();
     if (a.mode == MODE_FORWARD) mj_forward_dev<G>(m, c, &status);
     else {
@@ -72,7 +76,7 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
     }
   } else {   // MODE_ENV_STEP
     if (t.kind == MYO_TASK_BAODING) baoding_targets<G>(m, t, c, ti, tf);
-    task_action<G>(m, t, c, a.in + (size_t)w * m.nu);
+    task_action<G>(m, t, c, a.in + (size_t)wi * m.nu);
     c.tile.sync();
     for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(m, c, &status);
     // get_obs: kinematics at the post-step state (MyoSuite get_obs -> sim.forward)
@@ -88,19 +92,21 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
     if (c.lane == 0) {
       ti[TI_ELAPSED] = elapsed;
       b.time[w] += (float)a.nsub * m.timestep;
-      a.reward[w] = reward;
-      a.done[w] = done ? 1 : 0;
-      if (a.truncated) a.truncated[w] = (limit && !env_done) ? 1 : 0;
+      if (io) {
+        a.reward[w] = reward;
+        a.done[w] = done ? 1 : 0;
+        if (a.truncated) a.truncated[w] = (limit && !env_done) ? 1 : 0;
+      }
     }
-    if (a.info) for (int k = c.lane; k < MYO_INFO_TERMS; k += G) a.info[(size_t)w * MYO_INFO_TERMS + k] = info[k];
+    if (a.info && io) for (int k = c.lane; k < MYO_INFO_TERMS; k += G) a.info[(size_t)w * MYO_INFO_TERMS + k] = info[k];
     if (done && t.auto_reset) {
-      if (a.terminal_obs) for (int i = c.lane; i < m.nobs; i += G) a.terminal_obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
+      if (a.terminal_obs && io) for (int i = c.lane; i < m.nobs; i += G) a.terminal_obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
       task_reset<G>(m, t, c, b, w, ti, tf, ptarget);
       if (c.lane == 0) b.time[w] = 0.f;
       phase_tree_forward<G>(m, c, false);
       task_obs<G>(m, t, c, ptarget);
     }
-    for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
+    if (io) for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
   }
   // status flags
   for (int i = c.lane; i < m.nq; i += G) if (!isfinite(SF(o_qpos)[i])) status |= ST_NONFINITE;
@@ -108,7 +114,7 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
   for (int o = G / 2; o > 0; o >>= 1) status |= c.tile.shfl_xor(status, o);
   if (c.lane == 0) {
     misc[MI_STATUS] = status;
-    if (status) atomicOr(b.status, status);
+    if (status && io) atomicOr(b.status, status);
   }
   store_world<G>(m, c, b, w, true);
   if (b.dump && a.mode != MODE_ENV_STEP) {
@@ -142,7 +148,9 @@ __global__ void __launch_bounds__(kThreads) world_kernel(const __grid_constant__
   const int tid = threadIdx.x / G;
   c.s = smem + (size_t)tid * m.scratch_words;
   c.wp = c.s + m.o_wparam;
-  for (int w = blockIdx.x * wpc + tid; w < b.n_worlds; w += gridDim.x * wpc) {
+  // state arrays are padded to a multiple of wpc worlds, so every tile of a CTA runs the same number of
+  // iterations (the phases contain CTA-wide barriers); padding worlds are stepped but have no I/O
+  for (int w = blockIdx.x * wpc + tid; w < b.n_alloc; w += gridDim.x * wpc) {
     run_world<G>(m, t, b, a, c, w);
     c.tile.sync();
   }
@@ -246,7 +254,7 @@ __global__ void extract_kernel(const __grid_constant__ DevModel m, const float* 
 __global__ void init_worlds_kernel(const __grid_constant__ DevModel m, BatchPtrs b, int fixed_task) {
   stage_tables(m);
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= b.n_worlds) return;
+  if (w >= b.n_alloc) return;
   for (int i = 0; i < m.nq4; i++) { b.qpos[(size_t)w * m.nq4 + i] = i < m.nq ? m.init_qpos[i] : 0.f; b.pose_target[(size_t)w * m.nq4 + i] = 0.f; }
   for (int i = 0; i < m.nv4; i++) { b.qvel[(size_t)w * m.nv4 + i] = 0.f; b.warm[(size_t)w * m.nv4 + i] = 0.f; }
   for (int i = 0; i < m.na4; i++) b.act[(size_t)w * m.na4 + i] = 0.f;
@@ -414,8 +422,11 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
     return fail(MYO_E_CUDA);
   }
   b->pm.dm.g_tables = b->pm.d_tables;
-  const size_t n = (size_t)n_worlds;
+  MYO_LANES_CASES(b, configure, b)
+  if (rc) return fail(rc);
   b->p.n_worlds = n_worlds; b->p.seed = seed;
+  b->p.n_alloc = (n_worlds + b->wpc - 1) / b->wpc * b->wpc;
+  const size_t n = (size_t)b->p.n_alloc;
   if ((rc = dev_alloc(b, &b->p.qpos, n * dm.nq4)) || (rc = dev_alloc(b, &b->p.qvel, n * dm.nv4)) ||
       (rc = dev_alloc(b, &b->p.act, n * dm.na4)) || (rc = dev_alloc(b, &b->p.warm, n * dm.nv4)) ||
       (rc = dev_alloc(b, &b->p.time, n)) || (rc = dev_alloc(b, &b->p.wparam, n * dm.nparam4)) ||
@@ -423,9 +434,7 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
       (rc = dev_alloc(b, &b->p.task_i, n * myo::TI_WORDS)) || (rc = dev_alloc(b, &b->p.status, 4)))
     return fail(rc);
   b->p.dump = nullptr;
-  MYO_LANES_CASES(b, configure, b)
-  if (rc) return fail(rc);
-  MYO_LAUNCH(myo::init_worlds_kernel, (n_worlds + 127) / 128, 128, b->tab_bytes, (cudaStream_t)0, dm, b->p, cfg->fixed_task);
+  MYO_LAUNCH(myo::init_worlds_kernel, (b->p.n_alloc + 127) / 128, 128, b->tab_bytes, (cudaStream_t)0, dm, b->p, cfg->fixed_task);
   b->launches++;
   if (cudaDeviceSynchronize() != cudaSuccess) { myo::set_error("world initialisation failed"); return fail(MYO_E_CUDA); }
   *out = b;
@@ -480,7 +489,7 @@ int myo_batch_step(myo_batch* b, const float* actions_dev, float* obs_dev, float
 
 static int ensure_dump(myo_batch* b) {
   if (b->p.dump) return MYO_OK;
-  return dev_alloc(b, &b->p.dump, (size_t)b->n * b->pm.dm.scratch_words);
+  return dev_alloc(b, &b->p.dump, (size_t)b->p.n_alloc * b->pm.dm.scratch_words);
 }
 
 int myo_batch_mj_step(myo_batch* b, const float* ctrl_dev, int nsub, void* stream) {

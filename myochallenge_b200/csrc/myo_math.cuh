@@ -7,6 +7,8 @@
 namespace myo {
 
 #define MYO_DI __device__ __forceinline__
+// phases are real functions: one copy of each in the instruction stream keeps the kernel inside the instruction cache
+#define MYO_PHASE __device__ __noinline__
 constexpr float kMinVal = 1e-15f;
 constexpr float kPi = 3.14159265358979323846f;
 

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -388,6 +389,10 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   d.nefc_max = d.nlim_max + 4 * d.ncon_max;
   if (nv > 64) { status = MYO_E_LIMIT; return "nv exceeds the dense solver limit (64)"; }
   out.lanes = nv <= 8 ? 8 : (nv <= 16 ? 16 : 32);
+  if (const char* ov = getenv("MYO_LANES")) {   // development override of the tile width (8, 16 or 32)
+    const int g = atoi(ov);
+    if (g == 8 || g == 16 || g == 32) out.lanes = g;
+  }
 
   int off = 0;
   auto take = [&](int words) { int o = off; off += pad4(std::max(words, 1)); return o; };

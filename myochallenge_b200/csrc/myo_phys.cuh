@@ -39,7 +39,7 @@ template <int G> MYO_DI float tile_max(const Ctx<G>& c, float v) {
 // Reference point of every kinematic tree = xipos of its root body (MuJoCo uses the subtree COM;
 // the dynamics are invariant to that choice and a nearby point keeps fp32 cross products small).
 template <int G>
-__device__ void body_forward(const DevModel& m, Ctx<G>& c, int b, bool dyn) {
+MYO_PHASE void body_forward(const DevModel& m, Ctx<G>& c, int b, bool dyn) {
   const float* qpos = SF(o_qpos);
   const float* qvel = SF(o_qvel);
   float* cdof = SF(o_cdof);
@@ -196,7 +196,7 @@ __device__ void body_forward(const DevModel& m, Ctx<G>& c, int b, bool dyn) {
 }
 
 template <int G>
-__device__ void phase_tree_forward(const DevModel& m, Ctx<G>& c, bool dyn) {
+MYO_PHASE void phase_tree_forward(const DevModel& m, Ctx<G>& c, bool dyn) {
   if (c.lane == 0) {
     float* xp = SF(o_xpos); float* xq = SF(o_xquat); float* xm = SF(o_xmat); float* xi = SF(o_xipos);
     xp[0] = xp[1] = xp[2] = 0.f; xi[0] = xi[1] = xi[2] = 0.f;
@@ -221,7 +221,7 @@ __device__ void phase_tree_forward(const DevModel& m, Ctx<G>& c, bool dyn) {
 
 // mj_crb backward accumulation + mj_rne backward pass, children gathered in a fixed order
 template <int G>
-__device__ void phase_tree_backward(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_tree_backward(const DevModel& m, Ctx<G>& c) {
   float* ci = SF(o_cinert); float* cf = SF(o_cfrc);
   for (int L = m.nlevel - 2; L >= 0; L--) {
     for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) {
@@ -240,7 +240,7 @@ __device__ void phase_tree_backward(const DevModel& m, Ctx<G>& c) {
 
 // a10.4 mass matrix in MuJoCo's sparse dof_Madr layout (row i: i, parent(i), ...) + qfrc_bias
 template <int G>
-__device__ void phase_mass_bias(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_mass_bias(const DevModel& m, Ctx<G>& c) {
   const float* cdof = SF(o_cdof); const float* crb = SF(o_cinert); const float* cf = SF(o_cfrc);
   float* M = SF(o_M); float* bias = SF(o_bias);
   for (int i = c.lane; i < m.nv; i += G) {
@@ -276,7 +276,7 @@ __device__ void phase_mass_bias(const DevModel& m, Ctx<G>& c) {
 //   L(i,j) = (M(i,j) - sum_k L(k,i) L(k,j) D(k)) / D(i)      j ancestor of i
 // LD holds D on the diagonal slot and L on the ancestor slots. hdamp adds h*damping (mj_Euler).
 template <int G>
-__device__ void factor_sparse(const DevModel& m, Ctx<G>& c, float* LD, const float* M, float hdamp) {
+MYO_PHASE void factor_sparse(const DevModel& m, Ctx<G>& c, float* LD, const float* M, float hdamp) {
   for (int L = m.ndlevel - 1; L >= 0; L--) {
     for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
       const int i = m.dlvl_dof[idx];
@@ -308,7 +308,7 @@ __device__ void factor_sparse(const DevModel& m, Ctx<G>& c, float* LD, const flo
 }
 // x <- (L' D L)^-1 x   (mj_solveLD, gather form)
 template <int G>
-__device__ void solve_sparse(const DevModel& m, Ctx<G>& c, const float* LD, float* x) {
+MYO_PHASE void solve_sparse(const DevModel& m, Ctx<G>& c, const float* LD, float* x) {
   for (int L = m.ndlevel - 1; L >= 0; L--) {     // x <- L^-T x, deepest first
     for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
       const int i = m.dlvl_dof[idx];
@@ -337,7 +337,7 @@ __device__ void solve_sparse(const DevModel& m, Ctx<G>& c, const float* LD, floa
 }
 // y = M x using the sparse symmetric layout (mj_mulM)
 template <int G>
-__device__ void mul_M(const DevModel& m, Ctx<G>& c, const float* M, const float* x, float* y) {
+MYO_PHASE void mul_M(const DevModel& m, Ctx<G>& c, const float* M, const float* x, float* y) {
   for (int i = c.lane; i < m.nv; i += G) {
     const int dep = m.d_depth[i];
     int adr = m.d_Madr[i], j = i;
@@ -373,7 +373,7 @@ MYO_DI bool seg_intersect(const float* p1, const float* p2, const float* p3, con
 }
 // 2-D wrap around a circle (MuJoCo wrap_circle). Arc angle via atan2(|cross|, dot): same value as
 // MuJoCo's acos(dot) but well conditioned in fp32 for small arcs.
-__device__ float wrap_circle(float* pnt, const float* d, const float* sd, float rad) {
+MYO_PHASE float wrap_circle(float* pnt, const float* d, const float* sd, float rad) {
   const float sqlen0 = d[0] * d[0] + d[1] * d[1], sqlen1 = d[2] * d[2] + d[3] * d[3], sqrad = rad * rad;
   const float dif[2] = {d[2] - d[0], d[3] - d[1]};
   const float dd = dif[0] * dif[0] + dif[1] * dif[1];
@@ -415,7 +415,7 @@ __device__ float wrap_circle(float* pnt, const float* d, const float* sd, float 
   return rad * angle;
 }
 // returns curved length (>= 0) and two world points in wpnt[0..5]; -1 no wrap; -2 unsupported (inside wrap)
-__device__ float wrap_geom(float* wpnt, const float* x0, const float* x1, const float* gpos, const float* gmat, float radius,
+MYO_PHASE float wrap_geom(float* wpnt, const float* x0, const float* x1, const float* gpos, const float* gmat, float radius,
                            int type, const float* side) {
   float p0[3], p1[3], dif[3], axis0[3], axis1[3], normal[3];
   sub3(dif, x0, gpos); mulmatTvec3(p0, gmat, dif);
@@ -497,7 +497,7 @@ MYO_DI int common_prefix(const DevModel& m, int ba, int bb) {
   while (cp < na && cp < nb && m.b_chain[ba * KC + cp] == m.b_chain[bb * KC + cp]) cp++;
   return cp;
 }
-MYO_DI void segment_moment(const DevModel& m, const float* s, int ba, const float* pa, int bb, const float* pb, float inv_div,
+MYO_PHASE void segment_moment(const DevModel& m, const float* s, int ba, const float* pa, int bb, const float* pb, float inv_div,
                            const int* tdof, int ntd, float* J) {
   if (ba == bb) return;
   float dir[3];
@@ -509,7 +509,7 @@ MYO_DI void segment_moment(const DevModel& m, const float* s, int ba, const floa
 }
 
 template <int G>
-__device__ void phase_tendon(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void phase_tendon(const DevModel& m, Ctx<G>& c, int* status) {
   const float* qvel = SF(o_qvel);
   for (int t = c.lane; t < m.ntendon; t += G) {
     const int adr = m.t_adr[t], num = m.t_num[t], ntd = m.t_ndof[t];
@@ -591,7 +591,7 @@ MYO_DI float muscle_FL(float L, float lmin, float lmax) {
   return 0.5f * x * x;
 }
 template <int G>
-__device__ void phase_actuation(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_actuation(const DevModel& m, Ctx<G>& c) {
   const float* ctrl = SF(o_ctrl); const float* act = SF(o_act);
   for (int i = c.lane; i < m.nu; i += G) {
     const int t = m.a_tendon[i];
@@ -713,7 +713,7 @@ MYO_DI bool sphere_sphere(float margin, const float* p1, float r1, const float* 
 }
 
 template <int G>
-__device__ void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
   int* misc = SI(o_misc);
   int ncon = 0;
   for (int base = 0; base < m.npair; base += G) {
@@ -794,7 +794,7 @@ __device__ void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
 }
 
 // impedance, regularisation and reference-acceleration coefficients of one row (mj_makeImpedance)
-MYO_DI void row_params(const DevModel& m, const float* solref, const float* solimp, float pos, float margin, float diag,
+MYO_PHASE void row_params(const DevModel& m, const float* solref, const float* solimp, float pos, float margin, float diag,
                        float* R, float* K, float* B, float* imp) {
   const float s0 = clipf(solimp[0], 0.0001f, 0.9999f), s1 = clipf(solimp[1], 0.0001f, 0.9999f);
   const float s2 = fmaxf(0.f, solimp[2]), s3 = clipf(solimp[3], 0.0001f, 0.9999f), s4 = fmaxf(1.f, solimp[4]);
@@ -829,7 +829,7 @@ MYO_DI void row_params(const DevModel& m, const float* solref, const float* soli
 // a limit has one basis vector over <= KT dofs, a contact has (normal, tangent1, tangent2) over
 // the <= KS dofs in chain(body1) xor chain(body2).
 template <int G>
-__device__ void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
   int* misc = SI(o_misc);
   const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel);
   int nlim = 0;
@@ -1057,7 +1057,7 @@ __device__ void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
 // ------------------------------------------------------------------------------------------------
 // row helper: J_r . x for every row -> rows[r][field]; optionally subtract aref (jar = J a - aref)
 template <int G>
-__device__ void rows_dot(const DevModel& m, Ctx<G>& c, const float* x, int field, bool sub_aref) {
+MYO_PHASE void rows_dot(const DevModel& m, Ctx<G>& c, const float* x, int field, bool sub_aref) {
   const int* misc = SI(o_misc);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
   float* rows = SF(o_row);
@@ -1092,7 +1092,7 @@ __device__ void rows_dot(const DevModel& m, Ctx<G>& c, const float* x, int field
 // out[dof] += sum_r J_r[dof] * w_r  with w_r = (jar_r < 0 ? -D_r jar_r : 0) * scale  (forces)
 // blocks applied one after the other, lanes across the block's support: no atomics, fixed order.
 template <int G>
-__device__ void rows_JT_force(const DevModel& m, Ctx<G>& c, float* out, float scale) {
+MYO_PHASE void rows_JT_force(const DevModel& m, Ctx<G>& c, float* out, float scale) {
   const int* misc = SI(o_misc);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
   const float* rows = SF(o_row);
@@ -1126,7 +1126,7 @@ MYO_DI int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, 
 
 // H = M + sum_{active rows} D_r J_r' J_r  (packed lower triangle)
 template <int G>
-__device__ void build_hessian(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void build_hessian(const DevModel& m, Ctx<G>& c) {
   float* H = SF(o_H); const float* M = SF(o_M);
   const int nv = m.nv;
   for (int e = c.lane; e < nv * (nv + 1) / 2; e += G) H[e] = 0.f;
@@ -1189,7 +1189,7 @@ __device__ void build_hessian(const DevModel& m, Ctx<G>& c) {
 
 // in-place dense Cholesky (left-looking, lane per row) and solve; n <= 2*G
 template <int G>
-__device__ void chol_factor(Ctx<G>& c, float* H, int n) {
+MYO_PHASE void chol_factor(Ctx<G>& c, float* H, int n) {
   for (int j = 0; j < n; j++) {
     const float* Lj = H + tri(j, 0);
     for (int i = j + c.lane; i < n; i += G) {
@@ -1206,7 +1206,7 @@ __device__ void chol_factor(Ctx<G>& c, float* H, int n) {
   }
 }
 template <int G>
-__device__ void chol_solve(Ctx<G>& c, const float* H, float* x, int n) {
+MYO_PHASE void chol_solve(Ctx<G>& c, const float* H, float* x, int n) {
   for (int j = 0; j < n; j++) {          // forward: column oriented
     if (c.lane == 0) x[j] = x[j] / sqrtf(fmaxf(H[tri(j, j)], kMinVal));
     c.tile.sync();
@@ -1227,7 +1227,7 @@ __device__ void chol_solve(Ctx<G>& c, const float* H, float* x, int n) {
 //   cost(a) = 1/2 (a - a_s)' M (a - a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
 // warm-started from the better of (qacc_warmstart, qacc_smooth) as MuJoCo's warmstart() does.
 template <int G>
-__device__ void phase_solve(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_solve(const DevModel& m, Ctx<G>& c) {
   int* misc = SI(o_misc);
   const int nv = m.nv, nefc = misc[MI_NEFC];
   float* a = SF(o_qacc); float* qcon = SF(o_qcon);
@@ -1303,8 +1303,18 @@ __device__ void phase_solve(const DevModel& m, Ctx<G>& c) {
       if (nxt == alpha) break;
       alpha = nxt;
     }
+    // did any row change side along the step? if not, and the full Newton step was taken, a + p is the
+    // exact minimiser of a cost that is quadratic on this active set: converged without a checking pass
+    int changed = 0;
+    for (int r = c.lane; r < nefc; r += G) {
+      const float* row = rows + r * ROW_WORDS;
+      const float x0 = row[R_JAR], x1 = x0 + alpha * row[R_JP];
+      if ((x0 < 0.f) != (x1 < 0.f)) changed = 1;
+    }
+    changed = c.tile.ballot(changed != 0) != 0u;
     for (int i = c.lane; i < nv; i += G) a[i] += alpha * p[i];
     c.tile.sync();
+    if (!changed && fabsf(alpha - 1.f) <= 1e-3f) { iter++; break; }
 #ifdef MYO_SOLVER_DEBUG
     if (iter > 8) printf("it %d gnorm*scale %.3e alpha %.6f pmax %.3e amax %.3e gp %.3e pMp %.3e nefc %d\n", iter, sqrtf(g2) * scale, alpha, pmax, amax, gp, pMp, nefc);
 #endif
@@ -1325,7 +1335,7 @@ __device__ void phase_solve(const DevModel& m, Ctx<G>& c) {
 
 // a10.9 mj_Euler (implicit in joint damping) + mj_advance
 template <int G>
-__device__ void phase_integrate(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_integrate(const DevModel& m, Ctx<G>& c) {
   const float h = m.timestep;
   float* qacc = SF(o_qacc); float* qvel = SF(o_qvel); float* qpos = SF(o_qpos); float* act = SF(o_act);
   float* x = SF(o_grad);
@@ -1374,26 +1384,31 @@ __device__ unsigned long long g_prof[16];
 #define MYO_PH(i)
 #endif
 
+// All warps of a CTA walk the phases together: the step is ~200 KB of straight-line code, far more
+// than the instruction cache holds, so keeping the CTA inside one phase at a time lets every fetched
+// line serve all of its warps. (Every tile of the CTA executes every phase of every substep.)
+#define MYO_CTA_SYNC __syncthreads();
+
 // one full mj_step on the world in scratch
 template <int G>
-__device__ void mj_forward_dev(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void mj_forward_dev(const DevModel& m, Ctx<G>& c, int* status) {
   MYO_PH_BEGIN
-  phase_tree_forward<G>(m, c, true); MYO_PH(0)
-  phase_tendon<G>(m, c, status); MYO_PH(1)
-  phase_tree_backward<G>(m, c); MYO_PH(2)
+  MYO_CTA_SYNC phase_tree_forward<G>(m, c, true); MYO_PH(0)
+  MYO_CTA_SYNC phase_tendon<G>(m, c, status); MYO_PH(1)
+  MYO_CTA_SYNC phase_tree_backward<G>(m, c); MYO_PH(2)
   phase_mass_bias<G>(m, c); MYO_PH(3)
   factor_sparse<G>(m, c, SF(o_LD), SF(o_M), 0.f); MYO_PH(4)
-  phase_collision<G>(m, c, status); MYO_PH(5)
-  phase_constraints<G>(m, c, status); MYO_PH(6)
-  phase_actuation<G>(m, c); MYO_PH(7)
+  MYO_CTA_SYNC phase_collision<G>(m, c, status); MYO_PH(5)
+  MYO_CTA_SYNC phase_constraints<G>(m, c, status); MYO_PH(6)
+  MYO_CTA_SYNC phase_actuation<G>(m, c); MYO_PH(7)
   solve_sparse<G>(m, c, SF(o_LD), SF(o_qaccs)); MYO_PH(8)
-  phase_solve<G>(m, c); MYO_PH(9)
+  MYO_CTA_SYNC phase_solve<G>(m, c); MYO_PH(9)
 }
 template <int G>
-__device__ void mj_step_dev(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void mj_step_dev(const DevModel& m, Ctx<G>& c, int* status) {
   mj_forward_dev<G>(m, c, status);
   MYO_PH_BEGIN
-  phase_integrate<G>(m, c); MYO_PH(10)
+  MYO_CTA_SYNC phase_integrate<G>(m, c); MYO_PH(10)
 }
 
 }  // namespace myo

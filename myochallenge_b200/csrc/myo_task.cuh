@@ -11,14 +11,14 @@
 namespace myo {
 
 template <int G>
-__device__ void copy_words(Ctx<G>& c, float* dst, const float* src, int n4) {   // n4: multiple of 4 words
+MYO_PHASE void copy_words(Ctx<G>& c, float* dst, const float* src, int n4) {   // n4: multiple of 4 words
   const float4* s4 = reinterpret_cast<const float4*>(src);
   float4* d4 = reinterpret_cast<float4*>(dst);
   for (int i = c.lane; i < n4 / 4; i += G) d4[i] = s4[i];
 }
 
 template <int G>
-__device__ void load_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int w) {
+MYO_PHASE void load_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int w) {
   copy_words<G>(c, SF(o_qpos), b.qpos + (size_t)w * m.nq4, m.nq4);
   copy_words<G>(c, SF(o_qvel), b.qvel + (size_t)w * m.nv4, m.nv4);
   copy_words<G>(c, SF(o_warm), b.warm + (size_t)w * m.nv4, m.nv4);
@@ -27,7 +27,7 @@ __device__ void load_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int
   c.tile.sync();
 }
 template <int G>
-__device__ void store_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int w, bool params) {
+MYO_PHASE void store_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int w, bool params) {
   c.tile.sync();
   copy_words<G>(c, b.qpos + (size_t)w * m.nq4, SF(o_qpos), m.nq4);
   copy_words<G>(c, b.qvel + (size_t)w * m.nv4, SF(o_qvel), m.nv4);
@@ -39,7 +39,7 @@ __device__ void store_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, in
 // BaseV0.step: muscle actuators with normalize_act get ctrl = 1/(1+exp(-5(a-0.5))); other actuators
 // are de-normalised linearly into ctrlrange (MyoSuite Robot.normalize_actions).
 template <int G>
-__device__ void task_action(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const float* a) {
+MYO_PHASE void task_action(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const float* a) {
   float* ctrl = SF(o_ctrl);
   for (int i = c.lane; i < m.nu; i += G) {
     float u = a[i];
@@ -56,7 +56,7 @@ __device__ void task_action(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c,
 
 // BaodingEnvV1.step: target sites follow goal[counter] = sign*2*pi*counter*dt/period (a6, a7)
 template <int G>
-__device__ void baoding_targets(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const int* ti, const float* tf) {
+MYO_PHASE void baoding_targets(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const int* ti, const float* tf) {
   if (c.lane == 0) {
     const int task = ti[TI_TASK], counter = ti[TI_ELAPSED];
     const float sign = task == MYO_BAODING_CW ? -1.f : (task == MYO_BAODING_CCW ? 1.f : 0.f);
@@ -78,15 +78,14 @@ __device__ void baoding_targets(const DevModel& m, const myo_task_cfg& t, Ctx<G>
 
 // observation vector into scratch o_obs (kinematics must be current)
 template <int G>
-__device__ void task_obs(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const float* pose_target) {
+MYO_PHASE void task_obs(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const float* pose_target) {
   float* obs = SF(o_obs);
   const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel); const float* act = SF(o_act);
   if (t.kind == MYO_TASK_BAODING) {
     const int nh = m.nq - 14;
     for (int i = c.lane; i < nh; i += G) obs[i] = qpos[i];
     for (int i = c.lane; i < m.na; i += G) obs[nh + 24 + i] = act[i];
-    if (c.lane < 2) {
-      const int k = c.lane;
+    for (int k = c.lane; k < 2; k += G) {
       float o[3], g[3];
       site_world(m, c.s, c.wp, t.ball_site[k], o);
       site_world(m, c.s, c.wp, t.target_site[k], g);
@@ -113,7 +112,7 @@ __device__ void task_obs(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, co
 
 // reward terms + dense reward + termination from the observation in scratch. info: MYO_INFO_TERMS floats.
 template <int G>
-__device__ void task_reward(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, float* info, float* reward, bool* done) {
+MYO_PHASE void task_reward(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, float* info, float* reward, bool* done) {
   const float* obs = SF(o_obs); const float* act = SF(o_act);
   float a2 = 0.f;
   for (int i = c.lane; i < m.na; i += G) a2 += act[i] * act[i];
@@ -155,7 +154,7 @@ __device__ void task_reward(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c,
 // env.reset(): sample the task's reset distribution with a counter-based RNG keyed by
 // (seed, world, episode) and write the initial state into scratch.
 template <int G>
-__device__ void task_reset(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const BatchPtrs& b, int w, int* ti,
+MYO_PHASE void task_reset(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const BatchPtrs& b, int w, int* ti,
                            float* tf, float* pose_target) {
   float* qpos = SF(o_qpos);
   const int episode = ti[TI_EPISODE] + 1;

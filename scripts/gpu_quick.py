@@ -25,8 +25,15 @@ def run(path, kind, n, steps=20):
     print(f"{path} n={n} {ms:.3f} ms/step {n / ms * 1e3:.3e} env-steps/s status={sim.status()} info={sim.launch_info()} done_frac={sim.done.float().mean().item():.3f}", flush=True)
 
 if __name__ == "__main__":
-    for n in (4096, 65536):
-        run("finger/myo_finger_v0.mjb", _capi.TASK_POSE, n)
-    if os.path.exists(os.path.join(os.path.dirname(asset_path("finger/myo_finger_v0.mjb")), "..", "hand", "myo_hand_baoding.mjb")):
-        for n in (4096, 32768):
-            run("hand/myo_hand_baoding.mjb", _capi.TASK_BAODING, n)
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--model", default="all")
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=20)
+    args = ap.parse_args()
+    if args.model in ("all", "finger"):
+        for n in ([args.n] if args.n else [4096, 65536]):
+            run("finger/myo_finger_v0.mjb", _capi.TASK_POSE, n, args.steps)
+    if args.model in ("all", "hand"):
+        for n in ([args.n] if args.n else [4096, 32768]):
+            run("hand/myo_hand_baoding.mjb", _capi.TASK_BAODING, n, args.steps)

@@ -12,6 +12,7 @@
 #define __global__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __grid_constant__
 #define __launch_bounds__(...)
 #define __shared__

@@ -1,0 +1,25 @@
+"""CPU-side check of the kernel *logic*: the product's kernel sources compiled for the host, one lane per
+world (tests/emul), against the oracle. The GPU run of the same checks is tests/test_gpu_parity.py."""
+import pytest
+
+from conftest import ELBOW, FINGER, HAND_BAODING, HAND_POSE
+from myochallenge_b200 import _capi
+import parity_common as pc
+
+CASES = [("elbow", ELBOW, _capi.TASK_POSE, 8), ("finger", FINGER, _capi.TASK_POSE, 24),
+         ("hand_pose", HAND_POSE, _capi.TASK_POSE, 6), ("baoding", HAND_BAODING, _capi.TASK_BAODING, 10)]
+
+
+@pytest.mark.parametrize("name,path,kind,n", CASES, ids=[c[0] for c in CASES])
+def test_one_step_state_and_contact_parity(emul_lib, name, path, kind, n):
+    pc.check_one_step(emul_lib, "cpu", path, kind, n, seed=11)
+
+
+@pytest.mark.parametrize("name,path,kind,n", CASES, ids=[c[0] for c in CASES])
+def test_stage_parity(emul_lib, name, path, kind, n):
+    pc.check_stages(emul_lib, "cpu", path, kind, n, seed=12)
+
+
+@pytest.mark.parametrize("name,path,kind,n", [CASES[1], CASES[3]], ids=["finger", "baoding"])
+def test_env_step(emul_lib, name, path, kind, n):
+    pc.check_env_step_matches_mj_steps(emul_lib, "cpu", path, kind, min(n, 6))
