@@ -220,6 +220,14 @@ int myo_policy_set_weight(myo_policy* p, const char* name, const float* data_dev
 int myo_policy_forward(myo_policy* p, int n, const float* obs_dev, float* h_dev, float* c_dev,
                        const float* episode_start_dev, const float* noise_dev, float* actions_dev,
                        float* values_dev, float* logp_dev, void* stream);
+/* VecNormalize.normalize_obs fused into the policy's input load (/root/reference/src/main_eval.py:65-67,
+ * /root/reference/src/main_baoding.py:75): obs <- clip((obs - mean) / sqrt(var + epsilon), +-clip_obs).
+ * mean_dev / var_dev: float[obs_dim] device pointers; NULL switches normalisation off. */
+int myo_policy_set_obs_norm(myo_policy* p, const float* mean_dev, const float* var_dev, float epsilon, float clip_obs,
+                            void* stream);
+/* seed != 0: when noise_dev is NULL, myo_policy_forward samples the Gaussian action noise in-kernel from a
+ * counter-based stream keyed by (seed, world, forward-call counter); seed 0 restores the deterministic mean. */
+int myo_policy_seed(myo_policy* p, uint64_t seed);
 int64_t myo_policy_launch_count(const myo_policy* p);
 
 #ifdef __cplusplus

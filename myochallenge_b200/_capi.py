@@ -92,6 +92,8 @@ SIGNATURES = {
     "myo_policy_destroy": (None, [_vp]),
     "myo_policy_set_weight": (_i, [_vp, _cp, _fp, C.c_int64, _vp]),
     "myo_policy_forward": (_i, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
+    "myo_policy_set_obs_norm": (_i, [_vp, _fp, _fp, C.c_float, C.c_float, _vp]),
+    "myo_policy_seed": (_i, [_vp, C.c_uint64]),
     "myo_policy_launch_count": (C.c_int64, [_vp]),
 }
 
