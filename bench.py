@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py - Baoding env-steps/s with the recurrent policy in the loop (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W             # own arm (B200 kernels)
+    python bench.py --impl reference --gpus N --steps K ...   # reference arm: CPU path on the host cores
+
+A step = one pass of the hot path over every world of one GPU: policy forward on the current observations
+(VecNormalize.normalize_obs fused, Gaussian sample) -> action clip -> env step (frame_skip x mj_step, obs, reward,
+termination, TimeLimit, auto-reset).  Workload: configs[4] of BASELINE.json, myoChallengeBaodingP2-v1 with the
+registration defaults of /root/reference/src/envs/__init__.py:58-74, 32768 worlds per GPU, random-init
+MlpLstmPolicy (LSTM 256, pi = vf = [256, 256], ortho_init False, log_std_init -2) as the winning runs use
+(/root/reference/trained_models/curriculum_steps_complete_baoding_winner/01_rsi_static/main.py:178-200).
+
+One JSON line on stdout (rank 0).  `value` times the device-resident loop with CUDA events, max over ranks;
+`e2e` times the same loop through the host-array VecEnv API (pinned host buffers, H2D + D2H every step);
+`roofline` is the world kernel (dominant launch) against the measured HBM copy bandwidth; `cpu_baseline` times
+the oracle (CPU restatement, the one thing bench.py may run from oracle/) on the host cores for a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "Baoding env-steps/sec (1/2/4/8 B200, policy in loop) vs host MuJoCo SubprocVecEnv"
+UNIT = "env-steps/s"
+ENV_ID = "CustomMyoChallengeBaodingP2-v1"
+# winning curriculum reward weights (step 32 config.json of the reference)
+RWD = {"pos_dist_1": 5, "pos_dist_2": 5, "act_reg": 0, "alive": 1, "solved": 5, "done": 0, "sparse": 0}
+
+
+def algorithmic_bytes_per_env_step(nq, nv, na, nu, nobs, nparam):
+    """fp32 bytes one env step must move through HBM: action in, obs/reward/flags out, state +
+    warm start read and written once, per-world randomised parameters read."""
+    return 4 * (nu + nobs + 1) + 2 + 2 * 4 * (nq + nv + na + nv) + 4 * nparam
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason samples during the timed region (NVML)."""
+
+    def __init__(self, index: int, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.max_mhz = index, period, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle (fp64 C restatement of the MuJoCo 2.1.0 step subset) on the host cores
+def cpu_env_steps_per_s(seconds: float, threads: int, frame_skip: int = 10, states=None):
+    """Steps a bounded sample of Baoding worlds with the oracle, one thread per core, `frame_skip` mj_steps per env
+    step under constant controls; returns (env-steps/s, sample description). ctypes releases the GIL per call."""
+    import ctypes
+
+    import numpy as np
+
+    from myochallenge_b200.assets import asset_path
+    from oracle import mjb, oracle
+
+    path = asset_path("hand/myo_hand_baoding.mjb")
+    L = oracle.lib()
+    per = 4                                  # worlds per thread per call
+    nw = threads * per
+    rng = np.random.default_rng(0)
+    src = mjb.load(path)
+    models = [oracle.OracleModel(src) for _ in range(threads)]
+    datas = [oracle.OracleData(m) for m in models]
+    m0 = models[0]
+    q0r = np.array(m0.qpos0, np.float64).copy()
+    q0r[:23] = 0.0
+    q0r[0] = -1.57                             # reference init pose (/root/reference/src/envs/baoding.py:400-401)
+    if states is None:
+        qpos = np.tile(q0r, (nw, 1))
+        qvel = np.zeros((nw, m0.nv))
+        act = np.zeros((nw, m0.na))
+    else:
+        qpos, qvel, act = [np.ascontiguousarray(np.resize(np.asarray(a, np.float64), (nw, a.shape[1]))) for a in states]
+    warm = np.zeros((nw, m0.nv))
+    dp = ctypes.POINTER(ctypes.c_double)
+
+    def ptr(a):
+        return a.ctypes.data_as(dp)
+
+    counts = [0] * threads
+    stop = time.perf_counter() + seconds
+
+    def work(t):
+        lo, hi = t * per, (t + 1) * per
+        r = np.random.default_rng(t)
+        while time.perf_counter() < stop:
+            a = r.uniform(-1, 1, (nw, m0.nu))
+            ctrl = np.ascontiguousarray(1.0 / (1.0 + np.exp(-5.0 * (a - 0.5))))    # BaseV0.step muscle remap
+            L.o_batch_step(models[t]._p, datas[t]._p, lo, hi, frame_skip, ptr(qpos), ptr(qvel), ptr(act), ptr(warm), ptr(ctrl))
+            # worlds whose balls fell are reset, as the env would do
+            for w in range(lo, hi):
+                if not np.isfinite(qpos[w]).all() or qpos[w, 25] < 1.25 or qpos[w, 32] < 1.25:
+                    qpos[w] = q0r; qvel[w] = 0; act[w] = 0; warm[w] = 0
+            counts[t] += per
+
+    t0 = time.perf_counter()
+    ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    dt = time.perf_counter() - t0
+    total = sum(counts)
+    return total / dt, f"{total} env steps ({frame_skip} mj_steps each, fp64 oracle) of {nw} Baoding worlds in {dt:.1f} s on {threads} threads; physics only, no policy"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    # each "step" = a bounded sample: `--cpu-seconds` / steps of oracle stepping on all host cores
+    per_step = max(0.5, args.cpu_seconds / max(1, args.steps))
+    for _ in range(min(args.warmup, 1)):
+        cpu_env_steps_per_s(0.5, threads)
+    vals = []
+    sample = ""
+    for _ in range(args.steps):
+        v, sample = cpu_env_steps_per_s(per_step, threads)
+        vals.append(v)
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{ENV_ID}, host CPU path", "worlds_per_gpu": 0, "frame_skip": 10,
+                   "note": "MuJoCo/MyoSuite/SB3 are not installable offline (no wheels, no network): the reference's CPU path is "
+                           "represented by the fp64 C restatement of its mj_step subset (oracle/), one thread per host core"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from myochallenge_b200 import _capi
+    from myochallenge_b200.envs import make_vec_env
+    from myochallenge_b200.policy import RecurrentPolicy
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path for the product arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.worlds
+
+    env = make_vec_env(ENV_ID, n, device=dev, seed=1000 * rank + args.seed, weighted_reward_keys=RWD, clip_actions=True)
+    sim = env.sim
+    pol = RecurrentPolicy(sim.nobs, sim.nu, lstm_hidden=256, pi=(256, 256), vf=(256, 256), max_batch=n, device=dev)
+    pol.init_random(seed=0, log_std_init=-2.0)             # same weights on every rank
+    pol.seed(0x5EED + rank)
+    stats = os.path.join(ROOT, "tests", "golden", "vecnormalize_baoding_step32.npz")
+    if os.path.exists(stats):                               # the reference's own running moments (fixture), applied as
+        g = np.load(stats)                                  # VecNormalize.normalize_obs in the policy's input load
+        pol.set_obs_norm(torch.from_numpy(g["obs_mean"]).float(), torch.from_numpy(g["obs_var"]).float(), float(g["epsilon"]), float(g["clip_obs"]))
+    h, c = pol.initial_state(n)
+    out = (torch.empty(n, sim.nu, device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev))
+    starts = torch.ones(n, dtype=torch.uint8, device=dev)
+
+    obs = env.reset_device()
+    torch.cuda.synchronize()
+
+    def step_device():
+        nonlocal obs, starts
+        actions, _, _, _ = pol.forward(obs, (h, c), starts, out=out)
+        obs, rew, done, trunc = env.step_device(actions)
+        starts = done
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    l0 = sim.launch_count + pol.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    ev[0].record()
+    for i in range(args.steps):
+        actions, _, _, _ = pol.forward(obs, (h, c), starts, out=out)
+        ev[2 * i + 1].record()                              # brackets the world kernel on its own stream
+        obs, rew, done, trunc = env.step_device(actions)
+        ev[2 * i + 2].record()
+        starts = done
+    ev[-1].record()
+    barrier()
+    clocks = sampler.stop()
+    launches = sim.launch_count + pol.launch_count - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    world_ms = sum(ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)) / args.steps
+    policy_ms = total_ms / args.steps - world_ms
+    status = sim.status()
+
+    # ---- e2e: the SB3-shaped host-array API, H2D + D2H inside the timed region -------------------------------
+    pin = dict(dtype=torch.float32, pin_memory=True)
+    h_obs = torch.zeros(n, sim.nobs, **pin)
+    h_act = torch.zeros(n, sim.nu, **pin)
+    d_obs = torch.zeros(n, sim.nobs, device=dev)
+    ob, _, dn, _ = env.step(np.zeros((n, sim.nu), np.float32))      # warm the host path
+    h_obs.copy_(torch.from_numpy(ob))
+    starts_h = torch.from_numpy(dn.astype(np.uint8)).to(dev)
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        d_obs.copy_(h_obs, non_blocking=True)                             # H2D: observations for the policy
+        actions, _, _, _ = pol.forward(d_obs, (h, c), starts_h, out=out)
+        h_act.copy_(actions, non_blocking=True)                           # D2H: sampled actions
+        torch.cuda.current_stream().synchronize()
+        env.step_async(np.clip(h_act.numpy(), -1.0, 1.0))                 # H2D: actions (inside step_async)
+        ob, rw, dn, _ = env.step_wait(with_infos=False)                   # D2H: obs, reward, done
+        h_obs.copy_(torch.from_numpy(ob))
+        starts_h = torch.from_numpy(dn.astype(np.uint8)).to(dev, non_blocking=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    h2d = env.h2d_bytes_per_step + n * sim.nobs * 4 + n
+    d2h = env.d2h_bytes_per_step + n * sim.nu * 4
+
+    # max over ranks
+    t = torch.tensor([total_ms, world_ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, world_ms, e2e_s = [float(x) for x in t]
+    ms_per_step = total_ms / args.steps
+    value = world * n * args.steps / (total_ms * 1e-3)
+    e2e_value = world * n * e2e_steps / e2e_s
+
+    # ---- roofline of the dominant kernel -----------------------------------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    b_env = algorithmic_bytes_per_env_step(sim.nq, sim.nv, sim.na, sim.nu, sim.nobs, sim.nparam)
+    achieved = b_env * n / (world_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "world_kernel_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic = tj.get("dram_bytes_per_launch_at_32768_worlds")
+    roofline = {"kernel": "myo::world_kernel<32> (frame_skip x mj_step + obs/reward/reset, one launch per env step)", "bound": "hbm",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_env_step": b_env, "kernel_ms": world_ms, "kernel_share_of_step": world_ms / ms_per_step,
+                "note": "state stays in shared memory across the 10 substeps: the kernel is FP32-issue/latency bound, not HBM bound (DESIGN.md)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 physics, bf16 x bf16 -> f32 policy GEMMs", "data": "synthetic",
+        "config": {"workload": f"{ENV_ID} (BASELINE configs[4]), {n} worlds per GPU, frame_skip 10, horizon 200, full physics randomisation, "
+                               "random-init MlpLstmPolicy LSTM-256 + [256,256] actor/critic in the loop",
+                   "worlds_per_gpu": n, "parallelism": f"worlds sharded over {world} GPU(s), no data-path collective",
+                   "l2": "per-step working set (state + LSTM h/c + obs, ~190 MB at 32768 worlds) exceeds the 126 MB L2; no explicit flush",
+                   "policy_ms": policy_ms, "world_kernel_ms": world_ms, "status_flags": status},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "api": "MyoVecEnv.step_async/step_wait with numpy arrays + RecurrentPolicy.forward on H2D-copied observations"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        q, v, a, _ = [x.double().cpu().numpy() for x in sim.get_state()]
+        threads = os.cpu_count() or 1
+        val, sample = cpu_env_steps_per_s(args.cpu_seconds, threads, states=(q[:256], v[:256], a[:256]))
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=32768, help="worlds per GPU")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    return run_reference(args) if args.impl == "reference" else run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -112,6 +112,9 @@ typedef struct myo_task_cfg {
   int32_t n_ovr_body, ovr_body[MYO_MAX_OVERRIDE];
   int32_t n_ovr_geom, ovr_geom[MYO_MAX_OVERRIDE];
   int32_t n_ovr_site, ovr_site[MYO_MAX_OVERRIDE];
+  /* ---- rollout glue ---- */
+  int32_t clip_actions;         /* 1: clip actions to [-1, 1] first, as RecurrentPPO.collect_rollouts does (np.clip to the
+                                   action space) before VecEnv.step; 0: use them as given (plain gym env.step) */
 } myo_task_cfg;
 
 const char* myo_last_error(void);
@@ -214,11 +217,12 @@ void myo_policy_destroy(myo_policy* p);
 /* name follows the SB3 state-dict key (e.g. "lstm_actor.weight_ih_l0", "action_net.bias", "log_std");
  * data_dev: fp32 device tensor in torch layout */
 int myo_policy_set_weight(myo_policy* p, const char* name, const float* data_dev, int64_t numel, void* stream);
-/* obs[n,obs_dim] (already normalised); h/c: [2][n][H] (0 = actor, 1 = critic), updated in place;
- * episode_start[n] (float 0/1) zeroes the state first; noise[n,act_dim] ~ N(0,1) or NULL for the
+/* obs[n,obs_dim] (already normalised unless myo_policy_set_obs_norm is active); h/c: [2][n][H] (0 = actor,
+ * 1 = critic), updated in place; episode_start[n] (uint8 0/1, SB3's bool `_last_episode_starts`; the `done`
+ * array of myo_batch_step can be passed as is) zeroes the state first; noise[n,act_dim] ~ N(0,1) or NULL for the
  * deterministic mean; outputs: actions[n,act_dim] (unclipped), values[n], logp[n]. */
 int myo_policy_forward(myo_policy* p, int n, const float* obs_dev, float* h_dev, float* c_dev,
-                       const float* episode_start_dev, const float* noise_dev, float* actions_dev,
+                       const uint8_t* episode_start_dev, const float* noise_dev, float* actions_dev,
                        float* values_dev, float* logp_dev, void* stream);
 /* VecNormalize.normalize_obs fused into the policy's input load (/root/reference/src/main_eval.py:65-67,
  * /root/reference/src/main_baoding.py:75): obs <- clip((obs - mean) / sqrt(var + epsilon), +-clip_obs).

@@ -47,6 +47,7 @@ class TaskCfg(C.Structure):
         ("n_ovr_body", C.c_int32), ("ovr_body", C.c_int32 * MYO_MAX_OVERRIDE),
         ("n_ovr_geom", C.c_int32), ("ovr_geom", C.c_int32 * MYO_MAX_OVERRIDE),
         ("n_ovr_site", C.c_int32), ("ovr_site", C.c_int32 * MYO_MAX_OVERRIDE),
+        ("clip_actions", C.c_int32),
     ]
 
 

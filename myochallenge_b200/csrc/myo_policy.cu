@@ -66,7 +66,7 @@ struct FwdArgs {
   const float* obs;
   float* h;
   float* c;
-  const float* start;
+  const uint8_t* start;
   const float* noise;
   float* actions;
   float* values;
@@ -212,7 +212,7 @@ policy_forward_kernel(const __grid_constant__ FwdArgs a, const __grid_constant__
     for (int rr = 0; rr < 32; rr++) {
       const int row = warp * 32 + rr, w = row0 + row;
       const bool live = w < a.n;
-      const float keep = live ? 1.f - a.start[w] : 0.f;
+      const float keep = (live && !a.start[w]) ? 1.f : 0.f;
       // observation: obs_pad / 2 float2 slots, lanes take 2 consecutive k
       for (int k = 2 * lane; k < a.obs_pad; k += 64) {
         float x0 = 0.f, x1 = 0.f;
@@ -241,7 +241,7 @@ policy_forward_kernel(const __grid_constant__ FwdArgs a, const __grid_constant__
     // ================= epilogues =================
     const int row = threadIdx.x, w = row0 + row;
     const bool live = w < a.n;
-    const float keep = live ? 1.f - a.start[w] : 0.f;
+    const float keep = (live && !a.start[w]) ? 1.f : 0.f;
     const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float* bias = a.bias[net];
     for (int i = 0; i < prog.n_ops; i++) {
@@ -658,7 +658,7 @@ int myo_policy_seed(myo_policy* p, uint64_t seed) {
   return MYO_OK;
 }
 
-int myo_policy_forward(myo_policy* p, int n, const float* obs_dev, float* h_dev, float* c_dev, const float* episode_start_dev,
+int myo_policy_forward(myo_policy* p, int n, const float* obs_dev, float* h_dev, float* c_dev, const uint8_t* episode_start_dev,
                        const float* noise_dev, float* actions_dev, float* values_dev, float* logp_dev, void* stream) {
   if (!p || n <= 0 || !obs_dev || !h_dev || !c_dev || !episode_start_dev || !actions_dev) { myo::set_error("bad argument to myo_policy_forward"); return MYO_E_ARG; }
   if (n > p->max_batch) { myo::set_error("batch exceeds max_batch given to myo_policy_create"); return MYO_E_ARG; }

@@ -43,6 +43,7 @@ MYO_PHASE void task_action(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, 
   float* ctrl = SF(o_ctrl);
   for (int i = c.lane; i < m.nu; i += G) {
     float u = a[i];
+    if (t.clip_actions) u = clipf(u, -1.f, 1.f);
     if (t.normalize_act) {
       if (m.a_dyntype[i] == 3) u = 1.f / (1.f + expf(-5.f * (u - 0.5f)));
       else {

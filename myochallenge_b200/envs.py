@@ -1,0 +1,197 @@
+"""Environment registry and factory: the gym registrations of /root/reference/src/envs/__init__.py and the
+name dispatch of /root/reference/src/envs/environment_factory.py:8-63, producing batched ``MyoVecEnv`` objects
+instead of one ``gym.Env`` per process.
+
+``EnvironmentFactory.create(env_name, num_envs=..., **kwargs)`` accepts the same names and the same kwargs
+the reference passes through ``gym.make(id, **kwargs)`` into ``CustomBaodingP2Env._setup``
+(/root/reference/src/envs/baoding.py:300-401), ``CustomBaodingEnv._setup`` (:96-176) and
+``CustomPoseEnv._setup`` (/root/reference/src/envs/pose.py:7-51); they are translated into the C-ABI task
+configuration (``myo_task_cfg``) that the world kernel evaluates per world on the device.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any, Dict
+
+import numpy as np
+
+from . import _capi
+from .assets import asset_path
+from .sim import Model
+from .vec_env import BAODING_KEYS, POSE_KEYS, MyoVecEnv
+
+_JNT_HAND = ['pro_sup', 'deviation', 'flexion', 'cmc_abduction', 'cmc_flexion', 'mp_flexion', 'ip_flexion', 'mcp2_flexion',
+             'mcp2_abduction', 'pm2_flexion', 'md2_flexion', 'mcp3_flexion', 'mcp3_abduction', 'pm3_flexion', 'md3_flexion',
+             'mcp4_flexion', 'mcp4_abduction', 'pm4_flexion', 'md4_flexion', 'mcp5_flexion', 'mcp5_abduction', 'pm5_flexion',
+             'md5_flexion']
+# per-joint (min, max) over the ten ASL poses of /root/reference/src/envs/__init__.py:174-183,204-207
+_ASL = np.array([
+    [0, 0, 0, 0.5624, 0.28272, -0.75573, -1.309, 1.30045, -0.006982, 1.45492, 0.998897, 1.26466, 0, 1.40604, 0.227795, 1.07614, -0.020944, 1.46103, 0.06284, 0.83263, -0.14399, 1.571, 1.38248],
+    [0, 0, 0, 0.0248, 0.04536, -0.7854, -1.309, 0.366605, 0.010473, 0.269258, 0.111722, 1.48459, 0, 1.45318, 1.44532, 1.44532, -0.204204, 1.46103, 1.44532, 1.48459, -0.2618, 1.47674, 1.48459],
+    [0, 0, 0, 0.0248, 0.04536, -0.7854, -1.13447, 0.514973, 0.010473, 0.128305, 0.111722, 0.510575, 0, 0.37704, 0.117825, 1.44532, -0.204204, 1.46103, 1.44532, 1.48459, -0.2618, 1.47674, 1.48459],
+    [0, 0, 0, 0.3384, 0.25305, 0.01569, -0.0262045, 0.645885, 0.010473, 0.128305, 0.111722, 0.510575, 0, 0.37704, 0.117825, 1.571, -0.036652, 1.52387, 1.45318, 1.40604, -0.068068, 1.39033, 1.571],
+    [0, 0, 0, 0.6392, -0.147495, -0.7854, -1.309, 0.637158, 0.010473, 0.128305, 0.111722, 0.510575, 0, 0.37704, 0.117825, 0.306345, -0.010472, 0.400605, 0.133535, 0.21994, -0.068068, 0.274925, 0.01571],
+    [0, 0, 0, 0.3384, 0.25305, 0.01569, -0.0262045, 0.645885, 0.010473, 0.128305, 0.111722, 0.510575, 0, 0.37704, 0.117825, 0.306345, -0.010472, 0.400605, 0.133535, 0.21994, -0.068068, 0.274925, 0.01571],
+    [0, 0, 0, 0.6392, -0.147495, -0.7854, -1.309, 0.637158, 0.010473, 0.128305, 0.111722, 0.510575, 0, 0.37704, 0.117825, 0.306345, -0.010472, 0.400605, 0.133535, 1.1861, -0.2618, 1.35891, 1.48459],
+    [0, 0, 0, 0.524, 0.01569, -0.7854, -1.309, 0.645885, -0.006982, 0.128305, 0.111722, 0.510575, 0, 0.37704, 0.117825, 1.28036, -0.115192, 1.52387, 1.45318, 0.432025, -0.068068, 0.18852, 0.149245],
+    [0, 0, 0, 0.428, 0.22338, -0.7854, -1.309, 0.645885, -0.006982, 0.128305, 0.194636, 1.39033, 0, 1.08399, 0.573415, 0.667675, -0.020944, 0, 0.06284, 0.432025, -0.068068, 0.18852, 0.149245],
+    [0, 0, 0, 0.5624, 0.28272, -0.75573, -1.309, 1.30045, -0.006982, 1.45492, 0.998897, 0.39275, 0, 0.18852, 0.227795, 0.667675, -0.020944, 0, 0.06284, 0.432025, -0.068068, 0.18852, 0.149245],
+])
+
+# id -> (task kind, model, horizon, default kwargs)   [REF src/envs/__init__.py:12-229]
+REGISTRY: Dict[str, Dict[str, Any]] = {
+    "CustomMyoChallengeBaodingP1-v1": dict(kind=_capi.TASK_BAODING, model="hand/myo_hand_baoding.mjb", horizon=200, phase=1,
+                                           kwargs=dict(normalize_act=True, goal_xrange=(0.025, 0.025), goal_yrange=(0.028, 0.028))),
+    "CustomMyoChallengeBaodingP2-v1": dict(kind=_capi.TASK_BAODING, model="hand/myo_hand_baoding.mjb", horizon=200, phase=2,
+                                           kwargs=dict(normalize_act=True, goal_time_period=(4, 6), goal_xrange=(0.020, 0.030),
+                                                       goal_yrange=(0.022, 0.032), obj_size_range=(0.018, 0.024),
+                                                       obj_mass_range=(0.030, 0.300), obj_friction_change=(0.2, 0.001, 0.00002),
+                                                       task_choice="random")),
+    "CustomMyoElbowPoseFixed-v0": dict(kind=_capi.TASK_POSE, model="arm/myo_elbow_1dof6muscles.mjb", horizon=100,
+                                       kwargs=dict(target_jnt_range={"r_elbow_flex": (2, 2)}, normalize_act=True, pose_thd=.175, reset_type="random")),
+    "CustomMyoElbowPoseRandom-v0": dict(kind=_capi.TASK_POSE, model="arm/myo_elbow_1dof6muscles.mjb", horizon=100,
+                                        kwargs=dict(target_jnt_range={"r_elbow_flex": (0, 2.27)}, normalize_act=True, pose_thd=.175, reset_type="random")),
+    "CustomMyoFingerPoseFixed-v0": dict(kind=_capi.TASK_POSE, model="finger/myo_finger_v0.mjb", horizon=100,
+                                        kwargs=dict(target_jnt_range={"IFadb": (0, 0), "IFmcp": (0, 0), "IFpip": (.75, .75), "IFdip": (.75, .75)},
+                                                    normalize_act=True)),
+    "CustomMyoFingerPoseRandom-v0": dict(kind=_capi.TASK_POSE, model="finger/myo_finger_v0.mjb", horizon=100,
+                                         kwargs=dict(target_jnt_range={"IFadb": (-.2, .2), "IFmcp": (-.4, 1), "IFpip": (.1, 1), "IFdip": (.1, 1)},
+                                                     normalize_act=True)),
+    "CustomMyoHandPoseFixed-v0": dict(kind=_capi.TASK_POSE, model="hand/myo_hand_pose.mjb", horizon=100,
+                                      kwargs=dict(target_jnt_value=np.array([0, 0, 0, -0.0904, 0.0824475, -0.681555, -0.514888, 0, -0.013964, -0.0458132, 0,
+                                                                             0.67553, -0.020944, 0.76979, 0.65982, 0, 0, 0, 0, 0.479155, -0.099484, 0.95831, 0]),
+                                                  normalize_act=True, pose_thd=.7, reset_type="init", target_type="fixed")),
+    "CustomMyoHandPoseRandom-v0": dict(kind=_capi.TASK_POSE, model="hand/myo_hand_pose.mjb", horizon=100,
+                                       kwargs=dict(target_jnt_range={n: (float(_ASL[:, i].min()), float(_ASL[:, i].max())) for i, n in enumerate(_JNT_HAND)},
+                                                   normalize_act=True, pose_thd=.8, reset_type="random", target_type="generate")),
+}
+for _k in range(10):
+    REGISTRY[f"CustomMyoHandPose{_k}Fixed-v0"] = dict(kind=_capi.TASK_POSE, model="hand/myo_hand_pose.mjb", horizon=100,
+                                                      kwargs=dict(target_jnt_value=_ASL[_k].copy(), normalize_act=True, pose_thd=.7,
+                                                                  reset_type="init", target_type="fixed"))
+# stock MyoSuite ids the factory also exposes (same models and defaults as MyoSuite 1.2.3 registers them)
+REGISTRY["myoFingerPoseRandom-v0"] = REGISTRY["CustomMyoFingerPoseRandom-v0"]
+REGISTRY["myoFingerPoseFixed-v0"] = REGISTRY["CustomMyoFingerPoseFixed-v0"]
+REGISTRY["myoChallengeBaodingP2-v1"] = REGISTRY["CustomMyoChallengeBaodingP2-v1"]
+REGISTRY["myoChallengeBaodingP1-v1"] = REGISTRY["CustomMyoChallengeBaodingP1-v1"]
+REGISTRY["myoHandPoseRandom-v0"] = REGISTRY["CustomMyoHandPoseRandom-v0"]
+REGISTRY["myoElbowPose1D6MRandom-v0"] = REGISTRY["CustomMyoElbowPoseRandom-v0"]
+
+# EnvironmentFactory names -> gym ids   [REF src/envs/environment_factory.py:22-61]
+FACTORY_NAMES = {
+    "MyoFingerPoseFixed": "myoFingerPoseFixed-v0", "MyoFingerPoseRandom": "myoFingerPoseRandom-v0",
+    "MyoBaodingBallsP1": "myoChallengeBaodingP1-v1", "CustomMyoBaodingBallsP1": "CustomMyoChallengeBaodingP1-v1",
+    "MyoBaodingBallsP2": "myoChallengeBaodingP2-v1", "CustomMyoBaodingBallsP2": "CustomMyoChallengeBaodingP2-v1",
+    "CustomMyoElbowPoseFixed": "CustomMyoElbowPoseFixed-v0", "CustomMyoElbowPoseRandom": "CustomMyoElbowPoseRandom-v0",
+    "CustomMyoFingerPoseFixed": "CustomMyoFingerPoseFixed-v0", "CustomMyoFingerPoseRandom": "CustomMyoFingerPoseRandom-v0",
+    "CustomMyoHandPoseFixed": "CustomMyoHandPoseFixed-v0", "CustomMyoHandPoseRandom": "CustomMyoHandPoseRandom-v0",
+}
+# names the reference factory knows whose models / task kernels are outside this build (die, pen, key-turn, reach, mixture)
+UNSUPPORTED = {"MyoFingerReachFixed", "MyoFingerReachRandom", "MyoHandKeyTurnFixed", "MyoHandKeyTurnRandom", "CustomMyoReorientP1",
+               "CustomMyoReorientP2", "MixtureModelBaodingEnv", "CustomMyoPenTwirlRandom"}
+
+
+def _weights(cfg, keys, weighted_reward_keys):
+    for i in range(_capi.MYO_INFO_TERMS):
+        cfg.rwd_weight[i] = 0.0
+    for k, w in weighted_reward_keys.items():
+        if k not in keys:
+            raise ValueError(f"unknown reward key {k!r} (known: {keys})")
+        cfg.rwd_weight[keys.index(k)] = float(w)
+
+
+def make_task_cfg(model: Model, env_id: str, **overrides) -> _capi.TaskCfg:
+    """Translate a registration + kwargs into the C-ABI task configuration."""
+    if env_id not in REGISTRY:
+        raise ValueError("Environment name not recognized:", env_id)
+    reg = REGISTRY[env_id]
+    kw = dict(reg["kwargs"])
+    kw.update(overrides)
+    cfg = model.default_task_cfg(reg["kind"])
+    cfg.max_episode_steps = int(kw.pop("max_episode_steps", reg["horizon"]))
+    cfg.frame_skip = int(kw.pop("frame_skip", 10))
+    cfg.normalize_act = int(bool(kw.pop("normalize_act", True)))
+    cfg.auto_reset = int(bool(kw.pop("auto_reset", True)))
+    cfg.clip_actions = int(bool(kw.pop("clip_actions", False)))
+    if reg["kind"] == _capi.TASK_BAODING:
+        if "weighted_reward_keys" in kw:
+            _weights(cfg, BAODING_KEYS, kw.pop("weighted_reward_keys"))
+        cfg.drop_th = float(kw.pop("drop_th", 1.25))
+        cfg.proximity_th = float(kw.pop("proximity_th", 0.015))
+        for name, default in (("goal_time_period", (5, 5)), ("goal_xrange", (0.025, 0.025)), ("goal_yrange", (0.028, 0.028)),
+                              ("obj_size_range", (0.018, 0.024)), ("obj_mass_range", (0.030, 0.300))):
+            lo, hi = kw.pop(name, default)
+            getattr(cfg, name)[0], getattr(cfg, name)[1] = float(lo), float(hi)
+        fc = kw.pop("obj_friction_change", (0.2, 0.001, 0.00002))
+        for i in range(3):
+            cfg.obj_friction_change[i] = float(fc[i])
+        task_choice = kw.pop("task_choice", "fixed")
+        if task_choice not in ("fixed", "random"):
+            raise ValueError(f"task_choice must be 'fixed' or 'random', got {task_choice!r}")
+        cfg.task_choice_random = int(task_choice == "random")
+        cfg.randomize_physics = int(reg.get("phase", 2) == 2)     # P1's reset keeps the nominal balls
+        cfg.overlap_probability = float(kw.pop("overlap_probability", 0.0))
+        kw.pop("balls_overlap", None)   # stored but never read by the reference's reset (/root/reference/src/envs/baoding.py:494-538)
+        lim = kw.pop("limit_init_angle", False)
+        cfg.limit_init_angle = float(lim) if lim else 0.0
+        cfg.noise_fingers = float(kw.pop("noise_fingers", 0.0))
+        for k in ("enable_rsi", "rsi_probability", "beta_init_angle", "beta_ball_size", "beta_ball_mass"):
+            v = kw.pop(k, None)
+            if v:
+                raise NotImplementedError(f"curriculum knob {k}={v!r} is not part of the device reset yet")
+    else:
+        if "weighted_reward_keys" in kw:
+            _weights(cfg, POSE_KEYS, kw.pop("weighted_reward_keys"))
+        cfg.pose_thd = float(kw.pop("pose_thd", 0.35))
+        cfg.target_distance = float(kw.pop("target_distance", 1.0))
+        rt = kw.pop("reset_type", "init")
+        if rt not in ("none", "init", "random"):
+            raise NotImplementedError(f"reset_type {rt!r}")
+        cfg.reset_type = {"none": 0, "init": 1, "random": 2}[rt]
+        tt = kw.pop("target_type", "generate")
+        if tt not in ("generate", "fixed"):
+            raise NotImplementedError(f"target_type {tt!r}")
+        cfg.target_type = {"fixed": 0, "generate": 1}[tt]
+        rng = kw.pop("target_jnt_range", None)
+        val = kw.pop("target_jnt_value", None)
+        if rng:
+            if len(rng) > 64:
+                raise ValueError("at most 64 target joints")
+            cfg.n_target_jnt = len(rng)
+            for i, (jn, (lo, hi)) in enumerate(rng.items()):
+                cfg.target_jnt_ids[i] = model.name2id("joint", jn)
+                cfg.target_jnt_range[i][0], cfg.target_jnt_range[i][1] = float(lo), float(hi)
+        elif val is not None:
+            cfg.n_target_jnt = 0
+            for i, v in enumerate(np.asarray(val, float).reshape(-1)):
+                cfg.target_jnt_value[i] = float(v)
+        for k in ("viz_site_targets", "weight_bodyname", "weight_range", "sds_distance"):
+            v = kw.pop(k, None)
+            if k in ("weight_bodyname", "weight_range", "sds_distance") and v:
+                raise NotImplementedError(f"{k}={v!r} is not part of the device reset yet")
+    kw.pop("model_path", None)
+    kw.pop("obs_keys", None)
+    if kw:
+        raise TypeError(f"unexpected env kwargs: {sorted(kw)}")
+    return cfg
+
+
+def make_vec_env(env_id: str, num_envs: int, device="cuda:0", seed: int = 0, **kwargs) -> MyoVecEnv:
+    reg = REGISTRY.get(env_id)
+    if reg is None:
+        raise ValueError("Environment name not recognized:", env_id)
+    model = Model(kwargs.pop("model_path", None) or asset_path(reg["model"]))
+    cfg = make_task_cfg(model, env_id, **kwargs)
+    return MyoVecEnv(model, cfg, num_envs, device=device, seed=seed)
+
+
+class EnvironmentFactory:
+    """Same static interface as the reference's factory; ``num_envs`` worlds instead of one env."""
+
+    @staticmethod
+    def create(env_name: str, num_envs: int = 1, device="cuda:0", seed: int = 0, **kwargs) -> MyoVecEnv:
+        if env_name in UNSUPPORTED:
+            raise NotImplementedError(f"{env_name}: the model / task kernel for this reference env is outside this build")
+        if env_name not in FACTORY_NAMES:
+            raise ValueError("Environment name not recognized:", env_name)
+        return make_vec_env(FACTORY_NAMES[env_name], num_envs, device=device, seed=seed, **kwargs)

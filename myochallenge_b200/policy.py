@@ -137,8 +137,8 @@ class RecurrentPolicy:
         if obs.dtype != torch.float32 or not obs.is_contiguous() or obs.device != self.device:
             obs = obs.to(device=self.device, dtype=torch.float32).contiguous()
         es = episode_starts
-        if es.dtype != torch.float32 or es.device != self.device:
-            es = es.to(device=self.device, dtype=torch.float32)
+        if es.dtype != torch.uint8 or es.device != self.device or not es.is_contiguous():
+            es = (es != 0).to(device=self.device, dtype=torch.uint8).contiguous()
         if out is None:
             actions = torch.empty(n, self.act_dim, dtype=torch.float32, device=self.device)
             values = torch.empty(n, dtype=torch.float32, device=self.device)
