@@ -101,6 +101,18 @@ struct DevModel {
   float frame_dt;           // frame_skip * timestep (MyoSuite env.dt)
 };
 
+// Model descriptors live in constant memory, one slot per live batch: the (noinline) phases receive the slot index and
+// read sizes / table offsets with LDC instead of generic loads through a by-reference kernel parameter
+// (round-1 profile: 622 M generic loads in table lookups per 8192-world step).
+constexpr int kModelSlots = 16;
+#if defined(MYO_EMUL)
+static DevModel c_models[kModelSlots];
+#define MYO_M const DevModel& m = c_models[mslot];
+#elif defined(__CUDACC__)
+__constant__ DevModel c_models[kModelSlots];
+#define MYO_M const DevModel& m = c_models[mslot];
+#endif
+
 // per-batch device pointers
 struct BatchPtrs {
   int n_worlds;   // worlds the caller sees

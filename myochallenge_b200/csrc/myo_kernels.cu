@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -37,7 +38,8 @@ namespace myo {
 constexpr int kThreads = 256;
 
 template <int G>
-__device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G>& c, int w) {
+__device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G>& c, int w) {
+  MYO_M
   int status = 0;
   int* ti = b.task_i + (size_t)w * TI_WORDS;
   float* tf = b.task_f + (size_t)w * TF_WORDS;
@@ -47,44 +49,44 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
   const int wi = io ? w : b.n_worlds - 1;
   if (a.mode == MODE_RESET) {
     if (a.mask && !a.mask[wi]) return;
-    load_world<G>(m, c, b, w);
-    task_reset<G>(m, t, c, b, w, ti, tf, ptarget);
+    load_world<G>(mslot, c, b, w);
+    task_reset<G>(mslot, t, c, b, w, ti, tf, ptarget);
     if (c.lane == 0) b.time[w] = 0.f;
     if (a.obs && io) {
-      phase_tree_forward<G>(m, c, false);
-      task_obs<G>(m, t, c, ptarget);
+      phase_tree_forward<G>(mslot, c, false);
+      task_obs<G>(mslot, t, c, ptarget);
       for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
     }
-    store_world<G>(m, c, b, w, true);
+    store_world<G>(mslot, c, b, w, true);
     return;
   }
-  load_world<G>(m, c, b, w);
+  load_world<G>(mslot, c, b, w);
   if (a.mode == MODE_GET_OBS) {
     if (!io) return;
-    phase_tree_forward<G>(m, c, false);
-    task_obs<G>(m, t, c, ptarget);
+    phase_tree_forward<G>(mslot, c, false);
+    task_obs<G>(mslot, t, c, ptarget);
     for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
     return;
   }
   if (a.mode == MODE_FORWARD || a.mode == MODE_MJ_STEP) {
     for (int i = c.lane; i < m.nu; i += G) SF(o_ctrl)[i] = a.in ? a.in[(size_t)wi * m.nu + i] : 0.f;
     c.tile.sync();
-    if (a.mode == MODE_FORWARD) mj_forward_dev<G>(m, c, &status);
+    if (a.mode == MODE_FORWARD) mj_forward_dev<G>(mslot, c, &status);
     else {
-      for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(m, c, &status);
+      for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(mslot, c, &status);
       if (c.lane == 0) b.time[w] += (float)a.nsub * m.timestep;
     }
   } else {   // MODE_ENV_STEP
-    if (t.kind == MYO_TASK_BAODING) baoding_targets<G>(m, t, c, ti, tf);
-    task_action<G>(m, t, c, a.in + (size_t)wi * m.nu);
+    if (t.kind == MYO_TASK_BAODING) baoding_targets<G>(mslot, t, c, ti, tf);
+    task_action<G>(mslot, t, c, a.in + (size_t)wi * m.nu);
     c.tile.sync();
-    for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(m, c, &status);
+    for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(mslot, c, &status);
     // get_obs: kinematics at the post-step state (MyoSuite get_obs -> sim.forward)
-    phase_tree_forward<G>(m, c, false);
-    task_obs<G>(m, t, c, ptarget);
+    phase_tree_forward<G>(mslot, c, false);
+    task_obs<G>(mslot, t, c, ptarget);
     float info[MYO_INFO_TERMS], reward;
     bool env_done;
-    task_reward<G>(m, t, c, info, &reward, &env_done);
+    task_reward<G>(mslot, t, c, info, &reward, &env_done);
     const int elapsed = ti[TI_ELAPSED] + 1;
     const bool limit = t.max_episode_steps > 0 && elapsed >= t.max_episode_steps;
     const bool done = env_done || limit;
@@ -101,10 +103,10 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
     if (a.info && io) for (int k = c.lane; k < MYO_INFO_TERMS; k += G) a.info[(size_t)w * MYO_INFO_TERMS + k] = info[k];
     if (done && t.auto_reset) {
       if (a.terminal_obs && io) for (int i = c.lane; i < m.nobs; i += G) a.terminal_obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
-      task_reset<G>(m, t, c, b, w, ti, tf, ptarget);
+      task_reset<G>(mslot, t, c, b, w, ti, tf, ptarget);
       if (c.lane == 0) b.time[w] = 0.f;
-      phase_tree_forward<G>(m, c, false);
-      task_obs<G>(m, t, c, ptarget);
+      phase_tree_forward<G>(mslot, c, false);
+      task_obs<G>(mslot, t, c, ptarget);
     }
     if (io) for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
   }
@@ -116,11 +118,11 @@ __device__ void run_world(const DevModel& m, const myo_task_cfg& t, const BatchP
     misc[MI_STATUS] = status;
     if (status && io) atomicOr(b.status, status);
   }
-  store_world<G>(m, c, b, w, true);
+  store_world<G>(mslot, c, b, w, true);
   if (b.dump && a.mode != MODE_ENV_STEP) {
     c.tile.sync();
     float* out = b.dump + (size_t)w * m.scratch_words;
-    for (int i = c.lane; i < m.scratch_words; i += G) out[i] = c.s[i];
+    for (int i = c.lane; i < m.scratch_words; i += G) out[i] = c.sp()[i];
   }
 }
 
@@ -137,21 +139,20 @@ __device__ void stage_tables(const DevModel& m) {
 }
 
 template <int G>
-__global__ void __launch_bounds__(kThreads) world_kernel(const __grid_constant__ DevModel m, const __grid_constant__ myo_task_cfg t,
+__global__ void __launch_bounds__(kThreads) world_kernel(int mslot, const __grid_constant__ myo_task_cfg t,
                                                         const __grid_constant__ BatchPtrs b, const __grid_constant__ StepArgs a) {
+  MYO_M
   stage_tables(m);
-  float* smem = MYO_SMEM_WORDS + m.tab_words;
   cg::thread_block block = cg::this_thread_block();
   cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
   Ctx<G> c(tile);
   const int wpc = blockDim.x / G;
   const int tid = threadIdx.x / G;
-  c.s = smem + (size_t)tid * m.scratch_words;
-  c.wp = c.s + m.o_wparam;
+  c.soff = m.tab_words + tid * m.scratch_words;
   // state arrays are padded to a multiple of wpc worlds, so every tile of a CTA runs the same number of
   // iterations (the phases contain CTA-wide barriers); padding worlds are stepped but have no I/O
   for (int w = blockIdx.x * wpc + tid; w < b.n_alloc; w += gridDim.x * wpc) {
-    run_world<G>(m, t, b, a, c, w);
+    run_world<G>(mslot, t, b, a, c, w);
     c.tile.sync();
   }
 }
@@ -282,7 +283,7 @@ struct myo_batch {
   myo::PackedModel pm;
   myo_task_cfg cfg;
   myo::BatchPtrs p{};
-  int device = 0, n = 0;
+  int device = 0, n = 0, slot = -1;
   int grid = 0, threads = myo::kThreads, smem = 0, regs = 0, wpc = 0, tab_bytes = 0;
   int64_t launches = 0;
   std::vector<void*> allocs;
@@ -310,8 +311,33 @@ template <class T> int dev_alloc(myo_batch* b, T** p, size_t count) {
   return MYO_OK;
 }
 
+// constant-memory model slots, per device
+std::mutex g_slot_mu;
+bool g_slot_busy[64][kModelSlots];
+int acquire_slot(myo_batch* b) {
+  std::lock_guard<std::mutex> lk(g_slot_mu);
+  const int d = b->device & 63;
+  for (int s = 0; s < kModelSlots; s++)
+    if (!g_slot_busy[d][s]) { g_slot_busy[d][s] = true; b->slot = s; return MYO_OK; }
+  set_error("too many live batches on one device (16 model slots in constant memory)");
+  return MYO_E_LIMIT;
+}
+void release_slot(myo_batch* b) {
+  std::lock_guard<std::mutex> lk(g_slot_mu);
+  if (b->slot >= 0) g_slot_busy[b->device & 63][b->slot] = false;
+  b->slot = -1;
+}
+int upload_slot(myo_batch* b) {
+#ifdef MYO_EMUL
+  c_models[b->slot] = b->pm.dm;
+#else
+  CK(cudaMemcpyToSymbol(c_models, &b->pm.dm, sizeof(DevModel), (size_t)b->slot * sizeof(DevModel)));
+#endif
+  return MYO_OK;
+}
+
 template <int G> int launch_world(myo_batch* b, const StepArgs& a, cudaStream_t st) {
-  MYO_LAUNCH(world_kernel<G>, b->grid, b->threads, b->smem, st, b->pm.dm, b->cfg, b->p, a);
+  MYO_LAUNCH(world_kernel<G>, b->grid, b->threads, b->smem, st, b->slot, b->cfg, b->p, a);
   b->launches++;
   CK(cudaGetLastError());
   return MYO_OK;
@@ -424,6 +450,7 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
   b->pm.dm.g_tables = b->pm.d_tables;
   MYO_LANES_CASES(b, configure, b)
   if (rc) return fail(rc);
+  if ((rc = acquire_slot(b)) || (rc = upload_slot(b))) return fail(rc);
   b->p.n_worlds = n_worlds; b->p.seed = seed;
   b->p.n_alloc = (n_worlds + b->wpc - 1) / b->wpc * b->wpc;
   const size_t n = (size_t)b->p.n_alloc;
@@ -445,6 +472,7 @@ void myo_batch_destroy(myo_batch* b) {
   if (!b) return;
   cudaSetDevice(b->device);
   for (void* p : b->allocs) cudaFree(p);
+  release_slot(b);
   delete b;
 }
 

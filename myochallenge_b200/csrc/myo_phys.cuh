@@ -15,13 +15,18 @@ template <int G>
 struct Ctx {
   cg::thread_block_tile<G> tile;
   int lane;
-  float* s;          // this world's scratch (shared memory)
-  float* wp;         // this world's override parameters (global memory)
-  __device__ Ctx(cg::thread_block_tile<G> t) : tile(t), lane(t.thread_rank()), s(nullptr), wp(nullptr) {}
+  int soff;          // word offset of this world's scratch inside the CTA's dynamic shared memory
+  __device__ Ctx(cg::thread_block_tile<G> t) : tile(t), lane(t.thread_rank()), soff(0) {}
+  // Scratch pointers are always re-derived from the __shared__ base, never carried as pointers: the compiler then
+  // knows the address space inside the (noinline) phases and emits LDS/STS with 32-bit addresses instead of
+  // generic LD/ST + memory descriptors (round-1 profile: 739 M generic loads, 1054 M R2UR per 8192-world step).
+  MYO_DI float* sp() const { return MYO_SMEM_WORDS + soff; }
+  MYO_DI float* wpp(const DevModel& m) const { return MYO_SMEM_WORDS + soff + m.o_wparam; }   // per-world override parameters
 };
 
-#define SF(field) (c.s + m.field)
-#define SI(field) (reinterpret_cast<int*>(c.s + m.field))
+#define SF(field) (MYO_SMEM_WORDS + c.soff + m.field)
+#define SI(field) (reinterpret_cast<int*>(MYO_SMEM_WORDS + c.soff + m.field))
+#define SO(off) (MYO_SMEM_WORDS + c.soff + (off))   // scratch word offset -> pointer (noinline phases take offsets, not pointers)
 
 template <int G> MYO_DI float tile_sum(const Ctx<G>& c, float v) {
 #pragma unroll
@@ -39,7 +44,8 @@ template <int G> MYO_DI float tile_max(const Ctx<G>& c, float v) {
 // Reference point of every kinematic tree = xipos of its root body (MuJoCo uses the subtree COM;
 // the dynamics are invariant to that choice and a nearby point keeps fp32 cross products small).
 template <int G>
-MYO_PHASE void body_forward(const DevModel& m, Ctx<G>& c, int b, bool dyn) {
+MYO_PHASE void body_forward(int mslot, Ctx<G>& c, int b, bool dyn) {
+  MYO_M
   const float* qpos = SF(o_qpos);
   const float* qvel = SF(o_qvel);
   float* cdof = SF(o_cdof);
@@ -129,7 +135,7 @@ MYO_PHASE void body_forward(const DevModel& m, Ctx<G>& c, int b, bool dyn) {
   {
     float off[3], mass = m.b_mass[b];
     const int slot = m.b_mass_slot[b];
-    if (slot >= 0) mass = c.wp[slot];
+    if (slot >= 0) mass = c.wpp(m)[slot];
     sub3(off, ip, cref);
     float* ci = SF(o_cinert) + 10 * b;
     if (m.b_sameframe[b]) inert_com(ci, m.b_inertia + 3 * b, R, off, mass);
@@ -196,7 +202,8 @@ MYO_PHASE void body_forward(const DevModel& m, Ctx<G>& c, int b, bool dyn) {
 }
 
 template <int G>
-MYO_PHASE void phase_tree_forward(const DevModel& m, Ctx<G>& c, bool dyn) {
+MYO_PHASE void phase_tree_forward(int mslot, Ctx<G>& c, bool dyn) {
+  MYO_M
   if (c.lane == 0) {
     float* xp = SF(o_xpos); float* xq = SF(o_xquat); float* xm = SF(o_xmat); float* xi = SF(o_xipos);
     xp[0] = xp[1] = xp[2] = 0.f; xi[0] = xi[1] = xi[2] = 0.f;
@@ -214,14 +221,15 @@ MYO_PHASE void phase_tree_forward(const DevModel& m, Ctx<G>& c, bool dyn) {
   }
   c.tile.sync();
   for (int L = 0; L < m.nlevel; L++) {
-    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) body_forward<G>(m, c, m.lvl_body[i], dyn);
+    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) body_forward<G>(mslot, c, m.lvl_body[i], dyn);
     c.tile.sync();
   }
 }
 
 // mj_crb backward accumulation + mj_rne backward pass, children gathered in a fixed order
 template <int G>
-MYO_PHASE void phase_tree_backward(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_tree_backward(int mslot, Ctx<G>& c) {
+  MYO_M
   float* ci = SF(o_cinert); float* cf = SF(o_cfrc);
   for (int L = m.nlevel - 2; L >= 0; L--) {
     for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) {
@@ -240,7 +248,8 @@ MYO_PHASE void phase_tree_backward(const DevModel& m, Ctx<G>& c) {
 
 // a10.4 mass matrix in MuJoCo's sparse dof_Madr layout (row i: i, parent(i), ...) + qfrc_bias
 template <int G>
-MYO_PHASE void phase_mass_bias(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_mass_bias(int mslot, Ctx<G>& c) {
+  MYO_M
   const float* cdof = SF(o_cdof); const float* crb = SF(o_cinert); const float* cf = SF(o_cfrc);
   float* M = SF(o_M); float* bias = SF(o_bias);
   for (int i = c.lane; i < m.nv; i += G) {
@@ -276,7 +285,9 @@ MYO_PHASE void phase_mass_bias(const DevModel& m, Ctx<G>& c) {
 //   L(i,j) = (M(i,j) - sum_k L(k,i) L(k,j) D(k)) / D(i)      j ancestor of i
 // LD holds D on the diagonal slot and L on the ancestor slots. hdamp adds h*damping (mj_Euler).
 template <int G>
-MYO_PHASE void factor_sparse(const DevModel& m, Ctx<G>& c, float* LD, const float* M, float hdamp) {
+MYO_PHASE void factor_sparse(int mslot, Ctx<G>& c, int oLD, int oM, float hdamp) {
+  MYO_M
+  float* LD = SO(oLD); const float* M = SO(oM);
   for (int L = m.ndlevel - 1; L >= 0; L--) {
     for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
       const int i = m.dlvl_dof[idx];
@@ -308,7 +319,9 @@ MYO_PHASE void factor_sparse(const DevModel& m, Ctx<G>& c, float* LD, const floa
 }
 // x <- (L' D L)^-1 x   (mj_solveLD, gather form)
 template <int G>
-MYO_PHASE void solve_sparse(const DevModel& m, Ctx<G>& c, const float* LD, float* x) {
+MYO_PHASE void solve_sparse(int mslot, Ctx<G>& c, int oLD, int ox) {
+  MYO_M
+  const float* LD = SO(oLD); float* x = SO(ox);
   for (int L = m.ndlevel - 1; L >= 0; L--) {     // x <- L^-T x, deepest first
     for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
       const int i = m.dlvl_dof[idx];
@@ -337,7 +350,9 @@ MYO_PHASE void solve_sparse(const DevModel& m, Ctx<G>& c, const float* LD, float
 }
 // y = M x using the sparse symmetric layout (mj_mulM)
 template <int G>
-MYO_PHASE void mul_M(const DevModel& m, Ctx<G>& c, const float* M, const float* x, float* y) {
+MYO_PHASE void mul_M(int mslot, Ctx<G>& c, int oM, int ox, int oy) {
+  MYO_M
+  const float* M = SO(oM); const float* x = SO(ox); float* y = SO(oy);
   for (int i = c.lane; i < m.nv; i += G) {
     const int dep = m.d_depth[i];
     int adr = m.d_Madr[i], j = i;
@@ -497,9 +512,11 @@ MYO_DI int common_prefix(const DevModel& m, int ba, int bb) {
   while (cp < na && cp < nb && m.b_chain[ba * KC + cp] == m.b_chain[bb * KC + cp]) cp++;
   return cp;
 }
-MYO_PHASE void segment_moment(const DevModel& m, const float* s, int ba, const float* pa, int bb, const float* pb, float inv_div,
+MYO_PHASE void segment_moment(int mslot, int soff, int ba, const float* pa, int bb, const float* pb, float inv_div,
                            const int* tdof, int ntd, float* J) {
+  MYO_M
   if (ba == bb) return;
+  const float* s = MYO_SMEM_WORDS + soff;
   float dir[3];
   sub3(dir, pb, pa);
   normalize3(dir);
@@ -509,7 +526,8 @@ MYO_PHASE void segment_moment(const DevModel& m, const float* s, int ba, const f
 }
 
 template <int G>
-MYO_PHASE void phase_tendon(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void phase_tendon(int mslot, Ctx<G>& c, int* status) {
+  MYO_M
   const float* qvel = SF(o_qvel);
   for (int t = c.lane; t < m.ntendon; t += G) {
     const int adr = m.t_adr[t], num = m.t_num[t], ntd = m.t_ndof[t];
@@ -529,7 +547,7 @@ MYO_PHASE void phase_tendon(const DevModel& m, Ctx<G>& c, int* status) {
       const int id0 = m.w_obj[adr + j];
       int id1 = m.w_obj[adr + j + 1];
       float x0[3], x1[3];
-      site_world(m, c.s, c.wp, id0, x0);
+      site_world(m, c.sp(), c.wpp(m), id0, x0);
       const int b0 = m.s_body[id0];
       const bool isgeom = (tp1 == W_SPHERE || tp1 == W_CYLINDER);
       float wlen = -1.f, wp2[6];
@@ -537,7 +555,7 @@ MYO_PHASE void phase_tendon(const DevModel& m, Ctx<G>& c, int* status) {
       if (isgeom) {
         const int g = id1;
         id1 = m.w_obj[adr + j + 2];
-        site_world(m, c.s, c.wp, id1, x1);
+        site_world(m, c.sp(), c.wpp(m), id1, x1);
         bw = m.g_body[g];
         float gpos[3], gmat[9];
         mulmatvec3(gpos, SF(o_xmat) + 9 * bw, m.g_pos + 3 * g);
@@ -545,26 +563,26 @@ MYO_PHASE void phase_tendon(const DevModel& m, Ctx<G>& c, int* status) {
         mulmat3(gmat, SF(o_xmat) + 9 * bw, m.g_mat + 9 * g);
         const int side = m.w_side[adr + j + 1];
         float sp[3];
-        if (side >= 0) site_world(m, c.s, c.wp, side, sp);
+        if (side >= 0) site_world(m, c.sp(), c.wpp(m), side, sp);
         float radius = m.g_size[3 * g];
-        if (m.g_size_slot[g] >= 0) radius = c.wp[m.g_size_slot[g]];
+        if (m.g_size_slot[g] >= 0) radius = c.wpp(m)[m.g_size_slot[g]];
         wlen = wrap_geom(wp2, x0, x1, gpos, gmat, radius, tp1, side >= 0 ? sp : nullptr);
         if (wlen == -2.f) { *status |= ST_UNSUPPORTED; wlen = -1.f; }
       } else {
-        site_world(m, c.s, c.wp, id1, x1);
+        site_world(m, c.sp(), c.wpp(m), id1, x1);
       }
       const int b1 = m.s_body[id1];
       if (wlen < 0.f) {
         float d[3];
         sub3(d, x1, x0);
         len += norm3(d) * inv_div;
-        segment_moment(m, c.s, b0, x0, b1, x1, inv_div, tdof, ntd, J);
+        segment_moment(mslot, c.soff, b0, x0, b1, x1, inv_div, tdof, ntd, J);
       } else {
         float d0[3], d1[3];
         sub3(d0, wp2, x0); sub3(d1, x1, wp2 + 3);
         len += (norm3(d0) + wlen + norm3(d1)) * inv_div;
-        segment_moment(m, c.s, b0, x0, bw, wp2, inv_div, tdof, ntd, J);
-        segment_moment(m, c.s, bw, wp2 + 3, b1, x1, inv_div, tdof, ntd, J);
+        segment_moment(mslot, c.soff, b0, x0, bw, wp2, inv_div, tdof, ntd, J);
+        segment_moment(mslot, c.soff, bw, wp2 + 3, b1, x1, inv_div, tdof, ntd, J);
       }
       j += isgeom ? 2 : 1;
     }
@@ -591,7 +609,8 @@ MYO_DI float muscle_FL(float L, float lmin, float lmax) {
   return 0.5f * x * x;
 }
 template <int G>
-MYO_PHASE void phase_actuation(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_actuation(int mslot, Ctx<G>& c) {
+  MYO_M
   const float* ctrl = SF(o_ctrl); const float* act = SF(o_act);
   for (int i = c.lane; i < m.nu; i += G) {
     const int t = m.a_tendon[i];
@@ -713,7 +732,8 @@ MYO_DI bool sphere_sphere(float margin, const float* p1, float r1, const float* 
 }
 
 template <int G>
-MYO_PHASE void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void phase_collision(int mslot, Ctx<G>& c, int* status) {
+  MYO_M
   int* misc = SI(o_misc);
   int ncon = 0;
   for (int base = 0; base < m.npair; base += G) {
@@ -725,8 +745,8 @@ MYO_PHASE void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
       g1 = m.p_g1[p]; g2 = m.p_g2[p];
       const float margin = fmaxf(m.g_margin[g1], m.g_margin[g2]);
       float p1[3], p2[3];
-      geom_world_pos(m, c.s, g1, p1);
-      geom_world_pos(m, c.s, g2, p2);
+      geom_world_pos(m, c.sp(), g1, p1);
+      geom_world_pos(m, c.sp(), g2, p2);
       const float rb1 = m.g_rbound[g1], rb2 = m.g_rbound[g2];
       bool pass = true;
       const int t1 = m.g_type[g1], t2 = m.g_type[g2];
@@ -737,7 +757,7 @@ MYO_PHASE void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
         const float bound = rb1 + rb2 + margin;
         pass = dot3(d, d) <= bound * bound;
       } else if (t1 == G_PLANE && rb2 > 0.f) {
-        geom_world_zaxis(m, c.s, g1, z1);
+        geom_world_zaxis(m, c.sp(), g1, z1);
         float d[3];
         sub3(d, p2, p1);
         pass = dot3(d, z1) <= margin + rb2;
@@ -746,15 +766,15 @@ MYO_PHASE void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
         if (!m.p_supported[p]) *status |= ST_UNSUPPORTED;
         else {
           float s1 = m.g_size[3 * g1], s2 = m.g_size[3 * g2];
-          if (m.g_size_slot[g1] >= 0) s1 = c.wp[m.g_size_slot[g1]];
-          if (m.g_size_slot[g2] >= 0) s2 = c.wp[m.g_size_slot[g2]];
+          if (m.g_size_slot[g1] >= 0) s1 = c.wpp(m)[m.g_size_slot[g1]];
+          if (m.g_size_slot[g2] >= 0) s2 = c.wpp(m)[m.g_size_slot[g2]];
           if (t1 == G_SPHERE && t2 == G_SPHERE) hit = sphere_sphere(margin, p1, s1, p2, s2, &dist, pos, nrm);
           else if (t1 == G_SPHERE && t2 == G_CAPSULE) {
             float ax[3], v[3];
-            geom_world_zaxis(m, c.s, g2, ax);
+            geom_world_zaxis(m, c.sp(), g2, ax);
             sub3(v, p1, p2);
             float half = m.g_size[3 * g2 + 1];
-            if (m.g_size_slot[g2] >= 0) half = c.wp[m.g_size_slot[g2] + 1];
+            if (m.g_size_slot[g2] >= 0) half = c.wpp(m)[m.g_size_slot[g2] + 1];
             const float x = clipf(dot3(ax, v), -half, half);
             v[0] = p2[0] + ax[0] * x; v[1] = p2[1] + ax[1] * x; v[2] = p2[2] + ax[2] * x;
             hit = sphere_sphere(margin, p1, s1, v, s2, &dist, pos, nrm);
@@ -794,8 +814,9 @@ MYO_PHASE void phase_collision(const DevModel& m, Ctx<G>& c, int* status) {
 }
 
 // impedance, regularisation and reference-acceleration coefficients of one row (mj_makeImpedance)
-MYO_PHASE void row_params(const DevModel& m, const float* solref, const float* solimp, float pos, float margin, float diag,
+MYO_PHASE void row_params(int mslot, const float* solref, const float* solimp, float pos, float margin, float diag,
                        float* R, float* K, float* B, float* imp) {
+  MYO_M
   const float s0 = clipf(solimp[0], 0.0001f, 0.9999f), s1 = clipf(solimp[1], 0.0001f, 0.9999f);
   const float s2 = fmaxf(0.f, solimp[2]), s3 = clipf(solimp[3], 0.0001f, 0.9999f), s4 = fmaxf(1.f, solimp[4]);
   float im;
@@ -829,7 +850,8 @@ MYO_PHASE void row_params(const DevModel& m, const float* solref, const float* s
 // a limit has one basis vector over <= KT dofs, a contact has (normal, tangent1, tangent2) over
 // the <= KS dofs in chain(body1) xor chain(body2).
 template <int G>
-MYO_PHASE void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
+  MYO_M
   int* misc = SI(o_misc);
   const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel);
   int nlim = 0;
@@ -903,10 +925,10 @@ MYO_PHASE void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
     const int id = li[L_ID];
     float R, K, B, imp, vel = 0.f;
     if (li[L_KIND] == EFC_LIMIT_JOINT) {
-      row_params(m, m.j_solref + 2 * id, m.j_solimp + 5 * id, lr[L_POS], lr[L_MARGIN], m.d_invweight0[m.j_dofadr[id]], &R, &K, &B, &imp);
+      row_params(mslot, m.j_solref + 2 * id, m.j_solimp + 5 * id, lr[L_POS], lr[L_MARGIN], m.d_invweight0[m.j_dofadr[id]], &R, &K, &B, &imp);
       vel = lr[L_J] * qvel[li[L_IDX]];
     } else {
-      row_params(m, m.t_solref + 2 * id, m.t_solimp + 5 * id, lr[L_POS], lr[L_MARGIN], m.t_invweight0[id], &R, &K, &B, &imp);
+      row_params(mslot, m.t_solref + 2 * id, m.t_solimp + 5 * id, lr[L_POS], lr[L_MARGIN], m.t_invweight0[id], &R, &K, &B, &imp);
       for (int e = 0; e < li[L_NSUP]; e++) vel += lr[L_J + e] * qvel[li[L_IDX + e]];
     }
     float* row = rows + r * ROW_WORDS;
@@ -927,8 +949,8 @@ MYO_PHASE void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
       float f1[3], f2[3];
 #pragma unroll
       for (int e = 0; e < 3; e++) {
-        f1[e] = (m.g_fri_slot[g1] >= 0) ? c.wp[m.g_fri_slot[g1] + e] : m.g_friction[3 * g1 + e];
-        f2[e] = (m.g_fri_slot[g2] >= 0) ? c.wp[m.g_fri_slot[g2] + e] : m.g_friction[3 * g2 + e];
+        f1[e] = (m.g_fri_slot[g1] >= 0) ? c.wpp(m)[m.g_fri_slot[g1] + e] : m.g_friction[3 * g1 + e];
+        f2[e] = (m.g_fri_slot[g2] >= 0) ? c.wpp(m)[m.g_fri_slot[g2] + e] : m.g_friction[3 * g2 + e];
       }
       const int pr1 = m.g_priority[g1], pr2 = m.g_priority[g2];
       if (pr1 != pr2) {
@@ -1037,7 +1059,7 @@ MYO_PHASE void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
     const float mu = cr[C_MU];
     float R, K, B, imp;
     // diagApprox of the first row: tran + mu^2 * tran (pyramidal) or tran (frictionless)
-    row_params(m, cr + C_SOLREF, cr + C_SOLIMP, cr[C_DIST], cr[C_MARGIN], dim == 1 ? tran : tran + mu * mu * tran, &R, &K, &B, &imp);
+    row_params(mslot, cr + C_SOLREF, cr + C_SOLIMP, cr[C_DIST], cr[C_MARGIN], dim == 1 ? tran : tran + mu * mu * tran, &R, &K, &B, &imp);
     if (dim == 3) { const float mu_r = mu * m.inv_sqrt_impratio; R = 2.f * mu_r * mu_r * R; }
     const float D = 1.f / R, ref = -K * imp * (cr[C_DIST] - cr[C_MARGIN]);
     const int nr = dim == 1 ? 1 : 4;
@@ -1057,7 +1079,9 @@ MYO_PHASE void phase_constraints(const DevModel& m, Ctx<G>& c, int* status) {
 // ------------------------------------------------------------------------------------------------
 // row helper: J_r . x for every row -> rows[r][field]; optionally subtract aref (jar = J a - aref)
 template <int G>
-MYO_PHASE void rows_dot(const DevModel& m, Ctx<G>& c, const float* x, int field, bool sub_aref) {
+MYO_PHASE void rows_dot(int mslot, Ctx<G>& c, int ox, int field, bool sub_aref) {
+  MYO_M
+  const float* x = SO(ox);
   const int* misc = SI(o_misc);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
   float* rows = SF(o_row);
@@ -1092,7 +1116,9 @@ MYO_PHASE void rows_dot(const DevModel& m, Ctx<G>& c, const float* x, int field,
 // out[dof] += sum_r J_r[dof] * w_r  with w_r = (jar_r < 0 ? -D_r jar_r : 0) * scale  (forces)
 // blocks applied one after the other, lanes across the block's support: no atomics, fixed order.
 template <int G>
-MYO_PHASE void rows_JT_force(const DevModel& m, Ctx<G>& c, float* out, float scale) {
+MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
+  MYO_M
+  float* out = SO(oout);
   const int* misc = SI(o_misc);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
   const float* rows = SF(o_row);
@@ -1126,7 +1152,8 @@ MYO_DI int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, 
 
 // H = M + sum_{active rows} D_r J_r' J_r  (packed lower triangle)
 template <int G>
-MYO_PHASE void build_hessian(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
+  MYO_M
   float* H = SF(o_H); const float* M = SF(o_M);
   const int nv = m.nv;
   for (int e = c.lane; e < nv * (nv + 1) / 2; e += G) H[e] = 0.f;
@@ -1189,7 +1216,8 @@ MYO_PHASE void build_hessian(const DevModel& m, Ctx<G>& c) {
 
 // in-place dense Cholesky (left-looking, lane per row) and solve; n <= 2*G
 template <int G>
-MYO_PHASE void chol_factor(Ctx<G>& c, float* H, int n) {
+MYO_PHASE void chol_factor(Ctx<G>& c, int oH, int n) {
+  float* H = SO(oH);
   for (int j = 0; j < n; j++) {
     const float* Lj = H + tri(j, 0);
     for (int i = j + c.lane; i < n; i += G) {
@@ -1206,7 +1234,8 @@ MYO_PHASE void chol_factor(Ctx<G>& c, float* H, int n) {
   }
 }
 template <int G>
-MYO_PHASE void chol_solve(Ctx<G>& c, const float* H, float* x, int n) {
+MYO_PHASE void chol_solve(Ctx<G>& c, int oH, int ox, int n) {
+  const float* H = SO(oH); float* x = SO(ox);
   for (int j = 0; j < n; j++) {          // forward: column oriented
     if (c.lane == 0) x[j] = x[j] / sqrtf(fmaxf(H[tri(j, j)], kMinVal));
     c.tile.sync();
@@ -1227,7 +1256,8 @@ MYO_PHASE void chol_solve(Ctx<G>& c, const float* H, float* x, int n) {
 //   cost(a) = 1/2 (a - a_s)' M (a - a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
 // warm-started from the better of (qacc_warmstart, qacc_smooth) as MuJoCo's warmstart() does.
 template <int G>
-MYO_PHASE void phase_solve(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
+  MYO_M
   int* misc = SI(o_misc);
   const int nv = m.nv, nefc = misc[MI_NEFC];
   float* a = SF(o_qacc); float* qcon = SF(o_qcon);
@@ -1245,13 +1275,13 @@ MYO_PHASE void phase_solve(const DevModel& m, Ctx<G>& c) {
   float cost_w, cost_s;
   {
     const float* w = SF(o_warm);
-    rows_dot<G>(m, c, w, R_JAR, true);
-    mul_M<G>(m, c, M, w, Ma);
+    rows_dot<G>(mslot, c, m.o_warm, R_JAR, true);
+    mul_M<G>(mslot, c, m.o_M, m.o_warm, m.o_Ma);
     float part = 0.f;
     for (int r = c.lane; r < nefc; r += G) { const float* row = rows + r * ROW_WORDS; if (row[R_JAR] < 0.f) part += 0.5f * row[R_D] * row[R_JAR] * row[R_JAR]; }
     for (int i = c.lane; i < nv; i += G) part += 0.5f * (Ma[i] - fs[i]) * (w[i] - as[i]);
     cost_w = tile_sum<G>(c, part);
-    rows_dot<G>(m, c, as, R_JAR, true);
+    rows_dot<G>(mslot, c, m.o_qaccs, R_JAR, true);
     part = 0.f;
     for (int r = c.lane; r < nefc; r += G) { const float* row = rows + r * ROW_WORDS; if (row[R_JAR] < 0.f) part += 0.5f * row[R_D] * row[R_JAR] * row[R_JAR]; }
     cost_s = tile_sum<G>(c, part);
@@ -1263,23 +1293,23 @@ MYO_PHASE void phase_solve(const DevModel& m, Ctx<G>& c) {
   int iter = 0;
   float prev_step = 3.0e38f;
   for (; iter < m.solver_iter; iter++) {
-    rows_dot<G>(m, c, a, R_JAR, true);
-    mul_M<G>(m, c, M, a, Ma);
+    rows_dot<G>(mslot, c, m.o_qacc, R_JAR, true);
+    mul_M<G>(mslot, c, m.o_M, m.o_qacc, m.o_Ma);
     for (int i = c.lane; i < nv; i += G) grad[i] = Ma[i] - fs[i];
     c.tile.sync();
-    rows_JT_force<G>(m, c, grad, -1.f);
+    rows_JT_force<G>(mslot, c, m.o_grad, -1.f);
     float g2 = 0.f, amax = 0.f;
     for (int i = c.lane; i < nv; i += G) { g2 += grad[i] * grad[i]; amax = fmaxf(amax, fabsf(a[i])); }
     g2 = tile_sum<G>(c, g2);
     amax = tile_max<G>(c, amax);
     if (sqrtf(g2) * scale < m.solver_tol) break;
-    build_hessian<G>(m, c);
-    chol_factor<G>(c, SF(o_H), nv);
+    build_hessian<G>(mslot, c);
+    chol_factor<G>(c, m.o_H, nv);
     for (int i = c.lane; i < nv; i += G) p[i] = -grad[i];
     c.tile.sync();
-    chol_solve<G>(c, SF(o_H), p, nv);
-    rows_dot<G>(m, c, p, R_JP, false);
-    mul_M<G>(m, c, M, p, Mp);
+    chol_solve<G>(c, m.o_H, m.o_p, nv);
+    rows_dot<G>(mslot, c, m.o_p, R_JP, false);
+    mul_M<G>(mslot, c, m.o_M, m.o_p, m.o_Mp);
     float pMp = 0.f, gp = 0.f, pmax = 0.f;
     for (int i = c.lane; i < nv; i += G) { pMp += p[i] * Mp[i]; gp += (Ma[i] - fs[i]) * p[i]; pmax = fmaxf(pmax, fabsf(p[i])); }
     pMp = tile_sum<G>(c, pMp); gp = tile_sum<G>(c, gp); pmax = tile_max<G>(c, pmax);
@@ -1325,25 +1355,26 @@ MYO_PHASE void phase_solve(const DevModel& m, Ctx<G>& c) {
     prev_step = step;
   }
   // final forces at the solution
-  rows_dot<G>(m, c, a, R_JAR, true);
+  rows_dot<G>(mslot, c, m.o_qacc, R_JAR, true);
   for (int i = c.lane; i < nv; i += G) { qcon[i] = 0.f; SF(o_warm)[i] = a[i]; }
   c.tile.sync();
-  rows_JT_force<G>(m, c, qcon, 1.f);
+  rows_JT_force<G>(mslot, c, m.o_qcon, 1.f);
   if (c.lane == 0) misc[MI_ITER] = iter;
   c.tile.sync();
 }
 
 // a10.9 mj_Euler (implicit in joint damping) + mj_advance
 template <int G>
-MYO_PHASE void phase_integrate(const DevModel& m, Ctx<G>& c) {
+MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
+  MYO_M
   const float h = m.timestep;
   float* qacc = SF(o_qacc); float* qvel = SF(o_qvel); float* qpos = SF(o_qpos); float* act = SF(o_act);
   float* x = SF(o_grad);
   if (m.any_damping) {
-    factor_sparse<G>(m, c, SF(o_LD), SF(o_M), h);
+    factor_sparse<G>(mslot, c, m.o_LD, m.o_M, h);
     for (int i = c.lane; i < m.nv; i += G) x[i] = SF(o_smooth)[i] + SF(o_qcon)[i];
     c.tile.sync();
-    solve_sparse<G>(m, c, SF(o_LD), x);
+    solve_sparse<G>(mslot, c, m.o_LD, m.o_grad);
   } else {
     for (int i = c.lane; i < m.nv; i += G) x[i] = qacc[i];
     c.tile.sync();
@@ -1391,24 +1422,26 @@ __device__ unsigned long long g_prof[16];
 
 // one full mj_step on the world in scratch
 template <int G>
-MYO_PHASE void mj_forward_dev(const DevModel& m, Ctx<G>& c, int* status) {
+MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status) {
+  MYO_M
   MYO_PH_BEGIN
-  MYO_CTA_SYNC phase_tree_forward<G>(m, c, true); MYO_PH(0)
-  MYO_CTA_SYNC phase_tendon<G>(m, c, status); MYO_PH(1)
-  MYO_CTA_SYNC phase_tree_backward<G>(m, c); MYO_PH(2)
-  phase_mass_bias<G>(m, c); MYO_PH(3)
-  factor_sparse<G>(m, c, SF(o_LD), SF(o_M), 0.f); MYO_PH(4)
-  MYO_CTA_SYNC phase_collision<G>(m, c, status); MYO_PH(5)
-  MYO_CTA_SYNC phase_constraints<G>(m, c, status); MYO_PH(6)
-  MYO_CTA_SYNC phase_actuation<G>(m, c); MYO_PH(7)
-  solve_sparse<G>(m, c, SF(o_LD), SF(o_qaccs)); MYO_PH(8)
-  MYO_CTA_SYNC phase_solve<G>(m, c); MYO_PH(9)
+  MYO_CTA_SYNC phase_tree_forward<G>(mslot, c, true); MYO_PH(0)
+  MYO_CTA_SYNC phase_tendon<G>(mslot, c, status); MYO_PH(1)
+  MYO_CTA_SYNC phase_tree_backward<G>(mslot, c); MYO_PH(2)
+  phase_mass_bias<G>(mslot, c); MYO_PH(3)
+  factor_sparse<G>(mslot, c, m.o_LD, m.o_M, 0.f); MYO_PH(4)
+  MYO_CTA_SYNC phase_collision<G>(mslot, c, status); MYO_PH(5)
+  MYO_CTA_SYNC phase_constraints<G>(mslot, c, status); MYO_PH(6)
+  MYO_CTA_SYNC phase_actuation<G>(mslot, c); MYO_PH(7)
+  solve_sparse<G>(mslot, c, m.o_LD, m.o_qaccs); MYO_PH(8)
+  MYO_CTA_SYNC phase_solve<G>(mslot, c); MYO_PH(9)
 }
 template <int G>
-MYO_PHASE void mj_step_dev(const DevModel& m, Ctx<G>& c, int* status) {
-  mj_forward_dev<G>(m, c, status);
+MYO_PHASE void mj_step_dev(int mslot, Ctx<G>& c, int* status) {
+  MYO_M
+  mj_forward_dev<G>(mslot, c, status);
   MYO_PH_BEGIN
-  MYO_CTA_SYNC phase_integrate<G>(m, c); MYO_PH(10)
+  MYO_CTA_SYNC phase_integrate<G>(mslot, c); MYO_PH(10)
 }
 
 }  // namespace myo

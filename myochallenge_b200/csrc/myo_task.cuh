@@ -18,7 +18,8 @@ MYO_PHASE void copy_words(Ctx<G>& c, float* dst, const float* src, int n4) {   /
 }
 
 template <int G>
-MYO_PHASE void load_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int w) {
+MYO_PHASE void load_world(int mslot, Ctx<G>& c, const BatchPtrs& b, int w) {
+  MYO_M
   copy_words<G>(c, SF(o_qpos), b.qpos + (size_t)w * m.nq4, m.nq4);
   copy_words<G>(c, SF(o_qvel), b.qvel + (size_t)w * m.nv4, m.nv4);
   copy_words<G>(c, SF(o_warm), b.warm + (size_t)w * m.nv4, m.nv4);
@@ -27,7 +28,8 @@ MYO_PHASE void load_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int 
   c.tile.sync();
 }
 template <int G>
-MYO_PHASE void store_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int w, bool params) {
+MYO_PHASE void store_world(int mslot, Ctx<G>& c, const BatchPtrs& b, int w, bool params) {
+  MYO_M
   c.tile.sync();
   copy_words<G>(c, b.qpos + (size_t)w * m.nq4, SF(o_qpos), m.nq4);
   copy_words<G>(c, b.qvel + (size_t)w * m.nv4, SF(o_qvel), m.nv4);
@@ -39,7 +41,8 @@ MYO_PHASE void store_world(const DevModel& m, Ctx<G>& c, const BatchPtrs& b, int
 // BaseV0.step: muscle actuators with normalize_act get ctrl = 1/(1+exp(-5(a-0.5))); other actuators
 // are de-normalised linearly into ctrlrange (MyoSuite Robot.normalize_actions).
 template <int G>
-MYO_PHASE void task_action(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const float* a) {
+MYO_PHASE void task_action(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float* a) {
+  MYO_M
   float* ctrl = SF(o_ctrl);
   for (int i = c.lane; i < m.nu; i += G) {
     float u = a[i];
@@ -57,7 +60,8 @@ MYO_PHASE void task_action(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, 
 
 // BaodingEnvV1.step: target sites follow goal[counter] = sign*2*pi*counter*dt/period (a6, a7)
 template <int G>
-MYO_PHASE void baoding_targets(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const int* ti, const float* tf) {
+MYO_PHASE void baoding_targets(int mslot, const myo_task_cfg& t, Ctx<G>& c, const int* ti, const float* tf) {
+  MYO_M
   if (c.lane == 0) {
     const int task = ti[TI_TASK], counter = ti[TI_ELAPSED];
     const float sign = task == MYO_BAODING_CW ? -1.f : (task == MYO_BAODING_CCW ? 1.f : 0.f);
@@ -69,8 +73,8 @@ MYO_PHASE void baoding_targets(const DevModel& m, const myo_task_cfg& t, Ctx<G>&
       sincosf(th, &sn, &cs);
       const int slot = m.s_pos_slot[t.target_site[k]];
       if (slot >= 0) {
-        c.wp[slot] = tf[TF_XR] * cs + t.center_pos[0];
-        c.wp[slot + 1] = tf[TF_YR] * sn + t.center_pos[1];
+        c.wpp(m)[slot] = tf[TF_XR] * cs + t.center_pos[0];
+        c.wpp(m)[slot + 1] = tf[TF_YR] * sn + t.center_pos[1];
       }
     }
   }
@@ -79,7 +83,8 @@ MYO_PHASE void baoding_targets(const DevModel& m, const myo_task_cfg& t, Ctx<G>&
 
 // observation vector into scratch o_obs (kinematics must be current)
 template <int G>
-MYO_PHASE void task_obs(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const float* pose_target) {
+MYO_PHASE void task_obs(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float* pose_target) {
+  MYO_M
   float* obs = SF(o_obs);
   const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel); const float* act = SF(o_act);
   if (t.kind == MYO_TASK_BAODING) {
@@ -88,8 +93,8 @@ MYO_PHASE void task_obs(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, con
     for (int i = c.lane; i < m.na; i += G) obs[nh + 24 + i] = act[i];
     for (int k = c.lane; k < 2; k += G) {
       float o[3], g[3];
-      site_world(m, c.s, c.wp, t.ball_site[k], o);
-      site_world(m, c.s, c.wp, t.target_site[k], g);
+      site_world(m, c.sp(), c.wpp(m), t.ball_site[k], o);
+      site_world(m, c.sp(), c.wpp(m), t.target_site[k], g);
       const int da = t.ball_dofadr[k];
 #pragma unroll
       for (int e = 0; e < 3; e++) {
@@ -113,7 +118,8 @@ MYO_PHASE void task_obs(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, con
 
 // reward terms + dense reward + termination from the observation in scratch. info: MYO_INFO_TERMS floats.
 template <int G>
-MYO_PHASE void task_reward(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, float* info, float* reward, bool* done) {
+MYO_PHASE void task_reward(int mslot, const myo_task_cfg& t, Ctx<G>& c, float* info, float* reward, bool* done) {
+  MYO_M
   const float* obs = SF(o_obs); const float* act = SF(o_act);
   float a2 = 0.f;
   for (int i = c.lane; i < m.na; i += G) a2 += act[i] * act[i];
@@ -155,8 +161,9 @@ MYO_PHASE void task_reward(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, 
 // env.reset(): sample the task's reset distribution with a counter-based RNG keyed by
 // (seed, world, episode) and write the initial state into scratch.
 template <int G>
-MYO_PHASE void task_reset(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, const BatchPtrs& b, int w, int* ti,
+MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const BatchPtrs& b, int w, int* ti,
                            float* tf, float* pose_target) {
+  MYO_M
   float* qpos = SF(o_qpos);
   const int episode = ti[TI_EPISODE] + 1;
   c.tile.sync();
@@ -190,7 +197,7 @@ MYO_PHASE void task_reset(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, c
 #pragma unroll
         for (int k = 0; k < 2; k++) {
           const int ms = m.b_mass_slot[t.ball_body[k]];
-          if (ms >= 0) c.wp[ms] = rng.uniform(t.obj_mass_range[0], t.obj_mass_range[1]);
+          if (ms >= 0) c.wpp(m)[ms] = rng.uniform(t.obj_mass_range[0], t.obj_mass_range[1]);
         }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -198,14 +205,14 @@ MYO_PHASE void task_reset(const DevModel& m, const myo_task_cfg& t, Ctx<G>& c, c
           for (int e = 0; e < 3; e++) {
             const float nominal = m.g_friction[3 * t.ball_geom[0] + e];
             const float v = rng.uniform(nominal - t.obj_friction_change[e], nominal + t.obj_friction_change[e]);
-            if (fs >= 0) c.wp[fs + e] = v;
+            if (fs >= 0) c.wpp(m)[fs + e] = v;
           }
         }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
           const int ss = m.g_size_slot[t.ball_geom[k]];
           const float v = rng.uniform(t.obj_size_range[0], t.obj_size_range[1]);
-          if (ss >= 0) { c.wp[ss] = v; c.wp[ss + 1] = v; c.wp[ss + 2] = v; }
+          if (ss >= 0) { c.wpp(m)[ss] = v; c.wpp(m)[ss + 1] = v; c.wpp(m)[ss + 2] = v; }
         }
       }
       if (t.noise_fingers > 0.f && m.nq - 14 >= 23) {   // _add_noise_to_finger_positions: one draw per group
