@@ -184,6 +184,7 @@ def run_b200(args):
     from myochallenge_b200 import _capi
     from myochallenge_b200.envs import make_vec_env
     from myochallenge_b200.policy import RecurrentPolicy
+    from myochallenge_b200.vec_env import rank_seed
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -196,7 +197,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     n = args.worlds
 
-    env = make_vec_env(ENV_ID, n, device=dev, seed=1000 * rank + args.seed, weighted_reward_keys=RWD, clip_actions=True)
+    env = make_vec_env(ENV_ID, n, device=dev, seed=rank_seed(args.seed, rank), weighted_reward_keys=RWD, clip_actions=True)
     sim = env.sim
     pol = RecurrentPolicy(sim.nobs, sim.nu, lstm_hidden=256, pi=(256, 256), vf=(256, 256), max_batch=n, device=dev)
     pol.init_random(seed=0, log_std_init=-2.0)             # same weights on every rank

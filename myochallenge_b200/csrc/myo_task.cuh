@@ -64,7 +64,10 @@ MYO_PHASE void baoding_targets(int mslot, const myo_task_cfg& t, Ctx<G>& c, cons
   MYO_M
   if (c.lane == 0) {
     const int task = ti[TI_TASK], counter = ti[TI_ELAPSED];
-    const float sign = task == MYO_BAODING_CW ? -1.f : (task == MYO_BAODING_CCW ? 1.f : 0.f);
+    // BaodingEnvV1.step moves the target sites only for the two rotation tasks; in a hold episode site_pos keeps what
+    // the world's previous episode left there (model state is not reset), SURVEY.md row a7
+    const float sign = task == MYO_BAODING_CW ? -1.f : 1.f;
+    if (task == MYO_BAODING_CW || task == MYO_BAODING_CCW) {
     const float ang = sign * 2.f * kPi * ((float)counter * m.frame_dt / tf[TF_PERIOD]);
 #pragma unroll
     for (int k = 0; k < 2; k++) {
@@ -76,6 +79,7 @@ MYO_PHASE void baoding_targets(int mslot, const myo_task_cfg& t, Ctx<G>& c, cons
         c.wpp(m)[slot] = tf[TF_XR] * cs + t.center_pos[0];
         c.wpp(m)[slot + 1] = tf[TF_YR] * sn + t.center_pos[1];
       }
+    }
     }
   }
   c.tile.sync();

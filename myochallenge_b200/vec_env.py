@@ -197,6 +197,29 @@ class RunningMeanStd:
     def update(self, x: np.ndarray) -> None:
         self.update_from_moments(x.mean(axis=0), x.var(axis=0), x.shape[0])
 
+    def update_distributed(self, x: np.ndarray, group=None) -> None:
+        """Same update when the batch is sharded over ranks (worlds are sharded over GPUs): the ranks
+        all-reduce (count, sum, sum of squares) of their shards, so every rank applies the moments of the global batch
+        and the statistics stay identical on all ranks. Falls back to ``update`` outside a process group."""
+        import torch
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            return self.update(x)
+        x = np.asarray(x, np.float64).reshape(x.shape[0], -1)
+        buf = torch.from_numpy(np.concatenate([[x.shape[0]], x.sum(0), np.square(x).sum(0)]))
+        dist.all_reduce(buf, group=group)
+        cnt = float(buf[0])
+        d = x.shape[1]
+        mean = buf[1:1 + d].numpy() / cnt
+        var = buf[1 + d:].numpy() / cnt - np.square(mean)
+        self.update_from_moments(mean.reshape(self.mean.shape), np.maximum(var, 0.0).reshape(self.var.shape), cnt)
+
+
+def rank_seed(base_seed: int, rank: int) -> int:
+    """Seed of the worlds owned by ``rank``: world w of rank r draws from the stream (base + 1000 r, w, episode)."""
+    return int(base_seed) + 1000 * int(rank)
+
 
 class VecNormalize:
     """SB3 ``VecNormalize`` over a ``MyoVecEnv`` (host-array path): running obs / return moments,

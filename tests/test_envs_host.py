@@ -1,0 +1,160 @@
+"""CPU: host logic of the env registry / factory (mirror of /root/reference/src/envs/__init__.py and
+environment_factory.py), the VecNormalize arithmetic and the multi-rank moment merge (gloo, world_size 2)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN
+from myochallenge_b200 import _capi
+from myochallenge_b200.assets import asset_path
+from myochallenge_b200.envs import FACTORY_NAMES, REGISTRY, EnvironmentFactory, make_task_cfg
+from myochallenge_b200.sim import Model
+from myochallenge_b200.vec_env import RunningMeanStd, VecNormalize, rank_seed
+
+# trained_models/curriculum_steps_complete_baoding_winner/32_phase_2_smaller_rate_resume/config.json of the reference
+STEP32 = {"weighted_reward_keys": {"pos_dist_1": 5, "pos_dist_2": 5, "act_reg": 0, "alive": 1, "solved": 5, "done": 0, "sparse": 0},
+          "enable_rsi": False, "rsi_probability": 0, "balls_overlap": False, "overlap_probability": 0, "noise_fingers": 0,
+          "limit_init_angle": 3.141592653589793, "goal_time_period": [4, 6], "goal_xrange": [0.02, 0.03], "goal_yrange": [0.022, 0.032],
+          "obj_size_range": [0.018, 0.024], "obj_mass_range": [0.03, 0.3], "obj_friction_change": [0.2, 0.001, 2e-05], "task_choice": "random"}
+
+
+def test_p2_registration_defaults(product_lib):
+    m = Model(asset_path("hand/myo_hand_baoding.mjb"), lib=product_lib)
+    cfg = make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1")
+    assert cfg.kind == _capi.TASK_BAODING and cfg.max_episode_steps == 200 and cfg.frame_skip == 10 and cfg.normalize_act == 1
+    assert tuple(cfg.goal_time_period) == (4.0, 6.0) and cfg.task_choice_random == 1 and cfg.randomize_physics == 1
+    np.testing.assert_allclose(list(cfg.obj_mass_range), [0.03, 0.3], rtol=1e-6)
+    np.testing.assert_allclose(list(cfg.obj_friction_change), [0.2, 0.001, 2e-5], rtol=1e-6)
+    assert cfg.drop_th == pytest.approx(1.25) and cfg.proximity_th == pytest.approx(0.015)
+    np.testing.assert_allclose(list(cfg.rwd_weight)[:7], [5, 5, 0, 0, 0, 0, 0])      # BaodingEnvV1 defaults
+
+
+def test_curriculum_config_json_maps(product_lib):
+    m = Model(asset_path("hand/myo_hand_baoding.mjb"), lib=product_lib)
+    cfg = make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1", **STEP32)
+    # order: pos_dist_1 pos_dist_2 act_reg alive sparse solved done
+    np.testing.assert_allclose(list(cfg.rwd_weight)[:7], [5, 5, 0, 1, 0, 5, 0])
+    assert cfg.limit_init_angle == pytest.approx(np.pi) and cfg.overlap_probability == 0.0
+    with pytest.raises(NotImplementedError):
+        make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1", enable_rsi=True, rsi_probability=0.9)
+    with pytest.raises(TypeError):
+        make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1", no_such_kwarg=1)
+
+
+def test_p1_keeps_nominal_balls(product_lib):
+    m = Model(asset_path("hand/myo_hand_baoding.mjb"), lib=product_lib)
+    cfg = make_task_cfg(m, "CustomMyoChallengeBaodingP1-v1")
+    assert cfg.randomize_physics == 0 and cfg.task_choice_random == 0 and cfg.fixed_task == 2     # WHICH_TASK = CCW
+    assert tuple(cfg.goal_xrange) == pytest.approx((0.025, 0.025))
+
+
+def test_pose_registrations(product_lib):
+    m = Model(asset_path("finger/myo_finger_v0.mjb"), lib=product_lib)
+    cfg = make_task_cfg(m, "CustomMyoFingerPoseRandom-v0")
+    assert cfg.kind == _capi.TASK_POSE and cfg.max_episode_steps == 100 and cfg.n_target_jnt == 4
+    names = [m.id2name("joint", cfg.target_jnt_ids[i]) for i in range(4)]
+    assert names == ["IFadb", "IFmcp", "IFpip", "IFdip"]
+    np.testing.assert_allclose([list(cfg.target_jnt_range[i]) for i in range(4)], [[-.2, .2], [-.4, 1], [.1, 1], [.1, 1]], rtol=1e-6)
+    h = Model(asset_path("hand/myo_hand_pose.mjb"), lib=product_lib)
+    cfg = make_task_cfg(h, "CustomMyoHandPoseRandom-v0")
+    assert cfg.n_target_jnt == 23 and cfg.reset_type == 2 and cfg.pose_thd == pytest.approx(0.8)
+    cfg = make_task_cfg(h, "CustomMyoHandPose3Fixed-v0")
+    assert cfg.n_target_jnt == 0 and cfg.target_type == 0 and cfg.target_jnt_value[3] == pytest.approx(0.3384)
+    e = Model(asset_path("arm/myo_elbow_1dof6muscles.mjb"), lib=product_lib)
+    cfg = make_task_cfg(e, "myoElbowPose1D6MRandom-v0")
+    assert cfg.n_target_jnt == 1 and cfg.pose_thd == pytest.approx(0.175)
+
+
+def test_factory_names_and_errors():
+    assert set(FACTORY_NAMES.values()) <= set(REGISTRY)
+    with pytest.raises(ValueError):
+        EnvironmentFactory.create("NoSuchEnv")
+    with pytest.raises(NotImplementedError):
+        EnvironmentFactory.create("CustomMyoReorientP2")
+    with pytest.raises(_capi.MyoError):           # no CPU path: creating worlds without a GPU fails loudly
+        if torch.cuda.is_available():
+            raise _capi.MyoError("gpu present")
+        EnvironmentFactory.create("CustomMyoFingerPoseRandom", num_envs=4, device="cuda:0")
+
+
+def test_running_mean_std_matches_numpy():
+    rng = np.random.default_rng(0)
+    x = rng.normal(3, 2, (1000, 5))
+    r = RunningMeanStd((5,))
+    for chunk in np.split(x, 10):
+        r.update(chunk)
+    # initial count 1e-4 with mean 0 / var 1 is part of SB3's definition
+    np.testing.assert_allclose(r.mean, x.mean(0), atol=1e-5)
+    np.testing.assert_allclose(r.var, x.var(0), rtol=1e-5)
+    assert r.count == pytest.approx(1000 + 1e-4)
+
+
+class _FakeVenv:
+    num_envs = 3
+
+    class _S:
+        shape = (86,)
+    observation_space = _S()
+    action_space = None
+
+
+def test_vecnormalize_constants_from_reference_pickle():
+    g = np.load(os.path.join(GOLDEN, "vecnormalize_baoding_step32.npz"))
+    v = VecNormalize.from_moments(_FakeVenv(), g["obs_mean"], g["obs_var"], g["obs_count"], g["ret_mean"], g["ret_var"], g["ret_count"],
+                                  clip_obs=float(g["clip_obs"]), clip_reward=float(g["clip_reward"]), gamma=float(g["gamma"]), epsilon=float(g["epsilon"]))
+    assert (v.clip_obs, v.clip_reward, v.gamma, v.epsilon) == (10.0, 10.0, 0.99, 1e-8)
+    assert v.obs_rms.count == pytest.approx(2.567e8, rel=1e-3)
+    obs = np.tile(g["obs_mean"], (3, 1)).astype(np.float32)
+    obs[1] += 3 * np.sqrt(g["obs_var"])
+    obs[2] += 1e6
+    out = v.normalize_obs(obs)
+    np.testing.assert_allclose(out[0], 0, atol=1e-3)
+    np.testing.assert_allclose(out[1], 3, atol=0.05)      # float32 observations: sigma of the velocity slots is ~1e-4 of the values
+    assert (out[2] == 10).all()
+    r = v.normalize_reward(np.array([1.0, 1e9]))
+    assert r[0] == pytest.approx(1 / np.sqrt(float(g["ret_var"]) + 1e-8), rel=1e-6) and r[1] == 10
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _moments_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7)
+    x = rng.normal(1, 3, (64, 6))                       # the global batch; each rank owns a shard of worlds
+    shard = x[rank * 32:(rank + 1) * 32]
+    r = RunningMeanStd((6,))
+    for _ in range(3):
+        r.update_distributed(shard)
+    q.put((rank, r.mean, r.var, r.count, rank_seed(5, rank)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_moment_merge_gloo():
+    """World shards on 2 ranks: the all-reduced Chan merge gives every rank the single-process statistics."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_moments_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+    rng = np.random.default_rng(7)
+    x = rng.normal(1, 3, (64, 6))
+    ref = RunningMeanStd((6,))
+    for _ in range(3):
+        ref.update(x)
+    for rank, mean, var, count, seed in res:
+        np.testing.assert_allclose(mean, ref.mean, rtol=1e-12)
+        np.testing.assert_allclose(var, ref.var, rtol=1e-10)
+        assert count == pytest.approx(ref.count)
+    assert res[0][4] != res[1][4]                    # ranks draw from disjoint world streams

@@ -1,0 +1,81 @@
+"""GPU: the SB3-shaped front end (MyoVecEnv) over the world kernel: shapes, auto-reset infos as the SubprocVecEnv
+worker + Monitor produce them, host-array API == device API, seeds, and the reset distribution of the P2 env
+(/root/reference/src/envs/baoding.py:494-604) checked through its observable effects."""
+import numpy as np
+import pytest
+import torch
+
+from myochallenge_b200 import _capi
+from myochallenge_b200.envs import EnvironmentFactory, make_vec_env
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vecenv_contract_and_autoreset(product_lib):
+    n = 256
+    env = EnvironmentFactory.create("CustomMyoBaodingBallsP2", num_envs=n, seed=3)
+    assert env.num_envs == n and env.observation_space.shape == (86,) and env.action_space.shape == (39,)
+    obs = env.reset()
+    assert obs.shape == (n, 86) and obs.dtype == np.float32 and np.isfinite(obs).all()
+    # just-reset Baoding observation: hand pose = init_qpos (palm up), act = 0   [src/envs/baoding.py:400-401]
+    assert np.allclose(obs[:, 0], -1.57) and np.allclose(obs[:, 1:23], 0) and np.allclose(obs[:, 47:], 0)
+    rng = np.random.default_rng(0)
+    lengths, seen_done, seen_trunc = np.zeros(n, int), 0, 0
+    for t in range(210):
+        obs, rew, done, infos = env.step(rng.uniform(-1, 1, (n, 39)).astype(np.float32))
+        lengths += 1
+        assert obs.shape == (n, 86) and rew.shape == (n,) and done.dtype == bool and len(infos) == n
+        for i in np.nonzero(done)[0][:4]:
+            d = infos[int(i)]
+            assert d["terminal_observation"].shape == (86,) and d["episode"]["l"] == lengths[i] and "TimeLimit.truncated" in d
+            assert lengths[i] <= 200 and (d["TimeLimit.truncated"] == (lengths[i] == 200 and not d["done"]))
+            seen_trunc += int(d["TimeLimit.truncated"])
+            # after auto-reset the returned observation is the new episode's first one
+            assert np.allclose(obs[i, 47:], 0) and obs[i, 0] == pytest.approx(-1.57)
+        i = int(np.nonzero(~done)[0][0])
+        assert "terminal_observation" not in infos[i] and set(infos[i]["rwd_dict"]) >= {"pos_dist_1", "alive", "solved", "done"}
+        seen_done += int(done.sum())
+        lengths[done] = 0
+    assert seen_done >= n       # every world finished at least once within 210 steps (horizon 200)
+    env.close()
+
+
+def test_host_api_equals_device_api_and_seeds(product_lib):
+    n = 64
+    a = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, seed=11)
+    b = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, seed=11)
+    c = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, seed=12)
+    oa, ob, oc = a.reset(), b.reset_device().cpu().numpy(), c.reset()
+    assert np.array_equal(oa, ob)                                        # same seed -> same worlds
+    act = np.random.default_rng(1).uniform(-1, 1, (n, 39)).astype(np.float32)
+    oc1, _, _, _ = c.step(act)
+    for _ in range(5):
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = [t.cpu().numpy() for t in b.step_device(torch.from_numpy(act).cuda())]
+        assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db.astype(bool))
+    a2 = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, seed=11)
+    a2.reset()
+    oa1, _, _, _ = a2.step(act)
+    assert not np.array_equal(oa1, oc1)                                  # another seed -> other tasks / radii / ball physics
+
+
+def test_p2_reset_distribution(product_lib):
+    """Physics randomisation ranges of the P2 registration show up in the per-world parameters after reset, and the
+    three tasks (hold / cw / ccw) are drawn uniformly."""
+    n = 4096
+    env = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, seed=5)
+    env.reset()
+    sim, cfg = env.sim, env.cfg
+    for k in range(2):
+        mass = sim.get_param(_capi.PARAM_BODY_MASS, cfg.ball_body[k]).cpu().numpy()[:, 0]
+        size = sim.get_param(_capi.PARAM_GEOM_SIZE, cfg.ball_geom[k]).cpu().numpy()[:, 0]
+        fri = sim.get_param(_capi.PARAM_GEOM_FRICTION, cfg.ball_geom[k]).cpu().numpy()
+        assert 0.03 <= mass.min() and mass.max() <= 0.3 and abs(mass.mean() - 0.165) < 0.01
+        assert 0.018 <= size.min() and size.max() <= 0.024 and abs(size.mean() - 0.021) < 3e-4
+        assert 0.8 <= fri[:, 0].min() and fri[:, 0].max() <= 1.2 and fri[:, 0].std() > 0.1
+    # targets move only for cw / ccw: after one step a third of the worlds keep their target (hold)
+    o0 = env.sim.get_obs().cpu().numpy().copy()
+    o1, _, _, _ = env.step(np.zeros((n, 39), np.float32))
+    moved = np.abs(o1[:, 35:37] - o0[:, 35:37]).max(1) > 1e-7
+    assert 0.6 < moved.mean() < 0.73
+    env.close()
