@@ -1252,6 +1252,18 @@ MYO_PHASE void chol_solve(Ctx<G>& c, int oH, int ox, int n) {
   }
 }
 
+// optional per-phase cycle counters (development builds: -DMYO_PROFILE)
+#ifdef MYO_PROFILE
+__device__ unsigned long long g_prof[16];
+#define MYO_PH_BEGIN long long ph_t0 = clock64();
+#define MYO_PH_RESTART ph_t0 = clock64();
+#define MYO_PH(i) { long long ph_t = clock64(); if (c.lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(ph_t - ph_t0)); ph_t0 = clock64(); }
+#else
+#define MYO_PH_BEGIN
+#define MYO_PH_RESTART
+#define MYO_PH(i)
+#endif
+
 // a10.8 constraint solve: primal Newton with exact line search on
 //   cost(a) = 1/2 (a - a_s)' M (a - a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
 // warm-started from the better of (qacc_warmstart, qacc_smooth) as MuJoCo's warmstart() does.
@@ -1291,6 +1303,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
   }
   const float scale = 1.f / (m.meaninertia * (float)max(1, nv));
   int iter = 0;
+  MYO_PH_BEGIN
   float prev_step = 3.0e38f;
   for (; iter < m.solver_iter; iter++) {
     rows_dot<G>(mslot, c, m.o_qacc, R_JAR, true);
@@ -1303,11 +1316,11 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
     g2 = tile_sum<G>(c, g2);
     amax = tile_max<G>(c, amax);
     if (sqrtf(g2) * scale < m.solver_tol) break;
-    build_hessian<G>(mslot, c);
-    chol_factor<G>(c, m.o_H, nv);
+    MYO_PH_RESTART build_hessian<G>(mslot, c); MYO_PH(11)
+    chol_factor<G>(c, m.o_H, nv); MYO_PH(12)
     for (int i = c.lane; i < nv; i += G) p[i] = -grad[i];
     c.tile.sync();
-    chol_solve<G>(c, m.o_H, m.o_p, nv);
+    chol_solve<G>(c, m.o_H, m.o_p, nv); MYO_PH(13)
     rows_dot<G>(mslot, c, m.o_p, R_JP, false);
     mul_M<G>(mslot, c, m.o_M, m.o_p, m.o_Mp);
     float pMp = 0.f, gp = 0.f, pmax = 0.f;
@@ -1333,6 +1346,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
       if (nxt == alpha) break;
       alpha = nxt;
     }
+    MYO_PH(14)
     // did any row change side along the step? if not, and the full Newton step was taken, a + p is the
     // exact minimiser of a cost that is quadratic on this active set: converged without a checking pass
     int changed = 0;
@@ -1405,16 +1419,6 @@ MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
   c.tile.sync();
 }
 
-// optional per-phase cycle counters (development builds: -DMYO_PROFILE)
-#ifdef MYO_PROFILE
-__device__ unsigned long long g_prof[16];
-#define MYO_PH_BEGIN long long ph_t0 = clock64();
-#define MYO_PH(i) { long long ph_t = clock64(); if (c.lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(ph_t - ph_t0)); ph_t0 = clock64(); }
-#else
-#define MYO_PH_BEGIN
-#define MYO_PH(i)
-#endif
-
 // All warps of a CTA walk the phases together: the step is ~200 KB of straight-line code, far more
 // than the instruction cache holds, so keeping the CTA inside one phase at a time lets every fetched
 // line serve all of its warps. (Every tile of the CTA executes every phase of every substep.)
@@ -1441,7 +1445,7 @@ MYO_PHASE void mj_step_dev(int mslot, Ctx<G>& c, int* status) {
   MYO_M
   mj_forward_dev<G>(mslot, c, status);
   MYO_PH_BEGIN
-  MYO_CTA_SYNC phase_integrate<G>(mslot, c); MYO_PH(10)
+  MYO_CTA_SYNC MYO_PH(15) phase_integrate<G>(mslot, c); MYO_PH(10)
 }
 
 }  // namespace myo

@@ -8,7 +8,7 @@ _capi._LIB = _capi.bind(os.path.join(ROOT, "scripts", "_prof", "libmyo_prof.so")
 from myochallenge_b200 import BatchSim, Model
 from myochallenge_b200.assets import asset_path
 
-NAMES = ["tree_fwd", "tendon", "tree_bwd", "mass_bias", "factor", "collision", "constraints", "actuation", "solveM", "newton", "integrate"]
+NAMES = ["tree_fwd", "tendon", "tree_bwd", "mass_bias", "factor", "collision", "constraints", "actuation", "solveM", "newton", "integrate", "  nt:hessian", "  nt:chol_factor", "  nt:chol_solve", "  nt:linesearch+dots", "barrier_pre_integrate"]
 
 def run(path, kind, n, steps=5):
     m = Model(asset_path(path))
@@ -28,7 +28,7 @@ def run(path, kind, n, steps=5):
         sim.step(a)
     e1.record(); torch.cuda.synchronize()
     _capi._LIB.myo_debug_profile(buf)
-    tot = sum(buf[:11])
+    tot = sum(buf[:11]) + buf[15]
     sub = steps * n * cfg.frame_skip
     print(f"{path} n={n}: {e0.elapsed_time(e1)/steps:.3f} ms/step; cycles per substep per world = {tot/sub:.0f}")
     sim.mj_step(None, 1)
