@@ -9,7 +9,7 @@ namespace myo {
 constexpr int KC = 8;    // max dofs on a body's ancestor chain (myoHand distal phalanx: 3 wrist + 4 finger)
 constexpr int KT = 8;    // max dofs a tendon's moment arm touches
 constexpr int KS = 16;   // max support of one contact block (chain A xor chain B)
-constexpr int LIM_WORDS = 28;   // scratch words per limit record
+constexpr int LIM_WORDS = 8;    // scratch words per limit record
 constexpr int CON_WORDS = 104;  // scratch words per contact record
 constexpr int ROW_WORDS = 6;    // scratch words per constraint row
 
@@ -20,7 +20,10 @@ enum { ST_UNSUPPORTED = 1, ST_CON_OVERFLOW = 2, ST_EFC_OVERFLOW = 4, ST_NONFINIT
 enum { EFC_LIMIT_JOINT = 3, EFC_LIMIT_TENDON = 4, EFC_CONTACT_FRICTIONLESS = 5, EFC_CONTACT_PYRAMIDAL = 6 };
 
 // limit record layout (floats/ints in scratch)
-enum { L_KIND = 0, L_ID = 1, L_NSUP = 2, L_POS = 3, L_MARGIN = 4, L_IDX = 8 /*KT ints*/, L_J = 16 /*KT floats*/ };
+// the support and Jacobian of a limit row are referenced, not copied: the dof indices are a slice of the model's int
+// tables (j_dofadr / t_dof, word offset L_IOFF), the values a slice of the world's scratch (word offset L_JOFF: the
+// constant 1 kept in o_misc for a joint, the tendon's ten_J row for a tendon) times L_SIGN
+enum { L_KIND = 0, L_ID = 1, L_NSUP = 2, L_POS = 3, L_MARGIN = 4, L_SIGN = 5, L_IOFF = 6, L_JOFF = 7 };
 // contact record layout
 enum { C_G1 = 0, C_G2 = 1, C_DIM = 2, C_NSUP = 3, C_DIST = 4, C_MARGIN = 5, C_MU = 6, C_ROW0 = 7, C_POS = 8 /*3*/,
        C_FRAME = 11 /*9*/, C_SOLREF = 20 /*2*/, C_SOLIMP = 22 /*5*/, C_BA = 27, C_BB = 28, C_FRI = 29 /*3*/,
@@ -60,6 +63,7 @@ struct DevModel {
   int nq, nv, nu, na, nbody, njnt, ngeom, nsite, ntendon, nwrap, nM, npair, nlevel, ndlevel;
   int nq4, nv4, na4, nu4, nparam, nparam4, nobs, nobs4;
   int nlim_max, ncon_max, nefc_max;
+  int hs;   // row stride (words) of the dense Newton Hessian: >= nv, multiple of 4 with hs/4 odd (conflict-free float4 rows)
   int solver_iter;
   float solver_tol, timestep, gravity[3], inv_sqrt_impratio, meaninertia;
   int any_damping, any_tendon_passive, any_joint_spring;
@@ -126,7 +130,7 @@ struct BatchPtrs {
 enum { TI_ELAPSED = 0, TI_EPISODE = 1, TI_TASK = 2, TI_FLAGS = 3, TI_WORDS = 4 };
 enum { TF_ANGLE1 = 0, TF_ANGLE2 = 1, TF_XR = 2, TF_YR = 3, TF_PERIOD = 4, TF_WORDS = 8 };
 // o_misc scratch words
-enum { MI_NLIM = 0, MI_NCON = 1, MI_NEFC = 2, MI_ITER = 3, MI_STATUS = 4, MI_WORDS = 8 };
+enum { MI_NLIM = 0, MI_NCON = 1, MI_NEFC = 2, MI_ITER = 3, MI_STATUS = 4, MI_ONE = 5 /*float 1*/, MI_WORDS = 8 };
 
 enum StepMode { MODE_ENV_STEP = 0, MODE_MJ_STEP = 1, MODE_FORWARD = 2, MODE_GET_OBS = 3, MODE_RESET = 4 };
 

@@ -226,7 +226,7 @@ __global__ void extract_kernel(const __grid_constant__ DevModel m, const float* 
         for (int r = 0; r < nlim; r++) {
           const float* lr = s + m.o_lim + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
           if (stage == MYO_STAGE_EFC_TYPE_ID) { oi[2 * r] = li[L_KIND]; oi[2 * r + 1] = li[L_ID]; }
-          else for (int e = 0; e < li[L_NSUP]; e++) of[r * m.nv + li[L_IDX + e]] = lr[L_J + e];
+          else for (int e = 0; e < li[L_NSUP]; e++) of[r * m.nv + lim_idx(li, e)] = lim_J(s, lr, li, e);
         }
         for (int k = 0; k < ncon; k++) {
           const float* cr = s + m.o_con + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);

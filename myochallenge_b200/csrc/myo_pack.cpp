@@ -413,7 +413,10 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     d.o_cvel = take(6 * nbody); d.o_cdofdot = take(6 * nv); d.o_cacc = take(6 * nbody); d.o_cfrc = take(6 * nbody);
     const int tmp_words = off - a0;
     d.o_H = a0;
-    off = a0 + std::max(tmp_words, pad4(nv * (nv + 1) / 2));
+    // dense Hessian: nv rows padded to a multiple of four + one right-hand-side row, row stride hs
+    d.hs = pad4(nv);
+    if ((d.hs / 4) % 2 == 0) d.hs += 4;
+    off = a0 + std::max(tmp_words, (pad4(nv) + 1) * d.hs);
   }
   // world stride: tiles of one warp land on different banks
   if (out.lanes < 32) { while (off % 32 != out.lanes) off += 4; }

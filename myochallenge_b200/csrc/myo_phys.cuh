@@ -39,6 +39,10 @@ template <int G> MYO_DI float tile_max(const Ctx<G>& c, float v) {
   return v;
 }
 
+// support index / Jacobian value e of a limit record (see L_IOFF / L_JOFF in myo_dev.hpp); s = the world's scratch
+MYO_DI int lim_idx(const int* li, int e) { return reinterpret_cast<const int*>(MYO_SMEM_WORDS)[li[L_IOFF] + e]; }
+MYO_DI float lim_J(const float* s, const float* lr, const int* li, int e) { return lr[L_SIGN] * s[li[L_JOFF] + e]; }
+
 // ------------------------------------------------------------------------------------------------
 // a10.1 kinematics + comPos (+ comVel + RNE forward when dyn): one level-synchronous sweep.
 // Reference point of every kinematic tree = xipos of its root body (MuJoCo uses the subtree COM;
@@ -873,7 +877,7 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
       if (slot < m.nlim_max) {
         float* r = SF(o_lim) + slot * LIM_WORDS; int* ri = reinterpret_cast<int*>(r);
         ri[L_KIND] = EFC_LIMIT_JOINT; ri[L_ID] = j; ri[L_NSUP] = 1; r[L_POS] = dlo; r[L_MARGIN] = margin;
-        ri[L_IDX] = m.j_dofadr[j]; r[L_J] = 1.f;
+        r[L_SIGN] = 1.f; ri[L_IOFF] = m.j_dofadr.off + j; ri[L_JOFF] = m.o_misc + MI_ONE;
       } else *status |= ST_EFC_OVERFLOW;
       slot++;
     }
@@ -881,7 +885,7 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
       if (slot < m.nlim_max) {
         float* r = SF(o_lim) + slot * LIM_WORDS; int* ri = reinterpret_cast<int*>(r);
         ri[L_KIND] = EFC_LIMIT_JOINT; ri[L_ID] = j; ri[L_NSUP] = 1; r[L_POS] = dhi; r[L_MARGIN] = margin;
-        ri[L_IDX] = m.j_dofadr[j]; r[L_J] = -1.f;
+        r[L_SIGN] = -1.f; ri[L_IOFF] = m.j_dofadr.off + j; ri[L_JOFF] = m.o_misc + MI_ONE;
       } else *status |= ST_EFC_OVERFLOW;
     }
     nlim += __popc(blo) + __popc(bhi);
@@ -905,10 +909,7 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
         float* r = SF(o_lim) + slot * LIM_WORDS; int* ri = reinterpret_cast<int*>(r);
         ri[L_KIND] = EFC_LIMIT_TENDON; ri[L_ID] = t; ri[L_NSUP] = m.t_ndof[t];
         r[L_POS] = side ? dhi : dlo; r[L_MARGIN] = margin;
-        for (int e = 0; e < m.t_ndof[t]; e++) {
-          ri[L_IDX + e] = m.t_dof[t * KT + e];
-          r[L_J + e] = (side ? -1.f : 1.f) * SF(o_tenJ)[t * KT + e];
-        }
+        r[L_SIGN] = side ? -1.f : 1.f; ri[L_IOFF] = m.t_dof.off + t * KT; ri[L_JOFF] = m.o_tenJ + t * KT;
       } else *status |= ST_EFC_OVERFLOW;
       slot++;
     }
@@ -926,10 +927,10 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
     float R, K, B, imp, vel = 0.f;
     if (li[L_KIND] == EFC_LIMIT_JOINT) {
       row_params(mslot, m.j_solref + 2 * id, m.j_solimp + 5 * id, lr[L_POS], lr[L_MARGIN], m.d_invweight0[m.j_dofadr[id]], &R, &K, &B, &imp);
-      vel = lr[L_J] * qvel[li[L_IDX]];
+      vel = lr[L_SIGN] * qvel[m.j_dofadr[id]];
     } else {
       row_params(mslot, m.t_solref + 2 * id, m.t_solimp + 5 * id, lr[L_POS], lr[L_MARGIN], m.t_invweight0[id], &R, &K, &B, &imp);
-      for (int e = 0; e < li[L_NSUP]; e++) vel += lr[L_J + e] * qvel[li[L_IDX + e]];
+      for (int e = 0; e < li[L_NSUP]; e++) vel += lim_J(c.sp(), lr, li, e) * qvel[lim_idx(li, e)];
     }
     float* row = rows + r * ROW_WORDS;
     row[R_D] = 1.f / R;
@@ -1088,7 +1089,7 @@ MYO_PHASE void rows_dot(int mslot, Ctx<G>& c, int ox, int field, bool sub_aref) 
   for (int r = c.lane; r < nlim; r += G) {
     const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
     float v = 0.f;
-    for (int e = 0; e < li[L_NSUP]; e++) v += lr[L_J + e] * x[li[L_IDX + e]];
+    for (int e = 0; e < li[L_NSUP]; e++) v += lim_J(c.sp(), lr, li, e) * x[lim_idx(li, e)];
     float* row = rows + r * ROW_WORDS;
     row[field] = sub_aref ? v - row[R_AREF] : v;
   }
@@ -1126,7 +1127,7 @@ MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
     const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
     const float* row = rows + r * ROW_WORDS;
     const float f = row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] * scale : 0.f;
-    if (f != 0.f && c.lane < li[L_NSUP]) out[li[L_IDX + c.lane]] += lr[L_J + c.lane] * f;
+    if (f != 0.f) for (int e = c.lane; e < li[L_NSUP]; e += G) out[lim_idx(li, e)] += lim_J(c.sp(), lr, li, e) * f;
     c.tile.sync();
   }
   for (int k = 0; k < ncon; k++) {
@@ -1148,38 +1149,62 @@ MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
   }
 }
 
-MYO_DI int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // packed lower, i >= j
-
-// H = M + sum_{active rows} D_r J_r' J_r  (packed lower triangle)
+// Dense Newton system in scratch: H row-major, row stride m.hs (multiple of 4, hs/4 odd, so a lane per row reads float4s
+// without bank conflicts), lower triangle valid; rows nv..n4-1 pad to a multiple of four (identity), row n4 holds the
+// right-hand side.
+// H = M + sum_{active rows} D_r J_r' J_r, right-hand side = -grad.
 template <int G>
 MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
   MYO_M
-  float* H = SF(o_H); const float* M = SF(o_M);
-  const int nv = m.nv;
-  for (int e = c.lane; e < nv * (nv + 1) / 2; e += G) H[e] = 0.f;
-  c.tile.sync();
+  float* H = SF(o_H); const float* M = SF(o_M); const float* grad = SF(o_grad);
+  const int nv = m.nv, hs = m.hs;
+  // a lane owns a row: clear it, then drop the row's mass-matrix entries (i, ancestors of i) into it
+  const int n4 = (nv + 3) & ~3;
+  for (int k = c.lane; k < n4; k += G) H[n4 * hs + k] = k < nv ? -grad[k] : 0.f;
+  for (int i = nv + c.lane; i < n4; i += G) {       // identity padding rows up to a multiple of four
+    for (int k = 0; k < n4; k++) H[i * hs + k] = (k == i) ? 1.f : 0.f;
+  }
   for (int i = c.lane; i < nv; i += G) {
+    float4* row4 = reinterpret_cast<float4*>(H + i * hs);
+    for (int k = 0; k <= i / 4; k++) row4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     int adr = m.d_Madr[i], j = i;
-    while (j >= 0) { H[tri(i, j)] = M[adr++]; j = m.d_parent[j]; }
+    while (j >= 0) { H[i * hs + j] = M[adr++]; j = m.d_parent[j]; }
   }
   c.tile.sync();
   const int* misc = SI(o_misc);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
   const float* rows = SF(o_row);
-  for (int r = 0; r < nlim; r++) {
-    const float* row = rows + r * ROW_WORDS;
-    if (row[R_JAR] < 0.f) {
+  // joint limits touch one diagonal entry each: a lane per dof gathers its rows in row order
+  bool any_tendon_row = false;
+  for (int i = c.lane; i < nv; i += G) {
+    float add = 0.f;
+    for (int r = 0; r < nlim; r++) {
       const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
-      const int ns = li[L_NSUP];
-      const float D = row[R_D];
-      for (int e = c.lane; e < ns * ns; e += G) {
-        const int a = e / ns, b = e - a * ns;
-        const int ia = li[L_IDX + a], ib = li[L_IDX + b];
-        if (ia >= ib) H[tri(ia, ib)] += D * lr[L_J + a] * lr[L_J + b];
-      }
+      if (li[L_KIND] != EFC_LIMIT_JOINT) { any_tendon_row = true; continue; }
+      const float* row = rows + r * ROW_WORDS;
+      if (row[R_JAR] < 0.f && lim_idx(li, 0) == i) add += row[R_D];
     }
-    c.tile.sync();
+    H[i * hs + i] += add;
   }
+  if (c.tile.ballot(any_tendon_row)) {
+    c.tile.sync();
+    for (int r = 0; r < nlim; r++) {
+      const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
+      if (li[L_KIND] == EFC_LIMIT_JOINT) continue;
+      const float* row = rows + r * ROW_WORDS;
+      if (row[R_JAR] < 0.f) {
+        const int ns = li[L_NSUP];
+        const float D = row[R_D];
+        for (int e = c.lane; e < ns * ns; e += G) {
+          const int a = e / ns, b = e - a * ns;
+          const int ia = lim_idx(li, a), ib = lim_idx(li, b);
+          if (ia >= ib) H[ia * hs + ib] += D * lim_J(c.sp(), lr, li, a) * lim_J(c.sp(), lr, li, b);
+        }
+      }
+      c.tile.sync();
+    }
+  }
+  c.tile.sync();
   for (int k = 0; k < ncon; k++) {
     const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
     const int row0 = ci[C_ROW0];
@@ -1200,56 +1225,106 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
       }
     }
     if (w00 != 0.f) {
-      for (int e = c.lane; e < ns * ns; e += G) {
-        const int a = e / ns, b = e - a * ns;
+      // every unordered pair (a >= b) of the support once: e = a (a + 1) / 2 + b
+      for (int e = c.lane; e < ns * (ns + 1) / 2; e += G) {
+        int a = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+        if ((a + 1) * (a + 2) / 2 <= e) a++;
+        if (a * (a + 1) / 2 > e) a--;
+        const int b = e - a * (a + 1) / 2;
         const int ia = ci[C_IDX + a], ib = ci[C_IDX + b];
-        if (ia >= ib) {
-          const float na = cr[C_N + a], ta = cr[C_N + KS + a], ua = cr[C_N + 2 * KS + a];
-          const float nb = cr[C_N + b], tb = cr[C_N + KS + b], ub = cr[C_N + 2 * KS + b];
-          H[tri(ia, ib)] += w00 * na * nb + w01 * (na * tb + ta * nb) + w02 * (na * ub + ua * nb) + w11 * ta * tb + w22 * ua * ub;
-        }
+        const float na = cr[C_N + a], ta = cr[C_N + KS + a], ua = cr[C_N + 2 * KS + a];
+        const float nb = cr[C_N + b], tb = cr[C_N + KS + b], ub = cr[C_N + 2 * KS + b];
+        H[max(ia, ib) * hs + min(ia, ib)] += w00 * na * nb + w01 * (na * tb + ta * nb) + w02 * (na * ub + ua * nb) + w11 * ta * tb + w22 * ua * ub;
       }
     }
     c.tile.sync();
   }
 }
 
-// in-place dense Cholesky (left-looking, lane per row) and solve; n <= 2*G
+// In-place dense Cholesky H = L L', left-looking by blocks of four columns, a lane per row. For a block the lane
+// accumulates four dot products of its row against the four pivot rows (float4 loads, 16 independent FMA chains), the
+// 4 x 4 diagonal block is gathered with shuffles and factored redundantly in registers, and the lane finishes its four
+// entries with a register triangular solve: one tile barrier per four columns. The forward substitution is fused in:
+// the right-hand-side row n4 is carried through like one more matrix row and ends as y = L^-1 rhs. Diagonal slots keep
+// 1 / L_jj. n4 = n rounded up to 4 (rows n..n4-1 are identity rows written by build_hessian).
+// Then the back substitution L' x = y, column oriented, with y held in registers (lane i owns y_i, y_{i+G}, ...)
+// and each finished x_j broadcast by a shuffle; x goes to scratch at ox.
 template <int G>
-MYO_PHASE void chol_factor(Ctx<G>& c, int oH, int n) {
-  float* H = SO(oH);
-  for (int j = 0; j < n; j++) {
-    const float* Lj = H + tri(j, 0);
-    for (int i = j + c.lane; i < n; i += G) {
-      float* Li = H + tri(i, 0);
-      float s = Li[j];
-      for (int k = 0; k < j; k++) s -= Li[k] * Lj[k];
-      Li[j] = s;                        // unscaled column; diagonal holds the pivot
+MYO_PHASE void chol_factor_solve(Ctx<G>& c, int oH, int ox, int n, int hs) {
+  float* H = SO(oH); float* x = SO(ox);
+  const int n4 = (n + 3) & ~3;
+  if constexpr (G < 4) {   // single-lane host emulation (tests/emul): same storage convention, unblocked
+    for (int j = 0; j < n4; j++) {
+      float inv = 0.f;
+      for (int i = j; i <= n4; i++) {
+        float s = H[i * hs + j];
+        for (int k = 0; k < j; k++) s -= H[i * hs + k] * H[j * hs + k];
+        if (i == j) { inv = 1.f / sqrtf(fmaxf(s, kMinVal)); H[i * hs + j] = inv; } else H[i * hs + j] = s * inv;
+      }
+    }
+  } else
+  for (int J = 0; J < n4; J += 4) {
+    const float* P = H + J * hs;       // pivot rows J..J+3
+    float l10 = 0.f, l20 = 0.f, l21 = 0.f, l30 = 0.f, l31 = 0.f, l32 = 0.f, inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, inv3 = 0.f;
+    for (int i0 = J; i0 <= n4; i0 += G) {
+      const int i = i0 + c.lane;
+      const bool on = i <= n4;
+      float* Li = H + (on ? i : J) * hs;
+      float4 acc = *reinterpret_cast<const float4*>(Li + J);
+      for (int k = 0; k < J; k += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(Li + k);
+        const float4 b0 = *reinterpret_cast<const float4*>(P + k);
+        const float4 b1 = *reinterpret_cast<const float4*>(P + hs + k);
+        const float4 b2 = *reinterpret_cast<const float4*>(P + 2 * hs + k);
+        const float4 b3 = *reinterpret_cast<const float4*>(P + 3 * hs + k);
+        acc.x -= a.x * b0.x; acc.x -= a.y * b0.y; acc.x -= a.z * b0.z; acc.x -= a.w * b0.w;
+        acc.y -= a.x * b1.x; acc.y -= a.y * b1.y; acc.y -= a.z * b1.z; acc.y -= a.w * b1.w;
+        acc.z -= a.x * b2.x; acc.z -= a.y * b2.y; acc.z -= a.z * b2.z; acc.z -= a.w * b2.w;
+        acc.w -= a.x * b3.x; acc.w -= a.y * b3.y; acc.w -= a.z * b3.z; acc.w -= a.w * b3.w;
+      }
+      if (i0 == J) {   // first pass: lanes 0..3 hold the diagonal block
+        const float d00 = c.tile.shfl(acc.x, 0);
+        const float d10 = c.tile.shfl(acc.x, 1 % G), d11 = c.tile.shfl(acc.y, 1 % G);
+        const float d20 = c.tile.shfl(acc.x, 2 % G), d21 = c.tile.shfl(acc.y, 2 % G), d22 = c.tile.shfl(acc.z, 2 % G);
+        const float d30 = c.tile.shfl(acc.x, 3 % G), d31 = c.tile.shfl(acc.y, 3 % G), d32 = c.tile.shfl(acc.z, 3 % G), d33 = c.tile.shfl(acc.w, 3 % G);
+        inv0 = rsqrtf(fmaxf(d00, kMinVal));
+        l10 = d10 * inv0; l20 = d20 * inv0; l30 = d30 * inv0;
+        inv1 = rsqrtf(fmaxf(d11 - l10 * l10, kMinVal));
+        l21 = (d21 - l20 * l10) * inv1; l31 = (d31 - l30 * l10) * inv1;
+        inv2 = rsqrtf(fmaxf(d22 - l20 * l20 - l21 * l21, kMinVal));
+        l32 = (d32 - l30 * l20 - l31 * l21) * inv2;
+        inv3 = rsqrtf(fmaxf(d33 - l30 * l30 - l31 * l31 - l32 * l32, kMinVal));
+      }
+      float4 r;
+      r.x = acc.x * inv0;
+      r.y = (acc.y - r.x * l10) * inv1;
+      r.z = (acc.z - r.x * l20 - r.y * l21) * inv2;
+      r.w = (acc.w - r.x * l30 - r.y * l31 - r.z * l32) * inv3;
+      const int q = i - J;     // rows of the diagonal block: inverse pivot on the diagonal, zeros above it
+      if (q == 0) { r.x = inv0; r.y = 0.f; r.z = 0.f; r.w = 0.f; }
+      else if (q == 1) { r.y = inv1; r.z = 0.f; r.w = 0.f; }
+      else if (q == 2) { r.z = inv2; r.w = 0.f; }
+      else if (q == 3) r.w = inv3;
+      if (on) *reinterpret_cast<float4*>(Li + J) = r;
     }
     c.tile.sync();
-    // the diagonal keeps the pivot L_jj^2 (never rewritten, so no read/write race on it)
-    const float inv = 1.f / sqrtf(fmaxf(H[tri(j, j)], kMinVal));
-    for (int i = j + 1 + c.lane; i < n; i += G) H[tri(i, j)] *= inv;
-    c.tile.sync();
   }
-}
-template <int G>
-MYO_PHASE void chol_solve(Ctx<G>& c, int oH, int ox, int n) {
-  const float* H = SO(oH); float* x = SO(ox);
-  for (int j = 0; j < n; j++) {          // forward: column oriented
-    if (c.lane == 0) x[j] = x[j] / sqrtf(fmaxf(H[tri(j, j)], kMinVal));
-    c.tile.sync();
-    const float xj = x[j];
-    for (int i = j + 1 + c.lane; i < n; i += G) x[i] -= H[tri(i, j)] * xj;
-    c.tile.sync();
+  constexpr int NSET = 64 / G;     // nv <= 64 (pack_model)
+  float y[NSET];
+#pragma unroll
+  for (int q = 0; q < NSET; q++) { const int i = c.lane + q * G; y[q] = i < n ? H[n4 * hs + i] : 0.f; }
+  for (int j = n - 1; j >= 0; j--) {
+    const float* Lj = H + j * hs;
+    const int jq = j / G;
+    float v = y[0];
+#pragma unroll
+    for (int q = 1; q < NSET; q++) v = (jq == q) ? y[q] : v;
+    const float xj = c.tile.shfl(v, j - jq * G) * Lj[j];
+#pragma unroll
+    for (int q = 0; q < NSET; q++) { const int i = c.lane + q * G; if (i < j) y[q] -= Lj[i] * xj; }
+    if (c.lane == j - jq * G) x[j] = xj;
   }
-  for (int j = n - 1; j >= 0; j--) {     // backward with L'
-    if (c.lane == 0) x[j] = x[j] / sqrtf(fmaxf(H[tri(j, j)], kMinVal));
-    c.tile.sync();
-    const float xj = x[j];
-    for (int i = c.lane; i < j; i += G) x[i] -= H[tri(j, i)] * xj;
-    c.tile.sync();
-  }
+  c.tile.sync();
 }
 
 // optional per-phase cycle counters (development builds: -DMYO_PROFILE)
@@ -1317,10 +1392,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
     amax = tile_max<G>(c, amax);
     if (sqrtf(g2) * scale < m.solver_tol) break;
     MYO_PH_RESTART build_hessian<G>(mslot, c); MYO_PH(11)
-    chol_factor<G>(c, m.o_H, nv); MYO_PH(12)
-    for (int i = c.lane; i < nv; i += G) p[i] = -grad[i];
-    c.tile.sync();
-    chol_solve<G>(c, m.o_H, m.o_p, nv); MYO_PH(13)
+    chol_factor_solve<G>(c, m.o_H, m.o_p, nv, m.hs); MYO_PH(12)
     rows_dot<G>(mslot, c, m.o_p, R_JP, false);
     mul_M<G>(mslot, c, m.o_M, m.o_p, m.o_Mp);
     float pMp = 0.f, gp = 0.f, pmax = 0.f;

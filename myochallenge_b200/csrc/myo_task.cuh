@@ -25,6 +25,7 @@ MYO_PHASE void load_world(int mslot, Ctx<G>& c, const BatchPtrs& b, int w) {
   copy_words<G>(c, SF(o_warm), b.warm + (size_t)w * m.nv4, m.nv4);
   if (m.na) copy_words<G>(c, SF(o_act), b.act + (size_t)w * m.na4, m.na4);
   copy_words<G>(c, SF(o_wparam), b.wparam + (size_t)w * m.nparam4, m.nparam4);
+  if (c.lane == 0) SF(o_misc)[MI_ONE] = 1.f;
   c.tile.sync();
 }
 template <int G>

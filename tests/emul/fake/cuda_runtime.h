@@ -18,6 +18,8 @@
 #define __shared__
 
 struct float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float rsqrtf(float x) { return 1.f / sqrtf(x); }
 struct dim3e { unsigned x = 1, y = 1, z = 1; };
 extern thread_local dim3e blockIdx, threadIdx, blockDim, gridDim;
 extern thread_local float4* emul_smem;
