@@ -11,7 +11,7 @@ constexpr int KT = 8;    // max dofs a tendon's moment arm touches
 constexpr int KS = 16;   // max support of one contact block (chain A xor chain B)
 constexpr int LIM_WORDS = 8;    // scratch words per limit record
 constexpr int CON_WORDS = 104;  // scratch words per contact record
-constexpr int ROW_WORDS = 6;    // scratch words per constraint row
+constexpr int ROW_WORDS = 4;    // scratch words per constraint row (one float4)
 
 enum { J_FREE = 0, J_BALL = 1, J_SLIDE = 2, J_HINGE = 3 };
 enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_ELLIPSOID = 4, G_CYLINDER = 5, G_BOX = 6 };
@@ -29,7 +29,7 @@ enum { C_G1 = 0, C_G2 = 1, C_DIM = 2, C_NSUP = 3, C_DIST = 4, C_MARGIN = 5, C_MU
        C_FRAME = 11 /*9*/, C_SOLREF = 20 /*2*/, C_SOLIMP = 22 /*5*/, C_BA = 27, C_BB = 28, C_FRI = 29 /*3*/,
        C_IDX = 32 /*KS ints*/, C_N = 48 /*3*KS floats*/ };
 // row record
-enum { R_D = 0, R_AREF = 1, R_JAR = 2, R_JP = 3, R_BLOCK = 4 /*int: block | coef<<16*/, R_AUX = 5 };
+enum { R_D = 0, R_AREF = 1, R_JAR = 2, R_JP = 3 };
 
 // Model tables live in shared memory: every kernel stages the packed table block (ints, then floats)
 // at the start of its dynamic shared memory, and a table is just a word offset into that block.
@@ -63,10 +63,11 @@ struct DevModel {
   int nq, nv, nu, na, nbody, njnt, ngeom, nsite, ntendon, nwrap, nM, npair, nlevel, ndlevel;
   int nq4, nv4, na4, nu4, nparam, nparam4, nobs, nobs4;
   int nlim_max, ncon_max, nefc_max;
+  int nd;   // dofs [0, nd) couple through the mass matrix; dofs [nd, nv) are simple (diagonal)
   int hs;   // row stride (words) of the dense Newton Hessian: >= nv, multiple of 4 with hs/4 odd (conflict-free float4 rows)
   int solver_iter;
   float solver_tol, timestep, gravity[3], inv_sqrt_impratio, meaninertia;
-  int any_damping, any_tendon_passive, any_joint_spring;
+  int any_damping, any_tendon_passive, any_joint_spring, any_tendon_limit;
   // body tables
   TabI b_parent, b_root, b_jntadr, b_jntnum, b_dofadr, b_dofnum, b_nchain, b_chain, b_mass_slot,
       b_sameframe, b_childadr, b_child, lvl_adr, lvl_body;
@@ -95,7 +96,7 @@ struct DevModel {
   TabF a_dynprm, a_gainprm, a_biasprm, a_ctrlrange, a_forcerange, a_gear, a_acc0, a_lengthrange;
   // scratch offsets (words) inside one world's shared-memory block
   int o_qpos, o_qvel, o_act, o_ctrl, o_warm, o_xpos, o_xquat, o_xmat, o_xipos, o_cdof, o_cinert, o_cvel, o_cdofdot,
-      o_cacc, o_cfrc, o_M, o_LD, o_tenL, o_tenV, o_tenJ, o_actF, o_bias, o_passive, o_qact, o_smooth, o_qaccs,
+      o_cacc, o_cfrc, o_M, o_tenL, o_tenV, o_tenJ, o_actF, o_bias, o_passive, o_qact, o_smooth, o_qaccs,
       o_qacc, o_qcon, o_actdot, o_grad, o_p, o_Mp, o_Ma, o_H, o_lim, o_con, o_row, o_misc, o_obs, o_wparam,
       scratch_words;
   const float* g_tables;     // global copy of the table block

@@ -383,7 +383,8 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   // ---------------------------------------------------------------- capacities + scratch layout
   int nlim = 0;
   for (int j = 0; j < njnt; j++) if (jlimited[j] && (jtype[j] == J_HINGE || jtype[j] == J_SLIDE)) nlim++;
-  { std::vector<int> tl = ivec(m, "tendon_limited"); for (int t = 0; t < ntendon; t++) if (tl[t]) nlim++; }
+  d.any_tendon_limit = 0;
+  { std::vector<int> tl = ivec(m, "tendon_limited"); for (int t = 0; t < ntendon; t++) if (tl[t]) { nlim++; d.any_tendon_limit = 1; } }
   d.nlim_max = std::max(1, std::min(nlim, 32));
   d.ncon_max = std::max(1, std::min(d.npair, 16));
   d.nefc_max = d.nlim_max + 4 * d.ncon_max;
@@ -400,7 +401,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   d.o_wparam = take(d.nparam4);
   d.o_xpos = take(3 * nbody); d.o_xquat = take(4 * nbody); d.o_xmat = take(9 * nbody); d.o_xipos = take(3 * nbody);
   d.o_cdof = take(6 * nv); d.o_cinert = take(10 * nbody);
-  d.o_M = take(nM); d.o_LD = take(nM);
+  d.o_M = take(nM);
   d.o_tenL = take(ntendon); d.o_tenV = take(ntendon); d.o_tenJ = take(ntendon * KT); d.o_actF = take(nu);
   d.o_bias = take(nv); d.o_passive = take(nv); d.o_qact = take(nv); d.o_smooth = take(nv); d.o_qaccs = take(nv);
   d.o_qacc = take(nv); d.o_qcon = take(nv); d.o_actdot = take(na);
@@ -414,6 +415,8 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     const int tmp_words = off - a0;
     d.o_H = a0;
     // dense Hessian: nv rows padded to a multiple of four + one right-hand-side row, row stride hs
+    d.nd = 0;
+    for (int i = 0; i < nv; i++) if (!dsimple[i]) d.nd = i + 1;
     d.hs = pad4(nv);
     if ((d.hs / 4) % 2 == 0) d.hs += 4;
     off = a0 + std::max(tmp_words, (pad4(nv) + 1) * d.hs);

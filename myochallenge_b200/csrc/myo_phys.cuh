@@ -284,74 +284,6 @@ MYO_PHASE void phase_mass_bias(int mslot, Ctx<G>& c) {
   c.tile.sync();
 }
 
-// mj_factorM restated in gather form so dofs of one depth factor in parallel without atomics:
-//   D(i)   = M(i,i) - sum_{k in desc(i)} L(k,i)^2 D(k)
-//   L(i,j) = (M(i,j) - sum_k L(k,i) L(k,j) D(k)) / D(i)      j ancestor of i
-// LD holds D on the diagonal slot and L on the ancestor slots. hdamp adds h*damping (mj_Euler).
-template <int G>
-MYO_PHASE void factor_sparse(int mslot, Ctx<G>& c, int oLD, int oM, float hdamp) {
-  MYO_M
-  float* LD = SO(oLD); const float* M = SO(oM);
-  for (int L = m.ndlevel - 1; L >= 0; L--) {
-    for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
-      const int i = m.dlvl_dof[idx];
-      const int adr = m.d_Madr[i], dep = m.d_depth[i];
-      if (m.d_simple[i]) {
-        LD[adr] = fmaxf(M[adr] + hdamp * m.d_damping[i], kMinVal);
-        for (int s = 1; s <= dep; s++) LD[adr + s] = 0.f;
-        continue;
-      }
-      float acc[KC];
-#pragma unroll
-      for (int s = 0; s < KC; s++) acc[s] = (s <= dep) ? M[adr + s] : 0.f;
-      acc[0] += hdamp * m.d_damping[i];
-      for (int kk = m.d_descadr[i]; kk < m.d_descadr[i + 1]; kk++) {
-        const int k = m.d_desc[kk];
-        const int ka = m.d_Madr[k], t = m.d_depth[k] - dep;
-        const float w = LD[ka + t] * LD[ka];
-#pragma unroll
-        for (int s = 0; s < KC; s++) if (s <= dep) acc[s] -= w * LD[ka + t + s];
-      }
-      const float d = fmaxf(acc[0], kMinVal);
-      const float inv = 1.f / d;
-      LD[adr] = d;
-#pragma unroll
-      for (int s = 1; s < KC; s++) if (s <= dep) LD[adr + s] = acc[s] * inv;
-    }
-    c.tile.sync();
-  }
-}
-// x <- (L' D L)^-1 x   (mj_solveLD, gather form)
-template <int G>
-MYO_PHASE void solve_sparse(int mslot, Ctx<G>& c, int oLD, int ox) {
-  MYO_M
-  const float* LD = SO(oLD); float* x = SO(ox);
-  for (int L = m.ndlevel - 1; L >= 0; L--) {     // x <- L^-T x, deepest first
-    for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
-      const int i = m.dlvl_dof[idx];
-      const int dep = m.d_depth[i];
-      float v = x[i];
-      for (int kk = m.d_descadr[i]; kk < m.d_descadr[i + 1]; kk++) {
-        const int k = m.d_desc[kk];
-        v -= LD[m.d_Madr[k] + m.d_depth[k] - dep] * x[k];
-      }
-      x[i] = v;
-    }
-    c.tile.sync();
-  }
-  for (int i = c.lane; i < m.nv; i += G) x[i] /= LD[m.d_Madr[i]];
-  c.tile.sync();
-  for (int L = 1; L < m.ndlevel; L++) {          // x <- L^-1 x, shallowest first
-    for (int idx = m.dlvl_adr[L] + c.lane; idx < m.dlvl_adr[L + 1]; idx += G) {
-      const int i = m.dlvl_dof[idx];
-      int adr = m.d_Madr[i] + 1, j = m.d_parent[i];
-      float v = x[i];
-      while (j >= 0) { v -= LD[adr++] * x[j]; j = m.d_parent[j]; }
-      x[i] = v;
-    }
-    c.tile.sync();
-  }
-}
 // y = M x using the sparse symmetric layout (mj_mulM)
 template <int G>
 MYO_PHASE void mul_M(int mslot, Ctx<G>& c, int oM, int ox, int oy) {
@@ -935,7 +867,6 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
     float* row = rows + r * ROW_WORDS;
     row[R_D] = 1.f / R;
     row[R_AREF] = -B * vel - K * imp * (lr[L_POS] - lr[L_MARGIN]);
-    reinterpret_cast<int*>(row)[R_BLOCK] = r;   // block = limit index, coef 0
   }
   // contacts: mixing (mj_contactParam), frame, support and basis Jacobians, rows
   int nrow_con = 0, nrow_valid = 0;
@@ -1070,7 +1001,6 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
       float* row = rows + (row0 + q) * ROW_WORDS;
       row[R_D] = D;
       row[R_AREF] = -B * vel + ref;
-      reinterpret_cast<int*>(row)[R_BLOCK] = (m.nlim_max + k) | ((dim == 3 ? q + 1 : 0) << 16);
     }
   }
   if (c.lane == 0) { misc[MI_NLIM] = nlim; misc[MI_NEFC] = nefc; }
@@ -1114,8 +1044,24 @@ MYO_PHASE void rows_dot(int mslot, Ctx<G>& c, int ox, int field, bool sub_aref) 
   c.tile.sync();
 }
 
+// Joint-limit rows touch one dof each and come joint-major (lower side, then upper side), so a lane per row can apply
+// them without write conflicts: the lane of a joint's first row also applies the second row if both sides are present.
+// fn(r) -> contribution weight of row r; apply(dof, sign * weight)
+template <int G, class W, class A>
+MYO_DI void for_joint_limit_rows(const DevModel& m, const Ctx<G>& c, int nlim, W weight, A apply) {
+  for (int r = c.lane; r < nlim; r += G) {
+    const float* lr = MYO_SMEM_WORDS + c.soff + m.o_lim + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
+    if (li[L_KIND] != EFC_LIMIT_JOINT) continue;
+    if (r > 0 && li[L_KIND - LIM_WORDS] == EFC_LIMIT_JOINT && li[L_ID - LIM_WORDS] == li[L_ID]) continue;
+    float v = lr[L_SIGN] * weight(r);
+    if (r + 1 < nlim && li[L_KIND + LIM_WORDS] == EFC_LIMIT_JOINT && li[L_ID + LIM_WORDS] == li[L_ID]) v += lr[L_SIGN + LIM_WORDS] * weight(r + 1);
+    apply(lim_idx(li, 0), v);
+  }
+}
+
 // out[dof] += sum_r J_r[dof] * w_r  with w_r = (jar_r < 0 ? -D_r jar_r : 0) * scale  (forces)
-// blocks applied one after the other, lanes across the block's support: no atomics, fixed order.
+// joint-limit rows in parallel (above); tendon-limit rows and contacts one after the other, lanes across the block's
+// support: no atomics, fixed order.
 template <int G>
 MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
   MYO_M
@@ -1123,13 +1069,19 @@ MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
   const int* misc = SI(o_misc);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
   const float* rows = SF(o_row);
-  for (int r = 0; r < nlim; r++) {
-    const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
-    const float* row = rows + r * ROW_WORDS;
-    const float f = row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] * scale : 0.f;
-    if (f != 0.f) for (int e = c.lane; e < li[L_NSUP]; e += G) out[lim_idx(li, e)] += lim_J(c.sp(), lr, li, e) * f;
-    c.tile.sync();
-  }
+  for_joint_limit_rows<G>(m, c, nlim,
+      [&](int r) { const float* row = rows + r * ROW_WORDS; return row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] * scale : 0.f; },
+      [&](int dof, float v) { out[dof] += v; });
+  c.tile.sync();
+  if (m.any_tendon_limit)
+    for (int r = 0; r < nlim; r++) {
+      const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
+      if (li[L_KIND] == EFC_LIMIT_JOINT) continue;
+      const float* row = rows + r * ROW_WORDS;
+      const float f = row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] * scale : 0.f;
+      if (f != 0.f) for (int e = c.lane; e < li[L_NSUP]; e += G) out[lim_idx(li, e)] += lim_J(c.sp(), lr, li, e) * f;
+      c.tile.sync();
+    }
   for (int k = 0; k < ncon; k++) {
     const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
     const int row0 = ci[C_ROW0];
@@ -1174,20 +1126,13 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
   const int* misc = SI(o_misc);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
   const float* rows = SF(o_row);
-  // joint limits touch one diagonal entry each: a lane per dof gathers its rows in row order
-  bool any_tendon_row = false;
-  for (int i = c.lane; i < nv; i += G) {
-    float add = 0.f;
-    for (int r = 0; r < nlim; r++) {
-      const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
-      if (li[L_KIND] != EFC_LIMIT_JOINT) { any_tendon_row = true; continue; }
-      const float* row = rows + r * ROW_WORDS;
-      if (row[R_JAR] < 0.f && lim_idx(li, 0) == i) add += row[R_D];
-    }
-    H[i * hs + i] += add;
-  }
-  if (c.tile.ballot(any_tendon_row)) {
-    c.tile.sync();
+  // joint limits touch one diagonal entry each (J = +-1)
+  for_joint_limit_rows<G>(m, c, nlim,
+      [&](int r) { const float* row = rows + r * ROW_WORDS; const float* lr = SF(o_lim) + r * LIM_WORDS;
+                   return row[R_JAR] < 0.f ? row[R_D] * lr[L_SIGN] : 0.f; },     // sign * (sign * D) = D
+      [&](int dof, float v) { H[dof * hs + dof] += v; });
+  c.tile.sync();
+  if (m.any_tendon_limit)
     for (int r = 0; r < nlim; r++) {
       const float* lr = SF(o_lim) + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
       if (li[L_KIND] == EFC_LIMIT_JOINT) continue;
@@ -1203,8 +1148,6 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
       }
       c.tile.sync();
     }
-  }
-  c.tile.sync();
   for (int k = 0; k < ncon; k++) {
     const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
     const int row0 = ci[C_ROW0];
@@ -1327,6 +1270,31 @@ MYO_PHASE void chol_factor_solve(Ctx<G>& c, int oH, int ox, int n, int hs) {
   c.tile.sync();
 }
 
+// x <- (M + hdamp diag(damping))^-1 x  (mj_factorM + mj_solveM; hdamp = h in mj_Euler's implicit damping).
+// The coupled dofs [0, m.nd) go through the dense blocked Cholesky above (the Newton Hessian's scratch is free outside
+// the constraint solve); the simple dofs behind them (free bodies with diagonal inertia: dof_simplenum) divide by
+// their diagonal entry.
+template <int G>
+MYO_PHASE void solve_M_dense(int mslot, Ctx<G>& c, int ox, float hdamp) {
+  MYO_M
+  float* H = SF(o_H); const float* M = SF(o_M); float* x = SO(ox);
+  const int nd = m.nd, hs = m.hs, n4 = (nd + 3) & ~3;
+  for (int k = c.lane; k < n4; k += G) H[n4 * hs + k] = k < nd ? x[k] : 0.f;
+  for (int i = nd + c.lane; i < n4; i += G)
+    for (int k = 0; k < n4; k++) H[i * hs + k] = (k == i) ? 1.f : 0.f;
+  for (int i = c.lane; i < nd; i += G) {
+    float4* row4 = reinterpret_cast<float4*>(H + i * hs);
+    for (int k = 0; k <= i / 4; k++) row4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int adr = m.d_Madr[i], j = i;
+    H[i * hs + i] = M[adr++] + hdamp * m.d_damping[i];
+    j = m.d_parent[j];
+    while (j >= 0) { H[i * hs + j] = M[adr++]; j = m.d_parent[j]; }
+  }
+  for (int i = nd + c.lane; i < m.nv; i += G) x[i] = x[i] / fmaxf(M[m.d_Madr[i]] + hdamp * m.d_damping[i], kMinVal);
+  c.tile.sync();
+  if (nd > 0) chol_factor_solve<G>(c, m.o_H, ox, nd, hs);
+}
+
 // optional per-phase cycle counters (development builds: -DMYO_PROFILE)
 #ifdef MYO_PROFILE
 __device__ unsigned long long g_prof[16];
@@ -1357,23 +1325,30 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
     return;
   }
   float* Ma = SF(o_Ma); float* grad = SF(o_grad); float* p = SF(o_p); float* Mp = SF(o_Mp);
-  const float* M = SF(o_M);
-  // warm start selection
-  float cost_w, cost_s;
+  // constraint rows in registers for the reductions and the line search: lane owns rows lane, lane + G, ...
+  constexpr int RMAX = 96 / G > 0 ? 96 / G : 1;     // nefc_max <= 32 + 4 * 16 (pack_model)
+  auto row_cost = [&](int field) {
+    float part = 0.f;
+    for (int r = c.lane; r < nefc; r += G) { const float* row = rows + r * ROW_WORDS; const float j = row[field]; if (j < 0.f) part += 0.5f * row[R_D] * j * j; }
+    return part;
+  };
+  // warm start selection; jar and M a are then kept current incrementally (jar += alpha J p, Ma += alpha M p)
   {
     const float* w = SF(o_warm);
-    rows_dot<G>(mslot, c, m.o_warm, R_JAR, true);
-    mul_M<G>(mslot, c, m.o_M, m.o_warm, m.o_Ma);
-    float part = 0.f;
-    for (int r = c.lane; r < nefc; r += G) { const float* row = rows + r * ROW_WORDS; if (row[R_JAR] < 0.f) part += 0.5f * row[R_D] * row[R_JAR] * row[R_JAR]; }
-    for (int i = c.lane; i < nv; i += G) part += 0.5f * (Ma[i] - fs[i]) * (w[i] - as[i]);
-    cost_w = tile_sum<G>(c, part);
     rows_dot<G>(mslot, c, m.o_qaccs, R_JAR, true);
-    part = 0.f;
-    for (int r = c.lane; r < nefc; r += G) { const float* row = rows + r * ROW_WORDS; if (row[R_JAR] < 0.f) part += 0.5f * row[R_D] * row[R_JAR] * row[R_JAR]; }
-    cost_s = tile_sum<G>(c, part);
+    const float cost_s = tile_sum<G>(c, row_cost(R_JAR));          // Gauss term vanishes at qacc_smooth
+    rows_dot<G>(mslot, c, m.o_warm, R_JP, true);
+    mul_M<G>(mslot, c, m.o_M, m.o_warm, m.o_Ma);
+    float part = row_cost(R_JP);
+    for (int i = c.lane; i < nv; i += G) part += 0.5f * (Ma[i] - fs[i]) * (w[i] - as[i]);
+    const float cost_w = tile_sum<G>(c, part);
     const bool use_smooth = !(cost_w <= cost_s);   // also catches NaN in the warm start
-    for (int i = c.lane; i < nv; i += G) a[i] = use_smooth ? as[i] : w[i];
+    if (use_smooth) {
+      for (int i = c.lane; i < nv; i += G) { a[i] = as[i]; Ma[i] = fs[i]; }     // M a_s = f_s
+    } else {
+      for (int i = c.lane; i < nv; i += G) a[i] = w[i];
+      for (int r = c.lane; r < nefc; r += G) rows[r * ROW_WORDS + R_JAR] = rows[r * ROW_WORDS + R_JP];
+    }
     c.tile.sync();
   }
   const float scale = 1.f / (m.meaninertia * (float)max(1, nv));
@@ -1381,8 +1356,6 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
   MYO_PH_BEGIN
   float prev_step = 3.0e38f;
   for (; iter < m.solver_iter; iter++) {
-    rows_dot<G>(mslot, c, m.o_qacc, R_JAR, true);
-    mul_M<G>(mslot, c, m.o_M, m.o_qacc, m.o_Ma);
     for (int i = c.lane; i < nv; i += G) grad[i] = Ma[i] - fs[i];
     c.tile.sync();
     rows_JT_force<G>(mslot, c, m.o_grad, -1.f);
@@ -1398,14 +1371,21 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
     float pMp = 0.f, gp = 0.f, pmax = 0.f;
     for (int i = c.lane; i < nv; i += G) { pMp += p[i] * Mp[i]; gp += (Ma[i] - fs[i]) * p[i]; pmax = fmaxf(pmax, fabsf(p[i])); }
     pMp = tile_sum<G>(c, pMp); gp = tile_sum<G>(c, gp); pmax = tile_max<G>(c, pmax);
+    float rD[RMAX], rJ[RMAX], rP[RMAX];
+#pragma unroll
+    for (int q = 0; q < RMAX; q++) {
+      const int r = c.lane + q * G;
+      if (r < nefc) { const float4 v = *reinterpret_cast<const float4*>(rows + r * ROW_WORDS); rD[q] = v.x; rJ[q] = v.z; rP[q] = v.w; }
+      else { rD[q] = 0.f; rJ[q] = 1.f; rP[q] = 0.f; }      // inert: never active, never changes side
+    }
     // exact line search on the piecewise-quadratic phi(alpha): safeguarded Newton on phi'
     float alpha = 0.f, lo = 0.f, hi = -1.f, d1_0 = 0.f;
     for (int ls = 0; ls < 12; ls++) {
       float d1 = 0.f, d2 = 0.f;
-      for (int r = c.lane; r < nefc; r += G) {
-        const float* row = rows + r * ROW_WORDS;
-        const float x = row[R_JAR] + alpha * row[R_JP];
-        if (x < 0.f) { d1 += row[R_D] * x * row[R_JP]; d2 += row[R_D] * row[R_JP] * row[R_JP]; }
+#pragma unroll
+      for (int q = 0; q < RMAX; q++) {
+        const float x = rJ[q] + alpha * rP[q];
+        if (x < 0.f) { d1 += rD[q] * x * rP[q]; d2 += rD[q] * rP[q] * rP[q]; }
       }
       d1 = tile_sum<G>(c, d1) + gp + alpha * pMp;
       d2 = tile_sum<G>(c, d2) + pMp;
@@ -1422,13 +1402,15 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
     // did any row change side along the step? if not, and the full Newton step was taken, a + p is the
     // exact minimiser of a cost that is quadratic on this active set: converged without a checking pass
     int changed = 0;
-    for (int r = c.lane; r < nefc; r += G) {
-      const float* row = rows + r * ROW_WORDS;
-      const float x0 = row[R_JAR], x1 = x0 + alpha * row[R_JP];
-      if ((x0 < 0.f) != (x1 < 0.f)) changed = 1;
+#pragma unroll
+    for (int q = 0; q < RMAX; q++) {
+      const float x1 = rJ[q] + alpha * rP[q];
+      if ((rJ[q] < 0.f) != (x1 < 0.f)) changed = 1;
+      const int r = c.lane + q * G;
+      if (r < nefc) rows[r * ROW_WORDS + R_JAR] = x1;
     }
     changed = c.tile.ballot(changed != 0) != 0u;
-    for (int i = c.lane; i < nv; i += G) a[i] += alpha * p[i];
+    for (int i = c.lane; i < nv; i += G) { a[i] += alpha * p[i]; Ma[i] += alpha * Mp[i]; }
     c.tile.sync();
     if (!changed && fabsf(alpha - 1.f) <= 1e-3f) { iter++; break; }
 #ifdef MYO_SOLVER_DEBUG
@@ -1440,8 +1422,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
     if (step <= 2e-5f * aref_mag || (iter > 0 && step >= 0.5f * prev_step && step <= 1e-3f * aref_mag)) { iter++; break; }
     prev_step = step;
   }
-  // final forces at the solution
-  rows_dot<G>(mslot, c, m.o_qacc, R_JAR, true);
+  // final forces at the solution (jar is current)
   for (int i = c.lane; i < nv; i += G) { qcon[i] = 0.f; SF(o_warm)[i] = a[i]; }
   c.tile.sync();
   rows_JT_force<G>(mslot, c, m.o_qcon, 1.f);
@@ -1457,10 +1438,9 @@ MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
   float* qacc = SF(o_qacc); float* qvel = SF(o_qvel); float* qpos = SF(o_qpos); float* act = SF(o_act);
   float* x = SF(o_grad);
   if (m.any_damping) {
-    factor_sparse<G>(mslot, c, m.o_LD, m.o_M, h);
     for (int i = c.lane; i < m.nv; i += G) x[i] = SF(o_smooth)[i] + SF(o_qcon)[i];
     c.tile.sync();
-    solve_sparse<G>(mslot, c, m.o_LD, m.o_grad);
+    solve_M_dense<G>(mslot, c, m.o_grad, h);
   } else {
     for (int i = c.lane; i < m.nv; i += G) x[i] = qacc[i];
     c.tile.sync();
@@ -1505,11 +1485,11 @@ MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status) {
   MYO_CTA_SYNC phase_tendon<G>(mslot, c, status); MYO_PH(1)
   MYO_CTA_SYNC phase_tree_backward<G>(mslot, c); MYO_PH(2)
   phase_mass_bias<G>(mslot, c); MYO_PH(3)
-  factor_sparse<G>(mslot, c, m.o_LD, m.o_M, 0.f); MYO_PH(4)
+  MYO_PH(4)
   MYO_CTA_SYNC phase_collision<G>(mslot, c, status); MYO_PH(5)
   MYO_CTA_SYNC phase_constraints<G>(mslot, c, status); MYO_PH(6)
   MYO_CTA_SYNC phase_actuation<G>(mslot, c); MYO_PH(7)
-  solve_sparse<G>(mslot, c, m.o_LD, m.o_qaccs); MYO_PH(8)
+  solve_M_dense<G>(mslot, c, m.o_qaccs, 0.f); MYO_PH(8)
   MYO_CTA_SYNC phase_solve<G>(mslot, c); MYO_PH(9)
 }
 template <int G>
