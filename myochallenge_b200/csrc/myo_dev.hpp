@@ -11,6 +11,8 @@ constexpr int KT = 8;    // max dofs a tendon's moment arm touches
 constexpr int KS = 16;   // max support of one contact block (chain A xor chain B)
 constexpr int LIM_WORDS = 8;    // scratch words per limit record
 constexpr int CON_WORDS = 104;  // scratch words per contact record
+constexpr int SEG_WORDS = 8;    // table words per tendon segment record
+constexpr int SEG_OUT = 9;      // scratch words per tendon segment result: length, KT moment-arm slots
 constexpr int ROW_WORDS = 4;    // scratch words per constraint row (one float4)
 
 enum { J_FREE = 0, J_BALL = 1, J_SLIDE = 2, J_HINGE = 3 };
@@ -89,6 +91,9 @@ struct DevModel {
   TabF s_pos;
   // tendons + wraps
   TabI t_adr, t_num, t_limited, t_ndof, t_dof, w_type, w_obj, w_side;
+  TabI seg_rec, seg_list, t_segadr, t_seg;   // tendon path segments (myo_pack.cpp)
+  TabF seg_invdiv;
+  int nseg;
   TabF t_range, t_margin, t_solref, t_solimp, t_invweight0, t_stiffness, t_damping, t_lengthspring,
       w_prm;
   // actuators

@@ -322,6 +322,82 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     }
     d.any_tendon_passive = any_tp;
   }
+  // segment tasks of the tendon phase: one record per path segment (site -> site, or site -> wrap geom -> site), wrap
+  // segments first so the divergent wrap geometry shares one pass; moment-arm lists per (body, body) pair:
+  // header n | rootA << 8 | rootB << 20, then n entries dof | slot << 8 | end << 16 (slot in the tendon's dof list)
+  std::vector<int> seg_rec, seg_list, t_segadr(ntendon + 1, 0), t_seg;
+  std::vector<float> seg_invdiv;
+  {
+    const double* wprm = m.d("wrap_prm");
+    auto make_list = [&](int t, int ba, int bb) -> int {
+      if (ba == bb) return -1;
+      int cp = 0;
+      if (rootid[ba] == rootid[bb])
+        while (cp < nchain[ba] && cp < nchain[bb] && chain[(size_t)ba * KC + cp] == chain[(size_t)bb * KC + cp]) cp++;
+      const int adr = (int)seg_list.size();
+      seg_list.push_back(0);
+      int n = 0;
+      for (int end = 0; end < 2; end++) {
+        const int body = end ? bb : ba;
+        for (int k = cp; k < nchain[body]; k++) {
+          const int dof = chain[(size_t)body * KC + k];
+          int slot = -1;
+          for (int e = 0; e < tndof[t]; e++) if (tdof[(size_t)t * KT + e] == dof) slot = e;
+          seg_list.push_back(dof | (slot << 8) | (end << 16));
+          n++;
+        }
+      }
+      seg_list[adr] = n | (rootid[ba] << 8) | (rootid[bb] << 20);
+      return adr;
+    };
+    struct Seg { int t, type, s0, s1, g, side, l0, l1, l2; float inv_div; };
+    std::vector<Seg> segs;
+    for (int t = 0; t < ntendon; t++) {
+      const int adr = tadr[t], num = tnum[t];
+      float inv_div = 1.f;
+      int j = 0;
+      while (j < num - 1) {
+        const int tp0 = wtype[adr + j], tp1 = wtype[adr + j + 1];
+        if (tp0 == W_PULLEY || tp1 == W_PULLEY) {
+          if (tp0 == W_PULLEY) inv_div = (float)(1.0 / wprm[adr + j]);
+          j++;
+          continue;
+        }
+        Seg sg{};
+        sg.t = t; sg.s0 = wobj[adr + j]; sg.inv_div = inv_div; sg.g = -1; sg.side = -1; sg.l1 = sg.l2 = -1; sg.type = 0;
+        const int b0 = sbody[sg.s0];
+        if (tp1 == W_SPHERE || tp1 == W_CYLINDER) {
+          sg.type = tp1; sg.g = wobj[adr + j + 1]; sg.side = wside[adr + j + 1]; sg.s1 = wobj[adr + j + 2];
+          const int bw = gbody[sg.g], b1 = sbody[sg.s1];
+          sg.l0 = make_list(t, b0, b1); sg.l1 = make_list(t, b0, bw); sg.l2 = make_list(t, bw, b1);
+          j += 2;
+        } else {
+          sg.s1 = wobj[adr + j + 1];
+          sg.l0 = make_list(t, b0, sbody[sg.s1]);
+          j += 1;
+        }
+        segs.push_back(sg);
+      }
+    }
+    std::vector<int> order;
+    for (int k = 0; k < (int)segs.size(); k++) if (segs[k].type != 0) order.push_back(k);
+    for (int k = 0; k < (int)segs.size(); k++) if (segs[k].type == 0) order.push_back(k);
+    std::vector<int> newid(segs.size(), 0);
+    for (int k = 0; k < (int)order.size(); k++) newid[order[k]] = k;
+    if (seg_list.size() >= (1u << 16) || nbody >= 4096 || nv >= 256) { status = MYO_E_LIMIT; return "tendon segment tables exceed their packed field widths"; }
+    for (int k : order) {
+      const Seg& sg = segs[k];
+      seg_rec.insert(seg_rec.end(), {sg.t | (sg.type << 16), sg.s0, sg.s1, sg.g, sg.side, sg.l0, sg.l1, sg.l2});
+      seg_invdiv.push_back(sg.inv_div);
+    }
+    for (int t = 0, k = 0; t < ntendon; t++) {
+      t_segadr[t] = (int)t_seg.size();
+      for (; k < (int)segs.size() && segs[k].t == t; k++) t_seg.push_back(newid[k]);
+    }
+    t_segadr[ntendon] = (int)t_seg.size();
+    d.nseg = (int)segs.size();
+  }
+  B.I(d.seg_rec, seg_rec); B.I(d.seg_list, seg_list); B.I(d.t_segadr, t_segadr); B.I(d.t_seg, t_seg); B.F(d.seg_invdiv, seg_invdiv);
   B.I(d.t_adr, tadr); B.I(d.t_num, tnum); B.I(d.t_limited, ivec(m, "tendon_limited")); B.I(d.t_ndof, tndof); B.I(d.t_dof, tdof);
   B.I(d.w_type, wtype); B.I(d.w_obj, wobj); B.I(d.w_side, wside);
   B.F(d.t_range, fvec(m, "tendon_range")); B.F(d.t_margin, fvec(m, "tendon_margin")); B.F(d.t_solref, fvec(m, "tendon_solref_lim"));
@@ -419,7 +495,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     for (int i = 0; i < nv; i++) if (!dsimple[i]) d.nd = i + 1;
     d.hs = pad4(nv);
     if ((d.hs / 4) % 2 == 0) d.hs += 4;
-    off = a0 + std::max(tmp_words, (pad4(nv) + 1) * d.hs);
+    off = a0 + std::max(std::max(tmp_words, (pad4(nv) + 1) * d.hs), pad4(d.nseg * SEG_OUT));   // + per-segment tendon results
   }
   // world stride: tiles of one warp land on different banks
   if (out.lanes < 32) { while (off % 32 != out.lanes) off += 4; }

@@ -423,24 +423,6 @@ MYO_PHASE float wrap_geom(float* wpnt, const float* x0, const float* x1, const f
   mulmatvec3(wpnt + 3, gmat, res + 3); add3(wpnt + 3, wpnt + 3, gpos);
   return wlen;
 }
-// d(point on body)/dq . dir for every dof on `body`'s chain past the common prefix `cp`
-MYO_DI void moment_half(const DevModel& m, const float* s, int body, int cp, const float* pnt, const float* dir, float scale,
-                        const int* tdof, int ntd, float* J) {
-  const int n = m.b_nchain[body];
-  if (n <= cp) return;
-  float off[3];
-  sub3(off, pnt, s + m.o_xipos + 3 * m.b_root[body]);
-  const float* cdof = s + m.o_cdof;
-  for (int k = cp; k < n; k++) {
-    const int d = m.b_chain[body * KC + k];
-    const float* cd = cdof + 6 * d;
-    float t[3];
-    cross3(t, cd, off);
-    const float v = ((cd[3] + t[0]) * dir[0] + (cd[4] + t[1]) * dir[1] + (cd[5] + t[2]) * dir[2]) * scale;
-#pragma unroll
-    for (int e = 0; e < KT; e++) if (e < ntd && tdof[e] == d) J[e] += v;
-  }
-}
 MYO_DI int common_prefix(const DevModel& m, int ba, int bb) {
   if (m.b_root[ba] != m.b_root[bb]) return 0;
   const int na = m.b_nchain[ba], nb = m.b_nchain[bb];
@@ -448,79 +430,93 @@ MYO_DI int common_prefix(const DevModel& m, int ba, int bb) {
   while (cp < na && cp < nb && m.b_chain[ba * KC + cp] == m.b_chain[bb * KC + cp]) cp++;
   return cp;
 }
-MYO_PHASE void segment_moment(int mslot, int soff, int ba, const float* pa, int bb, const float* pb, float inv_div,
-                           const int* tdof, int ntd, float* J) {
+// Moment-arm contributions of the straight piece pa -> pb (points fixed to two bodies) to its tendon:
+//   d|pb - pa| / dq_d = +-dir . (lin_d + ang_d x off) = +-(lin_d . dir + ang_d . (off x dir)),  cdof_d = (ang_d; lin_d)
+// for the dofs on either body's chain past their common prefix (- on the pa side, + on the pb side). The dof list of the
+// (body, body) pair is precomputed (myo_pack.cpp seg_list): header n | rootA << 8 | rootB << 20, entries
+// dof | slot << 8 | end << 16, slot = position in the tendon's dof list = position in the segment's result row.
+MYO_PHASE void segment_moment(int mslot, int soff, int list, const float* pa, const float* pb, float inv_div, float* out) {
   MYO_M
-  if (ba == bb) return;
+  if (list < 0) return;
   const float* s = MYO_SMEM_WORDS + soff;
-  float dir[3];
+  const int* L = m.seg_list + list;
+  const int head = L[0], n = head & 255;
+  float dir[3], oa[3], ob[3], ta[3], tb[3];
   sub3(dir, pb, pa);
   normalize3(dir);
-  const int cp = common_prefix(m, ba, bb);
-  moment_half(m, s, ba, cp, pa, dir, -inv_div, tdof, ntd, J);
-  moment_half(m, s, bb, cp, pb, dir, inv_div, tdof, ntd, J);
+  sub3(oa, pa, s + m.o_xipos + 3 * ((head >> 8) & 4095));
+  sub3(ob, pb, s + m.o_xipos + 3 * ((head >> 20) & 4095));
+  cross3(ta, oa, dir);
+  cross3(tb, ob, dir);
+  const float* cdof = s + m.o_cdof;
+  for (int k = 1; k <= n; k++) {
+    const int e = L[k];
+    const float* cd = cdof + 6 * (e & 255);
+    const bool end = (e >> 16) & 1;
+    const float* t = end ? tb : ta;
+    const float v = cd[0] * t[0] + cd[1] * t[1] + cd[2] * t[2] + cd[3] * dir[0] + cd[4] * dir[1] + cd[5] * dir[2];
+    out[1 + ((e >> 8) & 255)] += end ? v * inv_div : -v * inv_div;
+  }
 }
 
+// One lane per path segment (results to scratch: length and moment-arm slots), then one lane per tendon adds its
+// segments in path order: ten_length, ten_J (KT slots over the tendon's dof list) and ten_velocity = J . qvel.
+// The per-segment results live in the Newton Hessian's scratch (free outside the constraint solve).
 template <int G>
 MYO_PHASE void phase_tendon(int mslot, Ctx<G>& c, int* status) {
   MYO_M
+  float* res = SF(o_H);
+  for (int sg = c.lane; sg < m.nseg; sg += G) {
+    const int* rec = m.seg_rec + sg * SEG_WORDS;
+    const int type = rec[0] >> 16, id0 = rec[1], id1 = rec[2], g = rec[3], side = rec[4];
+    const float inv_div = m.seg_invdiv[sg];
+    float* out = res + sg * SEG_OUT;
+#pragma unroll
+    for (int e = 0; e < SEG_OUT; e++) out[e] = 0.f;
+    float x0[3], x1[3];
+    site_world(m, c.sp(), c.wpp(m), id0, x0);
+    site_world(m, c.sp(), c.wpp(m), id1, x1);
+    float wlen = -1.f, wp2[6];
+    if (g >= 0) {
+      const int bw = m.g_body[g];
+      float gpos[3], gmat[9];
+      mulmatvec3(gpos, SF(o_xmat) + 9 * bw, m.g_pos + 3 * g);
+      add3(gpos, gpos, SF(o_xpos) + 3 * bw);
+      mulmat3(gmat, SF(o_xmat) + 9 * bw, m.g_mat + 9 * g);
+      float sp[3];
+      if (side >= 0) site_world(m, c.sp(), c.wpp(m), side, sp);
+      float radius = m.g_size[3 * g];
+      if (m.g_size_slot[g] >= 0) radius = c.wpp(m)[m.g_size_slot[g]];
+      wlen = wrap_geom(wp2, x0, x1, gpos, gmat, radius, type, side >= 0 ? sp : nullptr);
+      if (wlen == -2.f) { *status |= ST_UNSUPPORTED; wlen = -1.f; }
+    }
+    if (wlen < 0.f) {
+      float d[3];
+      sub3(d, x1, x0);
+      out[0] = norm3(d) * inv_div;
+      segment_moment(mslot, c.soff, rec[5], x0, x1, inv_div, out);
+    } else {
+      float d0[3], d1[3];
+      sub3(d0, wp2, x0); sub3(d1, x1, wp2 + 3);
+      out[0] = (norm3(d0) + wlen + norm3(d1)) * inv_div;
+      segment_moment(mslot, c.soff, rec[6], x0, wp2, inv_div, out);
+      segment_moment(mslot, c.soff, rec[7], wp2 + 3, x1, inv_div, out);
+    }
+  }
+  c.tile.sync();
   const float* qvel = SF(o_qvel);
   for (int t = c.lane; t < m.ntendon; t += G) {
-    const int adr = m.t_adr[t], num = m.t_num[t], ntd = m.t_ndof[t];
+    const int ntd = m.t_ndof[t];
     const int* tdof = m.t_dof + t * KT;
     float J[KT];
 #pragma unroll
     for (int e = 0; e < KT; e++) J[e] = 0.f;
-    float len = 0.f, inv_div = 1.f;
-    int j = 0;
-    while (j < num - 1) {
-      const int tp0 = m.w_type[adr + j], tp1 = m.w_type[adr + j + 1];
-      if (tp0 == W_PULLEY || tp1 == W_PULLEY) {
-        if (tp0 == W_PULLEY) inv_div = 1.f / m.w_prm[adr + j];
-        j++;
-        continue;
-      }
-      const int id0 = m.w_obj[adr + j];
-      int id1 = m.w_obj[adr + j + 1];
-      float x0[3], x1[3];
-      site_world(m, c.sp(), c.wpp(m), id0, x0);
-      const int b0 = m.s_body[id0];
-      const bool isgeom = (tp1 == W_SPHERE || tp1 == W_CYLINDER);
-      float wlen = -1.f, wp2[6];
-      int bw = -1;
-      if (isgeom) {
-        const int g = id1;
-        id1 = m.w_obj[adr + j + 2];
-        site_world(m, c.sp(), c.wpp(m), id1, x1);
-        bw = m.g_body[g];
-        float gpos[3], gmat[9];
-        mulmatvec3(gpos, SF(o_xmat) + 9 * bw, m.g_pos + 3 * g);
-        add3(gpos, gpos, SF(o_xpos) + 3 * bw);
-        mulmat3(gmat, SF(o_xmat) + 9 * bw, m.g_mat + 9 * g);
-        const int side = m.w_side[adr + j + 1];
-        float sp[3];
-        if (side >= 0) site_world(m, c.sp(), c.wpp(m), side, sp);
-        float radius = m.g_size[3 * g];
-        if (m.g_size_slot[g] >= 0) radius = c.wpp(m)[m.g_size_slot[g]];
-        wlen = wrap_geom(wp2, x0, x1, gpos, gmat, radius, tp1, side >= 0 ? sp : nullptr);
-        if (wlen == -2.f) { *status |= ST_UNSUPPORTED; wlen = -1.f; }
-      } else {
-        site_world(m, c.sp(), c.wpp(m), id1, x1);
-      }
-      const int b1 = m.s_body[id1];
-      if (wlen < 0.f) {
-        float d[3];
-        sub3(d, x1, x0);
-        len += norm3(d) * inv_div;
-        segment_moment(mslot, c.soff, b0, x0, b1, x1, inv_div, tdof, ntd, J);
-      } else {
-        float d0[3], d1[3];
-        sub3(d0, wp2, x0); sub3(d1, x1, wp2 + 3);
-        len += (norm3(d0) + wlen + norm3(d1)) * inv_div;
-        segment_moment(mslot, c.soff, b0, x0, bw, wp2, inv_div, tdof, ntd, J);
-        segment_moment(mslot, c.soff, bw, wp2 + 3, b1, x1, inv_div, tdof, ntd, J);
-      }
-      j += isgeom ? 2 : 1;
+    float len = 0.f;
+    for (int k = m.t_segadr[t]; k < m.t_segadr[t + 1]; k++) {
+      const float* r = res + m.t_seg[k] * SEG_OUT;
+      len += r[0];
+#pragma unroll
+      for (int e = 0; e < KT; e++) J[e] += r[1 + e];
     }
     float vel = 0.f;
     float* Jo = SF(o_tenJ) + t * KT;
@@ -1482,10 +1478,10 @@ MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status) {
   MYO_M
   MYO_PH_BEGIN
   MYO_CTA_SYNC phase_tree_forward<G>(mslot, c, true); MYO_PH(0)
-  MYO_CTA_SYNC phase_tendon<G>(mslot, c, status); MYO_PH(1)
   MYO_CTA_SYNC phase_tree_backward<G>(mslot, c); MYO_PH(2)
   phase_mass_bias<G>(mslot, c); MYO_PH(3)
-  MYO_PH(4)
+  // the velocity-stage temporaries are dead from here on: the tendon phase reuses their scratch (with the Hessian's)
+  MYO_CTA_SYNC phase_tendon<G>(mslot, c, status); MYO_PH(1)
   MYO_CTA_SYNC phase_collision<G>(mslot, c, status); MYO_PH(5)
   MYO_CTA_SYNC phase_constraints<G>(mslot, c, status); MYO_PH(6)
   MYO_CTA_SYNC phase_actuation<G>(mslot, c); MYO_PH(7)
