@@ -204,8 +204,14 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   B.I(d.b_dofadr, dofadr); B.I(d.b_dofnum, dofnum); B.I(d.b_nchain, nchain); B.I(d.b_chain, chain);
   B.I(d.b_mass_slot, mass_slot); B.I(d.b_sameframe, sameframe); B.I(d.b_childadr, childadr); B.I(d.b_child, child);
   B.I(d.lvl_adr, lvl_adr); B.I(d.lvl_body, lvl_body);
-  B.F(d.b_pos, fvec(m, "body_pos")); B.F(d.b_quat, fvec(m, "body_quat")); B.F(d.b_ipos, fvec(m, "body_ipos"));
-  B.F(d.b_iquat, fvec(m, "body_iquat")); B.F(d.b_mass, fvec(m, "body_mass")); B.F(d.b_inertia, fvec(m, "body_inertia"));
+  {   // body frame / inertial frame orientations as matrices: the kinematic sweep composes rotation matrices
+    std::vector<float> bmat((size_t)nbody * 9), bimat((size_t)nbody * 9);
+    const double* bq = m.d("body_quat"); const double* biq = m.d("body_iquat");
+    for (int b = 0; b < nbody; b++) { quat2mat_h(bq + 4 * b, bmat.data() + 9 * b); quat2mat_h(biq + 4 * b, bimat.data() + 9 * b); }
+    B.F(d.b_mat, bmat); B.F(d.b_imat, bimat);
+  }
+  B.F(d.b_pos, fvec(m, "body_pos")); B.F(d.b_ipos, fvec(m, "body_ipos"));
+  B.F(d.b_mass, fvec(m, "body_mass")); B.F(d.b_inertia, fvec(m, "body_inertia"));
   B.F(d.b_invweight0, fvec(m, "body_invweight0"));
 
   // ---------------------------------------------------------------- joints / dofs
@@ -475,7 +481,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   auto take = [&](int words) { int o = off; off += pad4(std::max(words, 1)); return o; };
   d.o_qpos = take(nq); d.o_qvel = take(nv); d.o_act = take(na); d.o_ctrl = take(nu); d.o_warm = take(nv);
   d.o_wparam = take(d.nparam4);
-  d.o_xpos = take(3 * nbody); d.o_xquat = take(4 * nbody); d.o_xmat = take(9 * nbody); d.o_xipos = take(3 * nbody);
+  d.o_xpos = take(3 * nbody); d.o_xmat = take(9 * nbody); d.o_xipos = take(3 * nbody);
   d.o_cdof = take(6 * nv); d.o_cinert = take(10 * nbody);
   d.o_M = take(nM);
   d.o_tenL = take(ntendon); d.o_tenV = take(ntendon); d.o_tenJ = take(ntendon * KT); d.o_actF = take(nu);

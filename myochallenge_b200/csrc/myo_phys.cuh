@@ -44,113 +44,77 @@ MYO_DI int lim_idx(const int* li, int e) { return reinterpret_cast<const int*>(M
 MYO_DI float lim_J(const float* s, const float* lr, const int* li, int e) { return lr[L_SIGN] * s[li[L_JOFF] + e]; }
 
 // ------------------------------------------------------------------------------------------------
-// a10.1 kinematics + comPos (+ comVel + RNE forward when dyn): one level-synchronous sweep.
+// a10.1 kinematics + comPos (+ comVel + RNE forward when dyn).
 // Reference point of every kinematic tree = xipos of its root body (MuJoCo uses the subtree COM;
 // the dynamics are invariant to that choice and a nearby point keeps fp32 cross products small).
+// Split so that only a short composition sits on the serial level-by-level path:
+//   A  (all bodies at once)  pose of the body in its PARENT's frame from qpos (Rodrigues per hinge, no quaternions);
+//                            hinge axis | anchor and slide axis in the parent's frame, parked in the dof's cdof slot
+//   B  (level by level)      world pose = parent's world pose o local pose (27 + 9 FMA per body)
+//   C  (all at once)         xipos, then cdof about the tree reference, cinert
+//   D  (level by level, dyn) cvel, cdof_dot, cacc (mj_comVel / mj_rne forward), cfrc
+MYO_DI void rodrigues(float* R, const float* a, float ang) {
+  float sn, cs;
+  sincosf(ang, &sn, &cs);
+  const float t = 1.f - cs;
+  R[0] = cs + t * a[0] * a[0];        R[1] = t * a[0] * a[1] - sn * a[2]; R[2] = t * a[0] * a[2] + sn * a[1];
+  R[3] = t * a[0] * a[1] + sn * a[2]; R[4] = cs + t * a[1] * a[1];        R[5] = t * a[1] * a[2] - sn * a[0];
+  R[6] = t * a[0] * a[2] - sn * a[1]; R[7] = t * a[1] * a[2] + sn * a[0]; R[8] = cs + t * a[2] * a[2];
+}
+
 template <int G>
-MYO_PHASE void body_forward(int mslot, Ctx<G>& c, int b, bool dyn) {
+MYO_PHASE void body_local_pose(int mslot, Ctx<G>& c, int b) {
   MYO_M
   const float* qpos = SF(o_qpos);
-  const float* qvel = SF(o_qvel);
   float* cdof = SF(o_cdof);
-  const int pid = m.b_parent[b], jadr = m.b_jntadr[b], jnum = m.b_jntnum[b];
-  float pos[3], q[4];
-  const bool is_free = (jnum == 1 && m.j_type[jadr] == J_FREE);
-  if (is_free) {
+  const int jadr = m.b_jntadr[b], jnum = m.b_jntnum[b];
+  float R[9], pos[3];
+  if (jnum == 1 && m.j_type[jadr] == J_FREE) {
     const int qa = m.j_qposadr[jadr];
+    float q[4] = {qpos[qa + 3], qpos[qa + 4], qpos[qa + 5], qpos[qa + 6]};
     pos[0] = qpos[qa]; pos[1] = qpos[qa + 1]; pos[2] = qpos[qa + 2];
-    q[0] = qpos[qa + 3]; q[1] = qpos[qa + 4]; q[2] = qpos[qa + 5]; q[3] = qpos[qa + 6];
     normalize4(q);
+    quat2mat(R, q);
   } else {
-    const float* pp = SF(o_xpos) + 3 * pid;
-    const float* pR = SF(o_xmat) + 9 * pid;
-    float v[3];
-    mulmatvec3(v, pR, m.b_pos + 3 * b);
-    add3(pos, v, pp);
-    mulquat(q, SF(o_xquat) + 4 * pid, m.b_quat + 4 * b);
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = m.b_mat[9 * b + k];
+    cpy3(pos, m.b_pos + 3 * b);
     for (int j = jadr; j < jadr + jnum; j++) {
       const int qa = m.j_qposadr[j], da = m.j_dofadr[j];
       const float dq = qpos[qa] - m.j_qpos0[j];
       float ax[3];
-      rotvecquat(ax, m.j_axis + 3 * j, q);
+      mulmatvec3(ax, R, m.j_axis + 3 * j);
       if (m.j_type[j] == J_SLIDE) {
         pos[0] += ax[0] * dq; pos[1] += ax[1] * dq; pos[2] += ax[2] * dq;
-        cdof[6 * da] = 0.f; cdof[6 * da + 1] = 0.f; cdof[6 * da + 2] = 0.f;
-        cdof[6 * da + 3] = ax[0]; cdof[6 * da + 4] = ax[1]; cdof[6 * da + 5] = ax[2];
-      } else {  // hinge: stash axis | anchor, finished below once the tree reference is known
-        float anchor[3], ql[4], vec[3];
-        rotvecquat(anchor, m.j_pos + 3 * j, q);
+        cdof[6 * da] = ax[0]; cdof[6 * da + 1] = ax[1]; cdof[6 * da + 2] = ax[2];
+      } else {
+        float anchor[3], Rj[9], vec[3];
+        mulmatvec3(anchor, R, m.j_pos + 3 * j);
         add3(anchor, anchor, pos);
-        float sn, cs;
-        sincosf(0.5f * dq, &sn, &cs);
-        ql[0] = cs; ql[1] = m.j_axis[3 * j] * sn; ql[2] = m.j_axis[3 * j + 1] * sn; ql[3] = m.j_axis[3 * j + 2] * sn;
-        mulquat(q, q, ql);
-        rotvecquat(vec, m.j_pos + 3 * j, q);
+        rodrigues(Rj, m.j_axis + 3 * j, dq);
+        mulmat3(R, R, Rj);
+        mulmatvec3(vec, R, m.j_pos + 3 * j);
         sub3(pos, anchor, vec);
         cdof[6 * da] = ax[0]; cdof[6 * da + 1] = ax[1]; cdof[6 * da + 2] = ax[2];
         cdof[6 * da + 3] = anchor[0]; cdof[6 * da + 4] = anchor[1]; cdof[6 * da + 5] = anchor[2];
       }
     }
-    normalize4(q);
   }
-  float R[9];
-  quat2mat(R, q);
   float* xp = SF(o_xpos) + 3 * b;
-  float* xq = SF(o_xquat) + 4 * b;
   float* xm = SF(o_xmat) + 9 * b;
   cpy3(xp, pos);
-  xq[0] = q[0]; xq[1] = q[1]; xq[2] = q[2]; xq[3] = q[3];
 #pragma unroll
   for (int k = 0; k < 9; k++) xm[k] = R[k];
-  float ip[3];
-  mulmatvec3(ip, R, m.b_ipos + 3 * b);
-  add3(ip, ip, pos);
-  cpy3(SF(o_xipos) + 3 * b, ip);
-  const int root = m.b_root[b];
-  float cref[3];
-  if (root == b) cpy3(cref, ip); else cpy3(cref, SF(o_xipos) + 3 * root);
+}
 
-  // finish cdof (mj_comPos)
-  if (is_free) {
-    const int da = m.j_dofadr[jadr];
-    float off[3];
-    sub3(off, cref, pos);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      float* t = cdof + 6 * (da + k);
-      t[0] = t[1] = t[2] = 0.f; t[3] = (k == 0); t[4] = (k == 1); t[5] = (k == 2);
-      float* r = cdof + 6 * (da + 3 + k);
-      float ax[3] = {R[k], R[3 + k], R[6 + k]};
-      cpy3(r, ax);
-      cross3(r + 3, ax, off);
-    }
-  } else {
-    for (int j = jadr; j < jadr + jnum; j++) {
-      if (m.j_type[j] != J_HINGE) continue;
-      float* t = cdof + 6 * m.j_dofadr[j];
-      float off[3];
-      sub3(off, cref, t + 3);
-      cross3(t + 3, t, off);
-    }
-  }
-  if (!dyn) return;
-
-  // cinert
-  {
-    float off[3], mass = m.b_mass[b];
-    const int slot = m.b_mass_slot[b];
-    if (slot >= 0) mass = c.wpp(m)[slot];
-    sub3(off, ip, cref);
-    float* ci = SF(o_cinert) + 10 * b;
-    if (m.b_sameframe[b]) inert_com(ci, m.b_inertia + 3 * b, R, off, mass);
-    else {
-      float qi[4], Ri[9];
-      mulquat(qi, q, m.b_iquat + 4 * b);
-      quat2mat(Ri, qi);
-      inert_com(ci, m.b_inertia + 3 * b, Ri, off, mass);
-    }
-  }
-  // cvel, cdof_dot (mj_comVel) and cacc, cfrc (mj_rne forward, flg_acc = 0)
+// mj_comVel + mj_rne forward (flg_acc = 0) for one body, parent already done
+template <int G>
+MYO_PHASE void body_velocity(int mslot, Ctx<G>& c, int b) {
+  MYO_M
+  const float* qvel = SF(o_qvel);
+  const float* cdof = SF(o_cdof);
+  const int pid = m.b_parent[b], jadr = m.b_jntadr[b], jnum = m.b_jntnum[b];
+  const bool is_free = (jnum == 1 && m.j_type[jadr] == J_FREE);
   float cv[6], ca[6];
   {
     const float* pv = SF(o_cvel) + 6 * pid;
@@ -209,9 +173,8 @@ template <int G>
 MYO_PHASE void phase_tree_forward(int mslot, Ctx<G>& c, bool dyn) {
   MYO_M
   if (c.lane == 0) {
-    float* xp = SF(o_xpos); float* xq = SF(o_xquat); float* xm = SF(o_xmat); float* xi = SF(o_xipos);
+    float* xp = SF(o_xpos); float* xm = SF(o_xmat); float* xi = SF(o_xipos);
     xp[0] = xp[1] = xp[2] = 0.f; xi[0] = xi[1] = xi[2] = 0.f;
-    xq[0] = 1.f; xq[1] = xq[2] = xq[3] = 0.f;
 #pragma unroll
     for (int k = 0; k < 9; k++) xm[k] = (k % 4 == 0) ? 1.f : 0.f;
     if (dyn) {
@@ -223,9 +186,81 @@ MYO_PHASE void phase_tree_forward(int mslot, Ctx<G>& c, bool dyn) {
       for (int k = 0; k < 10; k++) ci[k] = 0.f;
     }
   }
+  // A: poses in the parent's frame
+  for (int b = 1 + c.lane; b < m.nbody; b += G) body_local_pose<G>(mslot, c, b);
   c.tile.sync();
+  // B: compose down the tree (children of the world are already in world coordinates)
+  for (int L = 1; L < m.nlevel; L++) {
+    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) {
+      const int b = m.lvl_body[i], pid = m.b_parent[b];
+      float* xp = SF(o_xpos) + 3 * b; float* xm = SF(o_xmat) + 9 * b;
+      const float* pR = SF(o_xmat) + 9 * pid;
+      float v[3];
+      mulmatvec3(v, pR, xp);
+      add3(xp, v, SF(o_xpos) + 3 * pid);
+      mulmat3(xm, pR, xm);
+    }
+    c.tile.sync();
+  }
+  // C: inertial frame origins, then cdof about the tree reference and cinert
+  for (int b = 1 + c.lane; b < m.nbody; b += G) {
+    float ip[3];
+    mulmatvec3(ip, SF(o_xmat) + 9 * b, m.b_ipos + 3 * b);
+    add3(SF(o_xipos) + 3 * b, ip, SF(o_xpos) + 3 * b);
+  }
+  c.tile.sync();
+  float* cdof = SF(o_cdof);
+  for (int j = c.lane; j < m.njnt; j += G) {
+    const int b = m.j_body[j], pid = m.b_parent[b], da = m.j_dofadr[j], jt = m.j_type[j];
+    const float* cref = SF(o_xipos) + 3 * m.b_root[b];
+    if (jt == J_FREE) {
+      const float* R = SF(o_xmat) + 9 * b;
+      float off[3];
+      sub3(off, cref, SF(o_xpos) + 3 * b);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        float* t = cdof + 6 * (da + k);
+        t[0] = t[1] = t[2] = 0.f; t[3] = (k == 0); t[4] = (k == 1); t[5] = (k == 2);
+        float* r = cdof + 6 * (da + 3 + k);
+        float ax[3] = {R[k], R[3 + k], R[6 + k]};
+        cpy3(r, ax);
+        cross3(r + 3, ax, off);
+      }
+    } else {
+      const float* pR = SF(o_xmat) + 9 * pid;
+      float* t = cdof + 6 * da;
+      float ax[3];
+      mulmatvec3(ax, pR, t);
+      if (jt == J_SLIDE) { t[0] = t[1] = t[2] = 0.f; cpy3(t + 3, ax); }
+      else {
+        float anchor[3], off[3];
+        mulmatvec3(anchor, pR, t + 3);
+        add3(anchor, anchor, SF(o_xpos) + 3 * pid);
+        sub3(off, cref, anchor);
+        cpy3(t, ax);
+        cross3(t + 3, ax, off);
+      }
+    }
+  }
+  if (!dyn) { c.tile.sync(); return; }
+  for (int b = 1 + c.lane; b < m.nbody; b += G) {
+    float off[3], mass = m.b_mass[b];
+    const int slot = m.b_mass_slot[b];
+    if (slot >= 0) mass = c.wpp(m)[slot];
+    sub3(off, SF(o_xipos) + 3 * b, SF(o_xipos) + 3 * m.b_root[b]);
+    float* ci = SF(o_cinert) + 10 * b;
+    const float* R = SF(o_xmat) + 9 * b;
+    if (m.b_sameframe[b]) inert_com(ci, m.b_inertia + 3 * b, R, off, mass);
+    else {
+      float Ri[9];
+      mulmat3(Ri, R, m.b_imat + 9 * b);
+      inert_com(ci, m.b_inertia + 3 * b, Ri, off, mass);
+    }
+  }
+  c.tile.sync();
+  // D: velocities, bias accelerations and forces down the tree
   for (int L = 0; L < m.nlevel; L++) {
-    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) body_forward<G>(mslot, c, m.lvl_body[i], dyn);
+    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) body_velocity<G>(mslot, c, m.lvl_body[i]);
     c.tile.sync();
   }
 }
