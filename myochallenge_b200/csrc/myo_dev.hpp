@@ -78,7 +78,7 @@ struct DevModel {
   TabI j_type, j_qposadr, j_dofadr, j_body, j_limited;
   TabF j_pos, j_axis, j_qpos0, j_range, j_margin, j_solref, j_solimp, j_stiffness, j_qpos_spring;
   // dofs
-  TabI d_body, d_parent, d_simple, d_Madr, d_depth, d_descadr, d_desc, dlvl_adr, dlvl_dof, d_jnt,
+  TabI d_body, d_parent, d_simple, d_Madr, d_depth, d_descadr, d_desc, d_jnt,
       d_actadr, d_actlist;
   TabF d_armature, d_damping, d_invweight0, d_M0;
   // geoms
@@ -90,12 +90,11 @@ struct DevModel {
   TabI s_body, s_pos_slot;
   TabF s_pos;
   // tendons + wraps
-  TabI t_adr, t_num, t_limited, t_ndof, t_dof, w_type, w_obj, w_side;
+  TabI t_limited, t_ndof, t_dof;
   TabI seg_rec, seg_list, t_segadr, t_seg;   // tendon path segments (myo_pack.cpp)
   TabF seg_invdiv;
   int nseg;
-  TabF t_range, t_margin, t_solref, t_solimp, t_invweight0, t_stiffness, t_damping, t_lengthspring,
-      w_prm;
+  TabF t_range, t_margin, t_solref, t_solimp, t_invweight0, t_stiffness, t_damping, t_lengthspring;
   // actuators
   TabI a_tendon, a_dyntype, a_gaintype, a_biastype, a_ctrllimited, a_forcelimited;
   TabF a_dynprm, a_gainprm, a_biasprm, a_ctrlrange, a_forcerange, a_gear, a_acc0, a_lengthrange;

@@ -12,6 +12,17 @@ namespace myo {
 constexpr float kMinVal = 1e-15f;
 constexpr float kPi = 3.14159265358979323846f;
 
+// 1/sqrt(x) for x known to be a normal positive number (callers clamp to kMinVal): the bare MUFU.RSQ, without the
+// denormal rescaling rsqrtf() wraps around it
+MYO_DI float rsqrt_pos(float x) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return 1.f / sqrtf(x);
+#endif
+}
 MYO_DI float dot3(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 MYO_DI void cross3(float* r, const float* a, const float* b) {
   float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];

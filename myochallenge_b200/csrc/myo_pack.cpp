@@ -404,12 +404,11 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     d.nseg = (int)segs.size();
   }
   B.I(d.seg_rec, seg_rec); B.I(d.seg_list, seg_list); B.I(d.t_segadr, t_segadr); B.I(d.t_seg, t_seg); B.F(d.seg_invdiv, seg_invdiv);
-  B.I(d.t_adr, tadr); B.I(d.t_num, tnum); B.I(d.t_limited, ivec(m, "tendon_limited")); B.I(d.t_ndof, tndof); B.I(d.t_dof, tdof);
-  B.I(d.w_type, wtype); B.I(d.w_obj, wobj); B.I(d.w_side, wside);
+  B.I(d.t_limited, ivec(m, "tendon_limited")); B.I(d.t_ndof, tndof); B.I(d.t_dof, tdof);
   B.F(d.t_range, fvec(m, "tendon_range")); B.F(d.t_margin, fvec(m, "tendon_margin")); B.F(d.t_solref, fvec(m, "tendon_solref_lim"));
   B.F(d.t_solimp, fvec(m, "tendon_solimp_lim")); B.F(d.t_invweight0, fvec(m, "tendon_invweight0"));
   B.F(d.t_stiffness, fvec(m, "tendon_stiffness")); B.F(d.t_damping, fvec(m, "tendon_damping"));
-  B.F(d.t_lengthspring, fvec(m, "tendon_lengthspring")); B.F(d.w_prm, fvec(m, "wrap_prm"));
+  B.F(d.t_lengthspring, fvec(m, "tendon_lengthspring"));
 
   // ---------------------------------------------------------------- actuators
   std::vector<int> atendon(nu, 0);
@@ -440,7 +439,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   }
   actadr[nv] = (int)actlist.size();
   B.I(d.d_body, dbody); B.I(d.d_parent, dparent); B.I(d.d_simple, dsimple); B.I(d.d_Madr, dMadr); B.I(d.d_depth, ddepth);
-  B.I(d.d_descadr, descadr); B.I(d.d_desc, desc); B.I(d.dlvl_adr, dlvl_adr); B.I(d.dlvl_dof, dlvl_dof); B.I(d.d_jnt, djnt);
+  B.I(d.d_descadr, descadr); B.I(d.d_desc, desc); B.I(d.d_jnt, djnt);
   B.I(d.d_actadr, actadr); B.I(d.d_actlist, actlist);
   B.F(d.d_armature, fvec(m, "dof_armature")); B.F(d.d_damping, fvec(m, "dof_damping"));
   B.F(d.d_invweight0, fvec(m, "dof_invweight0")); B.F(d.d_M0, fvec(m, "dof_M0"));
@@ -482,18 +481,26 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   d.o_qpos = take(nq); d.o_qvel = take(nv); d.o_act = take(na); d.o_ctrl = take(nu); d.o_warm = take(nv);
   d.o_wparam = take(d.nparam4);
   d.o_xpos = take(3 * nbody); d.o_xmat = take(9 * nbody); d.o_xipos = take(3 * nbody);
-  d.o_cdof = take(6 * nv); d.o_cinert = take(10 * nbody);
+  d.o_cdof = take(6 * nv);
   d.o_M = take(nM);
   d.o_tenL = take(ntendon); d.o_tenV = take(ntendon); d.o_tenJ = take(ntendon * KT); d.o_actF = take(nu);
   d.o_bias = take(nv); d.o_passive = take(nv); d.o_qact = take(nv); d.o_smooth = take(nv); d.o_qaccs = take(nv);
   d.o_qacc = take(nv); d.o_qcon = take(nv); d.o_actdot = take(na);
-  d.o_grad = take(nv); d.o_p = take(nv); d.o_Mp = take(nv); d.o_Ma = take(nv);
+  // solver vectors; the observation (assembled after the last substep, when they are dead) shares their words
+  {
+    const int a0 = off;
+    d.o_grad = take(nv); d.o_p = take(nv); d.o_Mp = take(nv); d.o_Ma = take(nv);
+    d.o_obs = a0;
+    off = a0 + std::max(off - a0, pad4(d.nobs));
+  }
   d.o_lim = take(d.nlim_max * LIM_WORDS); d.o_con = take(d.ncon_max * CON_WORDS); d.o_row = take(d.nefc_max * ROW_WORDS);
-  d.o_misc = take(MI_WORDS); d.o_obs = take(d.nobs);
-  // velocity-stage temporaries are dead once qfrc_bias exists; the Newton Hessian reuses their words
+  d.o_misc = take(MI_WORDS);
+  // velocity-stage temporaries and the composite inertias are dead once M and qfrc_bias exist; the Newton Hessian
+  // (and the tendon phase's per-segment results) reuse their words
   {
     const int a0 = off;
     d.o_cvel = take(6 * nbody); d.o_cdofdot = take(6 * nv); d.o_cacc = take(6 * nbody); d.o_cfrc = take(6 * nbody);
+    d.o_cinert = take(10 * nbody);
     const int tmp_words = off - a0;
     d.o_H = a0;
     // dense Hessian: nv rows padded to a multiple of four + one right-hand-side row, row stride hs

@@ -1261,13 +1261,13 @@ MYO_PHASE void chol_factor_solve(Ctx<G>& c, int oH, int ox, int n, int hs) {
         const float d10 = c.tile.shfl(acc.x, 1 % G), d11 = c.tile.shfl(acc.y, 1 % G);
         const float d20 = c.tile.shfl(acc.x, 2 % G), d21 = c.tile.shfl(acc.y, 2 % G), d22 = c.tile.shfl(acc.z, 2 % G);
         const float d30 = c.tile.shfl(acc.x, 3 % G), d31 = c.tile.shfl(acc.y, 3 % G), d32 = c.tile.shfl(acc.z, 3 % G), d33 = c.tile.shfl(acc.w, 3 % G);
-        inv0 = rsqrtf(fmaxf(d00, kMinVal));
+        inv0 = rsqrt_pos(fmaxf(d00, kMinVal));
         l10 = d10 * inv0; l20 = d20 * inv0; l30 = d30 * inv0;
-        inv1 = rsqrtf(fmaxf(d11 - l10 * l10, kMinVal));
+        inv1 = rsqrt_pos(fmaxf(d11 - l10 * l10, kMinVal));
         l21 = (d21 - l20 * l10) * inv1; l31 = (d31 - l30 * l10) * inv1;
-        inv2 = rsqrtf(fmaxf(d22 - l20 * l20 - l21 * l21, kMinVal));
+        inv2 = rsqrt_pos(fmaxf(d22 - l20 * l20 - l21 * l21, kMinVal));
         l32 = (d32 - l30 * l20 - l31 * l21) * inv2;
-        inv3 = rsqrtf(fmaxf(d33 - l30 * l30 - l31 * l31 - l32 * l32, kMinVal));
+        inv3 = rsqrt_pos(fmaxf(d33 - l30 * l30 - l31 * l31 - l32 * l32, kMinVal));
       }
       float4 r;
       r.x = acc.x * inv0;
@@ -1275,10 +1275,11 @@ MYO_PHASE void chol_factor_solve(Ctx<G>& c, int oH, int ox, int n, int hs) {
       r.z = (acc.z - r.x * l20 - r.y * l21) * inv2;
       r.w = (acc.w - r.x * l30 - r.y * l31 - r.z * l32) * inv3;
       const int q = i - J;     // rows of the diagonal block: inverse pivot on the diagonal, zeros above it
-      if (q == 0) { r.x = inv0; r.y = 0.f; r.z = 0.f; r.w = 0.f; }
-      else if (q == 1) { r.y = inv1; r.z = 0.f; r.w = 0.f; }
-      else if (q == 2) { r.z = inv2; r.w = 0.f; }
-      else if (q == 3) r.w = inv3;
+      const bool q0 = q == 0, q1 = q == 1, q2 = q == 2, q3 = q == 3;
+      r.x = q0 ? inv0 : r.x;
+      r.y = q1 ? inv1 : (q0 ? 0.f : r.y);
+      r.z = q2 ? inv2 : ((q0 || q1) ? 0.f : r.z);
+      r.w = q3 ? inv3 : ((q0 || q1 || q2) ? 0.f : r.w);
       if (on) *reinterpret_cast<float4*>(Li + J) = r;
     }
     c.tile.sync();
@@ -1505,7 +1506,20 @@ MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
 // All warps of a CTA walk the phases together: the step is ~200 KB of straight-line code, far more
 // than the instruction cache holds, so keeping the CTA inside one phase at a time lets every fetched
 // line serve all of its warps. (Every tile of the CTA executes every phase of every substep.)
-#define MYO_CTA_SYNC __syncthreads();
+#ifndef MYO_LOCKSTEP_WARPS
+#define MYO_LOCKSTEP_WARPS 0      // 0: the whole CTA walks the phases together; k: groups of k warps do (named barriers)
+#endif
+MYO_DI void lockstep_sync() {
+#if defined(MYO_EMUL) || MYO_LOCKSTEP_WARPS == 0
+  __syncthreads();
+#else
+  const unsigned nw = blockDim.x >> 5;
+  if (nw % MYO_LOCKSTEP_WARPS) { __syncthreads(); return; }
+  const unsigned group = (threadIdx.x >> 5) / MYO_LOCKSTEP_WARPS;
+  asm volatile("bar.sync %0, %1;" ::"r"(1u + group), "r"(32u * MYO_LOCKSTEP_WARPS) : "memory");
+#endif
+}
+#define MYO_CTA_SYNC lockstep_sync();
 
 // one full mj_step on the world in scratch
 template <int G>

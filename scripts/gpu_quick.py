@@ -30,7 +30,10 @@ if __name__ == "__main__":
     ap.add_argument("--model", default="all")
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--lib", default="", help="alternate build of the library (development experiments)")
     args = ap.parse_args()
+    if args.lib:
+        _capi._LIB = _capi.bind(args.lib)
     if args.model in ("all", "finger"):
         for n in ([args.n] if args.n else [4096, 65536]):
             run("finger/myo_finger_v0.mjb", _capi.TASK_POSE, n, args.steps)
