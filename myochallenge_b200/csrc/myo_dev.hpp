@@ -10,7 +10,7 @@ constexpr int KC = 8;    // max dofs on a body's ancestor chain (myoHand distal 
 constexpr int KT = 8;    // max dofs a tendon's moment arm touches
 constexpr int KS = 16;   // max support of one contact block (chain A xor chain B)
 constexpr int LIM_WORDS = 8;    // scratch words per limit record
-constexpr int CON_WORDS = 104;  // scratch words per contact record
+constexpr int CON_WORDS = 24;   // scratch words per contact record
 constexpr int SEG_WORDS = 8;    // table words per tendon segment record
 constexpr int SEG_OUT = 9;      // scratch words per tendon segment result: length, KT moment-arm slots
 constexpr int ROW_WORDS = 4;    // scratch words per constraint row (one float4)
@@ -27,9 +27,11 @@ enum { EFC_LIMIT_JOINT = 3, EFC_LIMIT_TENDON = 4, EFC_CONTACT_FRICTIONLESS = 5, 
 // constant 1 kept in o_misc for a joint, the tendon's ten_J row for a tendon) times L_SIGN
 enum { L_KIND = 0, L_ID = 1, L_NSUP = 2, L_POS = 3, L_MARGIN = 4, L_SIGN = 5, L_IOFF = 6, L_JOFF = 7 };
 // contact record layout
+// The contact Jacobian is not stored: its support is the dofs of chain(body A) and chain(body B) past their common
+// prefix (C_CP = prefix length | count on the A side << 8; C_NSUP entries in all, A side first) and an entry is
+// recomputed from cdof, the contact point and the frame wherever it is needed (contact_entry in myo_phys.cuh).
 enum { C_G1 = 0, C_G2 = 1, C_DIM = 2, C_NSUP = 3, C_DIST = 4, C_MARGIN = 5, C_MU = 6, C_ROW0 = 7, C_POS = 8 /*3*/,
-       C_FRAME = 11 /*9*/, C_SOLREF = 20 /*2*/, C_SOLIMP = 22 /*5*/, C_BA = 27, C_BB = 28, C_FRI = 29 /*3*/,
-       C_IDX = 32 /*KS ints*/, C_N = 48 /*3*KS floats*/ };
+       C_FRAME = 11 /*9*/, C_BA = 20, C_BB = 21, C_CP = 22 };
 // row record
 enum { R_D = 0, R_AREF = 1, R_JAR = 2, R_JP = 3 };
 
@@ -66,7 +68,7 @@ struct DevModel {
   int nq4, nv4, na4, nu4, nparam, nparam4, nobs, nobs4;
   int nlim_max, ncon_max, nefc_max;
   int nd;   // dofs [0, nd) couple through the mass matrix; dofs [nd, nv) are simple (diagonal)
-  int hs;   // row stride (words) of the dense Newton Hessian: >= nv, multiple of 4 with hs/4 odd (conflict-free float4 rows)
+  TabI h_roff;   // word offset of row i of the packed lower-triangular Newton Hessian (rows 0..pad4(nv); the last is the rhs)
   int solver_iter;
   float solver_tol, timestep, gravity[3], inv_sqrt_impratio, meaninertia;
   int any_damping, any_tendon_passive, any_joint_spring, any_tendon_limit;

@@ -239,9 +239,11 @@ __global__ void extract_kernel(const __grid_constant__ DevModel m, const float* 
             else {
               const float mu = cr[C_MU];
               for (int e = 0; e < ci[C_NSUP]; e++) {
-                float v = cr[C_N + e];
-                if (nr == 4) v += ((q & 1) ? -mu : mu) * ((q < 2) ? cr[C_N + KS + e] : cr[C_N + 2 * KS + e]);
-                of[r * m.nv + ci[C_IDX + e]] = v;
+                float jn, jt1, jt2;
+                const int dof = contact_entry(m, s, cr, ci, e, &jn, &jt1, &jt2);
+                float v = jn;
+                if (nr == 4) v += ((q & 1) ? -mu : mu) * ((q < 2) ? jt1 : jt2);
+                of[r * m.nv + dof] = v;
               }
             }
           }
@@ -361,6 +363,7 @@ template <int G> int configure(myo_batch* b) {
   const size_t max_smem = prop.sharedMemPerBlockOptin - tab_bytes;
   // worlds per CTA: fill the SM's shared memory with as few CTAs as keep threads <= kThreads
   int wpc = kThreads / G;
+  if (const char* ov = getenv("MYO_WPC")) { const int v = atoi(ov); if (v >= 1 && v < wpc) wpc = v; }   // development override
   while (wpc > 1 && wpc * world_bytes > max_smem) wpc--;
   if (wpc * world_bytes > max_smem) { set_error("one world's scratch exceeds shared memory per CTA"); return MYO_E_LIMIT; }
   b->wpc = wpc;

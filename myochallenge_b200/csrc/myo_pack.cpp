@@ -493,7 +493,6 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     d.o_obs = a0;
     off = a0 + std::max(off - a0, pad4(d.nobs));
   }
-  d.o_lim = take(d.nlim_max * LIM_WORDS); d.o_con = take(d.ncon_max * CON_WORDS); d.o_row = take(d.nefc_max * ROW_WORDS);
   d.o_misc = take(MI_WORDS);
   // velocity-stage temporaries and the composite inertias are dead once M and qfrc_bias exist; the Newton Hessian
   // (and the tendon phase's per-segment results) reuse their words
@@ -503,12 +502,21 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     d.o_cinert = take(10 * nbody);
     const int tmp_words = off - a0;
     d.o_H = a0;
-    // dense Hessian: nv rows padded to a multiple of four + one right-hand-side row, row stride hs
+    // dense Hessian, lower triangle by rows: rows 4a..4a+3 have the same length, ((a + 1) | 1) float4s (odd, so the four
+    // rows of a group start on different banks); one more row (pad4(nv) words) for the right-hand side
     d.nd = 0;
     for (int i = 0; i < nv; i++) if (!dsimple[i]) d.nd = i + 1;
-    d.hs = pad4(nv);
-    if ((d.hs / 4) % 2 == 0) d.hs += 4;
-    off = a0 + std::max(std::max(tmp_words, (pad4(nv) + 1) * d.hs), pad4(d.nseg * SEG_OUT));   // + per-segment tendon results
+    const int n4 = pad4(nv);
+    std::vector<int> roff(n4 + 1, 0);
+    int hw = 0;
+    for (int i = 0; i < n4; i++) { roff[i] = hw; hw += 4 * ((i / 4 + 1) | 1); }
+    roff[n4] = hw; hw += n4;
+    B.I(d.h_roff, roff);
+    off = a0 + std::max(tmp_words, hw);
+    // limit / contact / row records follow directly: the tendon phase runs before they are rebuilt, so its per-segment
+    // results may run on from the Hessian's words into theirs
+    d.o_lim = take(d.nlim_max * LIM_WORDS); d.o_con = take(d.ncon_max * CON_WORDS); d.o_row = take(d.nefc_max * ROW_WORDS);
+    off = std::max(off, a0 + pad4(d.nseg * SEG_OUT));
   }
   // world stride: tiles of one warp land on different banks
   if (out.lanes < 32) { while (off % 32 != out.lanes) off += 4; }

@@ -43,6 +43,25 @@ template <int G> MYO_DI float tile_max(const Ctx<G>& c, float v) {
 MYO_DI int lim_idx(const int* li, int e) { return reinterpret_cast<const int*>(MYO_SMEM_WORDS)[li[L_IOFF] + e]; }
 MYO_DI float lim_J(const float* s, const float* lr, const int* li, int e) { return lr[L_SIGN] * s[li[L_JOFF] + e]; }
 
+// Entry e of a contact's Jacobian block (see C_CP in myo_dev.hpp): the dof and the three basis rows (normal, tangent 1,
+// tangent 2) = +-frame . (lin_d + ang_d x (pos - tree reference)), - on the body-A side. s = the world's scratch.
+MYO_DI int contact_entry(const DevModel& m, const float* s, const float* cr, const int* ci, int e, float* jn, float* jt1, float* jt2) {
+  const int cp = ci[C_CP] & 255, na = ci[C_CP] >> 8;
+  const bool onb = e >= na;
+  const int body = onb ? ci[C_BB] : ci[C_BA];
+  const int d = m.b_chain[body * KC + cp + (onb ? e - na : e)];
+  const float sgn = onb ? 1.f : -1.f;
+  float off[3], t[3];
+  sub3(off, cr + C_POS, s + m.o_xipos + 3 * m.b_root[body]);
+  const float* cd = s + m.o_cdof + 6 * d;
+  cross3(t, cd, off);
+  const float v[3] = {cd[3] + t[0], cd[4] + t[1], cd[5] + t[2]};
+  *jn = sgn * dot3(cr + C_FRAME, v);
+  *jt1 = sgn * dot3(cr + C_FRAME + 3, v);
+  *jt2 = sgn * dot3(cr + C_FRAME + 6, v);
+  return d;
+}
+
 // ------------------------------------------------------------------------------------------------
 // a10.1 kinematics + comPos (+ comVel + RNE forward when dyn).
 // Reference point of every kinematic tree = xipos of its root body (MuJoCo uses the subtree COM;
@@ -899,16 +918,17 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
     row[R_D] = 1.f / R;
     row[R_AREF] = -B * vel - K * imp * (lr[L_POS] - lr[L_MARGIN]);
   }
-  // contacts: mixing (mj_contactParam), frame, support and basis Jacobians, rows
+  // contacts: mixing (mj_contactParam), frame, support, rows. A lane per contact; the row index comes from an exclusive
+  // scan of the row counts inside the tile (fixed contact order), then the same lane fills its rows.
   int nrow_con = 0, nrow_valid = 0;
   for (int base = 0; base < ncon; base += G) {
     const int k = base + c.lane;
-    int nr = 0;
+    int nr = 0, dim = 0;
+    float mu = 0.f, D = 0.f, Bc = 0.f, ref = 0.f, vn = 0.f, vt1 = 0.f, vt2 = 0.f;
     if (k < ncon) {
       float* cr = SF(o_con) + k * CON_WORDS; int* ci = reinterpret_cast<int*>(cr);
       const int g1 = ci[C_G1], g2 = ci[C_G2];
       float fri[3], solref[2], solimp[5];
-      int dim;
       float f1[3], f2[3];
 #pragma unroll
       for (int e = 0; e < 3; e++) {
@@ -940,12 +960,8 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
         for (int e = 0; e < 3; e++) fri[e] = fmaxf(f1[e], f2[e]);
       }
       const float margin = fmaxf(m.g_margin[g1], m.g_margin[g2]) - fmaxf(m.g_gap[g1], m.g_gap[g2]);
-      ci[C_DIM] = dim; cr[C_MARGIN] = margin; cr[C_MU] = fri[0];
-      cr[C_SOLREF] = solref[0]; cr[C_SOLREF + 1] = solref[1];
-#pragma unroll
-      for (int e = 0; e < 5; e++) cr[C_SOLIMP + e] = solimp[e];
-#pragma unroll
-      for (int e = 0; e < 3; e++) cr[C_FRI + e] = fri[e];
+      mu = fri[0];
+      ci[C_DIM] = dim; cr[C_MARGIN] = margin; cr[C_MU] = mu;
       float fr[9];
       cpy3(fr, cr + C_FRAME);
       make_frame(fr);
@@ -953,39 +969,31 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
       for (int e = 0; e < 9; e++) cr[C_FRAME + e] = fr[e];
       const int ba = m.g_body[g1], bb = m.g_body[g2];
       ci[C_BA] = ba; ci[C_BB] = bb;
-      // support + basis
       const int cp = common_prefix(m, ba, bb);
-      int ns = 0;
-      const float* cdof = SF(o_cdof);
-      for (int half = 0; half < 2; half++) {
-        const int body = half ? bb : ba;
-        const float sgn = half ? 1.f : -1.f;
-        const int n = m.b_nchain[body];
-        if (n <= cp) continue;
-        float off[3];
-        sub3(off, cr + C_POS, SF(o_xipos) + 3 * m.b_root[body]);
-        for (int q = cp; q < n; q++) {
-          const int d = m.b_chain[body * KC + q];
-          const float* cd = cdof + 6 * d;
-          float t[3];
-          cross3(t, cd, off);
-          const float v[3] = {cd[3] + t[0], cd[4] + t[1], cd[5] + t[2]};
-          if (ns < KS) {
-            ci[C_IDX + ns] = d;
-            cr[C_N + ns] = sgn * dot3(fr, v);
-            cr[C_N + KS + ns] = sgn * dot3(fr + 3, v);
-            cr[C_N + 2 * KS + ns] = sgn * dot3(fr + 6, v);
-            ns++;
-          } else *status |= ST_UNSUPPORTED;
-        }
-      }
+      const int na = max(m.b_nchain[ba] - cp, 0), nb = max(m.b_nchain[bb] - cp, 0);
+      int ns = na + nb;
+      if (ns > KS || cp > 255) { *status |= ST_UNSUPPORTED; ns = 0; }
+      ci[C_CP] = cp | (na << 8);
       ci[C_NSUP] = ns;
-      if (cr[C_DIST] < margin) {
+      // relative velocity of the contact point in the contact frame
+      for (int e = 0; e < ns; e++) {
+        float jn, jt1, jt2;
+        const int dof = contact_entry(m, c.sp(), cr, ci, e, &jn, &jt1, &jt2);
+        const float w = qvel[dof];
+        vn += jn * w; vt1 += jt1 * w; vt2 += jt2 * w;
+      }
+      const float dist = cr[C_DIST];
+      if (dist < margin) {
         if (dim == 1) nr = 1;
         else if (dim == 3) nr = 4;
         else *status |= ST_UNSUPPORTED;
       }
-      ci[C_ROW0] = nr;  // temporarily the row count; replaced by the first row index below
+      const float tran = m.b_invweight0[2 * ba] + m.b_invweight0[2 * bb];
+      float R, K, imp;
+      // diagApprox of the first row: tran + mu^2 * tran (pyramidal) or tran (frictionless)
+      row_params(mslot, solref, solimp, dist, margin, dim == 1 ? tran : tran + mu * mu * tran, &R, &K, &Bc, &imp);
+      if (dim == 3) { const float mu_r = mu * m.inv_sqrt_impratio; R = 2.f * mu_r * mu_r * R; }
+      D = 1.f / R; ref = -K * imp * (dist - margin);
     }
     // exclusive scan of row counts inside the tile (fixed contact order)
     int incl = nr;
@@ -995,9 +1003,16 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
     const int total = c.tile.shfl(incl, G - 1);
     if (k < ncon) {
       int* ci = SI(o_con) + k * CON_WORDS;
-      int row0 = nlim + nrow_con + excl;
+      const int row0 = nlim + nrow_con + excl;
       if (nr && row0 + nr > m.nefc_max) { *status |= ST_EFC_OVERFLOW; nr = 0; }
       ci[C_ROW0] = nr ? row0 : -1;
+      for (int q = 0; q < nr; q++) {
+        float vel = vn;
+        if (dim == 3) vel += ((q & 1) ? -mu : mu) * ((q < 2) ? vt1 : vt2);
+        float* row = rows + (row0 + q) * ROW_WORDS;
+        row[R_D] = D;
+        row[R_AREF] = -Bc * vel + ref;
+      }
     }
     int valid = nr;   // rows are dropped only at the tail, so valid rows stay contiguous
 #pragma unroll
@@ -1006,34 +1021,6 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
     nrow_con += total;
   }
   const int nefc = nlim + nrow_valid;
-  c.tile.sync();
-  // contact rows: one lane per contact fills its rows
-  for (int k = c.lane; k < ncon; k += G) {
-    const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
-    const int row0 = ci[C_ROW0];
-    if (row0 < 0) continue;
-    const int dim = ci[C_DIM], ns = ci[C_NSUP];
-    const float tran = m.b_invweight0[2 * ci[C_BA]] + m.b_invweight0[2 * ci[C_BB]];
-    float vn = 0.f, vt1 = 0.f, vt2 = 0.f;
-    for (int e = 0; e < ns; e++) {
-      const float w = qvel[ci[C_IDX + e]];
-      vn += cr[C_N + e] * w; vt1 += cr[C_N + KS + e] * w; vt2 += cr[C_N + 2 * KS + e] * w;
-    }
-    const float mu = cr[C_MU];
-    float R, K, B, imp;
-    // diagApprox of the first row: tran + mu^2 * tran (pyramidal) or tran (frictionless)
-    row_params(mslot, cr + C_SOLREF, cr + C_SOLIMP, cr[C_DIST], cr[C_MARGIN], dim == 1 ? tran : tran + mu * mu * tran, &R, &K, &B, &imp);
-    if (dim == 3) { const float mu_r = mu * m.inv_sqrt_impratio; R = 2.f * mu_r * mu_r * R; }
-    const float D = 1.f / R, ref = -K * imp * (cr[C_DIST] - cr[C_MARGIN]);
-    const int nr = dim == 1 ? 1 : 4;
-    for (int q = 0; q < nr; q++) {
-      float vel = vn;
-      if (dim == 3) vel += ((q & 1) ? -mu : mu) * ((q < 2) ? vt1 : vt2);
-      float* row = rows + (row0 + q) * ROW_WORDS;
-      row[R_D] = D;
-      row[R_AREF] = -B * vel + ref;
-    }
-  }
   if (c.lane == 0) { misc[MI_NLIM] = nlim; misc[MI_NEFC] = nefc; }
   c.tile.sync();
 }
@@ -1054,22 +1041,33 @@ MYO_PHASE void rows_dot(int mslot, Ctx<G>& c, int ox, int field, bool sub_aref) 
     float* row = rows + r * ROW_WORDS;
     row[field] = sub_aref ? v - row[R_AREF] : v;
   }
-  for (int k = c.lane; k < ncon; k += G) {
-    const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
-    const int row0 = ci[C_ROW0];
-    if (row0 < 0) continue;
+  // contacts: E lanes per contact, each taking every E-th support entry, partial sums combined by shuffles
+  constexpr int E = G >= KS ? KS : G;
+  const int sub = c.lane % E;
+  for (int base = 0; base < ncon; base += G / E) {
+    const int k = base + c.lane / E;
+    const bool on = k < ncon;
+    const float* cr = SF(o_con) + (on ? k : 0) * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+    const int row0 = on ? ci[C_ROW0] : -1;
     float vn = 0.f, vt1 = 0.f, vt2 = 0.f;
-    for (int e = 0; e < ci[C_NSUP]; e++) {
-      const float w = x[ci[C_IDX + e]];
-      vn += cr[C_N + e] * w; vt1 += cr[C_N + KS + e] * w; vt2 += cr[C_N + 2 * KS + e] * w;
-    }
-    const float mu = cr[C_MU];
-    const int nr = ci[C_DIM] == 1 ? 1 : 4;
-    for (int q = 0; q < nr; q++) {
-      float v = vn;
-      if (nr == 4) v += ((q & 1) ? -mu : mu) * ((q < 2) ? vt1 : vt2);
-      float* row = rows + (row0 + q) * ROW_WORDS;
-      row[field] = sub_aref ? v - row[R_AREF] : v;
+    if (row0 >= 0)
+      for (int e = sub; e < ci[C_NSUP]; e += E) {
+        float jn, jt1, jt2;
+        const int dof = contact_entry(m, c.sp(), cr, ci, e, &jn, &jt1, &jt2);
+        const float w = x[dof];
+        vn += jn * w; vt1 += jt1 * w; vt2 += jt2 * w;
+      }
+#pragma unroll
+    for (int o = E / 2; o > 0; o >>= 1) { vn += c.tile.shfl_xor(vn, o); vt1 += c.tile.shfl_xor(vt1, o); vt2 += c.tile.shfl_xor(vt2, o); }
+    if (row0 >= 0 && sub == 0) {
+      const float mu = cr[C_MU];
+      const int nr = ci[C_DIM] == 1 ? 1 : 4;
+      for (int q = 0; q < nr; q++) {
+        float v = vn;
+        if (nr == 4) v += ((q & 1) ? -mu : mu) * ((q < 2) ? vt1 : vt2);
+        float* row = rows + (row0 + q) * ROW_WORDS;
+        row[field] = sub_aref ? v - row[R_AREF] : v;
+      }
     }
   }
   c.tile.sync();
@@ -1126,32 +1124,37 @@ MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
       fn += f;
       if (nr == 4) { const float t = ((q & 1) ? -mu : mu) * f; if (q < 2) ft1 += t; else ft2 += t; }
     }
-    for (int e = c.lane; e < ci[C_NSUP]; e += G)
-      out[ci[C_IDX + e]] += cr[C_N + e] * fn + cr[C_N + KS + e] * ft1 + cr[C_N + 2 * KS + e] * ft2;
+    for (int e = c.lane; e < ci[C_NSUP]; e += G) {
+      float jn, jt1, jt2;
+      const int dof = contact_entry(m, c.sp(), cr, ci, e, &jn, &jt1, &jt2);
+      out[dof] += jn * fn + jt1 * ft1 + jt2 * ft2;
+    }
     c.tile.sync();
   }
 }
 
-// Dense Newton system in scratch: H row-major, row stride m.hs (multiple of 4, hs/4 odd, so a lane per row reads float4s
-// without bank conflicts), lower triangle valid; rows nv..n4-1 pad to a multiple of four (identity), row n4 holds the
-// right-hand side.
+// Dense Newton system in scratch: lower triangle of H by rows, row i starting at word m.h_roff[i] (float4 aligned; four
+// rows share a length that is an odd number of float4s, so a lane per row reads float4s with few bank conflicts);
+// rows nv..n4-1 pad to a multiple of four (identity), row n4 holds the right-hand side.
 // H = M + sum_{active rows} D_r J_r' J_r, right-hand side = -grad.
 template <int G>
 MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
   MYO_M
   float* H = SF(o_H); const float* M = SF(o_M); const float* grad = SF(o_grad);
-  const int nv = m.nv, hs = m.hs;
+  const int nv = m.nv;
+  const int* roff = m.h_roff.ptr();
   // a lane owns a row: clear it, then drop the row's mass-matrix entries (i, ancestors of i) into it
   const int n4 = (nv + 3) & ~3;
-  for (int k = c.lane; k < n4; k += G) H[n4 * hs + k] = k < nv ? -grad[k] : 0.f;
+  for (int k = c.lane; k < n4; k += G) H[roff[n4] + k] = k < nv ? -grad[k] : 0.f;
   for (int i = nv + c.lane; i < n4; i += G) {       // identity padding rows up to a multiple of four
-    for (int k = 0; k < n4; k++) H[i * hs + k] = (k == i) ? 1.f : 0.f;
+    for (int k = 0; k <= i; k++) H[roff[i] + k] = (k == i) ? 1.f : 0.f;
   }
   for (int i = c.lane; i < nv; i += G) {
-    float4* row4 = reinterpret_cast<float4*>(H + i * hs);
+    float* Hi = H + roff[i];
+    float4* row4 = reinterpret_cast<float4*>(Hi);
     for (int k = 0; k <= i / 4; k++) row4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     int adr = m.d_Madr[i], j = i;
-    while (j >= 0) { H[i * hs + j] = M[adr++]; j = m.d_parent[j]; }
+    while (j >= 0) { Hi[j] = M[adr++]; j = m.d_parent[j]; }
   }
   c.tile.sync();
   const int* misc = SI(o_misc);
@@ -1161,7 +1164,7 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
   for_joint_limit_rows<G>(m, c, nlim,
       [&](int r) { const float* row = rows + r * ROW_WORDS; const float* lr = SF(o_lim) + r * LIM_WORDS;
                    return row[R_JAR] < 0.f ? row[R_D] * lr[L_SIGN] : 0.f; },     // sign * (sign * D) = D
-      [&](int dof, float v) { H[dof * hs + dof] += v; });
+      [&](int dof, float v) { H[roff[dof] + dof] += v; });
   c.tile.sync();
   if (m.any_tendon_limit)
     for (int r = 0; r < nlim; r++) {
@@ -1174,7 +1177,7 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
         for (int e = c.lane; e < ns * ns; e += G) {
           const int a = e / ns, b = e - a * ns;
           const int ia = lim_idx(li, a), ib = lim_idx(li, b);
-          if (ia >= ib) H[ia * hs + ib] += D * lim_J(c.sp(), lr, li, a) * lim_J(c.sp(), lr, li, b);
+          if (ia >= ib) H[roff[ia] + ib] += D * lim_J(c.sp(), lr, li, a) * lim_J(c.sp(), lr, li, b);
         }
       }
       c.tile.sync();
@@ -1199,16 +1202,32 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
       }
     }
     if (w00 != 0.f) {
+      // lane e holds entry e of the block and pairs fetch both entries by shuffle (when the block fits the tile;
+      // narrower development tiles and the single-lane host emulation recompute the two entries instead)
+      const bool by_shfl = G > 1 && ns <= G;
+      float jn = 0.f, jt1 = 0.f, jt2 = 0.f;
+      int dof = 0;
+      if (by_shfl && c.lane < ns) dof = contact_entry(m, c.sp(), cr, ci, c.lane, &jn, &jt1, &jt2);
       // every unordered pair (a >= b) of the support once: e = a (a + 1) / 2 + b
-      for (int e = c.lane; e < ns * (ns + 1) / 2; e += G) {
+      const int npair = ns * (ns + 1) / 2;
+      for (int e0 = 0; e0 < npair; e0 += G) {
+        const int e = e0 + c.lane;
         int a = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
         if ((a + 1) * (a + 2) / 2 <= e) a++;
         if (a * (a + 1) / 2 > e) a--;
-        const int b = e - a * (a + 1) / 2;
-        const int ia = ci[C_IDX + a], ib = ci[C_IDX + b];
-        const float na = cr[C_N + a], ta = cr[C_N + KS + a], ua = cr[C_N + 2 * KS + a];
-        const float nb = cr[C_N + b], tb = cr[C_N + KS + b], ub = cr[C_N + 2 * KS + b];
-        H[max(ia, ib) * hs + min(ia, ib)] += w00 * na * nb + w01 * (na * tb + ta * nb) + w02 * (na * ub + ua * nb) + w11 * ta * tb + w22 * ua * ub;
+        int b = e - a * (a + 1) / 2;
+        if (e >= npair) { a = 0; b = 0; }
+        int ia, ib;
+        float na, ta, ua, nb, tb, ub;
+        if (by_shfl) {
+          ia = c.tile.shfl(dof, a); na = c.tile.shfl(jn, a); ta = c.tile.shfl(jt1, a); ua = c.tile.shfl(jt2, a);
+          ib = c.tile.shfl(dof, b); nb = c.tile.shfl(jn, b); tb = c.tile.shfl(jt1, b); ub = c.tile.shfl(jt2, b);
+        } else {
+          ia = contact_entry(m, c.sp(), cr, ci, a, &na, &ta, &ua);
+          ib = contact_entry(m, c.sp(), cr, ci, b, &nb, &tb, &ub);
+        }
+        if (e < npair)
+          H[roff[max(ia, ib)] + min(ia, ib)] += w00 * na * nb + w01 * (na * tb + ta * nb) + w02 * (na * ub + ua * nb) + w11 * ta * tb + w22 * ua * ub;
       }
     }
     c.tile.sync();
@@ -1224,33 +1243,36 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
 // Then the back substitution L' x = y, column oriented, with y held in registers (lane i owns y_i, y_{i+G}, ...)
 // and each finished x_j broadcast by a shuffle; x goes to scratch at ox.
 template <int G>
-MYO_PHASE void chol_factor_solve(Ctx<G>& c, int oH, int ox, int n, int hs) {
+MYO_PHASE void chol_factor_solve(int mslot, Ctx<G>& c, int oH, int ox, int n) {
+  MYO_M
   float* H = SO(oH); float* x = SO(ox);
+  const int* roff = m.h_roff.ptr();
   const int n4 = (n + 3) & ~3;
   if constexpr (G < 4) {   // single-lane host emulation (tests/emul): same storage convention, unblocked
     for (int j = 0; j < n4; j++) {
       float inv = 0.f;
       for (int i = j; i <= n4; i++) {
-        float s = H[i * hs + j];
-        for (int k = 0; k < j; k++) s -= H[i * hs + k] * H[j * hs + k];
-        if (i == j) { inv = 1.f / sqrtf(fmaxf(s, kMinVal)); H[i * hs + j] = inv; } else H[i * hs + j] = s * inv;
+        float s = H[roff[i] + j];
+        for (int k = 0; k < j; k++) s -= H[roff[i] + k] * H[roff[j] + k];
+        if (i == j) { inv = 1.f / sqrtf(fmaxf(s, kMinVal)); H[roff[i] + j] = inv; } else H[roff[i] + j] = s * inv;
       }
     }
   } else
   for (int J = 0; J < n4; J += 4) {
-    const float* P = H + J * hs;       // pivot rows J..J+3
+    const float* P0 = H + roff[J];     // pivot rows J..J+3
+    const float* P1 = H + roff[J + 1]; const float* P2 = H + roff[J + 2]; const float* P3 = H + roff[J + 3];
     float l10 = 0.f, l20 = 0.f, l21 = 0.f, l30 = 0.f, l31 = 0.f, l32 = 0.f, inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, inv3 = 0.f;
     for (int i0 = J; i0 <= n4; i0 += G) {
       const int i = i0 + c.lane;
       const bool on = i <= n4;
-      float* Li = H + (on ? i : J) * hs;
+      float* Li = H + roff[on ? i : J];
       float4 acc = *reinterpret_cast<const float4*>(Li + J);
       for (int k = 0; k < J; k += 4) {
         const float4 a = *reinterpret_cast<const float4*>(Li + k);
-        const float4 b0 = *reinterpret_cast<const float4*>(P + k);
-        const float4 b1 = *reinterpret_cast<const float4*>(P + hs + k);
-        const float4 b2 = *reinterpret_cast<const float4*>(P + 2 * hs + k);
-        const float4 b3 = *reinterpret_cast<const float4*>(P + 3 * hs + k);
+        const float4 b0 = *reinterpret_cast<const float4*>(P0 + k);
+        const float4 b1 = *reinterpret_cast<const float4*>(P1 + k);
+        const float4 b2 = *reinterpret_cast<const float4*>(P2 + k);
+        const float4 b3 = *reinterpret_cast<const float4*>(P3 + k);
         acc.x -= a.x * b0.x; acc.x -= a.y * b0.y; acc.x -= a.z * b0.z; acc.x -= a.w * b0.w;
         acc.y -= a.x * b1.x; acc.y -= a.y * b1.y; acc.y -= a.z * b1.z; acc.y -= a.w * b1.w;
         acc.z -= a.x * b2.x; acc.z -= a.y * b2.y; acc.z -= a.z * b2.z; acc.z -= a.w * b2.w;
@@ -1287,9 +1309,9 @@ MYO_PHASE void chol_factor_solve(Ctx<G>& c, int oH, int ox, int n, int hs) {
   constexpr int NSET = 64 / G;     // nv <= 64 (pack_model)
   float y[NSET];
 #pragma unroll
-  for (int q = 0; q < NSET; q++) { const int i = c.lane + q * G; y[q] = i < n ? H[n4 * hs + i] : 0.f; }
+  for (int q = 0; q < NSET; q++) { const int i = c.lane + q * G; y[q] = i < n ? H[roff[n4] + i] : 0.f; }
   for (int j = n - 1; j >= 0; j--) {
-    const float* Lj = H + j * hs;
+    const float* Lj = H + roff[j];
     const int jq = j / G;
     float v = y[0];
 #pragma unroll
@@ -1310,21 +1332,23 @@ template <int G>
 MYO_PHASE void solve_M_dense(int mslot, Ctx<G>& c, int ox, float hdamp) {
   MYO_M
   float* H = SF(o_H); const float* M = SF(o_M); float* x = SO(ox);
-  const int nd = m.nd, hs = m.hs, n4 = (nd + 3) & ~3;
-  for (int k = c.lane; k < n4; k += G) H[n4 * hs + k] = k < nd ? x[k] : 0.f;
+  const int nd = m.nd, n4 = (nd + 3) & ~3;
+  const int* roff = m.h_roff.ptr();
+  for (int k = c.lane; k < n4; k += G) H[roff[n4] + k] = k < nd ? x[k] : 0.f;
   for (int i = nd + c.lane; i < n4; i += G)
-    for (int k = 0; k < n4; k++) H[i * hs + k] = (k == i) ? 1.f : 0.f;
+    for (int k = 0; k <= i; k++) H[roff[i] + k] = (k == i) ? 1.f : 0.f;
   for (int i = c.lane; i < nd; i += G) {
-    float4* row4 = reinterpret_cast<float4*>(H + i * hs);
+    float* Hi = H + roff[i];
+    float4* row4 = reinterpret_cast<float4*>(Hi);
     for (int k = 0; k <= i / 4; k++) row4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     int adr = m.d_Madr[i], j = i;
-    H[i * hs + i] = M[adr++] + hdamp * m.d_damping[i];
+    Hi[i] = M[adr++] + hdamp * m.d_damping[i];
     j = m.d_parent[j];
-    while (j >= 0) { H[i * hs + j] = M[adr++]; j = m.d_parent[j]; }
+    while (j >= 0) { Hi[j] = M[adr++]; j = m.d_parent[j]; }
   }
   for (int i = nd + c.lane; i < m.nv; i += G) x[i] = x[i] / fmaxf(M[m.d_Madr[i]] + hdamp * m.d_damping[i], kMinVal);
   c.tile.sync();
-  if (nd > 0) chol_factor_solve<G>(c, m.o_H, ox, nd, hs);
+  if (nd > 0) chol_factor_solve<G>(mslot, c, m.o_H, ox, nd);
 }
 
 // optional per-phase cycle counters (development builds: -DMYO_PROFILE)
@@ -1397,7 +1421,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c) {
     amax = tile_max<G>(c, amax);
     if (sqrtf(g2) * scale < m.solver_tol) break;
     MYO_PH_RESTART build_hessian<G>(mslot, c); MYO_PH(11)
-    chol_factor_solve<G>(c, m.o_H, m.o_p, nv, m.hs); MYO_PH(12)
+    chol_factor_solve<G>(mslot, c, m.o_H, m.o_p, nv); MYO_PH(12)
     rows_dot<G>(mslot, c, m.o_p, R_JP, false);
     mul_M<G>(mslot, c, m.o_M, m.o_p, m.o_Mp);
     float pMp = 0.f, gp = 0.f, pmax = 0.f;
