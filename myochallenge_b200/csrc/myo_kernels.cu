@@ -71,16 +71,16 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
   if (a.mode == MODE_FORWARD || a.mode == MODE_MJ_STEP) {
     for (int i = c.lane; i < m.nu; i += G) SF(o_ctrl)[i] = a.in ? a.in[(size_t)wi * m.nu + i] : 0.f;
     c.tile.sync();
-    if (a.mode == MODE_FORWARD) mj_forward_dev<G>(mslot, c, &status);
+    if (a.mode == MODE_FORWARD) mj_forward_dev<G>(mslot, c, &status, false);
     else {
-      for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(mslot, c, &status);
+      for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(mslot, c, &status, false);
       if (c.lane == 0) b.time[w] += (float)a.nsub * m.timestep;
     }
   } else {   // MODE_ENV_STEP
     if (t.kind == MYO_TASK_BAODING) baoding_targets<G>(mslot, t, c, ti, tf);
     task_action<G>(mslot, t, c, a.in + (size_t)wi * m.nu);
     c.tile.sync();
-    for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(mslot, c, &status);
+    for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(mslot, c, &status, true);
     // get_obs: kinematics at the post-step state (MyoSuite get_obs -> sim.forward)
     phase_tree_forward<G>(mslot, c, false);
     task_obs<G>(mslot, t, c, ptarget);
