@@ -24,6 +24,11 @@
  *                       geom_size / site_pos (/root/reference/src/envs/baoding.py:560-604).
  *   myo_policy_*     <- sb3_contrib RecurrentActorCriticPolicy.forward as constructed by
  *                       /root/reference/src/train/trainer.py:49-64.
+ *   myo_running_moments_* / myo_vecnorm_reward <- stable_baselines3 VecNormalize (RunningMeanStd.update,
+ *                       step_wait's return/reward handling) wrapped around the envs at
+ *                       /root/reference/src/main_baoding.py:75.
+ *   myo_gae          <- RecurrentRolloutBuffer.compute_returns_and_advantage, called by RecurrentPPO.learn
+ *                       (/root/reference/src/train/trainer.py:67-71).
  *
  * Conventions: every function returns 0 on success or a negative myo_status; the message for the
  * calling thread's last failure is myo_last_error().  Nothing throws across the boundary.  Handles
@@ -233,6 +238,32 @@ int myo_policy_set_obs_norm(myo_policy* p, const float* mean_dev, const float* v
  * counter-based stream keyed by (seed, world, forward-call counter); seed 0 restores the deterministic mean. */
 int myo_policy_seed(myo_policy* p, uint64_t seed);
 int64_t myo_policy_launch_count(const myo_policy* p);
+
+/* ---- rollout side: VecNormalize running moments, reward scaling, GAE ------------ */
+/* Running moments as SB3's RunningMeanStd keeps them, on the device in fp64: state_dev = mean[d], var[d], count
+ * (2 d + 1 doubles; initialise to 0, 1, epsilon as RunningMeanStd.__init__ does).
+ * myo_running_moments_update folds the batch x_dev[n][d] (fp32, row-major) into the state exactly as
+ * RunningMeanStd.update does (batch mean / population variance, Chan merge). scratch_dev: at least
+ * myo_running_moments_scratch(n, d) doubles. mean_f_dev / var_f_dev (optional, float[d]) receive fp32 copies of the new
+ * moments, in the form myo_policy_set_obs_norm takes (call it again after an update: it caches 1 / sqrt(var + eps)). */
+int myo_running_moments_scratch(int n, int d);
+int myo_running_moments_update(double* state_dev, const float* x_dev, int n, int d, double* scratch_dev, float* mean_f_dev,
+                               float* var_f_dev, void* stream);
+int myo_running_moments_export(const double* state_dev, int d, float* mean_f_dev, float* var_f_dev, void* stream);
+/* VecNormalize.step_wait's reward path for one step of n worlds: returns = returns * gamma + reward; (training)
+ * ret_rms.update(returns); out = clip(reward / sqrt(ret_rms.var + epsilon), +-clip_reward) (norm_reward) else reward;
+ * returns[done] = 0. ret_state_dev: the 3 doubles mean, var, count of ret_rms; returns_dev: double[n];
+ * scratch_dev: myo_running_moments_scratch(n, 1) doubles. gamma / epsilon / clip_reward are doubles because SB3 applies
+ * them as Python floats to its fp64 return accumulator. */
+int myo_vecnorm_reward(double* ret_state_dev, double* returns_dev, const float* reward_dev, const uint8_t* done_dev,
+                       float* out_reward_dev, int n, double gamma, double epsilon, double clip_reward, int training,
+                       int norm_reward, double* scratch_dev, void* stream);
+/* Generalised advantage estimation over a rollout stored step-major ([n_steps][n], SB3's buffer layout):
+ *   delta_t = r_t + gamma V_{t+1} (1 - start_{t+1}) - V_t,  A_t = delta_t + gamma lambda (1 - start_{t+1}) A_{t+1},
+ * with V_T = last_values and start_T = last_dones; returns = advantages + values. */
+int myo_gae(const float* rewards_dev, const float* values_dev, const uint8_t* episode_starts_dev,
+            const float* last_values_dev, const uint8_t* last_dones_dev, int n_steps, int n, float gamma, float gae_lambda,
+            float* advantages_dev, float* returns_dev, void* stream);
 
 #ifdef __cplusplus
 }

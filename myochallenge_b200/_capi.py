@@ -96,6 +96,11 @@ SIGNATURES = {
     "myo_policy_set_obs_norm": (_i, [_vp, _fp, _fp, C.c_float, C.c_float, _vp]),
     "myo_policy_seed": (_i, [_vp, C.c_uint64]),
     "myo_policy_launch_count": (C.c_int64, [_vp]),
+    "myo_running_moments_scratch": (_i, [_i, _i]),
+    "myo_running_moments_update": (_i, [_vp, _fp, _i, _i, _vp, _fp, _fp, _vp]),
+    "myo_running_moments_export": (_i, [_vp, _i, _fp, _fp, _vp]),
+    "myo_vecnorm_reward": (_i, [_vp, _vp, _fp, _vp, _fp, _i, C.c_double, C.c_double, C.c_double, _i, _i, _vp, _vp]),
+    "myo_gae": (_i, [_fp, _fp, _vp, _fp, _vp, _i, _i, C.c_float, C.c_float, _fp, _fp, _vp]),
 }
 
 

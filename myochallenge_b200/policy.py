@@ -117,7 +117,8 @@ class RecurrentPolicy:
         m = torch.as_tensor(mean).to(device=self.device, dtype=torch.float32).contiguous()
         v = torch.as_tensor(var).to(device=self.device, dtype=torch.float32).contiguous()
         check(self._L, self._L.myo_policy_set_obs_norm(self._h, _ptr(m), _ptr(v), C.c_float(epsilon), C.c_float(clip_obs), self._stream()))
-        torch.cuda.current_stream(self.device).synchronize()   # m, v may be temporaries
+        if m is not mean or v is not var:
+            torch.cuda.current_stream(self.device).synchronize()   # m, v are temporaries: keep them alive until the copy ran
 
     def seed(self, seed: int) -> None:
         check(self._L, self._L.myo_policy_seed(self._h, C.c_uint64(seed)))
@@ -161,6 +162,16 @@ class RecurrentPolicy:
         check(self._L, self._L.myo_policy_forward(self._h, int(n), _ptr(obs), _ptr(h), _ptr(c), _ptr(es), _ptr(nz), _ptr(actions),
                                                   _ptr(values), _ptr(logp), self._stream()))
         return actions, values, logp, (h, c)
+
+    def predict_values(self, obs: torch.Tensor, lstm_states: Tuple[torch.Tensor, torch.Tensor], episode_starts: Optional[torch.Tensor] = None):
+        """``RecurrentActorCriticPolicy.predict_values``: critic value of ``obs`` from the given LSTM states, which are
+        left untouched (the forward runs on copies)."""
+        h, c = lstm_states
+        h, c = h.clone().contiguous(), c.clone().contiguous()
+        n = obs.shape[0]
+        es = torch.zeros(n, dtype=torch.uint8, device=self.device) if episode_starts is None else episode_starts
+        _, values, _, _ = self.forward(obs, (h, c), es, deterministic=True)
+        return values
 
     @property
     def launch_count(self) -> int:

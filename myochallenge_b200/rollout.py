@@ -1,0 +1,246 @@
+"""Device-resident rollout side of the PPO loop: VecNormalize's running moments and
+reward scaling, sb3-contrib's RecurrentRolloutBuffer with GAE, and the rollout collection loop of
+``RecurrentPPO.collect_rollouts`` - the part of /root/reference/src/train/trainer.py:67-71 that runs between two
+policy updates - over a ``MyoVecEnv`` and a ``RecurrentPolicy`` without leaving HBM.
+
+PyTorch provides the tensors and streams; the arithmetic is in libmyo_b200.so (csrc/myo_rollout.cu, the world and
+policy kernels). Cross-rank: worlds are sharded, so the only exchange is the merge of the running moments
+(``DeviceRunningMeanStd.sync``: all-gather of (count, mean, M2), 2 d + 1 doubles per rank, Chan merge in rank order).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class DeviceRunningMeanStd:
+    """SB3 ``RunningMeanStd`` with the state (mean[d], var[d], count; fp64) on the device."""
+
+    def __init__(self, d: int, device, epsilon: float = 1e-4):
+        self.d, self.device = int(d), torch.device(device)
+        self.state = torch.zeros(2 * self.d + 1, dtype=torch.float64, device=self.device)
+        self.state[self.d: 2 * self.d] = 1.0
+        self.state[2 * self.d] = epsilon
+        self.mean_f = torch.zeros(self.d, dtype=torch.float32, device=self.device)
+        self.var_f = torch.ones(self.d, dtype=torch.float32, device=self.device)
+        self._scratch = None
+        self._L = _capi.lib()
+        self.launch_count = 0
+
+    def _scratch_for(self, n):
+        need = self._L.myo_running_moments_scratch(int(n), self.d)
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.float64, device=self.device)
+        return self._scratch
+
+    def update(self, x: torch.Tensor):
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+        assert (x.shape[-1] == self.d) if x.dim() > 1 else (self.d == 1)
+        n = x.shape[0]
+        s = self._scratch_for(n)
+        _capi.check(self._L, self._L.myo_running_moments_update(_p(self.state), _p(x), n, self.d, _p(s), _p(self.mean_f), _p(self.var_f), _stream_ptr(self.device)))
+        self.launch_count += 3
+
+    def load(self, mean, var, count):
+        self.state[: self.d] = torch.as_tensor(np.asarray(mean, np.float64).reshape(-1), device=self.device)
+        self.state[self.d: 2 * self.d] = torch.as_tensor(np.asarray(var, np.float64).reshape(-1), device=self.device)
+        self.state[2 * self.d] = float(count)
+        _capi.check(self._L, self._L.myo_running_moments_export(_p(self.state), self.d, _p(self.mean_f), _p(self.var_f), _stream_ptr(self.device)))
+
+    @property
+    def mean(self):
+        return self.state[: self.d]
+
+    @property
+    def var(self):
+        return self.state[self.d: 2 * self.d]
+
+    @property
+    def count(self):
+        return self.state[2 * self.d]
+
+    def sync(self, base: "DeviceRunningMeanStd | None" = None):
+        """Merge the moments of all ranks (each rank saw its own worlds). ``base``: the common state every rank started
+        the interval from (so it is counted once); without it the ranks' states are merged as independent samples."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        merged = merge_moment_states([t.cpu().numpy() for t in _all_gather(self.state)], self.d,
+                                     None if base is None else base.cpu().numpy())
+        self.state.copy_(torch.from_numpy(merged).to(self.device))
+        _capi.check(self._L, self._L.myo_running_moments_export(_p(self.state), self.d, _p(self.mean_f), _p(self.var_f), _stream_ptr(self.device)))
+
+
+def _all_gather(t):
+    import torch.distributed as dist
+
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return out
+
+
+def merge_moment_states(states, d, base=None):
+    """Chan merge, in rank order, of per-rank RunningMeanStd states [mean(d), var(d), count] (host, fp64). With ``base``
+    (the state all ranks started from) each rank contributes only what it added since: its state minus the base."""
+    def split(s):
+        return s[:d].copy(), s[d: 2 * d].copy(), float(s[2 * d])
+
+    def merge(a, b):
+        (ma, va, na), (mb, vb, nb) = a, b
+        if nb <= 0:
+            return a
+        tot = na + nb
+        delta = mb - ma
+        return ma + delta * nb / tot, (va * na + vb * nb + delta * delta * na * nb / tot) / tot, tot
+
+    def subtract(s, b):      # inverse of merge: the batch that turns b into s
+        (ms, vs, ns), (mb, vb, nb) = s, b
+        nx = ns - nb
+        if nx <= 0:
+            return ms, vs, 0.0
+        mx = (ms * ns - mb * nb) / nx
+        delta = mx - mb
+        vx = (vs * ns - vb * nb - delta * delta * nb * nx / ns) / nx
+        return mx, np.maximum(vx, 0.0), nx
+
+    acc = split(states[0]) if base is None else split(base)
+    for k, s in enumerate(states):
+        if base is None:
+            if k == 0:
+                continue
+            acc = merge(acc, split(s))
+        else:
+            acc = merge(acc, subtract(split(s), split(base)))
+    return np.concatenate([acc[0], acc[1], [acc[2]]])
+
+
+class DeviceVecNormalize:
+    """VecNormalize over the device path of a ``MyoVecEnv``: observations stay raw in HBM and are normalised inside
+    the policy kernel's input load (``policy.set_obs_norm`` is pointed at this object's fp32 moments, which every
+    ``obs_rms`` update refreshes); rewards are scaled by the std of the discounted return as SB3 does."""
+
+    def __init__(self, venv, policy=None, training=True, norm_obs=True, norm_reward=True, clip_obs=10.0, clip_reward=10.0,
+                 gamma=0.99, epsilon=1e-8):
+        self.venv, self.device = venv, venv.sim.device
+        self.num_envs = venv.num_envs
+        self.training, self.norm_obs, self.norm_reward = training, norm_obs, norm_reward
+        self.clip_obs, self.clip_reward, self.gamma, self.epsilon = clip_obs, clip_reward, gamma, epsilon
+        self.obs_rms = DeviceRunningMeanStd(venv.sim.nobs, self.device)
+        self.ret_rms = DeviceRunningMeanStd(1, self.device)
+        self.returns = torch.zeros(self.num_envs, dtype=torch.float64, device=self.device)
+        self._out_r = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+        self._L = _capi.lib()
+        self.launch_count = 0
+        self.policy = None
+        if policy is not None:
+            self.attach(policy)
+
+    def attach(self, policy):
+        self.policy = policy
+        self._push_obs_norm()
+
+    def _push_obs_norm(self):
+        if self.policy is not None and self.norm_obs:
+            self.policy.set_obs_norm(self.obs_rms.mean_f, self.obs_rms.var_f, self.epsilon, self.clip_obs)
+
+    def reset_device(self):
+        obs = self.venv.reset_device()
+        self.returns.zero_()
+        if self.training and self.norm_obs:
+            self.obs_rms.update(obs)
+            self._push_obs_norm()
+        return obs
+
+    def step_device(self, actions):
+        obs, rew, done, trunc = self.venv.step_device(actions)
+        if self.training and self.norm_obs:
+            self.obs_rms.update(obs)
+            self._push_obs_norm()
+        s = self.ret_rms._scratch_for(self.num_envs)
+        _capi.check(self._L, self._L.myo_vecnorm_reward(_p(self.ret_rms.state), _p(self.returns), _p(rew), _p(done), _p(self._out_r), self.num_envs,
+                                                        self.gamma, self.epsilon, self.clip_reward, int(self.training), int(self.norm_reward),
+                                                        _p(s), _stream_ptr(self.device)))
+        self.launch_count += 4 if self.training else 1
+        return obs, self._out_r, done, trunc
+
+    @property
+    def terminal_obs(self):
+        return self.venv.terminal_obs
+
+
+class RecurrentRolloutBuffer:
+    """sb3-contrib ``RecurrentRolloutBuffer`` storage, step-major on the device: observations (raw), actions, rewards,
+    episode_starts, values, log_probs and the LSTM states each step started from."""
+
+    def __init__(self, n_steps, n_envs, obs_dim, act_dim, lstm_hidden, device, gamma=0.99, gae_lambda=0.95):
+        dev = torch.device(device)
+        f = dict(dtype=torch.float32, device=dev)
+        self.n_steps, self.n_envs, self.gamma, self.gae_lambda, self.device = n_steps, n_envs, gamma, gae_lambda, dev
+        self.observations = torch.zeros(n_steps, n_envs, obs_dim, **f)
+        self.actions = torch.zeros(n_steps, n_envs, act_dim, **f)
+        self.rewards = torch.zeros(n_steps, n_envs, **f)
+        self.values = torch.zeros(n_steps, n_envs, **f)
+        self.log_probs = torch.zeros(n_steps, n_envs, **f)
+        self.advantages = torch.zeros(n_steps, n_envs, **f)
+        self.returns = torch.zeros(n_steps, n_envs, **f)
+        self.episode_starts = torch.zeros(n_steps, n_envs, dtype=torch.uint8, device=dev)
+        self.hidden_states = torch.zeros(n_steps, 2, n_envs, lstm_hidden, **f)      # [:, 0] actor, [:, 1] critic
+        self.cell_states = torch.zeros(n_steps, 2, n_envs, lstm_hidden, **f)
+        self.pos, self.full = 0, False
+        self._L = _capi.lib()
+        self.launch_count = 0
+
+    def reset(self):
+        self.pos, self.full = 0, False
+
+    def add(self, obs, action, reward, episode_start, value, log_prob, h, c):
+        t = self.pos
+        self.observations[t].copy_(obs); self.actions[t].copy_(action); self.rewards[t].copy_(reward)
+        self.episode_starts[t].copy_(episode_start); self.values[t].copy_(value); self.log_probs[t].copy_(log_prob)
+        self.hidden_states[t].copy_(h); self.cell_states[t].copy_(c)
+        self.pos += 1
+        self.full = self.pos == self.n_steps
+
+    def compute_returns_and_advantage(self, last_values, dones):
+        assert self.full, "rollout buffer is not full"
+        _capi.check(self._L, self._L.myo_gae(_p(self.rewards), _p(self.values), _p(self.episode_starts), _p(last_values.contiguous()),
+                                             _p(dones.contiguous()), self.n_steps, self.n_envs, self.gamma, self.gae_lambda,
+                                             _p(self.advantages), _p(self.returns), _stream_ptr(self.device)))
+        self.launch_count += 1
+
+
+def collect_rollouts(env, policy, buffer: RecurrentRolloutBuffer, state, obs, episode_starts, clip_actions=True):
+    """``RecurrentPPO.collect_rollouts``: n_steps of policy forward -> env step -> buffer.add, with the TimeLimit
+    bootstrap (reward += gamma * V(terminal_observation) for truncated worlds, values from the critic state the step
+    ended in) and the final GAE pass. ``env``: MyoVecEnv or DeviceVecNormalize (device path); ``state`` = (h, c) as
+    ``policy.initial_state`` returns them (updated in place). Returns (obs, episode_starts) for the next call."""
+    h, c = state
+    buffer.reset()
+    for _ in range(buffer.n_steps):
+        h0, c0 = h.clone(), c.clone()
+        actions, values, logp, _ = policy.forward(obs, (h, c), episode_starts)
+        env_actions = actions.clamp(-1.0, 1.0) if clip_actions else actions
+        new_obs, rewards, dones, trunc = env.step_device(env_actions)
+        rewards = rewards.clone()
+        idx = torch.nonzero(trunc, as_tuple=False).flatten()
+        if idx.numel():       # bootstrap with the value of the terminal observation (critic state after this step)
+            tv = policy.predict_values(env.terminal_obs.index_select(0, idx), (h.index_select(1, idx), c.index_select(1, idx)))
+            rewards.index_add_(0, idx, buffer.gamma * tv)
+        buffer.add(obs, actions, rewards, episode_starts, values, logp, h0, c0)
+        obs, episode_starts = new_obs.clone(), dones.clone()
+    last_values = policy.predict_values(obs, (h.clone(), c.clone()), episode_starts)
+    buffer.compute_returns_and_advantage(last_values, episode_starts)
+    return obs, episode_starts

@@ -114,6 +114,12 @@ class MyoVecEnv:
         """(obs, reward, done, truncated) as device tensors owned by the env (overwritten by the next step)."""
         return self.sim.step(actions)
 
+    @property
+    def terminal_obs(self) -> torch.Tensor:
+        """Device tensor [n, obs_dim]: the last observation of the episode for worlds whose ``done`` is set this step
+        (SB3's ``infos[i]["terminal_observation"]``)."""
+        return self.sim.terminal_obs
+
     # -- SB3 VecEnv API --------------------------------------------------------------------------
     def reset(self) -> np.ndarray:
         obs = self.reset_device()
