@@ -68,6 +68,7 @@ struct DevModel {
   int nq4, nv4, na4, nu4, nparam, nparam4, nobs, nobs4;
   int nlim_max, ncon_max, nefc_max;
   int nd;   // dofs [0, nd) couple through the mass matrix; dofs [nd, nv) are simple (diagonal)
+  TabI pair_ab;  // unordered support pairs of a contact block (myo_pack.cpp)
   TabI h_roff;   // word offset of row i of the packed lower-triangular Newton Hessian (rows 0..pad4(nv); the last is the rhs)
   int solver_iter;
   float solver_tol, timestep, gravity[3], inv_sqrt_impratio, meaninertia;

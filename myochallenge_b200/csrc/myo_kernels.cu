@@ -35,7 +35,7 @@ const myo::Model& myo_model_host(const myo_model* m);
 
 namespace myo {
 
-constexpr int kThreads = 416;   // up to 13 one-warp worlds per CTA (register cap 152)
+constexpr int kThreads = 448;   // up to 14 one-warp worlds per CTA (register cap 144)
 
 template <int G>
 __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G>& c, int w) {

@@ -31,14 +31,27 @@ struct Builder {
     if (v.empty()) pm.fbuf.push_back(0.f);
     while (pm.fbuf.size() % 4) pm.fbuf.push_back(0.f);
   }
+  // cold table: kept in the global copy only (read with plain loads through m.g_tables, served by L1 / L2), not staged
+  // into shared memory - for tables that are touched once per substep by a lane-per-item loop
+  void Fcold(TabF& field, const std::vector<float>& v) {
+    field.off = (int)cbuf.size();
+    cfix.push_back(&field);
+    cbuf.insert(cbuf.end(), v.begin(), v.end());
+    if (v.empty()) cbuf.push_back(0.f);
+    while (cbuf.size() % 4) cbuf.push_back(0.f);
+  }
   void finish() {
-    const int ni = (int)pm.ibuf.size();
+    const int ni = (int)pm.ibuf.size(), nf = (int)pm.fbuf.size();
     for (TabF* f : pm.ffix) f->off += ni;
-    pm.tables.resize(pm.ibuf.size() + pm.fbuf.size());
+    for (TabF* f : cfix) f->off += ni + nf;
+    pm.tables.resize(pm.ibuf.size() + pm.fbuf.size() + cbuf.size());
     memcpy(pm.tables.data(), pm.ibuf.data(), pm.ibuf.size() * sizeof(int));
     memcpy(pm.tables.data() + ni, pm.fbuf.data(), pm.fbuf.size() * sizeof(float));
-    pm.dm.tab_words = (int)pm.tables.size();
+    memcpy(pm.tables.data() + ni + nf, cbuf.data(), cbuf.size() * sizeof(float));
+    pm.dm.tab_words = ni + nf;      // the part staged into shared memory
   }
+  std::vector<float> cbuf;
+  std::vector<TabF*> cfix;
 };
 
 std::vector<int> ivec(const Model& m, const char* name) {
@@ -422,11 +435,11 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     B.I(d.a_tendon, atendon); B.I(d.a_dyntype, ivec(m, "actuator_dyntype")); B.I(d.a_gaintype, ivec(m, "actuator_gaintype"));
     B.I(d.a_biastype, ivec(m, "actuator_biastype")); B.I(d.a_ctrllimited, ivec(m, "actuator_ctrllimited"));
     B.I(d.a_forcelimited, ivec(m, "actuator_forcelimited"));
-    B.F(d.a_dynprm, take_cols(fvec(m, "actuator_dynprm"), nu, 10, 3));
-    B.F(d.a_gainprm, take_cols(fvec(m, "actuator_gainprm"), nu, 10, 9));
-    B.F(d.a_biasprm, take_cols(fvec(m, "actuator_biasprm"), nu, 10, 9));
-    B.F(d.a_ctrlrange, fvec(m, "actuator_ctrlrange")); B.F(d.a_forcerange, fvec(m, "actuator_forcerange"));
-    B.F(d.a_gear, gear); B.F(d.a_acc0, fvec(m, "actuator_acc0")); B.F(d.a_lengthrange, fvec(m, "actuator_lengthrange"));
+    B.Fcold(d.a_dynprm, take_cols(fvec(m, "actuator_dynprm"), nu, 10, 3));
+    B.Fcold(d.a_gainprm, take_cols(fvec(m, "actuator_gainprm"), nu, 10, 9));
+    B.Fcold(d.a_biasprm, take_cols(fvec(m, "actuator_biasprm"), nu, 10, 9));
+    B.Fcold(d.a_ctrlrange, fvec(m, "actuator_ctrlrange")); B.Fcold(d.a_forcerange, fvec(m, "actuator_forcerange"));
+    B.Fcold(d.a_gear, gear); B.Fcold(d.a_acc0, fvec(m, "actuator_acc0")); B.Fcold(d.a_lengthrange, fvec(m, "actuator_lengthrange"));
   }
   // per-dof actuator gather list: code = actuator << 8 | slot in the tendon's dof list
   std::vector<int> actadr(nv + 1, 0), actlist;
@@ -512,6 +525,10 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     for (int i = 0; i < n4; i++) { roff[i] = hw; hw += 4 * ((i / 4 + 1) | 1); }
     roff[n4] = hw; hw += n4;
     B.I(d.h_roff, roff);
+    // (a, b), a >= b, of pair e = a (a + 1) / 2 + b for the contact blocks of the Hessian: a | b << 8
+    std::vector<int> pair_ab;
+    for (int a = 0; a < KS; a++) for (int b2 = 0; b2 <= a; b2++) pair_ab.push_back(a | (b2 << 8));
+    B.I(d.pair_ab, pair_ab);
     off = a0 + std::max(tmp_words, hw);
     // limit / contact / row records follow directly: the tendon phase runs before they are rebuilt, so its per-segment
     // results may run on from the Hessian's words into theirs

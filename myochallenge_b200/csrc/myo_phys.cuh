@@ -24,6 +24,8 @@ struct Ctx {
   MYO_DI float* wpp(const DevModel& m) const { return MYO_SMEM_WORDS + soff + m.o_wparam; }   // per-world override parameters
 };
 
+// cold model table (global memory only, see Builder::Fcold in myo_pack.cpp)
+#define GT(field) (m.g_tables + m.field.off)
 #define SF(field) (MYO_SMEM_WORDS + c.soff + m.field)
 #define SI(field) (reinterpret_cast<int*>(MYO_SMEM_WORDS + c.soff + m.field))
 #define SO(off) (MYO_SMEM_WORDS + c.soff + (off))   // scratch word offset -> pointer (noinline phases take offsets, not pointers)
@@ -600,15 +602,15 @@ MYO_PHASE void phase_actuation(int mslot, Ctx<G>& c) {
   const float* ctrl = SF(o_ctrl); const float* act = SF(o_act);
   for (int i = c.lane; i < m.nu; i += G) {
     const int t = m.a_tendon[i];
-    const float gear = m.a_gear[i];
+    const float gear = GT(a_gear)[i];
     const float len = gear * SF(o_tenL)[t], vel = gear * SF(o_tenV)[t];
     float u = ctrl[i];
-    if (m.a_ctrllimited[i]) u = clipf(u, m.a_ctrlrange[2 * i], m.a_ctrlrange[2 * i + 1]);
+    if (m.a_ctrllimited[i]) u = clipf(u, GT(a_ctrlrange)[2 * i], GT(a_ctrlrange)[2 * i + 1]);
     const int ai = i - (m.nu - m.na);
-    const float* dp = m.a_dynprm + 3 * i;
-    const float* gp = m.a_gainprm + 9 * i;
-    const float* bp = m.a_biasprm + 9 * i;
-    const float lr0 = m.a_lengthrange[2 * i], lr1 = m.a_lengthrange[2 * i + 1], acc0 = m.a_acc0[i];
+    const float* dp = GT(a_dynprm) + 3 * i;
+    const float* gp = GT(a_gainprm) + 9 * i;
+    const float* bp = GT(a_biasprm) + 9 * i;
+    const float lr0 = GT(a_lengthrange)[2 * i], lr1 = GT(a_lengthrange)[2 * i + 1], acc0 = GT(a_acc0)[i];
     const int dyn = m.a_dyntype[i];
     float a_cur = (ai >= 0 && dyn != 0) ? act[ai] : 0.f;
     if (dyn == 3) {          // muscle
@@ -645,7 +647,7 @@ MYO_PHASE void phase_actuation(int mslot, Ctx<G>& c) {
       else { const float x = (L - b) / fmaxf(kMinVal, b - 1.f); bias = -F0 * bp[7] * (0.5f + x); }
     }
     float force = (dyn == 0 ? gain * u : gain * a_cur) + bias;
-    if (m.a_forcelimited[i]) force = clipf(force, m.a_forcerange[2 * i], m.a_forcerange[2 * i + 1]);
+    if (m.a_forcelimited[i]) force = clipf(force, GT(a_forcerange)[2 * i], GT(a_forcerange)[2 * i + 1]);
     SF(o_actF)[i] = force;
   }
   c.tile.sync();
@@ -656,7 +658,7 @@ MYO_PHASE void phase_actuation(int mslot, Ctx<G>& c) {
     for (int k = m.d_actadr[d]; k < m.d_actadr[d + 1]; k++) {
       const int code = m.d_actlist[k];
       const int a = code >> 8, slot = code & 255;
-      s += m.a_gear[a] * SF(o_tenJ)[m.a_tendon[a] * KT + slot] * SF(o_actF)[a];
+      s += GT(a_gear)[a] * SF(o_tenJ)[m.a_tendon[a] * KT + slot] * SF(o_actF)[a];
     }
     SF(o_qact)[d] = s;
     float p = -m.d_damping[d] * qvel[d];
@@ -1212,11 +1214,8 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
       const int npair = ns * (ns + 1) / 2;
       for (int e0 = 0; e0 < npair; e0 += G) {
         const int e = e0 + c.lane;
-        int a = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
-        if ((a + 1) * (a + 2) / 2 <= e) a++;
-        if (a * (a + 1) / 2 > e) a--;
-        int b = e - a * (a + 1) / 2;
-        if (e >= npair) { a = 0; b = 0; }
+        const int ab = m.pair_ab[e < npair ? e : 0];
+        const int a = ab & 255, b = ab >> 8;
         int ia, ib;
         float na, ta, ua, nb, tb, ub;
         if (by_shfl) {

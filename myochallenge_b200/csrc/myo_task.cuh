@@ -51,7 +51,7 @@ MYO_PHASE void task_action(int mslot, const myo_task_cfg& t, Ctx<G>& c, const fl
     if (t.normalize_act) {
       if (m.a_dyntype[i] == 3) u = 1.f / (1.f + expf(-5.f * (u - 0.5f)));
       else {
-        const float lo = m.a_ctrlrange[2 * i], hi = m.a_ctrlrange[2 * i + 1];
+        const float lo = (m.g_tables + m.a_ctrlrange.off)[2 * i], hi = (m.g_tables + m.a_ctrlrange.off)[2 * i + 1];
         u = 0.5f * (lo + hi) + clipf(u, -1.f, 1.f) * 0.5f * (hi - lo);
       }
     }
