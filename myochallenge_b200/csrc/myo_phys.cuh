@@ -1138,20 +1138,24 @@ MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
 // Dense Newton system in scratch: lower triangle of H by rows, row i starting at word m.h_roff[i] (float4 aligned; four
 // rows share a length that is an odd number of float4s, so a lane per row reads float4s with few bank conflicts);
 // rows nv..n4-1 pad to a multiple of four (identity), row n4 holds the right-hand side.
-// H = M + sum_{active rows} D_r J_r' J_r, right-hand side = -grad.
+//   grad = M a - f_smooth - J' f(jar)          (f_r = -D_r jar_r on active rows: jar_r < 0)
+//   H    = M + sum_{active rows} D_r J_r' J_r,  right-hand side = -grad
+// One walk over the constraint blocks feeds both: joint-limit rows lane-parallel (disjoint dofs), tendon-limit rows and
+// contacts one after the other, lanes across the block's support / support pairs (no atomics, fixed order).
 template <int G>
-MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
+MYO_PHASE void newton_system(int mslot, Ctx<G>& c) {
   MYO_M
-  float* H = SF(o_H); const float* M = SF(o_M); const float* grad = SF(o_grad);
+  float* H = SF(o_H); const float* M = SF(o_M); float* grad = SF(o_grad);
+  const float* Ma = SF(o_Ma); const float* fs = SF(o_smooth);
   const int nv = m.nv;
   const int* roff = m.h_roff.ptr();
-  // a lane owns a row: clear it, then drop the row's mass-matrix entries (i, ancestors of i) into it
   const int n4 = (nv + 3) & ~3;
-  for (int k = c.lane; k < n4; k += G) H[roff[n4] + k] = k < nv ? -grad[k] : 0.f;
   for (int i = nv + c.lane; i < n4; i += G) {       // identity padding rows up to a multiple of four
     for (int k = 0; k <= i; k++) H[roff[i] + k] = (k == i) ? 1.f : 0.f;
   }
+  // a lane owns a row: clear it, then drop the row's mass-matrix entries (i, ancestors of i) into it
   for (int i = c.lane; i < nv; i += G) {
+    grad[i] = Ma[i] - fs[i];
     float* Hi = H + roff[i];
     float4* row4 = reinterpret_cast<float4*>(Hi);
     for (int k = 0; k <= i / 4; k++) row4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1162,11 +1166,14 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
   const int* misc = SI(o_misc);
   const int nlim = misc[MI_NLIM], ncon = misc[MI_NCON];
   const float* rows = SF(o_row);
-  // joint limits touch one diagonal entry each (J = +-1)
+  // joint limits: J = +-1 on one dof: H_dd += D, grad_d -= sign * f = sign * D * jar
   for_joint_limit_rows<G>(m, c, nlim,
       [&](int r) { const float* row = rows + r * ROW_WORDS; const float* lr = SF(o_lim) + r * LIM_WORDS;
                    return row[R_JAR] < 0.f ? row[R_D] * lr[L_SIGN] : 0.f; },     // sign * (sign * D) = D
       [&](int dof, float v) { H[roff[dof] + dof] += v; });
+  for_joint_limit_rows<G>(m, c, nlim,
+      [&](int r) { const float* row = rows + r * ROW_WORDS; return row[R_JAR] < 0.f ? row[R_D] * row[R_JAR] : 0.f; },
+      [&](int dof, float v) { grad[dof] += v; });
   c.tile.sync();
   if (m.any_tendon_limit)
     for (int r = 0; r < nlim; r++) {
@@ -1175,7 +1182,8 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
       const float* row = rows + r * ROW_WORDS;
       if (row[R_JAR] < 0.f) {
         const int ns = li[L_NSUP];
-        const float D = row[R_D];
+        const float D = row[R_D], nf = D * row[R_JAR];     // -f
+        for (int e = c.lane; e < ns; e += G) grad[lim_idx(li, e)] += lim_J(c.sp(), lr, li, e) * nf;
         for (int e = c.lane; e < ns * ns; e += G) {
           const int a = e / ns, b = e - a * ns;
           const int ia = lim_idx(li, a), ib = lim_idx(li, b);
@@ -1190,16 +1198,16 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
     if (row0 < 0) continue;
     const int nr = ci[C_DIM] == 1 ? 1 : 4, ns = ci[C_NSUP];
     const float mu = cr[C_MU];
-    // W = sum_active D c c', c = (1, +-mu, 0) / (1, 0, +-mu)
-    float w00 = 0.f, w01 = 0.f, w02 = 0.f, w11 = 0.f, w22 = 0.f;
+    // W = sum_active D c c', c = (1, +-mu, 0) / (1, 0, +-mu); (gn, g1, g2) = -(force in the contact frame)
+    float w00 = 0.f, w01 = 0.f, w02 = 0.f, w11 = 0.f, w22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
     for (int q = 0; q < nr; q++) {
-      const float* row = rows + (row0 + q) * ROW_WORDS;
-      if (row[R_JAR] < 0.f) {
-        const float D = row[R_D];
-        w00 += D;
+      const float4 row = *reinterpret_cast<const float4*>(rows + (row0 + q) * ROW_WORDS);     // D, aref, jar, jp
+      if (row.z < 0.f) {
+        const float D = row.x, nf = D * row.z;
+        w00 += D; gn += nf;
         if (nr == 4) {
           const float s = (q & 1) ? -mu : mu;
-          if (q < 2) { w01 += D * s; w11 += D * s * s; } else { w02 += D * s; w22 += D * s * s; }
+          if (q < 2) { w01 += D * s; w11 += D * s * s; g1 += nf * s; } else { w02 += D * s; w22 += D * s * s; g2 += nf * s; }
         }
       }
     }
@@ -1209,7 +1217,11 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
       const bool by_shfl = G > 1 && ns <= G;
       float jn = 0.f, jt1 = 0.f, jt2 = 0.f;
       int dof = 0;
-      if (by_shfl && c.lane < ns) dof = contact_entry(m, c.sp(), cr, ci, c.lane, &jn, &jt1, &jt2);
+      if (by_shfl) {
+        if (c.lane < ns) { dof = contact_entry(m, c.sp(), cr, ci, c.lane, &jn, &jt1, &jt2); grad[dof] += jn * gn + jt1 * g1 + jt2 * g2; }
+      } else {
+        for (int e = c.lane; e < ns; e += G) { const int d = contact_entry(m, c.sp(), cr, ci, e, &jn, &jt1, &jt2); grad[d] += jn * gn + jt1 * g1 + jt2 * g2; }
+      }
       // every unordered pair (a >= b) of the support once: e = a (a + 1) / 2 + b
       const int npair = ns * (ns + 1) / 2;
       for (int e0 = 0; e0 < npair; e0 += G) {
@@ -1231,6 +1243,8 @@ MYO_PHASE void build_hessian(int mslot, Ctx<G>& c) {
     }
     c.tile.sync();
   }
+  for (int k = c.lane; k < n4; k += G) H[roff[n4] + k] = k < nv ? -grad[k] : 0.f;
+  c.tile.sync();
 }
 
 // In-place dense Cholesky H = L L', left-looking by blocks of four columns, a lane per row. For a block the lane
@@ -1309,16 +1323,35 @@ MYO_PHASE void chol_factor_solve(int mslot, Ctx<G>& c, int oH, int ox, int n) {
   float y[NSET];
 #pragma unroll
   for (int q = 0; q < NSET; q++) { const int i = c.lane + q * G; y[q] = i < n ? H[roff[n4] + i] : 0.f; }
-  for (int j = n - 1; j >= 0; j--) {
-    const float* Lj = H + roff[j];
+  // y_j from the lane that owns it
+  auto fetch = [&](int j) {
     const int jq = j / G;
     float v = y[0];
 #pragma unroll
     for (int q = 1; q < NSET; q++) v = (jq == q) ? y[q] : v;
-    const float xj = c.tile.shfl(v, j - jq * G) * Lj[j];
+    return c.tile.shfl(v, j - jq * G);
+  };
+  // back substitution L' x = y by blocks of four columns, last block first: the 4 x 4 diagonal block (stored as the
+  // factorisation left it: inverse pivots on the diagonal) is solved redundantly in registers, then every lane
+  // removes the four new x from the rows it owns
+  for (int J = n4 - 4; J >= 0; J -= 4) {
+    const float* R0 = H + roff[J]; const float* R1 = H + roff[J + 1]; const float* R2 = H + roff[J + 2]; const float* R3 = H + roff[J + 3];
+    const float4 d0 = *reinterpret_cast<const float4*>(R0 + J), d1 = *reinterpret_cast<const float4*>(R1 + J);
+    const float4 d2 = *reinterpret_cast<const float4*>(R2 + J), d3 = *reinterpret_cast<const float4*>(R3 + J);
+    const float y0 = fetch(J), y1 = fetch(J + 1), y2 = fetch(J + 2), y3 = fetch(J + 3);
+    const float x3 = y3 * d3.w;
+    const float x2 = (y2 - d3.z * x3) * d2.z;
+    const float x1 = (y1 - d3.y * x3 - d2.y * x2) * d1.y;
+    const float x0 = (y0 - d3.x * x3 - d2.x * x2 - d1.x * x1) * d0.x;
 #pragma unroll
-    for (int q = 0; q < NSET; q++) { const int i = c.lane + q * G; if (i < j) y[q] -= Lj[i] * xj; }
-    if (c.lane == j - jq * G) x[j] = xj;
+    for (int q = 0; q < NSET; q++) {
+      const int i = c.lane + q * G;
+      if (i < J) y[q] -= R0[i] * x0 + R1[i] * x1 + R2[i] * x2 + R3[i] * x3;
+    }
+    if (c.lane == 0) {
+      if (J + 3 < n) *reinterpret_cast<float4*>(x + J) = make_float4(x0, x1, x2, x3);
+      else { x[J] = x0; if (J + 1 < n) x[J + 1] = x1; if (J + 2 < n) x[J + 2] = x2; }
+    }
   }
   c.tile.sync();
 }
@@ -1429,15 +1462,12 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
   MYO_PH_BEGIN
   float prev_step = 3.0e38f;
   for (; iter < m.solver_iter; iter++) {
-    for (int i = c.lane; i < nv; i += G) grad[i] = Ma[i] - fs[i];
-    c.tile.sync();
-    rows_JT_force<G>(mslot, c, m.o_grad, -1.f);
+    MYO_PH_RESTART newton_system<G>(mslot, c); MYO_PH(11)
     float g2 = 0.f, amax = 0.f;
     for (int i = c.lane; i < nv; i += G) { g2 += grad[i] * grad[i]; amax = fmaxf(amax, fabsf(a[i])); }
     g2 = tile_sum<G>(c, g2);
     amax = tile_max<G>(c, amax);
     if (sqrtf(g2) * scale < m.solver_tol) break;
-    MYO_PH_RESTART build_hessian<G>(mslot, c); MYO_PH(11)
     chol_factor_solve<G>(mslot, c, m.o_H, m.o_p, nv); MYO_PH(12)
     rows_dot<G>(mslot, c, m.o_p, R_JP, false, false);
     mul_M<G>(mslot, c, m.o_M, m.o_p, m.o_Mp);
