@@ -75,13 +75,13 @@ struct DevModel {
   int any_damping, any_tendon_passive, any_joint_spring, any_tendon_limit;
   // body tables
   TabI b_parent, b_root, b_jntadr, b_jntnum, b_dofadr, b_dofnum, b_nchain, b_chain, b_mass_slot,
-      b_sameframe, b_childadr, b_child, lvl_adr, lvl_body;
+      b_sameframe, lvl_adr, lvl_body, b_subadr, b_sub;
   TabF b_pos, b_mat, b_ipos, b_imat, b_mass, b_inertia, b_invweight0;
   // joints
   TabI j_type, j_qposadr, j_dofadr, j_body, j_limited;
   TabF j_pos, j_axis, j_qpos0, j_range, j_margin, j_solref, j_solimp, j_stiffness, j_qpos_spring;
   // dofs
-  TabI d_body, d_parent, d_simple, d_Madr, d_depth, d_descadr, d_desc, d_jnt,
+  TabI d_body, d_parent, d_simple, d_Madr, d_depth, d_descadr, d_desc, d_jnt, d_prefadr, d_pref,
       d_actadr, d_actlist;
   TabF d_armature, d_damping, d_invweight0, d_M0;
   // geoms
@@ -102,8 +102,8 @@ struct DevModel {
   TabI a_tendon, a_dyntype, a_gaintype, a_biastype, a_ctrllimited, a_forcelimited;
   TabF a_dynprm, a_gainprm, a_biasprm, a_ctrlrange, a_forcerange, a_gear, a_acc0, a_lengthrange;
   // scratch offsets (words) inside one world's shared-memory block
-  int o_qpos, o_qvel, o_act, o_ctrl, o_warm, o_xpos, o_xmat, o_xipos, o_cdof, o_cinert, o_cvel, o_cdofdot,
-      o_cacc, o_cfrc, o_M, o_tenL, o_tenV, o_tenJ, o_actF, o_bias, o_passive, o_qact, o_smooth, o_qaccs,
+  int o_qpos, o_qvel, o_act, o_ctrl, o_warm, o_xpos, o_xmat, o_xipos, o_cdof, o_cinert, o_cdofdot,
+      o_cfrc, o_M, o_tenL, o_tenV, o_tenJ, o_actF, o_bias, o_passive, o_qact, o_smooth, o_qaccs,
       o_qacc, o_qcon, o_actdot, o_grad, o_p, o_Mp, o_Ma, o_H, o_lim, o_con, o_row, o_misc, o_obs, o_wparam,
       scratch_words;
   const float* g_tables;     // global copy of the table block

@@ -215,8 +215,21 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
 
   B.I(d.b_parent, parent); B.I(d.b_root, rootid); B.I(d.b_jntadr, jntadr); B.I(d.b_jntnum, jntnum);
   B.I(d.b_dofadr, dofadr); B.I(d.b_dofnum, dofnum); B.I(d.b_nchain, nchain); B.I(d.b_chain, chain);
-  B.I(d.b_mass_slot, mass_slot); B.I(d.b_sameframe, sameframe); B.I(d.b_childadr, childadr); B.I(d.b_child, child);
+  B.I(d.b_mass_slot, mass_slot); B.I(d.b_sameframe, sameframe);
   B.I(d.lvl_adr, lvl_adr); B.I(d.lvl_body, lvl_body);
+  {   // subtree of every body (itself first, then its descendants in body order): composite inertia / force sums
+    std::vector<int> subadr(nbody + 1, 0), sub;
+    for (int b = 0; b < nbody; b++) {
+      subadr[b] = (int)sub.size();
+      for (int k = b; k < nbody; k++) {
+        int a = k;
+        while (a > b) a = parent[a];
+        if (a == b && (b > 0 || k == 0)) sub.push_back(k);
+      }
+    }
+    subadr[nbody] = (int)sub.size();
+    B.I(d.b_subadr, subadr); B.I(d.b_sub, sub);
+  }
   {   // body frame / inertial frame orientations as matrices: the kinematic sweep composes rotation matrices
     std::vector<float> bmat((size_t)nbody * 9), bimat((size_t)nbody * 9);
     const double* bq = m.d("body_quat"); const double* biq = m.d("body_iquat");
@@ -453,6 +466,22 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   actadr[nv] = (int)actlist.size();
   B.I(d.d_body, dbody); B.I(d.d_parent, dparent); B.I(d.d_simple, dsimple); B.I(d.d_Madr, dMadr); B.I(d.d_depth, ddepth);
   B.I(d.d_descadr, descadr); B.I(d.d_desc, desc); B.I(d.d_jnt, djnt);
+  {   // dofs whose motion precedes dof i when mj_comVel forms cdof_dot_i = cvel_so_far x cdof_i: the dofs before it on its
+      // chain - except the rotational dofs of a free joint, which see the joint's three translations only
+    std::vector<int> prefadr(nv + 1, 0), pref;
+    for (int i = 0; i < nv; i++) {
+      prefadr[i] = (int)pref.size();
+      const int j = djnt[i], body = dbody[i];
+      if (jtype[j] == J_FREE) {
+        const int d0 = jdadr[j];
+        if (i >= d0 + 3) for (int k = d0; k < d0 + 3; k++) pref.push_back(k);
+      } else {
+        for (int k = 0; k < nchain[body]; k++) { const int dk = chain[(size_t)body * KC + k]; if (dk < i) pref.push_back(dk); }
+      }
+    }
+    prefadr[nv] = (int)pref.size();
+    B.I(d.d_prefadr, prefadr); B.I(d.d_pref, pref);
+  }
   B.I(d.d_actadr, actadr); B.I(d.d_actlist, actlist);
   B.F(d.d_armature, fvec(m, "dof_armature")); B.F(d.d_damping, fvec(m, "dof_damping"));
   B.F(d.d_invweight0, fvec(m, "dof_invweight0")); B.F(d.d_M0, fvec(m, "dof_M0"));
@@ -511,7 +540,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   // (and the tendon phase's per-segment results) reuse their words
   {
     const int a0 = off;
-    d.o_cvel = take(6 * nbody); d.o_cdofdot = take(6 * nv); d.o_cacc = take(6 * nbody); d.o_cfrc = take(6 * nbody);
+    d.o_cdofdot = take(6 * nv); d.o_cfrc = take(6 * nbody);
     d.o_cinert = take(10 * nbody);
     const int tmp_words = off - a0;
     d.o_H = a0;

@@ -128,68 +128,6 @@ MYO_PHASE void body_local_pose(int mslot, Ctx<G>& c, int b) {
   for (int k = 0; k < 9; k++) xm[k] = R[k];
 }
 
-// mj_comVel + mj_rne forward (flg_acc = 0) for one body, parent already done
-template <int G>
-MYO_PHASE void body_velocity(int mslot, Ctx<G>& c, int b) {
-  MYO_M
-  const float* qvel = SF(o_qvel);
-  const float* cdof = SF(o_cdof);
-  const int pid = m.b_parent[b], jadr = m.b_jntadr[b], jnum = m.b_jntnum[b];
-  const bool is_free = (jnum == 1 && m.j_type[jadr] == J_FREE);
-  float cv[6], ca[6];
-  {
-    const float* pv = SF(o_cvel) + 6 * pid;
-    const float* pa = SF(o_cacc) + 6 * pid;
-#pragma unroll
-    for (int k = 0; k < 6; k++) { cv[k] = pv[k]; ca[k] = pa[k]; }
-  }
-  float* cdd = SF(o_cdofdot);
-  const int d0 = m.b_dofadr[b], dn = m.b_dofnum[b];
-  if (is_free) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      float* t = cdd + 6 * (d0 + k);
-      t[0] = t[1] = t[2] = t[3] = t[4] = t[5] = 0.f;
-      cv[3 + k] += qvel[d0 + k];
-    }
-    float add[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const float* cd = cdof + 6 * (d0 + 3 + k);
-      float t[6];
-      cross_motion(t, cv, cd);
-      const float w = qvel[d0 + 3 + k];
-#pragma unroll
-      for (int e = 0; e < 6; e++) { cdd[6 * (d0 + 3 + k) + e] = t[e]; ca[e] += t[e] * w; add[e] += cd[e] * w; }
-    }
-#pragma unroll
-    for (int e = 0; e < 6; e++) cv[e] += add[e];
-  } else {
-    for (int d = d0; d < d0 + dn; d++) {
-      const float* cd = cdof + 6 * d;
-      float t[6];
-      cross_motion(t, cv, cd);
-      const float w = qvel[d];
-#pragma unroll
-      for (int e = 0; e < 6; e++) { cdd[6 * d + e] = t[e]; ca[e] += t[e] * w; cv[e] += cd[e] * w; }
-    }
-  }
-  float* ov = SF(o_cvel) + 6 * b;
-  float* oa = SF(o_cacc) + 6 * b;
-#pragma unroll
-  for (int k = 0; k < 6; k++) { ov[k] = cv[k]; oa[k] = ca[k]; }
-  {
-    const float* ci = SF(o_cinert) + 10 * b;
-    float f[6], t[6], t1[6];
-    mul_inert_vec(f, ci, ca);
-    mul_inert_vec(t, ci, cv);
-    cross_force(t1, cv, t);
-    float* of = SF(o_cfrc) + 6 * b;
-#pragma unroll
-    for (int k = 0; k < 6; k++) of[k] = f[k] + t1[k];
-  }
-}
-
 template <int G>
 MYO_PHASE void phase_tree_forward(int mslot, Ctx<G>& c, bool dyn) {
   MYO_M
@@ -199,10 +137,9 @@ MYO_PHASE void phase_tree_forward(int mslot, Ctx<G>& c, bool dyn) {
 #pragma unroll
     for (int k = 0; k < 9; k++) xm[k] = (k % 4 == 0) ? 1.f : 0.f;
     if (dyn) {
-      float* cv = SF(o_cvel); float* ca = SF(o_cacc); float* cf = SF(o_cfrc); float* ci = SF(o_cinert);
+      float* cf = SF(o_cfrc); float* ci = SF(o_cinert);
 #pragma unroll
-      for (int k = 0; k < 6; k++) { cv[k] = 0.f; cf[k] = 0.f; }
-      ca[0] = ca[1] = ca[2] = 0.f; ca[3] = -m.gravity[0]; ca[4] = -m.gravity[1]; ca[5] = -m.gravity[2];
+      for (int k = 0; k < 6; k++) cf[k] = 0.f;
 #pragma unroll
       for (int k = 0; k < 10; k++) ci[k] = 0.f;
     }
@@ -279,53 +216,82 @@ MYO_PHASE void phase_tree_forward(int mslot, Ctx<G>& c, bool dyn) {
     }
   }
   c.tile.sync();
-  // D: velocities, bias accelerations and forces down the tree
-  for (int L = 0; L < m.nlevel; L++) {
-    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) body_velocity<G>(mslot, c, m.lvl_body[i]);
-    c.tile.sync();
-  }
-}
-
-// mj_crb backward accumulation + mj_rne backward pass, children gathered in a fixed order
-template <int G>
-MYO_PHASE void phase_tree_backward(int mslot, Ctx<G>& c) {
-  MYO_M
-  float* ci = SF(o_cinert); float* cf = SF(o_cfrc);
-  for (int L = m.nlevel - 2; L >= 0; L--) {
-    for (int i = m.lvl_adr[L] + c.lane; i < m.lvl_adr[L + 1]; i += G) {
-      const int b = m.lvl_body[i];
-      for (int k = m.b_childadr[b]; k < m.b_childadr[b + 1]; k++) {
-        const int ch = m.b_child[k];
+  // D: mj_comVel + mj_rne forward (flg_acc = 0) without a sweep down the tree. All cdof share their tree's reference
+  // point, so a body's spatial velocity is the plain sum over its dof chain, and cdof_dot_i = (motion of the dofs that
+  // precede i: host list d_pref) x cdof_i needs no parent result either: a lane per dof, then a lane per body.
+  const float* qvel = SF(o_qvel);
+  float* cdd = SF(o_cdofdot);
+  for (int i = c.lane; i < m.nv; i += G) {
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, t[6];
+    for (int k = m.d_prefadr[i]; k < m.d_prefadr[i + 1]; k++) {
+      const int d = m.d_pref[k];
+      const float w = qvel[d];
 #pragma unroll
-        for (int e = 0; e < 10; e++) ci[10 * b + e] += ci[10 * ch + e];
-#pragma unroll
-        for (int e = 0; e < 6; e++) cf[6 * b + e] += cf[6 * ch + e];
-      }
+      for (int e = 0; e < 6; e++) v[e] += cdof[6 * d + e] * w;
     }
-    c.tile.sync();
+    cross_motion(t, v, cdof + 6 * i);
+#pragma unroll
+    for (int e = 0; e < 6; e++) cdd[6 * i + e] = t[e];
   }
+  c.tile.sync();
+  for (int b = 1 + c.lane; b < m.nbody; b += G) {
+    float cv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float ca[6] = {0.f, 0.f, 0.f, -m.gravity[0], -m.gravity[1], -m.gravity[2]};
+    for (int k = 0; k < m.b_nchain[b]; k++) {
+      const int d = m.b_chain[b * KC + k];
+      const float w = qvel[d];
+#pragma unroll
+      for (int e = 0; e < 6; e++) { cv[e] += cdof[6 * d + e] * w; ca[e] += cdd[6 * d + e] * w; }
+    }
+    const float* ci = SF(o_cinert) + 10 * b;
+    float f[6], t[6], t1[6];
+    mul_inert_vec(f, ci, ca);
+    mul_inert_vec(t, ci, cv);
+    cross_force(t1, cv, t);
+    float* of = SF(o_cfrc) + 6 * b;
+#pragma unroll
+    for (int k = 0; k < 6; k++) of[k] = f[k] + t1[k];
+  }
+  c.tile.sync();
 }
 
-// a10.4 mass matrix in MuJoCo's sparse dof_Madr layout (row i: i, parent(i), ...) + qfrc_bias
+// a10.4 mj_crb + mj_rne backward + qfrc_bias, a lane per dof and no sweep up the tree: the lane adds the composite
+// inertia and the force of its body's subtree itself (host list b_sub), then forms its mass-matrix row in MuJoCo's
+// sparse dof_Madr layout (row i: i, parent(i), ...) and qfrc_bias_i = cdof_i . (subtree force).
 template <int G>
 MYO_PHASE void phase_mass_bias(int mslot, Ctx<G>& c) {
   MYO_M
-  const float* cdof = SF(o_cdof); const float* crb = SF(o_cinert); const float* cf = SF(o_cfrc);
+  const float* cdof = SF(o_cdof); const float* cin = SF(o_cinert); const float* cf = SF(o_cfrc);
   float* M = SF(o_M); float* bias = SF(o_bias);
   for (int i = c.lane; i < m.nv; i += G) {
     const int body = m.d_body[i];
+    const bool simple = m.d_simple[i] != 0;
+    float crb[10], fs[6];
+#pragma unroll
+    for (int e = 0; e < 10; e++) crb[e] = 0.f;
+#pragma unroll
+    for (int e = 0; e < 6; e++) fs[e] = 0.f;
+    for (int k = m.b_subadr[body]; k < m.b_subadr[body + 1]; k++) {
+      const int b = m.b_sub[k];
+      if (!simple) {
+#pragma unroll
+        for (int e = 0; e < 10; e++) crb[e] += cin[10 * b + e];
+      }
+#pragma unroll
+      for (int e = 0; e < 6; e++) fs[e] += cf[6 * b + e];
+    }
     float s = 0.f;
 #pragma unroll
-    for (int e = 0; e < 6; e++) s += cdof[6 * i + e] * cf[6 * body + e];
+    for (int e = 0; e < 6; e++) s += cdof[6 * i + e] * fs[e];
     bias[i] = s;
     int adr = m.d_Madr[i];
-    if (m.d_simple[i]) {   // mj_crb: simple dofs take the stored dof_M0, off-diagonals stay zero
+    if (simple) {   // mj_crb: simple dofs take the stored dof_M0, off-diagonals stay zero
       M[adr] = m.d_M0[i];
-      for (int s = 1; s <= m.d_depth[i]; s++) M[adr + s] = 0.f;
+      for (int q = 1; q <= m.d_depth[i]; q++) M[adr + q] = 0.f;
       continue;
     }
     float buf[6];
-    mul_inert_vec(buf, crb + 10 * body, cdof + 6 * i);
+    mul_inert_vec(buf, crb, cdof + 6 * i);
     int j = i;
     bool first = true;
     while (j >= 0) {
@@ -1598,8 +1564,8 @@ MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_M
   MYO_PH_BEGIN
   MYO_CTA_SYNC phase_tree_forward<G>(mslot, c, true); MYO_PH(0)
-  MYO_CTA_SYNC phase_tree_backward<G>(mslot, c); MYO_PH(2)
-  phase_mass_bias<G>(mslot, c); MYO_PH(3)
+  MYO_PH(2)
+  MYO_CTA_SYNC phase_mass_bias<G>(mslot, c); MYO_PH(3)
   // the velocity-stage temporaries are dead from here on: the tendon phase reuses their scratch (with the Hessian's)
   MYO_CTA_SYNC phase_tendon<G>(mslot, c, status); MYO_PH(1)
   MYO_CTA_SYNC phase_collision<G>(mslot, c, status); MYO_PH(5)
