@@ -81,7 +81,7 @@ struct DevModel {
   TabI j_type, j_qposadr, j_dofadr, j_body, j_limited;
   TabF j_pos, j_axis, j_qpos0, j_range, j_margin, j_solref, j_solimp, j_stiffness, j_qpos_spring;
   // dofs
-  TabI d_body, d_parent, d_simple, d_Madr, d_depth, d_descadr, d_desc, d_jnt, d_prefadr, d_pref,
+  TabI d_body, d_parent, d_simple, d_Madr, d_depth, d_jnt, d_prefadr, d_pref, m_rowadr, m_row,
       d_actadr, d_actlist;
   TabF d_armature, d_damping, d_invweight0, d_M0;
   // geoms

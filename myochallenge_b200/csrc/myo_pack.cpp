@@ -465,7 +465,24 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   }
   actadr[nv] = (int)actlist.size();
   B.I(d.d_body, dbody); B.I(d.d_parent, dparent); B.I(d.d_simple, dsimple); B.I(d.d_Madr, dMadr); B.I(d.d_depth, ddepth);
-  B.I(d.d_descadr, descadr); B.I(d.d_desc, desc); B.I(d.d_jnt, djnt);
+  B.I(d.d_jnt, djnt);
+  {   // full symmetric rows of the mass matrix for mj_mulM: entry = column | index into qM << 8, columns ascending
+    std::vector<int> radr(nv + 1, 0), rlist;
+    for (int i = 0; i < nv; i++) {
+      radr[i] = (int)rlist.size();
+      std::vector<std::pair<int, int>> ent;
+      { int adr = dMadr[i], j = i; while (j >= 0) { ent.push_back({j, adr++}); j = dparent[j]; } }       // i and its ancestors
+      if (!dsimple[i])
+        for (int k = descadr[i]; k < descadr[i + 1]; k++) { const int dk = desc[k]; ent.push_back({dk, dMadr[dk] + ddepth[dk] - ddepth[i]}); }
+      std::sort(ent.begin(), ent.end());
+      for (auto& e : ent) {
+        if (e.second >= (1 << 23)) { status = MYO_E_LIMIT; return "mass matrix too large for the packed row table"; }
+        rlist.push_back(e.first | (e.second << 8));
+      }
+    }
+    radr[nv] = (int)rlist.size();
+    B.I(d.m_rowadr, radr); B.I(d.m_row, rlist);
+  }
   {   // dofs whose motion precedes dof i when mj_comVel forms cdof_dot_i = cvel_so_far x cdof_i: the dofs before it on its
       // chain - except the rotational dofs of a free joint, which see the joint's three translations only
     std::vector<int> prefadr(nv + 1, 0), pref;

@@ -306,22 +306,22 @@ MYO_PHASE void phase_mass_bias(int mslot, Ctx<G>& c) {
   c.tile.sync();
 }
 
-// y = M x using the sparse symmetric layout (mj_mulM)
+// y = M x (mj_mulM): a lane per row over the host-built list of the row's nonzeros (column | qM index << 8)
 template <int G>
 MYO_PHASE void mul_M(int mslot, Ctx<G>& c, int oM, int ox, int oy, bool sync = true) {
   MYO_M
   const float* M = SO(oM); const float* x = SO(ox); float* y = SO(oy);
   for (int i = c.lane; i < m.nv; i += G) {
-    const int dep = m.d_depth[i];
-    int adr = m.d_Madr[i], j = i;
-    float v = 0.f;
-    while (j >= 0) { v += M[adr++] * x[j]; j = m.d_parent[j]; }
-    if (!m.d_simple[i])
-      for (int kk = m.d_descadr[i]; kk < m.d_descadr[i + 1]; kk++) {
-        const int k = m.d_desc[kk];
-        v += M[m.d_Madr[k] + m.d_depth[k] - dep] * x[k];
-      }
-    y[i] = v;
+    float v0 = 0.f, v1 = 0.f;
+    int k = m.m_rowadr[i];
+    const int k1 = m.m_rowadr[i + 1];
+    for (; k + 1 < k1; k += 2) {
+      const int e0 = m.m_row[k], e1 = m.m_row[k + 1];
+      v0 += M[e0 >> 8] * x[e0 & 255];
+      v1 += M[e1 >> 8] * x[e1 & 255];
+    }
+    if (k < k1) { const int e0 = m.m_row[k]; v0 += M[e0 >> 8] * x[e0 & 255]; }
+    y[i] = v0 + v1;
   }
   if (sync) c.tile.sync();
 }
