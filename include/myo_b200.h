@@ -29,6 +29,10 @@
  *                       /root/reference/src/main_baoding.py:75.
  *   myo_gae          <- RecurrentRolloutBuffer.compute_returns_and_advantage, called by RecurrentPPO.learn
  *                       (/root/reference/src/train/trainer.py:67-71).
+ *   myo_ppo_*        <- RecurrentPPO.train (sb3-contrib), the policy update half of agent.learn()
+ *                       (/root/reference/src/train/trainer.py:67-71; hyper-parameters
+ *                       /root/reference/docs/summary.md:86-117): evaluate_actions over sequences, PPO loss,
+ *                       backward, clip_grad_norm_, Adam.
  *
  * Conventions: every function returns 0 on success or a negative myo_status; the message for the
  * calling thread's last failure is myo_last_error().  Nothing throws across the boundary.  Handles
@@ -50,6 +54,7 @@ extern "C" {
 typedef struct myo_model myo_model;
 typedef struct myo_batch myo_batch;
 typedef struct myo_policy myo_policy;
+typedef struct myo_ppo myo_ppo;
 
 typedef enum {
   MYO_OK = 0,
@@ -264,6 +269,43 @@ int myo_vecnorm_reward(double* ret_state_dev, double* returns_dev, const float* 
 int myo_gae(const float* rewards_dev, const float* values_dev, const uint8_t* episode_starts_dev,
             const float* last_values_dev, const uint8_t* last_dones_dev, int n_steps, int n, float gamma, float gae_lambda,
             float* advantages_dev, float* returns_dev, void* stream);
+
+/* VecNormalize.normalize_obs as a stand-alone pass (what the rollout buffer stores: the observation the policy saw):
+ * out[n][d] = clip((obs - mean) / sqrt(var + epsilon), +-clip_obs); mean_f / var_f as myo_running_moments_* export them. */
+int myo_normalize_obs(const float* obs_dev, const float* mean_f_dev, const float* var_f_dev, float epsilon, float clip_obs,
+                      float* out_dev, int n, int d, void* stream);
+
+/* ---- PPO update of the recurrent policy ------------------------------------------------ */
+typedef struct myo_ppo_hyper {
+  float clip_range;              /* PPO clip on the probability ratio */
+  float clip_range_vf;           /* <= 0: no value clipping (SB3 default None) */
+  float ent_coef, vf_coef;
+  int32_t normalize_advantage;   /* per-minibatch (adv - mean) / (std + 1e-8), torch's unbiased std */
+} myo_ppo_hyper;
+/* precision: 0 = fp32 GEMMs (parity tests), 1 = bf16 operands with fp32 accumulation (as the rollout kernel computes).
+ * max_steps x max_worlds bounds a minibatch (whole sequences of max_worlds worlds). */
+int myo_ppo_create(const myo_policy_cfg* cfg, int max_steps, int max_worlds, int precision, int device, myo_ppo** out);
+void myo_ppo_destroy(myo_ppo* p);
+/* All parameters live in ONE flat fp32 vector owned by the caller (so do the gradient and the Adam moments, same
+ * length): myo_ppo_param_count floats; a tensor named by its SB3 state-dict key sits at myo_ppo_param_offset. */
+int64_t myo_ppo_param_count(const myo_ppo* p);
+int myo_ppo_param_offset(const myo_ppo* p, const char* name, int64_t* offset, int64_t* numel);
+/* Loss and gradient of one minibatch = the full n_steps sequences of the n_worlds worlds world_idx_dev[] names, read
+ * from the step-major rollout buffers ([n_steps][n_envs][.]): obs (as the policy saw them, i.e. normalised), actions
+ * (unclipped samples), episode_starts, old values / log-probs, advantages, returns; h0 / c0: [2][n_envs][H] LSTM
+ * states the rollout started from (0 = actor, 1 = critic). Writes the flat gradient (every element) and
+ * stats_dev[8] = policy_loss, value_loss, entropy_loss, approx_kl, clip_fraction, loss, adv_mean, adv_std. */
+int myo_ppo_minibatch_grad(myo_ppo* p, const float* params_dev, int n_steps, int n_envs, const int32_t* world_idx_dev, int n_worlds,
+                           const float* obs_dev, const float* actions_dev, const uint8_t* episode_starts_dev,
+                           const float* old_values_dev, const float* old_logp_dev, const float* advantages_dev,
+                           const float* returns_dev, const float* h0_dev, const float* c0_dev, const myo_ppo_hyper* hyper,
+                           float* grad_dev, float* stats_dev, void* stream);
+/* g = grad * grad_scale (1 / world_size after a summing all-reduce); clip_grad_norm_(g, max_grad_norm) (<= 0: off);
+ * torch.optim.Adam step number `step` (1-based) on the flat vectors. grad_norm_dev (optional): the norm before clipping. */
+int myo_ppo_adam_step(myo_ppo* p, float* params_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int step,
+                      float lr, float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* grad_norm_dev,
+                      void* stream);
+int64_t myo_ppo_launch_count(const myo_ppo* p);
 
 #ifdef __cplusplus
 }

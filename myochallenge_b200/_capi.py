@@ -51,6 +51,13 @@ class TaskCfg(C.Structure):
     ]
 
 
+class PPOHyper(C.Structure):
+    """Mirror of ``struct myo_ppo_hyper``."""
+
+    _fields_ = [("clip_range", C.c_float), ("clip_range_vf", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float),
+                ("normalize_advantage", C.c_int32)]
+
+
 class PolicyCfg(C.Structure):
     _fields_ = [
         ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("lstm_hidden", C.c_int32),
@@ -101,6 +108,14 @@ SIGNATURES = {
     "myo_running_moments_export": (_i, [_vp, _i, _fp, _fp, _vp]),
     "myo_vecnorm_reward": (_i, [_vp, _vp, _fp, _vp, _fp, _i, C.c_double, C.c_double, C.c_double, _i, _i, _vp, _vp]),
     "myo_gae": (_i, [_fp, _fp, _vp, _fp, _vp, _i, _i, C.c_float, C.c_float, _fp, _fp, _vp]),
+    "myo_normalize_obs": (_i, [_fp, _fp, _fp, C.c_float, C.c_float, _fp, _i, _i, _vp]),
+    "myo_ppo_create": (_i, [C.POINTER(PolicyCfg), _i, _i, _i, _i, C.POINTER(_vp)]),
+    "myo_ppo_destroy": (None, [_vp]),
+    "myo_ppo_param_count": (C.c_int64, [_vp]),
+    "myo_ppo_param_offset": (_i, [_vp, _cp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "myo_ppo_minibatch_grad": (_i, [_vp, _fp, _i, _i, _vp, _i, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, C.POINTER(PPOHyper), _fp, _fp, _vp]),
+    "myo_ppo_adam_step": (_i, [_vp, _fp, _fp, _fp, _fp, _i, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _fp, _vp]),
+    "myo_ppo_launch_count": (C.c_int64, [_vp]),
 }
 
 

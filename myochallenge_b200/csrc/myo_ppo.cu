@@ -1,0 +1,726 @@
+// PPO update of the recurrent policy on the device: what sb3-contrib's
+// RecurrentPPO.train() does per minibatch - evaluate_actions over whole sequences (LSTM from the stored states,
+// episode starts zero the state), advantage normalisation, clipped surrogate + value + entropy loss, backward
+// (BPTT), clip_grad_norm_, Adam - reached from /root/reference/src/train/trainer.py:67-71 with the
+// hyper-parameters of /root/reference/docs/summary.md:86-117.
+//
+// Design (not sb3's): a minibatch is a set of B worlds, each with its whole T-step sequence, stored step-major
+// (row m = t * B + b). sb3-contrib splits sequences at episode starts and pads; here the sequences stay whole and
+// the state is multiplied by (1 - episode_start) inside the recurrence, which is the same function and the same
+// gradient (no gradient crosses a reset) without padding. GEMMs are plain library GEMMs (cuBLAS, bf16 operands with
+// fp32 accumulation as in the rollout kernel, or fp32 for the parity tests); everything between them - gathers, LSTM
+// cell forward / backward, bias + ReLU, the loss and its gradient, column sums, gradient-norm clipping and Adam - is
+// hand-written here. The gradient leaves as one flat fp32 bucket so the cross-rank exchange is a single all-reduce.
+//
+// Reference semantics (third-party, restated in oracle/ppo_oracle.py):
+//   sb3_contrib/ppo_recurrent/ppo_recurrent.py  RecurrentPPO.train
+//   sb3_contrib/common/recurrent/policies.py    RecurrentActorCriticPolicy.evaluate_actions / _process_sequence
+//   stable_baselines3/common/distributions.py   DiagGaussianDistribution.log_prob / entropy
+//   torch.nn.utils.clip_grad_norm_, torch.optim.Adam
+#include <cublas_v2.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/myo_b200.h"
+
+namespace myo { void set_error(const std::string& msg); }
+
+namespace {
+
+#define QCK(call)                                                                 \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      myo::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));        \
+      return MYO_E_CUDA;                                                          \
+    }                                                                             \
+  } while (0)
+#define BCK(call)                                                                 \
+  do {                                                                            \
+    cublasStatus_t s_ = (call);                                                   \
+    if (s_ != CUBLAS_STATUS_SUCCESS) {                                            \
+      myo::set_error(std::string(#call) + ": cuBLAS status " + std::to_string((int)s_)); \
+      return MYO_E_CUDA;                                                          \
+    }                                                                             \
+  } while (0)
+#define RCK(call) do { int rc_ = (call); if (rc_) return rc_; } while (0)
+
+typedef __nv_bfloat16 bf16;
+constexpr int kStatSlots = 8;          // policy_loss value_loss entropy_loss approx_kl clip_fraction loss adv_mean adv_std
+constexpr int kLossBlocks = 592;       // 4 x 148 CTAs, grid-stride over rows; partial sums merged in CTA order
+constexpr int kColsumRows = 296;       // row chunks of the two-stage column sum
+constexpr int kNormBlocks = 296;
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+template <typename T> __device__ __forceinline__ T to_op(float x);
+template <> __device__ __forceinline__ float to_op<float>(float x) { return x; }
+template <> __device__ __forceinline__ bf16 to_op<bf16>(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float from_op(float x) { return x; }
+__device__ __forceinline__ float from_op(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- operand copies of the weights: fp32 [rows][cols] -> OpT [rows_pad][cols_pad], zero padded -----------------
+template <typename T>
+__global__ void convert_pad_kernel(const float* __restrict__ src, T* __restrict__ dst, int rows, int cols, int rows_pad, int cols_pad) {
+  const int64_t total = (int64_t)rows_pad * cols_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols_pad), c = (int)(i % cols_pad);
+    dst[i] = to_op<T>((r < rows && c < cols) ? src[(int64_t)r * cols + c] : 0.f);
+  }
+}
+
+// ---- minibatch gather: rows m = t * B + b from the step-major rollout buffers [T][n][.] -------------------------
+template <typename T>
+__global__ void gather_rows_kernel(int Tn, int B, int n, int O, int Op, int A, const int32_t* __restrict__ idx,
+                                   const float* __restrict__ obs, const float* __restrict__ actions, const uint8_t* __restrict__ starts,
+                                   const float* __restrict__ old_values, const float* __restrict__ old_logp, const float* __restrict__ adv,
+                                   const float* __restrict__ ret, T* __restrict__ X, float* __restrict__ act, float* __restrict__ keep,
+                                   float* __restrict__ ov, float* __restrict__ ol, float* __restrict__ ad, float* __restrict__ rt) {
+  const int warps = (gridDim.x * blockDim.x) >> 5, lane = threadIdx.x & 31;
+  const int M = Tn * B;
+  for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < M; m += warps) {
+    const int t = m / B, b = m - t * B;
+    const int64_t src = (int64_t)t * n + idx[b];
+    for (int j = lane; j < Op; j += 32) X[(int64_t)m * Op + j] = to_op<T>(j < O ? obs[src * O + j] : 0.f);
+    for (int j = lane; j < A; j += 32) act[(int64_t)m * A + j] = actions[src * A + j];
+    if (lane == 0) {
+      keep[m] = starts[src] ? 0.f : 1.f;
+      ov[m] = old_values[src]; ol[m] = old_logp[src]; ad[m] = adv[src]; rt[m] = ret[src];
+    }
+  }
+}
+
+// initial LSTM state of one net for the minibatch worlds, already multiplied by keep_0:
+//   HP[0][b][:] = keep_0 h0[idx[b]][:]   (operand of the first recurrent GEMM),  C0[b][:] = keep_0 c0[idx[b]][:]
+template <typename T>
+__global__ void gather_state_kernel(int B, int H, const int32_t* __restrict__ idx, const float* __restrict__ h0, const float* __restrict__ c0,
+                                    const float* __restrict__ keep, T* __restrict__ HP, float* __restrict__ C0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i - b * H;
+  const int64_t src = (int64_t)idx[b] * H + j;
+  HP[i] = to_op<T>(keep[b] * h0[src]);
+  C0[i] = keep[b] * c0[src];
+}
+
+// ---- LSTM cell, step t of the sequence forward (torch gate order i f g o) -------------------------------------------
+// G[t]: x W_ih^T + h_prev W_hh^T (no bias yet) -> activated gates in place; Cs[t] = c_t; Hs[t] = h_t;
+// HP[t+1] = keep_{t+1} h_t (operand of the next recurrent GEMM)
+template <typename T>
+__global__ void lstm_cell_fwd_kernel(int t, int Tn, int B, int H, float* __restrict__ G, const float* __restrict__ bih, const float* __restrict__ bhh,
+                                     const float* __restrict__ keep, const float* __restrict__ C0, float* __restrict__ Cs,
+                                     T* __restrict__ Hs, T* __restrict__ HP) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i - b * H;
+  const int64_t m = (int64_t)t * B + b;
+  float* g = G + m * 4 * H;
+  const float gi = sigmoidf_(g[j] + bih[j] + bhh[j]);
+  const float gf = sigmoidf_(g[H + j] + bih[H + j] + bhh[H + j]);
+  const float gg = tanhf(g[2 * H + j] + bih[2 * H + j] + bhh[2 * H + j]);
+  const float go = sigmoidf_(g[3 * H + j] + bih[3 * H + j] + bhh[3 * H + j]);
+  const float cp = t == 0 ? C0[i] : keep[m] * Cs[(m - B) * H + j];
+  const float c = gf * cp + gi * gg;
+  const float h = go * tanhf(c);
+  g[j] = gi; g[H + j] = gf; g[2 * H + j] = gg; g[3 * H + j] = go;
+  Cs[m * H + j] = c;
+  Hs[m * H + j] = to_op<T>(h);
+  if (t + 1 < Tn) HP[(m + B) * H + j] = to_op<T>(keep[m + B] * h);
+}
+
+// step t of the backward recurrence. dHs: dL/dh_t from the layers above; dh_carry = dG_{t+1} W_hh (not yet masked);
+// dc_carry = dL/dc_t through c_{t+1} (already masked). Writes dG_t (gate pre-activations) and the new dc_carry.
+template <typename T>
+__global__ void lstm_cell_bwd_kernel(int t, int Tn, int B, int H, const float* __restrict__ G, const float* __restrict__ keep,
+                                     const float* __restrict__ C0, const float* __restrict__ Cs, const float* __restrict__ dHs,
+                                     const float* __restrict__ dh_carry, float* __restrict__ dc_carry, T* __restrict__ dG) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * H) return;
+  const int b = i / H, j = i - b * H;
+  const int64_t m = (int64_t)t * B + b;
+  const float* g = G + m * 4 * H;
+  const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
+  float dh = dHs[m * H + j], dc = 0.f;
+  if (t + 1 < Tn) { dh += keep[m + B] * dh_carry[i]; dc = dc_carry[i]; }
+  const float tc = tanhf(Cs[m * H + j]);
+  dc += dh * go * (1.f - tc * tc);
+  const float cp = t == 0 ? C0[i] : keep[m] * Cs[(m - B) * H + j];
+  T* d = dG + m * 4 * H;
+  d[j] = to_op<T>(dc * gg * gi * (1.f - gi));
+  d[H + j] = to_op<T>(dc * cp * gf * (1.f - gf));
+  d[2 * H + j] = to_op<T>(dc * gi * (1.f - gg * gg));
+  d[3 * H + j] = to_op<T>(dh * tc * go * (1.f - go));
+  dc_carry[i] = dc * gf * keep[m];
+}
+
+// ---- MLP glue ----------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bias_relu_kernel(const float* __restrict__ Z, const float* __restrict__ bias, T* __restrict__ A, int64_t total, int W) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    A[i] = to_op<T>(fmaxf(Z[i] + bias[i % W], 0.f));
+}
+template <typename T>
+__global__ void relu_bwd_kernel(const float* __restrict__ dA, const T* __restrict__ A, T* __restrict__ dZ, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    dZ[i] = to_op<T>(from_op(A[i]) > 0.f ? dA[i] : 0.f);
+}
+
+// column sums of Y[M][ld] (first N columns) -> part[chunk][N], then out[N] (and out2[N] if given): two stages, fixed order
+template <typename T>
+__global__ void colsum_partial_kernel(const T* __restrict__ Y, int64_t M, int N, int ld, float* __restrict__ part) {
+  __shared__ float s[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const int64_t rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float acc = 0.f;
+  if (col < N)
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += from_op(Y[r * ld + col]);
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < N) {
+    for (int k = 1; k < 8; k++) acc += s[k][threadIdx.x];
+    part[(int64_t)blockIdx.y * N + col] = acc;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, int chunks, int N, float* __restrict__ out, float* __restrict__ out2) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float acc = 0.f;
+  for (int k = 0; k < chunks; k++) acc += part[(int64_t)k * N + col];
+  out[col] = acc;
+  if (out2) out2[col] = acc;
+}
+
+// ---- loss ----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// mean and unbiased std of the gathered advantages (torch: advantages.mean(), advantages.std()); one CTA, fp64 sums
+__global__ void adv_stats_kernel(const float* __restrict__ adv, int64_t M, float* __restrict__ out) {
+  __shared__ double s1[32], s2[32];
+  double a = 0.0, q = 0.0;
+  for (int64_t i = threadIdx.x; i < M; i += blockDim.x) { const double v = adv[i]; a += v; q += v * v; }
+  a = warp_sum_d(a); q = warp_sum_d(q);
+  if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = a; s2[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    a = 0.0; q = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) { a += s1[k]; q += s2[k]; }
+    const double mean = a / (double)M;
+    const double var = M > 1 ? fmax(q - a * mean, 0.0) / (double)(M - 1) : 0.0;
+    out[0] = (float)mean; out[1] = (float)sqrt(var);
+  }
+}
+
+struct LossArgs {
+  int64_t M; int A, Ap;
+  const float* mean_raw;   // [M][Ap] action_net output without bias
+  const float* ba;         // action_net.bias
+  const float* log_std;
+  const float* act; const float* old_logp; const float* adv; const float* adv_stats;
+  float clip_range; int normalize_adv;
+};
+
+// policy part: one warp per row. dMEAN[m][k] = g_m z_k / sigma_k, partial sums of dlog_std and the statistics.
+// part layout per CTA: [0] policy_loss [1] approx_kl [2] clip_fraction, [kStatSlots + k] dlog_std_k
+template <typename T>
+__global__ void policy_loss_kernel(LossArgs a, T* __restrict__ dMEAN, float* __restrict__ part) {
+  extern __shared__ float sh[];      // [warps][kStatSlots + A]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int W = kStatSlots + a.A;
+  float* mine = sh + wib * W;
+  for (int k = lane; k < W; k += 32) mine[k] = 0.f;
+  __syncwarp();
+  const float invM = 1.f / (float)a.M;
+  const float amean = a.normalize_adv ? a.adv_stats[0] : 0.f, ainv = a.normalize_adv ? 1.f / (a.adv_stats[1] + 1e-8f) : 1.f;
+  float pl = 0.f, kl = 0.f, cf = 0.f;
+  for (int64_t m = (int64_t)blockIdx.x * nw + wib; m < a.M; m += (int64_t)gridDim.x * nw) {
+    float lp = 0.f;
+    for (int k = lane; k < a.A; k += 32) {
+      const float ls = a.log_std[k];
+      const float z = (a.act[m * a.A + k] - (a.mean_raw[m * a.Ap + k] + a.ba[k])) * expf(-ls);
+      lp += -0.5f * z * z - ls - 0.9189385332046727f;
+    }
+    lp = warp_sum(lp);
+    const float adv = (a.adv[m] - amean) * ainv;
+    const float lr = lp - a.old_logp[m];
+    const float ratio = expf(lr);
+    const float u = adv * ratio, v = adv * fminf(fmaxf(ratio, 1.f - a.clip_range), 1.f + a.clip_range);
+    const bool active = !(v < u);        // torch.min(u, v): the gradient reaches the ratio unless the clipped branch is the strict minimum
+    const float g = active ? -adv * ratio * invM : 0.f;
+    pl -= fminf(u, v); kl += (ratio - 1.f) - lr; cf += fabsf(ratio - 1.f) > a.clip_range ? 1.f : 0.f;
+    for (int k = lane; k < a.Ap; k += 32) {
+      float d = 0.f;
+      if (k < a.A) {
+        const float is = expf(-a.log_std[k]);
+        const float z = (a.act[m * a.A + k] - (a.mean_raw[m * a.Ap + k] + a.ba[k])) * is;
+        d = g * z * is;
+        mine[kStatSlots + k] += g * (z * z - 1.f);
+      }
+      dMEAN[m * a.Ap + k] = to_op<T>(d);
+    }
+  }
+  if (lane == 0) { mine[0] = pl; mine[1] = kl; mine[2] = cf; }
+  __syncthreads();
+  for (int k = threadIdx.x; k < W; k += blockDim.x) {
+    float acc = 0.f;
+    for (int w = 0; w < nw; w++) acc += sh[w * W + k];
+    part[(int64_t)blockIdx.x * W + k] = acc;
+  }
+}
+
+// value part: v = raw + bias; optional clipping around the old value; dV = vf_coef * 2 (v_pred - ret) / M
+template <typename T>
+__global__ void value_loss_kernel(int64_t M, const float* __restrict__ vraw, const float* __restrict__ bv, const float* __restrict__ old_values,
+                                  const float* __restrict__ ret, float clip_range_vf, float vf_coef, T* __restrict__ dV, float* __restrict__ part) {
+  __shared__ float s[32];
+  float vl = 0.f;
+  const float invM = 1.f / (float)M;
+  for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < M; m += (int64_t)gridDim.x * blockDim.x) {
+    float v = vraw[m] + bv[0];
+    float pass = 1.f;
+    if (clip_range_vf > 0.f) {
+      const float dv = v - old_values[m];
+      pass = fabsf(dv) <= clip_range_vf ? 1.f : 0.f;
+      v = old_values[m] + fminf(fmaxf(dv, -clip_range_vf), clip_range_vf);
+    }
+    const float e = v - ret[m];
+    vl += e * e;
+    dV[m] = to_op<T>(vf_coef * 2.f * e * invM * pass);
+  }
+  vl = warp_sum(vl);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = vl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    vl = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) vl += s[k];
+    part[blockIdx.x] = vl;
+  }
+}
+
+// merges the CTA partials in CTA order; writes the statistics and the log_std gradient
+__global__ void loss_finalize_kernel(const float* __restrict__ ppart, int pblocks, const float* __restrict__ vpart, int vblocks, int A, int64_t M,
+                                     const float* __restrict__ log_std, const float* __restrict__ adv_stats, float ent_coef, float vf_coef,
+                                     float* __restrict__ stats, float* __restrict__ dlog_std) {
+  const int W = kStatSlots + A;
+  __shared__ float s[kStatSlots];
+  const float invM = 1.f / (float)M;
+  for (int k = threadIdx.x; k < W; k += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < pblocks; b++) acc += ppart[(int64_t)b * W + k];
+    if (k < kStatSlots) s[k] = acc;
+    else dlog_std[k - kStatSlots] = acc - ent_coef;      // d(-ent_coef * mean entropy) / dlog_std_k = -ent_coef
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float vl = 0.f;
+    for (int b = 0; b < vblocks; b++) vl += vpart[b];
+    float ent = 0.f;
+    for (int k = 0; k < A; k++) ent += 1.4189385332046727f + log_std[k];
+    const float pl = s[0] * invM, value_loss = vl * invM, entropy_loss = -ent;
+    stats[0] = pl; stats[1] = value_loss; stats[2] = entropy_loss; stats[3] = s[1] * invM; stats[4] = s[2] * invM;
+    stats[5] = pl + ent_coef * entropy_loss + vf_coef * value_loss;
+    stats[6] = adv_stats[0]; stats[7] = adv_stats[1];
+  }
+}
+
+// ---- clip_grad_norm_ + Adam ------------------------------------------------------------------------------------------------
+__global__ void sumsq_partial_kernel(const float* __restrict__ g, int64_t n, float scale, double* __restrict__ part) {
+  __shared__ double s[32];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = (double)(g[i] * scale);
+    acc += v * v;
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    acc = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); k++) acc += s[k];
+    part[blockIdx.x] = acc;
+  }
+}
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                            const double* __restrict__ part, int nparts, float grad_scale, float max_grad_norm, float lr, float beta1,
+                            float beta2, float eps, float bc1, float bc2_sqrt, float* __restrict__ gnorm_out) {
+  double tot = 0.0;
+  for (int k = 0; k < nparts; k++) tot += part[k];      // every thread walks the same short list: same value everywhere
+  const float norm = (float)sqrt(tot);
+  float coef = 1.f;
+  if (max_grad_norm > 0.f) coef = fminf(max_grad_norm / (norm + 1e-6f), 1.f);
+  if (gnorm_out && blockIdx.x == 0 && threadIdx.x == 0) gnorm_out[0] = norm;
+  const float gs = grad_scale * coef, step = lr / bc1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gs;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step * mi / (sqrtf(vi) / bc2_sqrt + eps);
+  }
+}
+
+// ---- handle ------------------------------------------------------------------------------------------------------------------
+struct NetLayout {
+  int64_t wih, whh, bih, bhh;        // offsets into the flat parameter / gradient vector
+  int nl, width[4];
+  int64_t w[4], b[4];
+  int64_t head_w, head_b;
+  int head_n, head_np;               // outputs of the head (A or 1) and its padded operand width
+  // offsets into the operand-copy buffer (elements)
+  int64_t op_wih, op_whh, op_w[4], op_head;
+};
+
+}  // namespace
+
+struct myo_ppo {
+  myo_policy_cfg cfg{};
+  int device = 0, precision = 1, maxT = 0, maxB = 0;
+  int O = 0, Op = 0, A = 0, Ap = 0, H = 0, Dmax = 0;
+  int64_t n_params = 0, n_op = 0;
+  int64_t o_log_std = 0;
+  NetLayout net[2];
+  std::map<std::string, std::pair<int64_t, int64_t>> names;   // state-dict key -> (offset, numel)
+  cublasHandle_t blas = nullptr;
+  int64_t launches = 0;
+  // device buffers
+  void* wop = nullptr;
+  void *X = nullptr, *dG = nullptr, *Hs = nullptr, *HP = nullptr, *Al[4] = {nullptr, nullptr, nullptr, nullptr}, *dZ = nullptr, *dhead = nullptr;
+  float *G = nullptr, *Cs = nullptr, *C0 = nullptr, *T1 = nullptr, *head_out = nullptr, *dh_carry = nullptr, *dc_carry = nullptr;
+  float *act = nullptr, *keep = nullptr, *ov = nullptr, *ol = nullptr, *ad = nullptr, *rt = nullptr, *adv_stats = nullptr;
+  float *ppart = nullptr, *vpart = nullptr, *cpart = nullptr;
+  double* npart = nullptr;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+size_t op_size(const myo_ppo* p) { return p->precision ? sizeof(bf16) : sizeof(float); }
+
+template <typename T>
+int dev_alloc(myo_ppo* p, T** out, size_t bytes) {
+  void* q = nullptr;
+  if (cudaMalloc(&q, bytes ? bytes : 16) != cudaSuccess) {
+    cudaGetLastError();
+    myo::set_error("myo_ppo: device allocation of " + std::to_string(bytes) + " bytes failed");
+    return MYO_E_CUDA;
+  }
+  p->allocs.push_back(q);
+  *out = static_cast<T*>(q);
+  return MYO_OK;
+}
+
+void build_layout(myo_ppo* p) {
+  const myo_policy_cfg& c = p->cfg;
+  const int H = c.lstm_hidden, O = c.obs_dim, A = c.act_dim;
+  int64_t off = 0, op = 0;
+  auto add = [&](const std::string& key, int64_t numel) {
+    const int64_t o = off;
+    p->names[key] = {o, numel};
+    off += (numel + 7) / 8 * 8;
+    return o;
+  };
+  p->o_log_std = add("log_std", A);
+  const char* lstm_name[2] = {"lstm_actor", "lstm_critic"};
+  for (int k = 0; k < 2; k++) {
+    NetLayout& n = p->net[k];
+    n.wih = add(std::string(lstm_name[k]) + ".weight_ih_l0", (int64_t)4 * H * O);
+    n.whh = add(std::string(lstm_name[k]) + ".weight_hh_l0", (int64_t)4 * H * H);
+    n.bih = add(std::string(lstm_name[k]) + ".bias_ih_l0", 4 * H);
+    n.bhh = add(std::string(lstm_name[k]) + ".bias_hh_l0", 4 * H);
+  }
+  const char* mlp_name[2] = {"mlp_extractor.policy_net.", "mlp_extractor.value_net."};
+  for (int k = 0; k < 2; k++) {
+    NetLayout& n = p->net[k];
+    n.nl = k == 0 ? c.n_pi_layers : c.n_vf_layers;
+    int d = H;
+    for (int l = 0; l < n.nl; l++) {
+      n.width[l] = k == 0 ? c.pi_layers[l] : c.vf_layers[l];
+      n.w[l] = add(std::string(mlp_name[k]) + std::to_string(2 * l) + ".weight", (int64_t)n.width[l] * d);
+      n.b[l] = add(std::string(mlp_name[k]) + std::to_string(2 * l) + ".bias", n.width[l]);
+      d = n.width[l];
+    }
+  }
+  for (int k = 0; k < 2; k++) {
+    NetLayout& n = p->net[k];
+    const int d = n.nl ? n.width[n.nl - 1] : H;
+    n.head_n = k == 0 ? A : 1;
+    n.head_np = k == 0 ? p->Ap : 1;
+    n.head_w = add(k == 0 ? "action_net.weight" : "value_net.weight", (int64_t)n.head_n * d);
+    n.head_b = add(k == 0 ? "action_net.bias" : "value_net.bias", n.head_n);
+  }
+  p->n_params = off;
+  for (int k = 0; k < 2; k++) {
+    NetLayout& n = p->net[k];
+    n.op_wih = op; op += (int64_t)4 * H * p->Op;
+    n.op_whh = op; op += (int64_t)4 * H * H;
+    int d = H;
+    for (int l = 0; l < n.nl; l++) { n.op_w[l] = op; op += (int64_t)n.width[l] * d; d = n.width[l]; }
+    n.op_head = op; op += (int64_t)n.head_np * d;
+  }
+  p->n_op = op;
+}
+
+// row-major GEMMs on cuBLAS (column-major underneath). A, B: operand type; C: fp32.
+// nt: C[M][N] (ldc) = A[M][K] (lda) . B[N][K]^T (ldb) + beta C
+int gemm_nt(myo_ppo* p, int64_t M, int N, int K, const void* A, int lda, const void* B, int ldb, float beta, float* C, int ldc) {
+  const float alpha = 1.f;
+  const cudaDataType dt = p->precision ? CUDA_R_16BF : CUDA_R_32F;
+  BCK(cublasGemmEx(p->blas, CUBLAS_OP_T, CUBLAS_OP_N, N, (int)M, K, &alpha, B, dt, ldb, A, dt, lda, &beta, C, CUDA_R_32F, ldc,
+                   CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  p->launches++;
+  return MYO_OK;
+}
+// nn: C[M][N] (ldc) = A[M][K] (lda) . B[K][N] (ldb)
+int gemm_nn(myo_ppo* p, int64_t M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C, int ldc) {
+  const float alpha = 1.f, beta = 0.f;
+  const cudaDataType dt = p->precision ? CUDA_R_16BF : CUDA_R_32F;
+  BCK(cublasGemmEx(p->blas, CUBLAS_OP_N, CUBLAS_OP_N, N, (int)M, K, &alpha, B, dt, ldb, A, dt, lda, &beta, C, CUDA_R_32F, ldc,
+                   CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  p->launches++;
+  return MYO_OK;
+}
+// tn: dW[N][K] (ldc) = dY[M][N]^T (ldy) . X[M][K] (ldx)
+int gemm_tn(myo_ppo* p, int64_t M, int N, int K, const void* dY, int ldy, const void* X, int ldx, float* dW, int ldc) {
+  const float alpha = 1.f, beta = 0.f;
+  const cudaDataType dt = p->precision ? CUDA_R_16BF : CUDA_R_32F;
+  BCK(cublasGemmEx(p->blas, CUBLAS_OP_N, CUBLAS_OP_T, K, N, (int)M, &alpha, X, dt, ldx, dY, dt, ldy, &beta, dW, CUDA_R_32F, ldc,
+                   CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
+  p->launches++;
+  return MYO_OK;
+}
+
+inline int blocks_for(int64_t total, int threads, int cap = 148 * 16) {
+  const int64_t b = (total + threads - 1) / threads;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <typename T>
+int colsum(myo_ppo* p, const T* Y, int64_t M, int N, int ld, float* out, float* out2, cudaStream_t st) {
+  int chunks = (int)((M + 63) / 64);
+  if (chunks > kColsumRows) chunks = kColsumRows;
+  dim3 grid((N + 31) / 32, chunks), block(32, 8);
+  colsum_partial_kernel<T><<<grid, block, 0, st>>>(Y, M, N, ld, p->cpart);
+  colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(p->cpart, chunks, N, out, out2);
+  p->launches += 2;
+  QCK(cudaGetLastError());
+  return MYO_OK;
+}
+
+struct GradArgs {
+  const float* params; int T, n, B; const int32_t* idx;
+  const float *obs, *actions; const uint8_t* starts; const float *old_values, *old_logp, *adv, *ret, *h0, *c0;
+  myo_ppo_hyper hp; float* grad; float* stats;
+};
+
+template <typename T>
+int minibatch_grad(myo_ppo* p, const GradArgs& a, cudaStream_t st) {
+  const int H = p->H, O = p->O, Op = p->Op, A = p->A, Ap = p->Ap, B = a.B, Tn = a.T;
+  const int64_t M = (int64_t)Tn * B;
+  T* wop = static_cast<T*>(p->wop);
+  T* X = static_cast<T*>(p->X); T* dG = static_cast<T*>(p->dG); T* Hs = static_cast<T*>(p->Hs); T* HP = static_cast<T*>(p->HP);
+  T* dZ = static_cast<T*>(p->dZ); T* dhead = static_cast<T*>(p->dhead);
+  BCK(cublasSetStream(p->blas, st));
+  QCK(cudaMemsetAsync(a.grad, 0, sizeof(float) * p->n_params, st));
+  // operand copies of the weights
+  for (int k = 0; k < 2; k++) {
+    const NetLayout& n = p->net[k];
+    convert_pad_kernel<T><<<blocks_for((int64_t)4 * H * Op, 256), 256, 0, st>>>(a.params + n.wih, wop + n.op_wih, 4 * H, O, 4 * H, Op);
+    convert_pad_kernel<T><<<blocks_for((int64_t)4 * H * H, 256), 256, 0, st>>>(a.params + n.whh, wop + n.op_whh, 4 * H, H, 4 * H, H);
+    int d = H;
+    for (int l = 0; l < n.nl; l++) {
+      convert_pad_kernel<T><<<blocks_for((int64_t)n.width[l] * d, 256), 256, 0, st>>>(a.params + n.w[l], wop + n.op_w[l], n.width[l], d, n.width[l], d);
+      d = n.width[l];
+    }
+    convert_pad_kernel<T><<<blocks_for((int64_t)n.head_np * d, 256), 256, 0, st>>>(a.params + n.head_w, wop + n.op_head, n.head_n, d, n.head_np, d);
+    p->launches += 3 + n.nl;
+  }
+  gather_rows_kernel<T><<<blocks_for(M * 32, 256), 256, 0, st>>>(Tn, B, a.n, O, Op, A, a.idx, a.obs, a.actions, a.starts, a.old_values, a.old_logp,
+                                                                   a.adv, a.ret, X, p->act, p->keep, p->ov, p->ol, p->ad, p->rt);
+  adv_stats_kernel<<<1, 1024, 0, st>>>(p->ad, M, p->adv_stats);
+  p->launches += 2;
+  QCK(cudaGetLastError());
+
+  const int cell_blocks = (B * H + 255) / 256;
+  for (int k = 0; k < 2; k++) {
+    const NetLayout& n = p->net[k];
+    // ---- forward over the sequences ----
+    gather_state_kernel<T><<<cell_blocks, 256, 0, st>>>(B, H, a.idx, a.h0 + (int64_t)k * a.n * H, a.c0 + (int64_t)k * a.n * H, p->keep, HP, p->C0);
+    p->launches++;
+    RCK(gemm_nt(p, M, 4 * H, Op, X, Op, wop + n.op_wih, Op, 0.f, p->G, 4 * H));
+    for (int t = 0; t < Tn; t++) {
+      RCK(gemm_nt(p, B, 4 * H, H, HP + (int64_t)t * B * H, H, wop + n.op_whh, H, 1.f, p->G + (int64_t)t * B * 4 * H, 4 * H));
+      lstm_cell_fwd_kernel<T><<<cell_blocks, 256, 0, st>>>(t, Tn, B, H, p->G, a.params + n.bih, a.params + n.bhh, p->keep, p->C0, p->Cs, Hs, HP);
+      p->launches++;
+    }
+    const T* in = Hs;
+    int d = H;
+    for (int l = 0; l < n.nl; l++) {
+      T* Aout = static_cast<T*>(p->Al[l]);
+      RCK(gemm_nt(p, M, n.width[l], d, in, d, wop + n.op_w[l], d, 0.f, p->T1, n.width[l]));
+      bias_relu_kernel<T><<<blocks_for(M * n.width[l], 256), 256, 0, st>>>(p->T1, a.params + n.b[l], Aout, M * n.width[l], n.width[l]);
+      p->launches++;
+      in = Aout; d = n.width[l];
+    }
+    RCK(gemm_nt(p, M, n.head_np, d, in, d, wop + n.op_head, d, 0.f, p->head_out, n.head_np));
+    // ---- loss and its gradient at the head ----
+    if (k == 0) {
+      LossArgs la{M, A, Ap, p->head_out, a.params + n.head_b, a.params + p->o_log_std, p->act, p->ol, p->ad, p->adv_stats,
+                  a.hp.clip_range, a.hp.normalize_advantage};
+      policy_loss_kernel<T><<<kLossBlocks, 256, sizeof(float) * 8 * (kStatSlots + A), st>>>(la, dhead, p->ppart);
+    } else {
+      value_loss_kernel<T><<<kLossBlocks, 256, 0, st>>>(M, p->head_out, a.params + n.head_b, p->ov, p->rt, a.hp.clip_range_vf, a.hp.vf_coef, dhead,
+                                                         p->vpart);
+    }
+    p->launches++;
+    QCK(cudaGetLastError());
+    // ---- backward ----
+    const int ldh = n.head_np;
+    RCK(gemm_tn(p, M, n.head_n, d, dhead, ldh, in, d, a.grad + n.head_w, d));
+    RCK(colsum<T>(p, dhead, M, n.head_n, ldh, a.grad + n.head_b, nullptr, st));
+    // dA[M][d] = dhead[M][head_n] . W_head[head_n][d]
+    RCK(gemm_nn(p, M, d, n.head_np, dhead, ldh, wop + n.op_head, d, p->T1, d));
+    for (int l = n.nl - 1; l >= 0; l--) {
+      const T* Aout = static_cast<const T*>(p->Al[l]);
+      const T* inl = l > 0 ? static_cast<const T*>(p->Al[l - 1]) : Hs;
+      const int din = l > 0 ? n.width[l - 1] : H;
+      relu_bwd_kernel<T><<<blocks_for(M * n.width[l], 256), 256, 0, st>>>(p->T1, Aout, dZ, M * n.width[l]);
+      p->launches++;
+      RCK(gemm_tn(p, M, n.width[l], din, dZ, n.width[l], inl, din, a.grad + n.w[l], din));
+      RCK(colsum<T>(p, dZ, M, n.width[l], n.width[l], a.grad + n.b[l], nullptr, st));
+      RCK(gemm_nn(p, M, din, n.width[l], dZ, n.width[l], wop + n.op_w[l], din, p->T1, din));
+    }
+    // T1 = dL/dHs [M][H]; backward through time
+    for (int t = Tn - 1; t >= 0; t--) {
+      lstm_cell_bwd_kernel<T><<<cell_blocks, 256, 0, st>>>(t, Tn, B, H, p->G, p->keep, p->C0, p->Cs, p->T1, p->dh_carry, p->dc_carry, dG);
+      p->launches++;
+      if (t > 0) RCK(gemm_nn(p, B, H, 4 * H, dG + (int64_t)t * B * 4 * H, 4 * H, wop + n.op_whh, H, p->dh_carry, H));
+    }
+    RCK(gemm_tn(p, M, 4 * H, O, dG, 4 * H, X, Op, a.grad + n.wih, O));
+    RCK(gemm_tn(p, M, 4 * H, H, dG, 4 * H, HP, H, a.grad + n.whh, H));
+    RCK(colsum<T>(p, dG, M, 4 * H, 4 * H, a.grad + n.bih, a.grad + n.bhh, st));
+  }
+  loss_finalize_kernel<<<1, 128, 0, st>>>(p->ppart, kLossBlocks, p->vpart, kLossBlocks, A, M, a.params + p->o_log_std, p->adv_stats, a.hp.ent_coef,
+                                          a.hp.vf_coef, a.stats, a.grad + p->o_log_std);
+  p->launches++;
+  QCK(cudaGetLastError());
+  return MYO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int myo_ppo_create(const myo_policy_cfg* cfg, int max_steps, int max_worlds, int precision, int device, myo_ppo** out) {
+  if (!cfg || !out || max_steps <= 0 || max_worlds <= 0 || precision < 0 || precision > 1) { myo::set_error("bad argument to myo_ppo_create"); return MYO_E_ARG; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    myo::set_error("no CUDA device available (the PPO update has no CPU path)");
+    return MYO_E_CUDA;
+  }
+  if (cfg->lstm_hidden <= 0 || cfg->lstm_hidden % 8) { myo::set_error("lstm_hidden must be a multiple of 8"); return MYO_E_LIMIT; }
+  if (cfg->obs_dim <= 0 || cfg->act_dim <= 0) { myo::set_error("obs_dim and act_dim must be positive"); return MYO_E_LIMIT; }
+  if (cfg->n_pi_layers < 0 || cfg->n_pi_layers > 4 || cfg->n_vf_layers < 0 || cfg->n_vf_layers > 4) { myo::set_error("at most 4 MLP layers per head"); return MYO_E_LIMIT; }
+  for (int l = 0; l < cfg->n_pi_layers; l++) if (cfg->pi_layers[l] <= 0 || cfg->pi_layers[l] % 8) { myo::set_error("MLP widths must be multiples of 8"); return MYO_E_LIMIT; }
+  for (int l = 0; l < cfg->n_vf_layers; l++) if (cfg->vf_layers[l] <= 0 || cfg->vf_layers[l] % 8) { myo::set_error("MLP widths must be multiples of 8"); return MYO_E_LIMIT; }
+  QCK(cudaSetDevice(device));
+  myo_ppo* p = new myo_ppo();
+  p->cfg = *cfg; p->device = device; p->precision = precision; p->maxT = max_steps; p->maxB = max_worlds;
+  p->O = cfg->obs_dim; p->Op = round_up(cfg->obs_dim, 8); p->A = cfg->act_dim; p->Ap = round_up(cfg->act_dim, 8); p->H = cfg->lstm_hidden;
+  p->Dmax = p->H;
+  for (int l = 0; l < cfg->n_pi_layers; l++) p->Dmax = cfg->pi_layers[l] > p->Dmax ? cfg->pi_layers[l] : p->Dmax;
+  for (int l = 0; l < cfg->n_vf_layers; l++) p->Dmax = cfg->vf_layers[l] > p->Dmax ? cfg->vf_layers[l] : p->Dmax;
+  build_layout(p);
+  const size_t M = (size_t)max_steps * max_worlds, os = op_size(p), H = p->H, B = max_worlds;
+  int rc = MYO_OK;
+  auto A_ = [&](auto** q, size_t bytes) { if (!rc) rc = dev_alloc(p, q, bytes); };
+  A_(&p->wop, os * p->n_op);
+  A_(&p->X, os * M * p->Op); A_(&p->dG, os * M * 4 * H); A_(&p->Hs, os * M * H); A_(&p->HP, os * M * H);
+  const int nlmax = cfg->n_pi_layers > cfg->n_vf_layers ? cfg->n_pi_layers : cfg->n_vf_layers;
+  for (int l = 0; l < nlmax; l++) A_(&p->Al[l], os * M * p->Dmax);
+  A_(&p->dZ, os * M * p->Dmax); A_(&p->dhead, os * M * p->Ap);
+  A_(&p->G, sizeof(float) * M * 4 * H); A_(&p->Cs, sizeof(float) * M * H); A_(&p->C0, sizeof(float) * B * H);
+  A_(&p->T1, sizeof(float) * M * p->Dmax); A_(&p->head_out, sizeof(float) * M * p->Ap);
+  A_(&p->dh_carry, sizeof(float) * B * H); A_(&p->dc_carry, sizeof(float) * B * H);
+  A_(&p->act, sizeof(float) * M * p->A); A_(&p->keep, sizeof(float) * M); A_(&p->ov, sizeof(float) * M); A_(&p->ol, sizeof(float) * M);
+  A_(&p->ad, sizeof(float) * M); A_(&p->rt, sizeof(float) * M); A_(&p->adv_stats, sizeof(float) * 2);
+  A_(&p->ppart, sizeof(float) * kLossBlocks * (kStatSlots + p->A)); A_(&p->vpart, sizeof(float) * kLossBlocks);
+  A_(&p->cpart, sizeof(float) * kColsumRows * (4 * H > (size_t)p->Dmax ? 4 * H : (size_t)p->Dmax));
+  A_(&p->npart, sizeof(double) * kNormBlocks);
+  if (rc) { myo_ppo_destroy(p); return rc; }
+  if (cublasCreate(&p->blas) != CUBLAS_STATUS_SUCCESS) { myo::set_error("cublasCreate failed"); myo_ppo_destroy(p); return MYO_E_CUDA; }
+  *out = p;
+  return MYO_OK;
+}
+
+void myo_ppo_destroy(myo_ppo* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  if (p->blas) cublasDestroy(p->blas);
+  for (void* q : p->allocs) cudaFree(q);
+  delete p;
+}
+
+int64_t myo_ppo_param_count(const myo_ppo* p) { return p ? p->n_params : 0; }
+
+int myo_ppo_param_offset(const myo_ppo* p, const char* name, int64_t* offset, int64_t* numel) {
+  if (!p || !name || !offset || !numel) { myo::set_error("bad argument to myo_ppo_param_offset"); return MYO_E_ARG; }
+  auto it = p->names.find(name);
+  if (it == p->names.end()) { myo::set_error(std::string("unknown parameter ") + name); return MYO_E_ARG; }
+  *offset = it->second.first; *numel = it->second.second;
+  return MYO_OK;
+}
+
+int myo_ppo_minibatch_grad(myo_ppo* p, const float* params_dev, int n_steps, int n_envs, const int32_t* world_idx_dev, int n_worlds,
+                           const float* obs_dev, const float* actions_dev, const uint8_t* episode_starts_dev, const float* old_values_dev,
+                           const float* old_logp_dev, const float* advantages_dev, const float* returns_dev, const float* h0_dev,
+                           const float* c0_dev, const myo_ppo_hyper* hyper, float* grad_dev, float* stats_dev, void* stream) {
+  if (!p || !params_dev || !world_idx_dev || !obs_dev || !actions_dev || !episode_starts_dev || !old_values_dev || !old_logp_dev ||
+      !advantages_dev || !returns_dev || !h0_dev || !c0_dev || !hyper || !grad_dev || !stats_dev) {
+    myo::set_error("null argument to myo_ppo_minibatch_grad");
+    return MYO_E_ARG;
+  }
+  if (n_steps <= 0 || n_steps > p->maxT || n_worlds <= 0 || n_worlds > p->maxB || n_envs < n_worlds) {
+    myo::set_error("minibatch exceeds the sizes given to myo_ppo_create");
+    return MYO_E_ARG;
+  }
+  QCK(cudaSetDevice(p->device));
+  GradArgs a{params_dev, n_steps, n_envs, n_worlds, world_idx_dev, obs_dev, actions_dev, episode_starts_dev, old_values_dev, old_logp_dev,
+             advantages_dev, returns_dev, h0_dev, c0_dev, *hyper, grad_dev, stats_dev};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return p->precision ? minibatch_grad<bf16>(p, a, st) : minibatch_grad<float>(p, a, st);
+}
+
+int myo_ppo_adam_step(myo_ppo* p, float* params_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int step, float lr,
+                      float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, float* grad_norm_dev, void* stream) {
+  if (!p || !params_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev || step <= 0) { myo::set_error("bad argument to myo_ppo_adam_step"); return MYO_E_ARG; }
+  QCK(cudaSetDevice(p->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  sumsq_partial_kernel<<<kNormBlocks, 256, 0, st>>>(grad_dev, p->n_params, grad_scale, p->npart);
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<blocks_for(p->n_params, 256), 256, 0, st>>>(params_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, p->n_params, p->npart, kNormBlocks,
+                                                            grad_scale, max_grad_norm, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_norm_dev);
+  p->launches += 2;
+  QCK(cudaGetLastError());
+  return MYO_OK;
+}
+
+int64_t myo_ppo_launch_count(const myo_ppo* p) { return p ? p->launches : 0; }
+
+}  // extern "C"

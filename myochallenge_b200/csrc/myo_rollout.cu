@@ -152,6 +152,15 @@ int moments_geometry(int n, int d, int* dc, int* ctas) {
   return 0;
 }
 
+__global__ void normalize_obs_kernel(const float* __restrict__ obs, const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                     float clip, float* __restrict__ out, int64_t total, int d) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % d);
+    const float v = (obs[i] - mean[c]) / sqrtf(var[c] + eps);
+    out[i] = fminf(fmaxf(v, -clip), clip);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -215,6 +224,17 @@ int myo_gae(const float* rewards_dev, const float* values_dev, const uint8_t* ep
   gae_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(rewards_dev, values_dev, episode_starts_dev, last_values_dev,
                                                                               last_dones_dev, n_steps, n, gamma, gae_lambda, advantages_dev,
                                                                               returns_dev);
+  RCK(cudaGetLastError());
+  return MYO_OK;
+}
+
+int myo_normalize_obs(const float* obs_dev, const float* mean_f_dev, const float* var_f_dev, float epsilon, float clip_obs, float* out_dev,
+                      int n, int d, void* stream) {
+  if (!obs_dev || !mean_f_dev || !var_f_dev || !out_dev || n <= 0 || d <= 0) { myo::set_error("bad argument to myo_normalize_obs"); return MYO_E_ARG; }
+  const int64_t total = (int64_t)n * d;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  normalize_obs_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(obs_dev, mean_f_dev, var_f_dev, epsilon, clip_obs, out_dev, total, d);
   RCK(cudaGetLastError());
   return MYO_OK;
 }

@@ -1,0 +1,234 @@
+"""Policy update of the PPO loop on the device (``myo_ppo_*`` in the C ABI) and the
+``RecurrentPPO`` front end the reference's trainer drives.
+
+Mirrors what /root/reference/src/train/trainer.py:49-71 builds and calls - ``RecurrentPPO("MlpLstmPolicy", env,
+n_steps=..., batch_size=..., n_epochs=..., learning_rate=..., clip_range=..., ent_coef=..., vf_coef=...,
+max_grad_norm=..., policy_kwargs=...)`` then ``agent.learn(total_timesteps=...)`` - with sb3-contrib's argument names
+and defaults (``RecurrentPPO.__init__``: lr 3e-4, n_steps 128, batch_size 128, n_epochs 10, gamma 0.99, gae_lambda
+0.95, clip_range 0.2, ent_coef 0, vf_coef 0.5, max_grad_norm 0.5; Adam eps 1e-5 from ActorCriticPolicy).
+
+Differences by design, documented in DESIGN.md: a minibatch is ``batch_size // n_steps`` whole world sequences (chosen
+by a random permutation of the worlds each epoch) instead of ``batch_size`` consecutive samples of the flattened
+buffer cut at a random offset; the forward / backward GEMMs run on bf16 operands with fp32 accumulation, the same
+rounding the rollout kernel applies, unless ``precision="fp32"``.
+
+Across GPUs every rank updates from its own worlds' minibatch and the flat gradient bucket is summed with ONE
+all-reduce per optimiser step (NCCL over NVLink); the gradient norm for clipping is taken after the reduction, on
+identical data on every rank, so it needs no second collective.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _capi
+from ._capi import PolicyCfg, PPOHyper, check
+from .policy import RecurrentPolicy
+from .rollout import RecurrentRolloutBuffer, collect_rollouts
+
+STAT_NAMES = ("policy_loss", "value_loss", "entropy_loss", "approx_kl", "clip_fraction", "loss", "adv_mean", "adv_std")
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def allreduce_flat(grad: torch.Tensor) -> float:
+    """Sum the flat gradient bucket over the ranks in place (one collective per optimiser step); returns the scale that
+    turns the sum into the mean (1 / world_size), which the Adam kernel applies together with the clip factor."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+        return 1.0 / dist.get_world_size()
+    return 1.0
+
+
+class PPOUpdate:
+    """Flat-parameter PPO optimiser for a ``RecurrentPolicy`` architecture: loss + gradient of a minibatch of whole
+    sequences, gradient all-reduce, clip_grad_norm_ and Adam."""
+
+    def __init__(self, policy: RecurrentPolicy, n_steps: int, batch_worlds: int, precision: str = "bf16", learning_rate: float = 3e-4,
+                 clip_range: float = 0.2, clip_range_vf: Optional[float] = None, ent_coef: float = 0.0, vf_coef: float = 0.5,
+                 max_grad_norm: float = 0.5, normalize_advantage: bool = True, betas=(0.9, 0.999), adam_eps: float = 1e-5):
+        self._L = _capi.lib()
+        self.device = policy.device
+        self.policy = policy
+        self.n_steps, self.batch_worlds = int(n_steps), int(batch_worlds)
+        cfg = PolicyCfg()
+        cfg.obs_dim, cfg.act_dim, cfg.lstm_hidden = policy.obs_dim, policy.act_dim, policy.lstm_hidden
+        cfg.n_pi_layers, cfg.n_vf_layers = len(policy.pi), len(policy.vf)
+        for i, w in enumerate(policy.pi):
+            cfg.pi_layers[i] = w
+        for i, w in enumerate(policy.vf):
+            cfg.vf_layers[i] = w
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        h = C.c_void_p()
+        check(self._L, self._L.myo_ppo_create(C.byref(cfg), self.n_steps, self.batch_worlds, 1 if precision == "bf16" else 0,
+                                              self.device.index or 0, C.byref(h)))
+        self._h = h
+        self.n_params = int(self._L.myo_ppo_param_count(h))
+        f = dict(dtype=torch.float32, device=self.device)
+        self.params = torch.zeros(self.n_params, **f)
+        self.grad = torch.zeros(self.n_params, **f)
+        self.exp_avg = torch.zeros(self.n_params, **f)
+        self.exp_avg_sq = torch.zeros(self.n_params, **f)
+        self.stats = torch.zeros(len(STAT_NAMES), **f)
+        self.grad_norm = torch.zeros(1, **f)
+        self.learning_rate, self.betas, self.adam_eps, self.max_grad_norm = learning_rate, betas, adam_eps, max_grad_norm
+        self.hyper = PPOHyper(clip_range, -1.0 if clip_range_vf is None else clip_range_vf, ent_coef, vf_coef, int(normalize_advantage))
+        self.step_count = 0
+        self._views: Dict[str, torch.Tensor] = {}
+        off, num = C.c_int64(), C.c_int64()
+        for k, shape in policy.state_dict_shapes().items():
+            check(self._L, self._L.myo_ppo_param_offset(h, k.encode(), C.byref(off), C.byref(num)))
+            self._views[k] = self.params[off.value: off.value + num.value].view(shape)
+            self._views["grad/" + k] = self.grad[off.value: off.value + num.value].view(shape)
+        if policy.state_dict():
+            self.load_state_dict(policy.state_dict())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- parameters ---------------------------------------------------------------------------------------------------
+    def load_state_dict(self, sd):
+        for k in self.policy.state_dict_shapes():
+            self._views[k].copy_(torch.as_tensor(sd[k]).to(device=self.device, dtype=torch.float32))
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        """Views into the flat parameter vector under the SB3 state-dict keys."""
+        return {k: self._views[k] for k in self.policy.state_dict_shapes()}
+
+    def grad_dict(self) -> Dict[str, torch.Tensor]:
+        return {k: self._views["grad/" + k] for k in self.policy.state_dict_shapes()}
+
+    def push_to_policy(self):
+        """Hand the updated parameters to the rollout kernel (re-packs its bf16 weight images)."""
+        self.policy.load_state_dict({k: v.clone() for k, v in self.state_dict().items()})
+
+    # -- one optimiser step -----------------------------------------------------------------------------------------------
+    def minibatch_grad(self, buf: RecurrentRolloutBuffer, world_idx: torch.Tensor, n_steps: Optional[int] = None):
+        """Loss statistics + flat gradient of the sequences of ``world_idx`` (int32 device tensor)."""
+        idx = world_idx.to(device=self.device, dtype=torch.int32).contiguous()
+        T = buf.n_steps if n_steps is None else n_steps
+        check(self._L, self._L.myo_ppo_minibatch_grad(
+            self._h, _p(self.params), int(T), int(buf.n_envs), _p(idx), int(idx.numel()), _p(buf.observations), _p(buf.actions),
+            _p(buf.episode_starts), _p(buf.values), _p(buf.log_probs), _p(buf.advantages), _p(buf.returns), _p(buf.h0), _p(buf.c0),
+            C.byref(self.hyper), _p(self.grad), _p(self.stats), self._stream()))
+        return self.stats
+
+    def all_reduce_grad(self) -> float:
+        return allreduce_flat(self.grad)
+
+    def adam_step(self, grad_scale: float = 1.0, learning_rate: Optional[float] = None):
+        self.step_count += 1
+        lr = self.learning_rate if learning_rate is None else learning_rate
+        check(self._L, self._L.myo_ppo_adam_step(self._h, _p(self.params), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.step_count,
+                                                 lr, self.betas[0], self.betas[1], self.adam_eps,
+                                                 -1.0 if self.max_grad_norm is None else self.max_grad_norm, grad_scale, _p(self.grad_norm),
+                                                 self._stream()))
+
+    # -- RecurrentPPO.train ----------------------------------------------------------------------------------------------------
+    def train(self, buf: RecurrentRolloutBuffer, n_epochs: int = 10, generator: Optional[torch.Generator] = None, target_kl: Optional[float] = None,
+              learning_rate: Optional[float] = None) -> Dict[str, float]:
+        """``n_epochs`` passes over the rollout in minibatches of ``batch_worlds`` world sequences; returns the mean of the
+        per-minibatch statistics (SB3's ``train/*`` log entries)."""
+        n = buf.n_envs
+        acc = torch.zeros_like(self.stats)
+        count = 0
+        stop = False
+        for _ in range(n_epochs):
+            perm = torch.randperm(n, generator=generator, device="cpu").to(self.device, dtype=torch.int32)
+            for s in range(0, n, self.batch_worlds):
+                self.minibatch_grad(buf, perm[s: s + self.batch_worlds])
+                if target_kl is not None and float(self.stats[3]) > 1.5 * target_kl:
+                    stop = True
+                    break
+                scale = self.all_reduce_grad()
+                self.adam_step(scale, learning_rate)
+                acc += self.stats
+                count += 1
+            if stop:
+                break
+        self.push_to_policy()
+        mean = (acc / max(count, 1)).tolist()
+        out = {"train/" + k: v for k, v in zip(STAT_NAMES, mean)}
+        out["train/n_updates"] = count
+        out["train/grad_norm"] = float(self.grad_norm)
+        return out
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.myo_ppo_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._L.myo_ppo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RecurrentPPO:
+    """``sb3_contrib.RecurrentPPO`` as /root/reference/src/train/trainer.py:49-71 uses it, over the device path:
+    ``env`` is a ``rollout.DeviceVecNormalize`` (or a bare ``MyoVecEnv``); ``learn`` alternates ``collect_rollouts`` and
+    ``train`` without leaving HBM."""
+
+    def __init__(self, policy="MlpLstmPolicy", env=None, learning_rate=3e-4, n_steps=128, batch_size=128, n_epochs=10, gamma=0.99,
+                 gae_lambda=0.95, clip_range=0.2, clip_range_vf=None, normalize_advantage=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
+                 target_kl=None, policy_kwargs=None, seed=0, precision="bf16", device=None, **_ignored):
+        if policy != "MlpLstmPolicy":
+            raise ValueError("only MlpLstmPolicy is built (the policy every reference run uses)")
+        if env is None:
+            raise ValueError("env is required")
+        self.env = env
+        venv = getattr(env, "venv", env)
+        sim = venv.sim
+        self.device = sim.device if device is None else torch.device(device)
+        kw = dict(policy_kwargs or {})
+        arch = kw.get("net_arch", [dict(pi=[64, 64], vf=[64, 64])])
+        arch = arch[0] if isinstance(arch, (list, tuple)) and arch and isinstance(arch[0], dict) else dict(pi=list(arch), vf=list(arch))
+        self.policy = RecurrentPolicy(sim.nobs, sim.nu, kw.get("lstm_hidden_size", 256), tuple(arch.get("pi", ())), tuple(arch.get("vf", ())),
+                                      max_batch=venv.num_envs, device=self.device)
+        self.policy.init_random(seed, log_std_init=kw.get("log_std_init", 0.0))
+        self.policy.seed(seed + 1)
+        self.n_steps, self.n_epochs, self.gamma, self.gae_lambda, self.target_kl = n_steps, n_epochs, gamma, gae_lambda, target_kl
+        self.n_envs = venv.num_envs
+        self.batch_worlds = max(1, min(self.n_envs, batch_size // n_steps))
+        self.update = PPOUpdate(self.policy, n_steps, self.batch_worlds, precision, learning_rate if not callable(learning_rate) else learning_rate(1.0),
+                                clip_range, clip_range_vf, ent_coef, vf_coef, max_grad_norm, normalize_advantage)
+        self._lr_schedule = learning_rate if callable(learning_rate) else None
+        self.buffer = RecurrentRolloutBuffer(n_steps, self.n_envs, sim.nobs, sim.nu, self.policy.lstm_hidden, self.device, gamma, gae_lambda)
+        if hasattr(env, "attach"):
+            env.attach(self.policy)
+        self._gen = torch.Generator(device="cpu").manual_seed(seed)
+        self.num_timesteps = 0
+        self._state = None
+        self.logs = []
+
+    def learn(self, total_timesteps: int, callback=None, **_ignored):
+        if self._state is None:
+            self._obs = self.env.reset_device()
+            self._starts = torch.ones(self.n_envs, dtype=torch.uint8, device=self.device)
+            self._state = self.policy.initial_state(self.n_envs)
+        start = self.num_timesteps
+        while self.num_timesteps - start < total_timesteps:
+            self._obs, self._starts = collect_rollouts(self.env, self.policy, self.buffer, self._state, self._obs, self._starts)
+            self.num_timesteps += self.n_steps * self.n_envs
+            lr = None
+            if self._lr_schedule is not None:
+                lr = self._lr_schedule(max(0.0, 1.0 - (self.num_timesteps - start) / float(total_timesteps)))
+            log = self.update.train(self.buffer, self.n_epochs, self._gen, self.target_kl, lr)
+            log["time/total_timesteps"] = self.num_timesteps
+            log["rollout/reward_mean"] = float(self.buffer.rewards.mean())
+            self.logs.append(log)
+            if callback is not None and callback(self, log) is False:
+                break
+        return self

@@ -182,8 +182,11 @@ class DeviceVecNormalize:
 
 
 class RecurrentRolloutBuffer:
-    """sb3-contrib ``RecurrentRolloutBuffer`` storage, step-major on the device: observations (raw), actions, rewards,
-    episode_starts, values, log_probs and the LSTM states each step started from."""
+    """sb3-contrib ``RecurrentRolloutBuffer`` storage, step-major on the device: observations (as the policy saw them,
+    i.e. normalised when the env is a ``DeviceVecNormalize``), actions, rewards, episode_starts, values, log_probs and
+    the LSTM states the rollout started from (``h0`` / ``c0``). sb3-contrib stores the states of every step because its
+    minibatches may start anywhere; the update here (``ppo.PPOUpdate``) takes whole sequences, whose only start states
+    that matter are those of step 0 - every later sequence start is an episode start, where the state is zeroed."""
 
     def __init__(self, n_steps, n_envs, obs_dim, act_dim, lstm_hidden, device, gamma=0.99, gae_lambda=0.95):
         dev = torch.device(device)
@@ -197,8 +200,8 @@ class RecurrentRolloutBuffer:
         self.advantages = torch.zeros(n_steps, n_envs, **f)
         self.returns = torch.zeros(n_steps, n_envs, **f)
         self.episode_starts = torch.zeros(n_steps, n_envs, dtype=torch.uint8, device=dev)
-        self.hidden_states = torch.zeros(n_steps, 2, n_envs, lstm_hidden, **f)      # [:, 0] actor, [:, 1] critic
-        self.cell_states = torch.zeros(n_steps, 2, n_envs, lstm_hidden, **f)
+        self.h0 = torch.zeros(2, n_envs, lstm_hidden, **f)      # [0] actor, [1] critic
+        self.c0 = torch.zeros(2, n_envs, lstm_hidden, **f)
         self.pos, self.full = 0, False
         self._L = _capi.lib()
         self.launch_count = 0
@@ -206,11 +209,28 @@ class RecurrentRolloutBuffer:
     def reset(self):
         self.pos, self.full = 0, False
 
-    def add(self, obs, action, reward, episode_start, value, log_prob, h, c):
+    def put_obs(self, obs, obs_norm=None):
+        """Store the observation of the current step. ``obs_norm``: a ``DeviceVecNormalize`` whose CURRENT moments (the
+        ones the policy's fused normalisation uses for this step: call before the env step updates them) normalise
+        ``obs`` on the way in (one streaming kernel); None stores ``obs`` as given."""
         t = self.pos
-        self.observations[t].copy_(obs); self.actions[t].copy_(action); self.rewards[t].copy_(reward)
+        if obs_norm is not None and obs_norm.norm_obs:
+            _capi.check(self._L, self._L.myo_normalize_obs(_p(obs), _p(obs_norm.obs_rms.mean_f), _p(obs_norm.obs_rms.var_f), obs_norm.epsilon,
+                                                           obs_norm.clip_obs, _p(self.observations[t]), self.n_envs, obs.shape[1],
+                                                           _stream_ptr(self.device)))
+            self.launch_count += 1
+        else:
+            self.observations[t].copy_(obs)
+
+    def add(self, obs, action, reward, episode_start, value, log_prob, h=None, c=None):
+        """``obs`` None: already stored by ``put_obs``. ``h`` / ``c``: LSTM states this step started from (kept for step 0)."""
+        t = self.pos
+        if obs is not None:
+            self.observations[t].copy_(obs)
+        self.actions[t].copy_(action); self.rewards[t].copy_(reward)
         self.episode_starts[t].copy_(episode_start); self.values[t].copy_(value); self.log_probs[t].copy_(log_prob)
-        self.hidden_states[t].copy_(h); self.cell_states[t].copy_(c)
+        if t == 0 and h is not None:
+            self.h0.copy_(h); self.c0.copy_(c)
         self.pos += 1
         self.full = self.pos == self.n_steps
 
@@ -229,9 +249,12 @@ def collect_rollouts(env, policy, buffer: RecurrentRolloutBuffer, state, obs, ep
     ``policy.initial_state`` returns them (updated in place). Returns (obs, episode_starts) for the next call."""
     h, c = state
     buffer.reset()
-    for _ in range(buffer.n_steps):
-        h0, c0 = h.clone(), c.clone()
+    norm = env if isinstance(env, DeviceVecNormalize) else None
+    for t in range(buffer.n_steps):
+        if t == 0:
+            buffer.h0.copy_(h); buffer.c0.copy_(c)
         actions, values, logp, _ = policy.forward(obs, (h, c), episode_starts)
+        buffer.put_obs(obs, norm)
         env_actions = actions.clamp(-1.0, 1.0) if clip_actions else actions
         new_obs, rewards, dones, trunc = env.step_device(env_actions)
         rewards = rewards.clone()
@@ -239,7 +262,7 @@ def collect_rollouts(env, policy, buffer: RecurrentRolloutBuffer, state, obs, ep
         if idx.numel():       # bootstrap with the value of the terminal observation (critic state after this step)
             tv = policy.predict_values(env.terminal_obs.index_select(0, idx), (h.index_select(1, idx), c.index_select(1, idx)))
             rewards.index_add_(0, idx, buffer.gamma * tv)
-        buffer.add(obs, actions, rewards, episode_starts, values, logp, h0, c0)
+        buffer.add(None, actions, rewards, episode_starts, values, logp)
         obs, episode_starts = new_obs.clone(), dones.clone()
     last_values = policy.predict_values(obs, (h.clone(), c.clone()), episode_starts)
     buffer.compute_returns_and_advantage(last_values, episode_starts)

@@ -1,0 +1,208 @@
+"""GPU parity of the PPO update (``myo_ppo_*`` through the C ABI) against the torch restatement
+of sb3-contrib's RecurrentPPO.train in oracle/ppo_oracle.py (fp64 autograd, split-and-pad sequences).
+
+Tolerances (floating point; the loss is a mean over T x B samples, gradients are sums of ~T x B products):
+  precision="fp32" (fp32 cuBLAS GEMMs, fp32 elementwise): loss terms |err| <= 2e-5 + 1e-4 |ref|; each gradient tensor
+      max |err| <= 2e-4 * max |ref| + 1e-7 (fp32 accumulation order vs fp64 autograd);
+  precision="bf16" (bf16 operands, fp32 accumulation - the production mode, same rounding as the rollout kernel):
+      loss terms |err| <= 2e-2 + 5e-2 |ref|; each gradient tensor: cosine similarity with the oracle >= 0.98 and
+      norm within 10 % (operand rounding 2^-8 per product, no systematic bias) on the random-init winning architecture
+      and on the critic of the trained checkpoint. The ACTOR of the trained checkpoint has sigma ~ e^-2..e^-3, so the
+      rounding of the mean moves log_prob by z dmu / sigma ~ 0.1-0.5 against old log-probs the oracle computed WITHOUT
+      that rounding: ratios cross the clip boundary and the two gradients are gradients of different clip patterns
+      (bar there: cosine >= 0.5). The relevant bf16 bar is the end-to-end test at the bottom: rollout kernel and update
+      forward round alike, so approx_kl ~ 0 and clip_fraction ~ 0 before the first optimiser step.
+Adam + clip_grad_norm_: max |err| <= 1e-6 + 1e-5 |ref| against torch.optim.Adam / torch.nn.utils.clip_grad_norm_.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from myochallenge_b200.policy import RecurrentPolicy
+from myochallenge_b200.ppo import PPOUpdate, STAT_NAMES
+from myochallenge_b200.rollout import RecurrentRolloutBuffer
+from oracle import ppo_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _setup(O, A, H, pi, vf, T, B, n_envs, seed, precision, sd=None, start_prob=0.15, **hyper):
+    pol = RecurrentPolicy(O, A, lstm_hidden=H, pi=pi, vf=vf, max_batch=64, device=DEV)
+    if sd is None:
+        sd = pol.init_random(seed=seed, log_std_init=-0.7)
+    else:
+        pol.load_state_dict(sd)
+    sd64 = {k: np.asarray(v.cpu() if torch.is_tensor(v) else v, np.float64) for k, v in sd.items()}
+    batch = ppo_oracle.synthetic_batch(sd64, T, B, seed=seed + 1, start_prob=start_prob, dtype=np.float32)
+    upd = PPOUpdate(pol, T, B, precision=precision, **hyper)
+    buf = RecurrentRolloutBuffer(T, n_envs, O, A, H, DEV)
+    rng = np.random.default_rng(seed + 2)
+    idx = rng.permutation(n_envs)[:B].astype(np.int32)            # the minibatch worlds sit scattered in a wider buffer
+
+    def scatter(dst, src):                                        # src [T][B][..] -> dst [T][n_envs][..]
+        dst.normal_() if dst.dtype.is_floating_point else dst.zero_()
+        dst[:, torch.from_numpy(idx).long().to(DEV)] = torch.from_numpy(np.ascontiguousarray(src)).to(DEV).to(dst.dtype)
+
+    scatter(buf.observations, batch["obs"]); scatter(buf.actions, batch["actions"]); scatter(buf.episode_starts, batch["episode_starts"])
+    scatter(buf.values, batch["old_values"]); scatter(buf.log_probs, batch["old_log_prob"]); scatter(buf.advantages, batch["advantages"])
+    scatter(buf.returns, batch["returns"])
+    buf.h0.normal_(); buf.c0.normal_()
+    buf.h0[:, torch.from_numpy(idx).long().to(DEV)] = torch.from_numpy(batch["h0"]).to(DEV)
+    buf.c0[:, torch.from_numpy(idx).long().to(DEV)] = torch.from_numpy(batch["c0"]).to(DEV)
+    return pol, upd, buf, torch.from_numpy(idx).to(DEV), sd64, batch
+
+
+CASES = [
+    # O, A, H, pi, vf, T, B, n_envs
+    (17, 5, 64, (32,), (48, 16), 12, 7, 19),
+    (86, 39, 128, (), (), 8, 16, 16),
+    (86, 39, 256, (256, 256), (256, 256), 6, 33, 40),
+]
+
+
+@pytest.mark.parametrize("O,A,H,pi,vf,T,B,n_envs", CASES)
+def test_gradient_matches_oracle_fp32(product_lib, O, A, H, pi, vf, T, B, n_envs):
+    hyper = dict(clip_range=0.2, ent_coef=0.01, vf_coef=0.7, normalize_advantage=True)
+    pol, upd, buf, idx, sd64, batch = _setup(O, A, H, pi, vf, T, B, n_envs, 3, "fp32", **hyper)
+    stats = upd.minibatch_grad(buf, idx).cpu().numpy()
+    ref_grads, ref_stats = ppo_oracle.gradients(sd64, batch, **hyper)
+    for i, k in enumerate(STAT_NAMES[:6]):
+        assert abs(stats[i] - ref_stats[k]) <= 2e-5 + 1e-4 * abs(ref_stats[k]), (k, stats[i], ref_stats[k])
+    assert 0.0 < ref_stats["clip_fraction"] < 1.0
+    got = upd.grad_dict()
+    for k, r in ref_grads.items():
+        g = got[k].cpu().double()
+        tol = 2e-4 * float(r.abs().max()) + 1e-7
+        assert float((g - r).abs().max()) <= tol, (k, float((g - r).abs().max()), tol)
+
+
+def test_gradient_matches_oracle_bf16_winning_architecture(product_lib):
+    O, A, H, pi, vf, T, B, n_envs = CASES[2]
+    hyper = dict(clip_range=0.2, ent_coef=0.01, vf_coef=0.7, normalize_advantage=True)
+    pol, upd, buf, idx, sd64, batch = _setup(O, A, H, pi, vf, T, B, n_envs, 3, "bf16", **hyper)
+    stats = upd.minibatch_grad(buf, idx).cpu().numpy()
+    ref_grads, ref_stats = ppo_oracle.gradients(sd64, batch, **hyper)
+    for i, k in enumerate(STAT_NAMES[:6]):
+        assert abs(stats[i] - ref_stats[k]) <= 2e-2 + 5e-2 * abs(ref_stats[k]), (k, stats[i], ref_stats[k])
+    got = upd.grad_dict()
+    for k, r in ref_grads.items():
+        gk = got[k].cpu().double().flatten(); rk = r.flatten()
+        cos = float(torch.dot(gk, rk) / (gk.norm() * rk.norm() + 1e-30))
+        assert cos >= 0.98 and 0.9 <= float(gk.norm() / rk.norm()) <= 1.1, (k, cos, float(gk.norm() / rk.norm()))
+
+
+def test_value_clipping_and_raw_advantages_fp32(product_lib):
+    hyper = dict(clip_range=0.1, clip_range_vf=0.05, ent_coef=0.0, vf_coef=1.0, normalize_advantage=False)
+    pol, upd, buf, idx, sd64, batch = _setup(17, 5, 64, (), (32,), 10, 9, 12, 5, "fp32", **hyper)
+    stats = upd.minibatch_grad(buf, idx).cpu().numpy()
+    ref_grads, ref_stats = ppo_oracle.gradients(sd64, batch, **hyper)
+    for i, k in enumerate(STAT_NAMES[:6]):
+        assert abs(stats[i] - ref_stats[k]) <= 2e-5 + 1e-4 * abs(ref_stats[k]), (k, stats[i], ref_stats[k])
+    got = upd.grad_dict()
+    for k, r in ref_grads.items():
+        g = got[k].cpu().double()
+        assert float((g - r).abs().max()) <= 2e-4 * float(r.abs().max()) + 1e-7, k
+
+
+def test_phase1_checkpoint_gradient_fp32_and_bf16(product_lib):
+    """Real weights: the reference's shipped phase-1 policy (LSTM-128, no MLP layers)."""
+    g = np.load(os.path.join(GOLDEN, "policy_phase1.npz"))
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
+    hyper = dict(clip_range=0.2, ent_coef=0.001, vf_coef=0.5)
+    ref = None
+    for precision in ("fp32", "bf16"):
+        pol, upd, buf, idx, sd64, batch = _setup(86, 39, 128, (), (), 16, 24, 32, 7, precision, sd=sd, **hyper)
+        stats = upd.minibatch_grad(buf, idx).cpu().numpy()
+        if ref is None:
+            ref = ppo_oracle.gradients(sd64, batch, **hyper)
+        ref_grads, ref_stats = ref
+        got = upd.grad_dict()
+        for k, r in ref_grads.items():
+            gk = got[k].cpu().double().flatten(); rk = r.flatten()
+            if precision == "fp32":
+                assert float((gk - rk).abs().max()) <= 2e-4 * float(rk.abs().max()) + 1e-7, k
+            else:
+                cos = float(torch.dot(gk, rk) / (gk.norm() * rk.norm() + 1e-30))
+                if "critic" in k or "value_net" in k:
+                    assert cos >= 0.98 and 0.9 <= float(gk.norm() / rk.norm()) <= 1.1, (k, cos, float(gk.norm() / rk.norm()))
+                else:                   # actor side on the trained checkpoint: see the module docstring
+                    assert cos >= 0.5, (k, cos)
+        if precision == "bf16":
+            for i, k in enumerate(STAT_NAMES[:6]):
+                assert abs(stats[i] - ref_stats[k]) <= 2e-2 + 5e-2 * abs(ref_stats[k]), (k, stats[i], ref_stats[k])
+
+
+def test_adam_and_clip_match_torch(product_lib):
+    pol, upd, buf, idx, sd64, batch = _setup(17, 5, 64, (32,), (), 6, 5, 5, 11, "fp32", learning_rate=3e-3, max_grad_norm=0.5)
+    p = upd.params.cpu().clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in (1, 2, 3):
+        upd.minibatch_grad(buf, idx)
+        g = upd.grad.cpu().clone()
+        upd.adam_step()
+        p, m, v, norm = ppo_oracle.adam_step(p, g, m, v, step, 3e-3, (0.9, 0.999), 1e-5, 0.5)
+        assert abs(float(upd.grad_norm) - norm) <= 1e-5 * norm
+        assert float((upd.params.cpu() - p).abs().max()) <= 1e-6 + 1e-5 * float(p.abs().max())
+        assert torch.allclose(upd.exp_avg.cpu(), m, rtol=1e-4, atol=1e-9) and torch.allclose(upd.exp_avg_sq.cpu(), v, rtol=1e-4, atol=1e-12)
+    # the scale argument averages a summed bucket: a doubled gradient with scale 1/2 takes the same step
+    upd2 = PPOUpdate(pol, 6, 5, precision="fp32", learning_rate=3e-3, max_grad_norm=0.5)
+    upd2.load_state_dict(upd.state_dict()); upd2.exp_avg.copy_(upd.exp_avg); upd2.exp_avg_sq.copy_(upd.exp_avg_sq); upd2.step_count = upd.step_count
+    upd.minibatch_grad(buf, idx); upd2.grad.copy_(upd.grad * 2)
+    upd.adam_step(); upd2.adam_step(grad_scale=0.5)
+    assert torch.allclose(upd.params, upd2.params, rtol=1e-6, atol=1e-8)
+
+
+def test_train_epochs_lower_the_loss_and_push_weights(product_lib):
+    """A few epochs of the whole update loop on one synthetic rollout: the surrogate + value loss goes down, the policy
+    handle receives the new weights (its forward changes), gradient is deterministic run to run."""
+    hyper = dict(learning_rate=1e-3, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5)
+    pol, upd, buf, idx, sd64, batch = _setup(17, 5, 64, (32,), (32,), 10, 8, 32, 13, "bf16", **hyper)
+    all_idx = torch.arange(32, dtype=torch.int32, device=DEV)
+    s0 = upd.minibatch_grad(buf, all_idx[:8]).clone(); g0 = upd.grad.clone()
+    s1 = upd.minibatch_grad(buf, all_idx[:8]).clone()
+    assert torch.equal(g0, upd.grad) and torch.equal(s0, s1)           # bitwise reproducible (no atomics)
+    before = {k: v.clone() for k, v in upd.state_dict().items()}
+    first = float(upd.minibatch_grad(buf, idx)[1])
+    log = upd.train(buf, n_epochs=4, generator=torch.Generator().manual_seed(0))
+    assert log["train/n_updates"] == 4 * 4
+    last = float(upd.minibatch_grad(buf, idx)[1])
+    assert last < first, (first, last)                                   # value loss on the same minibatch went down
+    assert any(not torch.equal(before[k], v) for k, v in upd.state_dict().items())
+    assert torch.equal(pol.state_dict()["action_net.weight"], upd.state_dict()["action_net.weight"])
+
+
+def test_recurrent_ppo_learn_on_baoding_is_on_policy_at_the_first_minibatch(product_lib):
+    """The whole loop (reference: RecurrentPPO(...).learn, /root/reference/src/train/trainer.py:49-71) on Baoding worlds.
+    Before any optimiser step, re-evaluating the rollout's own actions must reproduce the rollout's log-probs and values:
+    the update's forward (cuBLAS, bf16 operands, sequences from h0 with in-sequence resets) and the rollout kernel
+    (tcgen05, one step at a time, VecNormalize fused) are two implementations of one function. Bars: approx_kl <= 2e-3,
+    clip_fraction <= 0.02, value loss vs stored returns consistent with GAE (returns - values = advantages)."""
+    from myochallenge_b200.envs import make_vec_env
+    from myochallenge_b200.ppo import RecurrentPPO
+    from myochallenge_b200.rollout import DeviceVecNormalize, collect_rollouts
+
+    n, T = 256, 16
+    env = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, device=DEV, seed=5, clip_actions=True, max_episode_steps=7)
+    vn = DeviceVecNormalize(env, gamma=0.99)
+    agent = RecurrentPPO("MlpLstmPolicy", vn, n_steps=T, batch_size=T * 64, n_epochs=2, learning_rate=1e-4, ent_coef=0.001,
+                         policy_kwargs=dict(lstm_hidden_size=64, net_arch=[dict(pi=[64], vf=[64])], log_std_init=-2.0, enable_critic_lstm=True),
+                         seed=1)
+    assert agent.batch_worlds == 64
+    # one rollout, then the loss at the unchanged parameters
+    agent._obs = vn.reset_device().clone()
+    agent._starts = torch.ones(n, dtype=torch.uint8, device=DEV)
+    agent._state = agent.policy.initial_state(n)
+    agent._obs, agent._starts = collect_rollouts(vn, agent.policy, agent.buffer, agent._state, agent._obs, agent._starts)
+    assert int(agent.buffer.episode_starts[1:].sum()) > n                  # resets inside the sequences (horizon 7)
+    stats = agent.update.minibatch_grad(agent.buffer, torch.arange(64, dtype=torch.int32, device=DEV)).cpu().numpy()
+    assert stats[3] <= 2e-3 and stats[4] <= 0.02, stats
+    adv = agent.buffer.advantages[:, :64]
+    assert abs(stats[1] - float((adv * adv).mean())) <= 5e-2 * float((adv * adv).mean()) + 1e-3, stats
+    # and the loop itself
+    agent.learn(total_timesteps=2 * n * T)
+    assert len(agent.logs) == 2 and agent.num_timesteps == 2 * n * T
+    for log in agent.logs:
+        assert log["train/n_updates"] == 2 * 4 and np.isfinite(log["train/loss"]) and log["train/approx_kl"] < 0.05
