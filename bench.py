@@ -322,6 +322,49 @@ def run_b200(args):
     e2e_s = time.perf_counter() - t0
     e2e_launches = sum(hv.sim.launch_count for hv in halves)
 
+    # ---- whole PPO iteration (BASELINE configs[4]: "... with PPO training"): rollout of n_steps + RecurrentPPO.train ------
+    ppo = None
+    if not args.no_train:
+        from myochallenge_b200.ppo import RecurrentPPO
+        from myochallenge_b200.rollout import DeviceVecNormalize, collect_rollouts
+
+        del halves, hb
+        torch.cuda.empty_cache()
+        vn = DeviceVecNormalize(env, gamma=0.99)
+        bw = min(n, args.ppo_batch_worlds)
+        # phase-2 hyper-parameters of the reference (/root/reference/docs/summary.md:103-117), winning architecture
+        agent = RecurrentPPO("MlpLstmPolicy", vn, n_steps=args.ppo_steps, batch_size=args.ppo_steps * bw, n_epochs=args.ppo_epochs,
+                             learning_rate=2.5e-5, clip_range=0.2, ent_coef=3e-5, max_grad_norm=0.8, gae_lambda=0.95, seed=0,
+                             policy_kwargs=dict(lstm_hidden_size=256, net_arch=[dict(pi=[256, 256], vf=[256, 256])], log_std_init=-2.0,
+                                                ortho_init=False, enable_critic_lstm=True))
+        agent.policy.seed(0x5EED + rank)
+        o = vn.reset_device().clone()
+        st = torch.ones(n, dtype=torch.uint8, device=dev)
+        state = agent.policy.initial_state(n)
+        times = []
+        for it in range(2):                                   # iteration 0 warms cuBLAS / allocator; iteration 1 is reported
+            barrier()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            lc0 = agent.update.launch_count
+            e[0].record()
+            o, st = collect_rollouts(vn, agent.policy, agent.buffer, state, o, st)
+            e[1].record()
+            log = agent.update.train(agent.buffer, args.ppo_epochs, agent._gen)
+            e[2].record()
+            barrier()
+            times = [e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])]
+        tt = torch.tensor(times, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        roll_ms, upd_ms = [float(x) for x in tt]
+        ppo = {"value": world * n * args.ppo_steps / ((roll_ms + upd_ms) * 1e-3), "unit": UNIT, "rollout_ms": roll_ms, "update_ms": upd_ms,
+               "n_steps": args.ppo_steps, "minibatch_worlds": bw, "n_epochs": args.ppo_epochs, "optimizer_steps": log["train/n_updates"],
+               "update_samples_per_s": world * log["train/n_updates"] * bw * args.ppo_steps / (upd_ms * 1e-3),
+               "update_launches": agent.update.launch_count - lc0, "approx_kl": log["train/approx_kl"], "clip_fraction": log["train/clip_fraction"],
+               "note": "one full RecurrentPPO iteration: collect_rollouts (policy + env + VecNormalize + buffer + GAE) then n_epochs over the "
+                       "rollout in minibatches of whole world sequences (bf16-operand cuBLAS GEMMs, own cell/loss/Adam kernels), "
+                       "one flat-bucket gradient all-reduce per optimiser step when n_gpus > 1"}
+
     # max over ranks
     t = torch.tensor([total_ms, world_ms, e2e_s, seq_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -362,7 +405,7 @@ def run_b200(args):
                 "sequential": seq_value,
                 "api": "MyoVecEnv.step_async/step_wait with numpy arrays + RecurrentPolicy.forward on H2D-copied observations; two half-size "
                        "envs stepped alternately on two streams (`sequential`: one env, every copy on the critical path)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "ppo_iteration": ppo,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         q, v, a, _ = [x.double().cpu().numpy() for x in sim.get_state()]
@@ -389,6 +432,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the whole-PPO-iteration leg")
+    ap.add_argument("--ppo-steps", type=int, default=128, help="n_steps of the PPO iteration leg")
+    ap.add_argument("--ppo-batch-worlds", type=int, default=2048, help="world sequences per minibatch")
+    ap.add_argument("--ppo-epochs", type=int, default=10)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
