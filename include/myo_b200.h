@@ -125,6 +125,12 @@ typedef struct myo_task_cfg {
   /* ---- rollout glue ---- */
   int32_t clip_actions;         /* 1: clip actions to [-1, 1] first, as RecurrentPPO.collect_rollouts does (np.clip to the
                                    action space) before VecEnv.step; 0: use them as given (plain gym env.step) */
+  /* ---- baoding curriculum knobs of CustomBaodingP2Env.reset (/root/reference/src/envs/baoding.py:494-647) ---- */
+  int32_t enable_rsi;           /* reference-state initialisation: balls start ON their targets (:606-638) */
+  float rsi_probability;
+  int32_t balls_overlap;        /* 0: after RSI the start angles are re-drawn uniformly (:634-638) */
+  float beta_init_angle[2];     /* (a, b) of np_random.beta; a <= 0: off. Used only with limit_init_angle (:504-520) */
+  float beta_ball_size[2], beta_ball_mass[2];   /* (:563-573, :590-600) */
 } myo_task_cfg;
 
 const char* myo_last_error(void);

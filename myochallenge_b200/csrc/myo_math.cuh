@@ -152,6 +152,28 @@ struct Philox {
     return (float)(u >> 8) * (1.0f / 16777216.0f);
   }
   MYO_DI float uniform(float lo, float hi) { return lo + (hi - lo) * uniform(); }
+  MYO_DI float normal() {      // Box-Muller, one value per call
+    const float u1 = 1.f - uniform(), u2 = uniform();
+    return sqrtf(-2.f * logf(u1)) * cosf(6.283185307179586f * u2);
+  }
+  MYO_DI float gamma(float a) {   // Marsaglia-Tsang; a < 1 through gamma(a + 1) u^(1/a)
+    float boost = 1.f;
+    if (a < 1.f) { boost = powf(1.f - uniform(), 1.f / a); a += 1.f; }
+    const float d = a - 1.f / 3.f, cc = 1.f / sqrtf(9.f * d);
+    for (int it = 0; it < 64; it++) {
+      const float x = normal();
+      float v = 1.f + cc * x;
+      if (v <= 0.f) continue;
+      v = v * v * v;
+      const float u = 1.f - uniform();
+      if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) return boost * d * v;
+    }
+    return boost * d;
+  }
+  MYO_DI float beta(float a, float b) {   // numpy Generator/RandomState.beta: X / (X + Y), X ~ Gamma(a), Y ~ Gamma(b)
+    const float x = gamma(a), y = gamma(b);
+    return x / fmaxf(x + y, 1e-30f);
+  }
 };
 
 }  // namespace myo

@@ -64,7 +64,7 @@ template <int G>
 MYO_PHASE void baoding_targets(int mslot, const myo_task_cfg& t, Ctx<G>& c, const int* ti, const float* tf) {
   MYO_M
   if (c.lane == 0) {
-    const int task = ti[TI_TASK], counter = ti[TI_ELAPSED];
+    const int task = ti[TI_TASK], counter = ti[TI_ELAPSED] + (ti[TI_FLAGS] & 1);   // bit 0: RSI's in-reset step already advanced self.counter
     // BaodingEnvV1.step moves the target sites only for the two rotation tasks; in a hold episode site_pos keeps what
     // the world's previous episode left there (model state is not reset), SURVEY.md row a7
     const float sign = task == MYO_BAODING_CW ? -1.f : 1.f;
@@ -188,7 +188,11 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         ti[TI_TASK] = min(2, (int)(rng.uniform() * 3.f));
         const float u = rng.uniform();
         if (u < t.overlap_probability) a1 = 0.75f * kPi;
-        else if (t.limit_init_angle > 0.f) a1 = 0.75f * kPi + rng.uniform(-t.limit_init_angle, t.limit_init_angle);
+        else if (t.limit_init_angle > 0.f) {
+          float phase = rng.uniform(-t.limit_init_angle, t.limit_init_angle);
+          if (t.beta_init_angle[0] > 0.f) phase = rng.beta(t.beta_init_angle[0], t.beta_init_angle[1]) * 2.f * kPi - kPi;
+          a1 = 0.75f * kPi + phase;
+        }
         else a1 = rng.uniform(0.f, 2.f * kPi);
       } else {
         ti[TI_TASK] = t.fixed_task;
@@ -203,6 +207,14 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         for (int k = 0; k < 2; k++) {
           const int ms = m.b_mass_slot[t.ball_body[k]];
           if (ms >= 0) c.wpp(m)[ms] = rng.uniform(t.obj_mass_range[0], t.obj_mass_range[1]);
+        }
+        if (t.beta_ball_mass[0] > 0.f) {
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const int ms = m.b_mass_slot[t.ball_body[k]];
+            const float v = rng.beta(t.beta_ball_mass[0], t.beta_ball_mass[1]) * (t.obj_mass_range[1] - t.obj_mass_range[0]) + t.obj_mass_range[0];
+            if (ms >= 0) c.wpp(m)[ms] = v;
+          }
         }
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -219,6 +231,36 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
           const float v = rng.uniform(t.obj_size_range[0], t.obj_size_range[1]);
           if (ss >= 0) { c.wpp(m)[ss] = v; c.wpp(m)[ss + 1] = v; c.wpp(m)[ss + 2] = v; }
         }
+        if (t.beta_ball_size[0] > 0.f) {
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            const int ss = m.g_size_slot[t.ball_geom[k]];
+            const float v = rng.beta(t.beta_ball_size[0], t.beta_ball_size[1]) * (t.obj_size_range[1] - t.obj_size_range[0]) + t.obj_size_range[0];
+            if (ss >= 0) { c.wpp(m)[ss] = v; c.wpp(m)[ss + 1] = v; c.wpp(m)[ss + 2] = v; }
+          }
+        }
+      }
+      // RSI (/root/reference/src/envs/baoding.py:606-638): new start angles, one env.step(zeros) on the freshly reset env,
+      // then the balls are put on the targets that step placed. What survives the final set_state(qpos, qvel) is: the
+      // target site positions (moved only for the rotation tasks, a7), self.counter = 1, and the muscle activations
+      // after one zero-action env step (set_state restores qpos / qvel only). All three are closed-form, so no physics
+      // step is run here: the kinematics pass below only reads the target sites' world positions.
+      ti[TI_FLAGS] = 0;
+      if (t.enable_rsi && rng.uniform() < t.rsi_probability) {
+        ti[TI_FLAGS] = 1;
+        const float phase = rng.uniform(-kPi, kPi);
+        a1 = 0.75f * kPi + phase;
+        tf[TF_ANGLE1] = a1; tf[TF_ANGLE2] = -0.25f * kPi + phase;
+        if (ti[TI_TASK] == MYO_BAODING_CW || ti[TI_TASK] == MYO_BAODING_CCW) {
+#pragma unroll
+          for (int k = 0; k < 2; k++) {          // goal[0] = 0: the targets sit at the start angles
+            float sn, cs;
+            sincosf(tf[TF_ANGLE1 + k], &sn, &cs);
+            const int slot = m.s_pos_slot[t.target_site[k]];
+            if (slot >= 0) { c.wpp(m)[slot] = tf[TF_XR] * cs + t.center_pos[0]; c.wpp(m)[slot + 1] = tf[TF_YR] * sn + t.center_pos[1]; }
+          }
+        }
+        if (!t.balls_overlap) { tf[TF_ANGLE1] = rng.uniform(0.f, 2.f * kPi); tf[TF_ANGLE2] = tf[TF_ANGLE1] - kPi; }
       }
       if (t.noise_fingers > 0.f && m.nq - 14 >= 23) {   // _add_noise_to_finger_positions: one draw per group
         const float th = rng.uniform(-kPi / 18.f * t.noise_fingers, kPi / 18.f * t.noise_fingers);
@@ -248,6 +290,43 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
     }
   }
   c.tile.sync();
+  if (t.kind == MYO_TASK_BAODING && t.enable_rsi && (ti[TI_FLAGS] & 1)) {
+    phase_tree_forward<G>(mslot, c, false);
+    if (c.lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 2; k++) {      // qpos[23,24] = obs[35,36]; qpos[30,31] = obs[38,39] (:627-631): ball xy <- target xy
+        float g[3];
+        site_world(m, c.sp(), c.wpp(m), t.target_site[k], g);
+        qpos[t.ball_qposadr[k]] = g[0]; qpos[t.ball_qposadr[k] + 1] = g[1];
+      }
+    }
+    // data.act after env.step(zeros): ctrl = remap(0) held for frame_skip substeps of the activation dynamics (mj_fwdActuation +
+    // mj_Euler's act += h act_dot, muscle activations clamped to [0, 1]), starting from act = 0
+    for (int i = c.lane; i < m.nu; i += G) {
+      const int ai = i - (m.nu - m.na);
+      if (ai < 0) continue;
+      const int dyn = m.a_dyntype[i];
+      const float lo = (m.g_tables + m.a_ctrlrange.off)[2 * i], hi = (m.g_tables + m.a_ctrlrange.off)[2 * i + 1];
+      float u = 0.f;
+      if (t.normalize_act) u = dyn == 3 ? 1.f / (1.f + expf(2.5f)) : 0.5f * (lo + hi);
+      if (m.a_ctrllimited[i]) u = clipf(u, lo, hi);
+      const float* dp = m.g_tables + m.a_dynprm.off + 3 * i;
+      float a = 0.f;
+      for (int s = 0; s < t.frame_skip; s++) {
+        float adot = 0.f;
+        if (dyn == 3) {
+          const float uc = clipf(u, 0.f, 1.f), ac = clipf(a, 0.f, 1.f);
+          const float tau = (uc > a) ? dp[0] * (0.5f + 1.5f * ac) : dp[1] / (0.5f + 1.5f * ac);
+          adot = (uc - a) / fmaxf(kMinVal, tau);
+        } else if (dyn == 1) adot = u;
+        else if (dyn == 2) adot = (u - a) / fmaxf(kMinVal, dp[0]);
+        a += m.timestep * adot;
+        if (dyn == 3) a = clipf(a, 0.f, 1.f);
+      }
+      SF(o_act)[ai] = a;
+    }
+    c.tile.sync();
+  }
 }
 
 }  // namespace myo

@@ -131,14 +131,18 @@ def make_task_cfg(model: Model, env_id: str, **overrides) -> _capi.TaskCfg:
         cfg.task_choice_random = int(task_choice == "random")
         cfg.randomize_physics = int(reg.get("phase", 2) == 2)     # P1's reset keeps the nominal balls
         cfg.overlap_probability = float(kw.pop("overlap_probability", 0.0))
-        kw.pop("balls_overlap", None)   # stored but never read by the reference's reset (/root/reference/src/envs/baoding.py:494-538)
+        cfg.balls_overlap = int(bool(kw.pop("balls_overlap", False)))    # read only inside the RSI branch (/root/reference/src/envs/baoding.py:634)
         lim = kw.pop("limit_init_angle", False)
         cfg.limit_init_angle = float(lim) if lim else 0.0
         cfg.noise_fingers = float(kw.pop("noise_fingers", 0.0))
-        for k in ("enable_rsi", "rsi_probability", "beta_init_angle", "beta_ball_size", "beta_ball_mass"):
+        cfg.enable_rsi = int(bool(kw.pop("enable_rsi", False)))
+        cfg.rsi_probability = float(kw.pop("rsi_probability", 1))
+        for k in ("beta_init_angle", "beta_ball_size", "beta_ball_mass"):
             v = kw.pop(k, None)
             if v:
-                raise NotImplementedError(f"curriculum knob {k}={v!r} is not part of the device reset yet")
+                if len(v) != 2 or min(v) <= 0:
+                    raise ValueError(f"{k} must be the (a, b) > 0 of a beta distribution, got {v!r}")
+                getattr(cfg, k)[0], getattr(cfg, k)[1] = float(v[0]), float(v[1])
     else:
         if "weighted_reward_keys" in kw:
             _weights(cfg, POSE_KEYS, kw.pop("weighted_reward_keys"))

@@ -40,8 +40,11 @@ def test_curriculum_config_json_maps(product_lib):
     # order: pos_dist_1 pos_dist_2 act_reg alive sparse solved done
     np.testing.assert_allclose(list(cfg.rwd_weight)[:7], [5, 5, 0, 1, 0, 5, 0])
     assert cfg.limit_init_angle == pytest.approx(np.pi) and cfg.overlap_probability == 0.0
-    with pytest.raises(NotImplementedError):
-        make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1", enable_rsi=True, rsi_probability=0.9)
+    rsi = make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1", enable_rsi=True, rsi_probability=0.9, beta_ball_mass=(2, 5))
+    assert rsi.enable_rsi == 1 and rsi.rsi_probability == pytest.approx(0.9) and tuple(rsi.beta_ball_mass) == (2.0, 5.0)
+    assert rsi.beta_init_angle[0] == 0.0 and rsi.balls_overlap == 0
+    with pytest.raises(ValueError):
+        make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1", beta_ball_size=(0, 1))
     with pytest.raises(TypeError):
         make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1", no_such_kwarg=1)
 

@@ -79,3 +79,31 @@ def test_p2_reset_distribution(product_lib):
     moved = np.abs(o1[:, 35:37] - o0[:, 35:37]).max(1) > 1e-7
     assert 0.6 < moved.mean() < 0.73
     env.close()
+
+
+def test_rsi_and_beta_reset_matches_host_emulation(product_lib, emul_lib):
+    """The curriculum knobs of the reset (RSI, beta-distributed angle / mass / size; /root/reference/src/envs/baoding.py:504-520,
+    563-638) on the GPU against the same kernel sources run on the host (tests/test_reset_knobs_emul.py checks those against
+    the reference's semantics): same counter-based draws, so observations and parameters agree to float rounding."""
+    from conftest import HAND_BAODING
+    from myochallenge_b200.envs import make_task_cfg
+    from myochallenge_b200.sim import BatchSim, Model
+
+    n = 64
+    kw = dict(enable_rsi=True, rsi_probability=0.7, limit_init_angle=np.pi, beta_init_angle=(2.0, 3.0), beta_ball_mass=(2.0, 5.0),
+              beta_ball_size=(0.5, 0.5), noise_fingers=0.5)
+    outs = []
+    for lib, dev in ((product_lib, "cuda:0"), (emul_lib, "cpu")):
+        m = Model(HAND_BAODING, lib=lib)
+        cfg = make_task_cfg(m, "CustomMyoChallengeBaodingP2-v1", **kw)
+        sim = BatchSim(m, n, cfg, device=dev, seed=21)
+        obs = sim.reset().cpu().numpy().copy()
+        mass = sim.get_param(_capi.PARAM_BODY_MASS, m.name2id("body", "ball2")).cpu().numpy().copy()
+        size = sim.get_param(_capi.PARAM_GEOM_SIZE, cfg.ball_geom[0]).cpu().numpy().copy()
+        o1 = sim.step(torch.zeros(n, sim.nu, device=dev))[0].cpu().numpy().copy()
+        outs.append((obs, mass, size, o1))
+    for a, b in zip(*outs):
+        np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5)
+    obs = outs[0][0]
+    on_target = np.abs(obs[:, 41:43]).max(1) < 1e-6
+    assert 0.5 < on_target.mean() < 0.9            # rsi_probability 0.7
