@@ -10,7 +10,7 @@ from myochallenge_b200.assets import asset_path
 
 NAMES = ["tree_fwd", "tendon", "tree_bwd", "mass_bias", "factor", "collision", "constraints", "actuation", "solveM", "newton", "integrate", "  nt:hessian", "  nt:chol_factor", "  nt:chol_solve", "  nt:linesearch+dots", "barrier_pre_integrate"]
 
-def run(path, kind, n, steps=5):
+def run(path, kind, n, steps=5, spinup=3):
     m = Model(asset_path(path))
     cfg = m.default_task_cfg(kind)
     if kind == _capi.TASK_BAODING:
@@ -18,7 +18,7 @@ def run(path, kind, n, steps=5):
     sim = BatchSim(m, n, cfg, device="cuda:0", seed=0)
     sim.reset()
     a = torch.rand(n, sim.nu, device="cuda:0") * 2 - 1
-    for _ in range(3):
+    for _ in range(spinup):
         sim.step(a)
     buf = (C.c_ulonglong * 16)()
     _capi._LIB.myo_debug_profile(buf)
@@ -42,3 +42,4 @@ if __name__ == "__main__":
     hand = os.path.join(ROOT, "myochallenge_b200", "assets", "hand", "myo_hand_baoding.mjb")
     if os.path.exists(hand):
         run("hand/myo_hand_baoding.mjb", _capi.TASK_BAODING, 4096)
+        run("hand/myo_hand_baoding.mjb", _capi.TASK_BAODING, 32768, spinup=int(os.environ.get("SPINUP", "150")))
