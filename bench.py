@@ -310,7 +310,14 @@ def run_b200(args):
 
     for k in range(2):
         with torch.cuda.stream(strm[k]):
-            hb[k]["h_obs"].copy_(torch.from_numpy(halves[k].reset()))
+            b = hb[k]
+            o = halves[k].reset_device()
+            for _ in range(args.spinup):                                   # same steady state as the device-resident loop
+                a_, _, _, _ = pol.forward(o, b["state"], b["starts"], out=b["out"])
+                o, _, dn_, _ = halves[k].step_device(a_)
+                b["starts"] = dn_.clone()
+            b["h_obs"].copy_(o)
+            strm[k].synchronize()
     for _ in range(2):                                                     # warm both halves
         for k in range(2):
             issue(k)

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -56,6 +57,7 @@ constexpr int kStatSlots = 8;          // policy_loss value_loss entropy_loss ap
 constexpr int kLossBlocks = 592;       // 4 x 148 CTAs, grid-stride over rows; partial sums merged in CTA order
 constexpr int kColsumRows = 296;       // row chunks of the two-stage column sum
 constexpr int kNormBlocks = 296;
+constexpr size_t kBlasWorkspace = 64u << 20;   // per cuBLAS handle (the library's own default for this architecture class is 32 MiB)
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -388,6 +390,20 @@ struct NetLayout {
 
 }  // namespace
 
+// activations / gradients of one network; the actor and the critic each own a set so their chains can run concurrently
+struct NetBufs {
+  void *dG = nullptr, *Hs = nullptr, *HP = nullptr, *Al[4] = {nullptr, nullptr, nullptr, nullptr}, *dZ = nullptr, *dhead = nullptr;
+  float *G = nullptr, *Cs = nullptr, *C0 = nullptr, *T1 = nullptr, *head_out = nullptr, *dh_carry = nullptr, *dc_carry = nullptr, *cpart = nullptr;
+  cublasHandle_t blas = nullptr;
+  void* workspace = nullptr;
+};
+
+struct GradKey {      // everything a captured graph bakes in
+  const void* ptr[12];
+  int T, n, B;
+  myo_ppo_hyper hp;
+};
+
 struct myo_ppo {
   myo_policy_cfg cfg{};
   int device = 0, precision = 1, maxT = 0, maxB = 0;
@@ -396,16 +412,24 @@ struct myo_ppo {
   int64_t o_log_std = 0;
   NetLayout net[2];
   std::map<std::string, std::pair<int64_t, int64_t>> names;   // state-dict key -> (offset, numel)
-  cublasHandle_t blas = nullptr;
   int64_t launches = 0;
   // device buffers
   void* wop = nullptr;
-  void *X = nullptr, *dG = nullptr, *Hs = nullptr, *HP = nullptr, *Al[4] = {nullptr, nullptr, nullptr, nullptr}, *dZ = nullptr, *dhead = nullptr;
-  float *G = nullptr, *Cs = nullptr, *C0 = nullptr, *T1 = nullptr, *head_out = nullptr, *dh_carry = nullptr, *dc_carry = nullptr;
+  void* X = nullptr;
+  NetBufs nb[2];
+  int32_t* idx = nullptr;
   float *act = nullptr, *keep = nullptr, *ov = nullptr, *ol = nullptr, *ad = nullptr, *rt = nullptr, *adv_stats = nullptr;
-  float *ppart = nullptr, *vpart = nullptr, *cpart = nullptr;
+  float *ppart = nullptr, *vpart = nullptr;
   double* npart = nullptr;
   std::vector<void*> allocs;
+  // the critic's chain runs on a second stream (fork / join by events) next to the actor's; the whole minibatch is
+  // captured once into a CUDA graph (about 1 100 short launches) and replayed while the arguments stay the same
+  cudaStream_t side = nullptr, main = nullptr;     // main: the graph's origin stream (the caller's may be the legacy default stream, which cannot be captured)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_in = nullptr, ev_out = nullptr;
+  bool use_graph = true, have_graph = false;
+  cudaGraphExec_t exec = nullptr;
+  GradKey key{};
+  int64_t graph_launches = 0;
 };
 
 namespace {
@@ -478,28 +502,28 @@ void build_layout(myo_ppo* p) {
 
 // row-major GEMMs on cuBLAS (column-major underneath). A, B: operand type; C: fp32.
 // nt: C[M][N] (ldc) = A[M][K] (lda) . B[N][K]^T (ldb) + beta C
-int gemm_nt(myo_ppo* p, int64_t M, int N, int K, const void* A, int lda, const void* B, int ldb, float beta, float* C, int ldc) {
+int gemm_nt(myo_ppo* p, cublasHandle_t blas, int64_t M, int N, int K, const void* A, int lda, const void* B, int ldb, float beta, float* C, int ldc) {
   const float alpha = 1.f;
   const cudaDataType dt = p->precision ? CUDA_R_16BF : CUDA_R_32F;
-  BCK(cublasGemmEx(p->blas, CUBLAS_OP_T, CUBLAS_OP_N, N, (int)M, K, &alpha, B, dt, ldb, A, dt, lda, &beta, C, CUDA_R_32F, ldc,
+  BCK(cublasGemmEx(blas, CUBLAS_OP_T, CUBLAS_OP_N, N, (int)M, K, &alpha, B, dt, ldb, A, dt, lda, &beta, C, CUDA_R_32F, ldc,
                    CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
   p->launches++;
   return MYO_OK;
 }
 // nn: C[M][N] (ldc) = A[M][K] (lda) . B[K][N] (ldb)
-int gemm_nn(myo_ppo* p, int64_t M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C, int ldc) {
+int gemm_nn(myo_ppo* p, cublasHandle_t blas, int64_t M, int N, int K, const void* A, int lda, const void* B, int ldb, float* C, int ldc) {
   const float alpha = 1.f, beta = 0.f;
   const cudaDataType dt = p->precision ? CUDA_R_16BF : CUDA_R_32F;
-  BCK(cublasGemmEx(p->blas, CUBLAS_OP_N, CUBLAS_OP_N, N, (int)M, K, &alpha, B, dt, ldb, A, dt, lda, &beta, C, CUDA_R_32F, ldc,
+  BCK(cublasGemmEx(blas, CUBLAS_OP_N, CUBLAS_OP_N, N, (int)M, K, &alpha, B, dt, ldb, A, dt, lda, &beta, C, CUDA_R_32F, ldc,
                    CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
   p->launches++;
   return MYO_OK;
 }
 // tn: dW[N][K] (ldc) = dY[M][N]^T (ldy) . X[M][K] (ldx)
-int gemm_tn(myo_ppo* p, int64_t M, int N, int K, const void* dY, int ldy, const void* X, int ldx, float* dW, int ldc) {
+int gemm_tn(myo_ppo* p, cublasHandle_t blas, int64_t M, int N, int K, const void* dY, int ldy, const void* X, int ldx, float* dW, int ldc) {
   const float alpha = 1.f, beta = 0.f;
   const cudaDataType dt = p->precision ? CUDA_R_16BF : CUDA_R_32F;
-  BCK(cublasGemmEx(p->blas, CUBLAS_OP_N, CUBLAS_OP_T, K, N, (int)M, &alpha, X, dt, ldx, dY, dt, ldy, &beta, dW, CUDA_R_32F, ldc,
+  BCK(cublasGemmEx(blas, CUBLAS_OP_N, CUBLAS_OP_T, K, N, (int)M, &alpha, X, dt, ldx, dY, dt, ldy, &beta, dW, CUDA_R_32F, ldc,
                    CUBLAS_COMPUTE_32F, CUBLAS_GEMM_DEFAULT));
   p->launches++;
   return MYO_OK;
@@ -511,12 +535,12 @@ inline int blocks_for(int64_t total, int threads, int cap = 148 * 16) {
 }
 
 template <typename T>
-int colsum(myo_ppo* p, const T* Y, int64_t M, int N, int ld, float* out, float* out2, cudaStream_t st) {
+int colsum(myo_ppo* p, float* cpart, const T* Y, int64_t M, int N, int ld, float* out, float* out2, cudaStream_t st) {
   int chunks = (int)((M + 63) / 64);
   if (chunks > kColsumRows) chunks = kColsumRows;
   dim3 grid((N + 31) / 32, chunks), block(32, 8);
-  colsum_partial_kernel<T><<<grid, block, 0, st>>>(Y, M, N, ld, p->cpart);
-  colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(p->cpart, chunks, N, out, out2);
+  colsum_partial_kernel<T><<<grid, block, 0, st>>>(Y, M, N, ld, cpart);
+  colsum_final_kernel<<<(N + 127) / 128, 128, 0, st>>>(cpart, chunks, N, out, out2);
   p->launches += 2;
   QCK(cudaGetLastError());
   return MYO_OK;
@@ -528,14 +552,85 @@ struct GradArgs {
   myo_ppo_hyper hp; float* grad; float* stats;
 };
 
+// forward, loss gradient at the head and backward of network k, all on stream st
 template <typename T>
-int minibatch_grad(myo_ppo* p, const GradArgs& a, cudaStream_t st) {
+int net_chain(myo_ppo* p, const GradArgs& a, int k, cudaStream_t st) {
   const int H = p->H, O = p->O, Op = p->Op, A = p->A, Ap = p->Ap, B = a.B, Tn = a.T;
   const int64_t M = (int64_t)Tn * B;
+  const NetLayout& n = p->net[k];
+  NetBufs& nb = p->nb[k];
+  cublasHandle_t blas = nb.blas;
+  BCK(cublasSetStream(blas, st));
   T* wop = static_cast<T*>(p->wop);
-  T* X = static_cast<T*>(p->X); T* dG = static_cast<T*>(p->dG); T* Hs = static_cast<T*>(p->Hs); T* HP = static_cast<T*>(p->HP);
-  T* dZ = static_cast<T*>(p->dZ); T* dhead = static_cast<T*>(p->dhead);
-  BCK(cublasSetStream(p->blas, st));
+  T* X = static_cast<T*>(p->X); T* dG = static_cast<T*>(nb.dG); T* Hs = static_cast<T*>(nb.Hs); T* HP = static_cast<T*>(nb.HP);
+  T* dZ = static_cast<T*>(nb.dZ); T* dhead = static_cast<T*>(nb.dhead);
+  const int cell_blocks = (B * H + 255) / 256;
+  // ---- forward over the sequences ----
+  gather_state_kernel<T><<<cell_blocks, 256, 0, st>>>(B, H, p->idx, a.h0 + (int64_t)k * a.n * H, a.c0 + (int64_t)k * a.n * H, p->keep, HP, nb.C0);
+  p->launches++;
+  RCK(gemm_nt(p, blas, M, 4 * H, Op, X, Op, wop + n.op_wih, Op, 0.f, nb.G, 4 * H));
+  for (int t = 0; t < Tn; t++) {
+    RCK(gemm_nt(p, blas, B, 4 * H, H, HP + (int64_t)t * B * H, H, wop + n.op_whh, H, 1.f, nb.G + (int64_t)t * B * 4 * H, 4 * H));
+    lstm_cell_fwd_kernel<T><<<cell_blocks, 256, 0, st>>>(t, Tn, B, H, nb.G, a.params + n.bih, a.params + n.bhh, p->keep, nb.C0, nb.Cs, Hs, HP);
+    p->launches++;
+  }
+  const T* in = Hs;
+  int d = H;
+  for (int l = 0; l < n.nl; l++) {
+    T* Aout = static_cast<T*>(nb.Al[l]);
+    RCK(gemm_nt(p, blas, M, n.width[l], d, in, d, wop + n.op_w[l], d, 0.f, nb.T1, n.width[l]));
+    bias_relu_kernel<T><<<blocks_for(M * n.width[l], 256), 256, 0, st>>>(nb.T1, a.params + n.b[l], Aout, M * n.width[l], n.width[l]);
+    p->launches++;
+    in = Aout; d = n.width[l];
+  }
+  RCK(gemm_nt(p, blas, M, n.head_np, d, in, d, wop + n.op_head, d, 0.f, nb.head_out, n.head_np));
+  // ---- loss and its gradient at the head ----
+  if (k == 0) {
+    LossArgs la{M, A, Ap, nb.head_out, a.params + n.head_b, a.params + p->o_log_std, p->act, p->ol, p->ad, p->adv_stats,
+                a.hp.clip_range, a.hp.normalize_advantage};
+    policy_loss_kernel<T><<<kLossBlocks, 256, sizeof(float) * 8 * (kStatSlots + A), st>>>(la, dhead, p->ppart);
+  } else {
+    value_loss_kernel<T><<<kLossBlocks, 256, 0, st>>>(M, nb.head_out, a.params + n.head_b, p->ov, p->rt, a.hp.clip_range_vf, a.hp.vf_coef, dhead,
+                                                       p->vpart);
+  }
+  p->launches++;
+  QCK(cudaGetLastError());
+  // ---- backward ----
+  const int ldh = n.head_np;
+  RCK(gemm_tn(p, blas, M, n.head_n, d, dhead, ldh, in, d, a.grad + n.head_w, d));
+  RCK(colsum<T>(p, nb.cpart, dhead, M, n.head_n, ldh, a.grad + n.head_b, nullptr, st));
+  // dA[M][d] = dhead[M][head_n] . W_head[head_n][d]
+  RCK(gemm_nn(p, blas, M, d, n.head_np, dhead, ldh, wop + n.op_head, d, nb.T1, d));
+  for (int l = n.nl - 1; l >= 0; l--) {
+    const T* Aout = static_cast<const T*>(nb.Al[l]);
+    const T* inl = l > 0 ? static_cast<const T*>(nb.Al[l - 1]) : Hs;
+    const int din = l > 0 ? n.width[l - 1] : H;
+    relu_bwd_kernel<T><<<blocks_for(M * n.width[l], 256), 256, 0, st>>>(nb.T1, Aout, dZ, M * n.width[l]);
+    p->launches++;
+    RCK(gemm_tn(p, blas, M, n.width[l], din, dZ, n.width[l], inl, din, a.grad + n.w[l], din));
+    RCK(colsum<T>(p, nb.cpart, dZ, M, n.width[l], n.width[l], a.grad + n.b[l], nullptr, st));
+    RCK(gemm_nn(p, blas, M, din, n.width[l], dZ, n.width[l], wop + n.op_w[l], din, nb.T1, din));
+  }
+  // T1 = dL/dHs [M][H]; backward through time
+  for (int t = Tn - 1; t >= 0; t--) {
+    lstm_cell_bwd_kernel<T><<<cell_blocks, 256, 0, st>>>(t, Tn, B, H, nb.G, p->keep, nb.C0, nb.Cs, nb.T1, nb.dh_carry, nb.dc_carry, dG);
+    p->launches++;
+    if (t > 0) RCK(gemm_nn(p, blas, B, H, 4 * H, dG + (int64_t)t * B * 4 * H, 4 * H, wop + n.op_whh, H, nb.dh_carry, H));
+  }
+  RCK(gemm_tn(p, blas, M, 4 * H, O, dG, 4 * H, X, Op, a.grad + n.wih, O));
+  RCK(gemm_tn(p, blas, M, 4 * H, H, dG, 4 * H, HP, H, a.grad + n.whh, H));
+  RCK(colsum<T>(p, nb.cpart, dG, M, 4 * H, 4 * H, a.grad + n.bih, a.grad + n.bhh, st));
+  QCK(cudaGetLastError());
+  return MYO_OK;
+}
+
+// the whole minibatch: shared prologue on st, the actor's chain on st and the critic's on the side stream, join, finalize
+template <typename T>
+int minibatch_issue(myo_ppo* p, const GradArgs& a, cudaStream_t st) {
+  const int H = p->H, O = p->O, Op = p->Op, A = p->A, B = a.B, Tn = a.T;
+  const int64_t M = (int64_t)Tn * B;
+  T* wop = static_cast<T*>(p->wop);
+  T* X = static_cast<T*>(p->X);
   QCK(cudaMemsetAsync(a.grad, 0, sizeof(float) * p->n_params, st));
   // operand copies of the weights
   for (int k = 0; k < 2; k++) {
@@ -550,75 +645,64 @@ int minibatch_grad(myo_ppo* p, const GradArgs& a, cudaStream_t st) {
     convert_pad_kernel<T><<<blocks_for((int64_t)n.head_np * d, 256), 256, 0, st>>>(a.params + n.head_w, wop + n.op_head, n.head_n, d, n.head_np, d);
     p->launches += 3 + n.nl;
   }
-  gather_rows_kernel<T><<<blocks_for(M * 32, 256), 256, 0, st>>>(Tn, B, a.n, O, Op, A, a.idx, a.obs, a.actions, a.starts, a.old_values, a.old_logp,
+  gather_rows_kernel<T><<<blocks_for(M * 32, 256), 256, 0, st>>>(Tn, B, a.n, O, Op, A, p->idx, a.obs, a.actions, a.starts, a.old_values, a.old_logp,
                                                                    a.adv, a.ret, X, p->act, p->keep, p->ov, p->ol, p->ad, p->rt);
   adv_stats_kernel<<<1, 1024, 0, st>>>(p->ad, M, p->adv_stats);
   p->launches += 2;
   QCK(cudaGetLastError());
-
-  const int cell_blocks = (B * H + 255) / 256;
-  for (int k = 0; k < 2; k++) {
-    const NetLayout& n = p->net[k];
-    // ---- forward over the sequences ----
-    gather_state_kernel<T><<<cell_blocks, 256, 0, st>>>(B, H, a.idx, a.h0 + (int64_t)k * a.n * H, a.c0 + (int64_t)k * a.n * H, p->keep, HP, p->C0);
-    p->launches++;
-    RCK(gemm_nt(p, M, 4 * H, Op, X, Op, wop + n.op_wih, Op, 0.f, p->G, 4 * H));
-    for (int t = 0; t < Tn; t++) {
-      RCK(gemm_nt(p, B, 4 * H, H, HP + (int64_t)t * B * H, H, wop + n.op_whh, H, 1.f, p->G + (int64_t)t * B * 4 * H, 4 * H));
-      lstm_cell_fwd_kernel<T><<<cell_blocks, 256, 0, st>>>(t, Tn, B, H, p->G, a.params + n.bih, a.params + n.bhh, p->keep, p->C0, p->Cs, Hs, HP);
-      p->launches++;
-    }
-    const T* in = Hs;
-    int d = H;
-    for (int l = 0; l < n.nl; l++) {
-      T* Aout = static_cast<T*>(p->Al[l]);
-      RCK(gemm_nt(p, M, n.width[l], d, in, d, wop + n.op_w[l], d, 0.f, p->T1, n.width[l]));
-      bias_relu_kernel<T><<<blocks_for(M * n.width[l], 256), 256, 0, st>>>(p->T1, a.params + n.b[l], Aout, M * n.width[l], n.width[l]);
-      p->launches++;
-      in = Aout; d = n.width[l];
-    }
-    RCK(gemm_nt(p, M, n.head_np, d, in, d, wop + n.op_head, d, 0.f, p->head_out, n.head_np));
-    // ---- loss and its gradient at the head ----
-    if (k == 0) {
-      LossArgs la{M, A, Ap, p->head_out, a.params + n.head_b, a.params + p->o_log_std, p->act, p->ol, p->ad, p->adv_stats,
-                  a.hp.clip_range, a.hp.normalize_advantage};
-      policy_loss_kernel<T><<<kLossBlocks, 256, sizeof(float) * 8 * (kStatSlots + A), st>>>(la, dhead, p->ppart);
-    } else {
-      value_loss_kernel<T><<<kLossBlocks, 256, 0, st>>>(M, p->head_out, a.params + n.head_b, p->ov, p->rt, a.hp.clip_range_vf, a.hp.vf_coef, dhead,
-                                                         p->vpart);
-    }
-    p->launches++;
-    QCK(cudaGetLastError());
-    // ---- backward ----
-    const int ldh = n.head_np;
-    RCK(gemm_tn(p, M, n.head_n, d, dhead, ldh, in, d, a.grad + n.head_w, d));
-    RCK(colsum<T>(p, dhead, M, n.head_n, ldh, a.grad + n.head_b, nullptr, st));
-    // dA[M][d] = dhead[M][head_n] . W_head[head_n][d]
-    RCK(gemm_nn(p, M, d, n.head_np, dhead, ldh, wop + n.op_head, d, p->T1, d));
-    for (int l = n.nl - 1; l >= 0; l--) {
-      const T* Aout = static_cast<const T*>(p->Al[l]);
-      const T* inl = l > 0 ? static_cast<const T*>(p->Al[l - 1]) : Hs;
-      const int din = l > 0 ? n.width[l - 1] : H;
-      relu_bwd_kernel<T><<<blocks_for(M * n.width[l], 256), 256, 0, st>>>(p->T1, Aout, dZ, M * n.width[l]);
-      p->launches++;
-      RCK(gemm_tn(p, M, n.width[l], din, dZ, n.width[l], inl, din, a.grad + n.w[l], din));
-      RCK(colsum<T>(p, dZ, M, n.width[l], n.width[l], a.grad + n.b[l], nullptr, st));
-      RCK(gemm_nn(p, M, din, n.width[l], dZ, n.width[l], wop + n.op_w[l], din, p->T1, din));
-    }
-    // T1 = dL/dHs [M][H]; backward through time
-    for (int t = Tn - 1; t >= 0; t--) {
-      lstm_cell_bwd_kernel<T><<<cell_blocks, 256, 0, st>>>(t, Tn, B, H, p->G, p->keep, p->C0, p->Cs, p->T1, p->dh_carry, p->dc_carry, dG);
-      p->launches++;
-      if (t > 0) RCK(gemm_nn(p, B, H, 4 * H, dG + (int64_t)t * B * 4 * H, 4 * H, wop + n.op_whh, H, p->dh_carry, H));
-    }
-    RCK(gemm_tn(p, M, 4 * H, O, dG, 4 * H, X, Op, a.grad + n.wih, O));
-    RCK(gemm_tn(p, M, 4 * H, H, dG, 4 * H, HP, H, a.grad + n.whh, H));
-    RCK(colsum<T>(p, dG, M, 4 * H, 4 * H, a.grad + n.bih, a.grad + n.bhh, st));
-  }
+  QCK(cudaEventRecord(p->ev_fork, st));
+  QCK(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+  int rc = net_chain<T>(p, a, 1, p->side);
+  if (cudaEventRecord(p->ev_join, p->side) != cudaSuccess && !rc) { myo::set_error("cudaEventRecord(join) failed"); rc = MYO_E_CUDA; }
+  const int rc0 = net_chain<T>(p, a, 0, st);
+  if (cudaStreamWaitEvent(st, p->ev_join, 0) != cudaSuccess && !rc) { myo::set_error("cudaStreamWaitEvent(join) failed"); rc = MYO_E_CUDA; }
+  if (rc0) return rc0;
+  if (rc) return rc;
   loss_finalize_kernel<<<1, 128, 0, st>>>(p->ppart, kLossBlocks, p->vpart, kLossBlocks, A, M, a.params + p->o_log_std, p->adv_stats, a.hp.ent_coef,
                                           a.hp.vf_coef, a.stats, a.grad + p->o_log_std);
   p->launches++;
   QCK(cudaGetLastError());
+  return MYO_OK;
+}
+
+GradKey make_key(const GradArgs& a) {
+  GradKey k;
+  memset(&k, 0, sizeof(k));
+  const void* ptrs[12] = {a.params, a.obs, a.actions, a.starts, a.old_values, a.old_logp, a.adv, a.ret, a.h0, a.c0, a.grad, a.stats};
+  for (int i = 0; i < 12; i++) k.ptr[i] = ptrs[i];
+  k.T = a.T; k.n = a.n; k.B = a.B; k.hp = a.hp;
+  return k;
+}
+
+template <typename T>
+int minibatch_grad(myo_ppo* p, const GradArgs& a, cudaStream_t st) {
+  QCK(cudaMemcpyAsync(p->idx, a.idx, sizeof(int32_t) * a.B, cudaMemcpyDeviceToDevice, st));
+  if (!p->use_graph) return minibatch_issue<T>(p, a, st);
+  // the graph runs on the handle's own stream, ordered after / before the caller's stream by events
+  QCK(cudaEventRecord(p->ev_in, st));
+  QCK(cudaStreamWaitEvent(p->main, p->ev_in, 0));
+  const GradKey key = make_key(a);
+  if (!p->have_graph || memcmp(&key, &p->key, sizeof(key)) != 0) {
+    if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
+    p->have_graph = false;
+    const int64_t l0 = p->launches;
+    QCK(cudaStreamBeginCapture(p->main, cudaStreamCaptureModeThreadLocal));
+    const int rc = minibatch_issue<T>(p, a, p->main);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(p->main, &graph);
+    p->graph_launches = p->launches - l0;
+    p->launches = l0;
+    if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+    if (e != cudaSuccess || !graph) { myo::set_error(std::string("graph capture of the PPO minibatch failed: ") + cudaGetErrorString(e)); cudaGetLastError(); return MYO_E_CUDA; }
+    const cudaError_t ei = cudaGraphInstantiate(&p->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) { myo::set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); cudaGetLastError(); return MYO_E_CUDA; }
+    p->key = key; p->have_graph = true;
+  }
+  QCK(cudaGraphLaunch(p->exec, p->main));
+  p->launches += p->graph_launches;
+  QCK(cudaEventRecord(p->ev_out, p->main));
+  QCK(cudaStreamWaitEvent(st, p->ev_out, 0));
   return MYO_OK;
 }
 
@@ -651,20 +735,42 @@ int myo_ppo_create(const myo_policy_cfg* cfg, int max_steps, int max_worlds, int
   int rc = MYO_OK;
   auto A_ = [&](auto** q, size_t bytes) { if (!rc) rc = dev_alloc(p, q, bytes); };
   A_(&p->wop, os * p->n_op);
-  A_(&p->X, os * M * p->Op); A_(&p->dG, os * M * 4 * H); A_(&p->Hs, os * M * H); A_(&p->HP, os * M * H);
-  const int nlmax = cfg->n_pi_layers > cfg->n_vf_layers ? cfg->n_pi_layers : cfg->n_vf_layers;
-  for (int l = 0; l < nlmax; l++) A_(&p->Al[l], os * M * p->Dmax);
-  A_(&p->dZ, os * M * p->Dmax); A_(&p->dhead, os * M * p->Ap);
-  A_(&p->G, sizeof(float) * M * 4 * H); A_(&p->Cs, sizeof(float) * M * H); A_(&p->C0, sizeof(float) * B * H);
-  A_(&p->T1, sizeof(float) * M * p->Dmax); A_(&p->head_out, sizeof(float) * M * p->Ap);
-  A_(&p->dh_carry, sizeof(float) * B * H); A_(&p->dc_carry, sizeof(float) * B * H);
+  A_(&p->X, os * M * p->Op);
+  A_(&p->idx, sizeof(int32_t) * B);
+  const size_t cpart_words = kColsumRows * (4 * H > (size_t)p->Dmax ? 4 * H : (size_t)p->Dmax);
+  for (int k = 0; k < 2; k++) {
+    NetBufs& nb = p->nb[k];
+    const int nl = k == 0 ? cfg->n_pi_layers : cfg->n_vf_layers;
+    A_(&nb.dG, os * M * 4 * H); A_(&nb.Hs, os * M * H); A_(&nb.HP, os * M * H);
+    for (int l = 0; l < nl; l++) A_(&nb.Al[l], os * M * p->Dmax);
+    A_(&nb.dZ, os * M * p->Dmax); A_(&nb.dhead, os * M * p->Ap);
+    A_(&nb.G, sizeof(float) * M * 4 * H); A_(&nb.Cs, sizeof(float) * M * H); A_(&nb.C0, sizeof(float) * B * H);
+    A_(&nb.T1, sizeof(float) * M * p->Dmax); A_(&nb.head_out, sizeof(float) * M * p->Ap);
+    A_(&nb.dh_carry, sizeof(float) * B * H); A_(&nb.dc_carry, sizeof(float) * B * H);
+    A_(&nb.cpart, sizeof(float) * cpart_words);
+    A_(&nb.workspace, kBlasWorkspace);
+  }
   A_(&p->act, sizeof(float) * M * p->A); A_(&p->keep, sizeof(float) * M); A_(&p->ov, sizeof(float) * M); A_(&p->ol, sizeof(float) * M);
   A_(&p->ad, sizeof(float) * M); A_(&p->rt, sizeof(float) * M); A_(&p->adv_stats, sizeof(float) * 2);
   A_(&p->ppart, sizeof(float) * kLossBlocks * (kStatSlots + p->A)); A_(&p->vpart, sizeof(float) * kLossBlocks);
-  A_(&p->cpart, sizeof(float) * kColsumRows * (4 * H > (size_t)p->Dmax ? 4 * H : (size_t)p->Dmax));
   A_(&p->npart, sizeof(double) * kNormBlocks);
   if (rc) { myo_ppo_destroy(p); return rc; }
-  if (cublasCreate(&p->blas) != CUBLAS_STATUS_SUCCESS) { myo::set_error("cublasCreate failed"); myo_ppo_destroy(p); return MYO_E_CUDA; }
+  for (int k = 0; k < 2; k++) {
+    // an explicit workspace per handle: the two handles run concurrently, and cuBLAS must not allocate inside a graph capture
+    if (cublasCreate(&p->nb[k].blas) != CUBLAS_STATUS_SUCCESS || cublasSetWorkspace(p->nb[k].blas, p->nb[k].workspace, kBlasWorkspace) != CUBLAS_STATUS_SUCCESS) {
+      myo::set_error("cublasCreate / cublasSetWorkspace failed");
+      myo_ppo_destroy(p);
+      return MYO_E_CUDA;
+    }
+  }
+  if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&p->main, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+    myo::set_error("stream / event creation failed");
+    myo_ppo_destroy(p);
+    return MYO_E_CUDA;
+  }
+  if (const char* e = getenv("MYO_PPO_NO_GRAPH")) p->use_graph = atoi(e) == 0;
   *out = p;
   return MYO_OK;
 }
@@ -672,7 +778,14 @@ int myo_ppo_create(const myo_policy_cfg* cfg, int max_steps, int max_worlds, int
 void myo_ppo_destroy(myo_ppo* p) {
   if (!p) return;
   cudaSetDevice(p->device);
-  if (p->blas) cublasDestroy(p->blas);
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  for (int k = 0; k < 2; k++) if (p->nb[k].blas) cublasDestroy(p->nb[k].blas);
+  if (p->side) cudaStreamDestroy(p->side);
+  if (p->main) cudaStreamDestroy(p->main);
+  if (p->ev_in) cudaEventDestroy(p->ev_in);
+  if (p->ev_out) cudaEventDestroy(p->ev_out);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->ev_join) cudaEventDestroy(p->ev_join);
   for (void* q : p->allocs) cudaFree(q);
   delete p;
 }
