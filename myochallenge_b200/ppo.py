@@ -199,6 +199,10 @@ class RecurrentPPO:
                                       max_batch=venv.num_envs, device=self.device)
         self.policy.init_random(seed, log_std_init=kw.get("log_std_init", 0.0))
         self.policy.seed(seed + 1)
+        if callable(clip_range):           # SB3 accepts schedules of the remaining progress; the kernels take the value at 1.0
+            clip_range = float(clip_range(1.0))
+        if callable(clip_range_vf):
+            clip_range_vf = float(clip_range_vf(1.0))
         self.n_steps, self.n_epochs, self.gamma, self.gae_lambda, self.target_kl = n_steps, n_epochs, gamma, gae_lambda, target_kl
         self.n_envs = venv.num_envs
         self.batch_worlds = max(1, min(self.n_envs, batch_size // n_steps))
@@ -212,6 +216,79 @@ class RecurrentPPO:
         self.num_timesteps = 0
         self._state = None
         self.logs = []
+
+    # -- SB3 zip interchange (RecurrentPPO.save / RecurrentPPO.load; /root/reference/src/main_eval.py:60-75) -----------------------
+    def get_parameters(self):
+        return {"policy": {k: v.detach().cpu().clone() for k, v in self.update.state_dict().items()}}
+
+    def set_parameters(self, state_dict):
+        sd = state_dict.get("policy", state_dict)
+        self.update.load_state_dict(sd)
+        self.update.push_to_policy()
+
+    def save(self, path: str):
+        from . import checkpoint
+
+        u = self.update
+        data = dict(n_envs=self.n_envs, num_timesteps=self.num_timesteps, n_steps=self.n_steps, batch_size=self.batch_worlds * self.n_steps,
+                    n_epochs=self.n_epochs, gamma=self.gamma, gae_lambda=self.gae_lambda, ent_coef=u.hyper.ent_coef, vf_coef=u.hyper.vf_coef,
+                    max_grad_norm=u.max_grad_norm, learning_rate=u.learning_rate, clip_range=u.hyper.clip_range,
+                    clip_range_vf=None if u.hyper.clip_range_vf <= 0 else u.hyper.clip_range_vf, normalize_advantage=bool(u.hyper.normalize_advantage),
+                    target_kl=self.target_kl, use_sde=False, _n_updates=u.step_count,
+                    policy_kwargs=dict(lstm_hidden_size=self.policy.lstm_hidden, net_arch=[dict(pi=list(self.policy.pi), vf=list(self.policy.vf))],
+                                       enable_critic_lstm=True, ortho_init=False))
+        # torch.optim.Adam state over the parameters in state-dict order, as policy.optimizer.pth holds it
+        names = checkpoint.sb3_parameter_order(list(self.policy.state_dict_shapes()))
+        views = lambda flat: [flat[o: o + n].view(shp).detach().cpu().clone() for (o, n, shp) in
+                              ((u._views[k].storage_offset(), u._views[k].numel(), u._views[k].shape) for k in names)]
+        m, v = views(u.exp_avg), views(u.exp_avg_sq)
+        opt = {"state": {i: {"step": torch.tensor(float(u.step_count)), "exp_avg": m[i], "exp_avg_sq": v[i]} for i in range(len(names))} if u.step_count else {},
+               "param_groups": [{"lr": u.learning_rate, "betas": tuple(u.betas), "eps": u.adam_eps, "weight_decay": 0, "amsgrad": False,
+                                 "params": list(range(len(names)))}]}
+        checkpoint.save_sb3_zip(path if path.endswith(".zip") else path + ".zip", self.get_parameters()["policy"], data, opt)
+
+    @classmethod
+    def load(cls, path: str, env=None, custom_objects=None, **kwargs):
+        """Rebuild an agent from an SB3 zip (the reference's ``RecurrentPPO.load(path, env=..., custom_objects=...)``):
+        architecture from the tensors, hyper-parameters from ``data`` (overridden by ``custom_objects`` / kwargs), Adam
+        moments from ``policy.optimizer.pth`` when present."""
+        from . import checkpoint
+
+        ck = checkpoint.load_sb3_zip(path if path.endswith(".zip") else path + ".zip")
+        d = dict(ck["data"])
+        d.update(custom_objects or {})
+        d.update(kwargs)
+        arch = checkpoint.architecture_of(ck["state_dict"])
+
+        def num(key, default):
+            v = d.get(key, default)
+            if callable(v):
+                return v
+            return default if isinstance(v, dict) or v is None else v       # serialised schedules come back as dict summaries
+
+        agent = cls("MlpLstmPolicy", env, learning_rate=num("learning_rate", 3e-4), n_steps=int(num("n_steps", 128)),
+                    batch_size=int(num("batch_size", 128)), n_epochs=int(num("n_epochs", 10)), gamma=float(num("gamma", 0.99)),
+                    gae_lambda=float(num("gae_lambda", 0.95)), clip_range=num("clip_range", 0.2), clip_range_vf=d.get("clip_range_vf") if not isinstance(d.get("clip_range_vf"), dict) else None,
+                    normalize_advantage=bool(num("normalize_advantage", True)), ent_coef=float(num("ent_coef", 0.0)), vf_coef=float(num("vf_coef", 0.5)),
+                    max_grad_norm=float(num("max_grad_norm", 0.5)), target_kl=d.get("target_kl") if not isinstance(d.get("target_kl"), dict) else None,
+                    policy_kwargs=dict(lstm_hidden_size=arch["lstm_hidden"], net_arch=[dict(pi=list(arch["pi"]), vf=list(arch["vf"]))]),
+                    seed=int(d["seed"]) if isinstance(d.get("seed"), int) else 0, precision=d.get("precision", "bf16"))
+        agent.set_parameters(ck["state_dict"])
+        agent.num_timesteps = int(d.get("num_timesteps", 0)) if not isinstance(d.get("num_timesteps"), dict) else 0
+        opt = ck.get("optimizer")
+        if opt and opt.get("state"):
+            u = agent.update
+            names = list(agent.policy.state_dict_shapes())
+            # SB3 registers parameters in module order, which is the state-dict order of policy.pth
+            order = list(ck["state_dict"].keys())
+            for i, k in enumerate(order):
+                st = opt["state"].get(i)
+                if st is None or k not in names:
+                    continue
+                o, n = u._views[k].storage_offset(), u._views[k].numel()
+                u.exp_avg[o: o + n].copy_(st["exp_avg"].reshape(-1)); u.exp_avg_sq[o: o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                u.step_count = int(st["step"])
+        return agent
 
     def learn(self, total_timesteps: int, callback=None, **_ignored):
         if self._state is None:

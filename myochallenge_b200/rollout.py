@@ -180,6 +180,32 @@ class DeviceVecNormalize:
     def terminal_obs(self):
         return self.venv.terminal_obs
 
+    # -- VecNormalize.save / VecNormalize.load(path, venv) (/root/reference/src/main_eval.py:65-67) ----------------------------
+    def stats(self):
+        o, r = self.obs_rms.state.cpu().numpy(), self.ret_rms.state.cpu().numpy()
+        d = self.obs_rms.d
+        return dict(obs_mean=o[:d].copy(), obs_var=o[d: 2 * d].copy(), obs_count=float(o[2 * d]), ret_mean=float(r[0]), ret_var=float(r[1]),
+                    ret_count=float(r[2]), clip_obs=self.clip_obs, clip_reward=self.clip_reward, gamma=self.gamma, epsilon=self.epsilon,
+                    training=self.training, norm_obs=self.norm_obs, norm_reward=self.norm_reward)
+
+    def save(self, path: str):
+        from . import checkpoint
+
+        checkpoint.save_vecnormalize(path, self.stats(), self.num_envs, self.venv.sim.nu)
+
+    @classmethod
+    def load(cls, path: str, venv, policy=None):
+        from . import checkpoint
+
+        st = checkpoint.load_vecnormalize(path)
+        vn = cls(venv, None, training=st["training"], norm_obs=st["norm_obs"], norm_reward=st["norm_reward"], clip_obs=st["clip_obs"],
+                 clip_reward=st["clip_reward"], gamma=st["gamma"], epsilon=st["epsilon"])
+        vn.obs_rms.load(st["obs_mean"], st["obs_var"], st["obs_count"])
+        vn.ret_rms.load([st["ret_mean"]], [st["ret_var"]], st["ret_count"])
+        if policy is not None:
+            vn.attach(policy)
+        return vn
+
 
 class RecurrentRolloutBuffer:
     """sb3-contrib ``RecurrentRolloutBuffer`` storage, step-major on the device: observations (as the policy saw them,

@@ -254,6 +254,24 @@ class VecNormalize:
         v.ret_rms.mean, v.ret_rms.var, v.ret_rms.count = float(ret_mean), float(ret_var), float(ret_count)
         return v
 
+    @classmethod
+    def load(cls, load_path: str, venv):
+        """``VecNormalize.load(path, venv)`` on an SB3 pickle (e.g. the reference's ``env.pkl``)."""
+        from . import checkpoint
+
+        st = checkpoint.load_vecnormalize(load_path)
+        return cls.from_moments(venv, st["obs_mean"], st["obs_var"], st["obs_count"], st["ret_mean"], st["ret_var"], st["ret_count"],
+                                training=st["training"], norm_obs=st["norm_obs"], norm_reward=st["norm_reward"], clip_obs=st["clip_obs"],
+                                clip_reward=st["clip_reward"], gamma=st["gamma"], epsilon=st["epsilon"])
+
+    def save(self, save_path: str) -> None:
+        from . import checkpoint
+
+        checkpoint.save_vecnormalize(save_path, dict(
+            obs_mean=self.obs_rms.mean, obs_var=self.obs_rms.var, obs_count=self.obs_rms.count, ret_mean=self.ret_rms.mean, ret_var=self.ret_rms.var,
+            ret_count=self.ret_rms.count, clip_obs=self.clip_obs, clip_reward=self.clip_reward, gamma=self.gamma, epsilon=self.epsilon,
+            training=self.training, norm_obs=self.norm_obs, norm_reward=self.norm_reward), self.num_envs, self.action_space.shape[0])
+
     def normalize_obs(self, obs: np.ndarray) -> np.ndarray:
         if not self.norm_obs:
             return obs

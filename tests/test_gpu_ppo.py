@@ -206,3 +206,36 @@ def test_recurrent_ppo_learn_on_baoding_is_on_policy_at_the_first_minibatch(prod
     assert len(agent.logs) == 2 and agent.num_timesteps == 2 * n * T
     for log in agent.logs:
         assert log["train/n_updates"] == 2 * 4 and np.isfinite(log["train/loss"]) and log["train/approx_kl"] < 0.05
+
+
+def test_recurrent_ppo_save_load_round_trip(product_lib, tmp_path):
+    """RecurrentPPO.save -> RecurrentPPO.load (SB3 zip layout) and DeviceVecNormalize.save -> load: parameters, Adam moments, step
+    count, hyper-parameters and running moments survive; the reloaded agent takes the same next optimiser step."""
+    from myochallenge_b200.envs import make_vec_env
+    from myochallenge_b200.ppo import RecurrentPPO
+    from myochallenge_b200.rollout import DeviceVecNormalize
+
+    n, T = 128, 8
+    env = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, device=DEV, seed=2, clip_actions=True, max_episode_steps=6)
+    vn = DeviceVecNormalize(env, gamma=0.99)
+    kw = dict(n_steps=T, batch_size=T * 32, n_epochs=1, learning_rate=3e-4, clip_range=0.25, ent_coef=0.002, vf_coef=0.8, max_grad_norm=0.7, gae_lambda=0.9,
+              policy_kwargs=dict(lstm_hidden_size=64, net_arch=[dict(pi=[32], vf=[48, 16])], log_std_init=-1.0))
+    agent = RecurrentPPO("MlpLstmPolicy", vn, seed=4, **kw)
+    agent.learn(total_timesteps=n * T)
+    zp, ep = str(tmp_path / "agent.zip"), str(tmp_path / "env.pkl")
+    agent.save(zp); vn.save(ep)
+    vn2 = DeviceVecNormalize.load(ep, env)
+    assert torch.equal(vn2.obs_rms.state, vn.obs_rms.state) and torch.equal(vn2.ret_rms.state, vn.ret_rms.state)
+    agent2 = RecurrentPPO.load(zp, env=vn2)
+    assert agent2.n_steps == T and agent2.batch_worlds == 32 and agent2.gae_lambda == 0.9 and agent2.num_timesteps == n * T
+    assert agent2.policy.pi == (32,) and agent2.policy.vf == (48, 16) and agent2.policy.lstm_hidden == 64
+    h1, h2 = agent.update.hyper, agent2.update.hyper
+    assert (h1.clip_range, h1.ent_coef, h1.vf_coef) == (h2.clip_range, h2.ent_coef, h2.vf_coef) and agent2.update.max_grad_norm == pytest.approx(0.7)
+    assert agent2.update.step_count == agent.update.step_count == 4
+    for a, b in ((agent.update.params, agent2.update.params), (agent.update.exp_avg, agent2.update.exp_avg), (agent.update.exp_avg_sq, agent2.update.exp_avg_sq)):
+        assert torch.equal(a, b)
+    # same next step from the same rollout data
+    idx = torch.arange(32, dtype=torch.int32, device=DEV)
+    agent.update.minibatch_grad(agent.buffer, idx); agent.update.adam_step()
+    agent2.update.minibatch_grad(agent.buffer, idx); agent2.update.adam_step()
+    assert torch.equal(agent.update.params, agent2.update.params)
