@@ -1364,6 +1364,44 @@ __device__ unsigned long long g_prof[16];
 // a10.8 constraint solve: primal Newton with exact line search on
 //   cost(a) = 1/2 (a - a_s)' M (a - a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
 // warm-started from the better of (qacc_warmstart, qacc_smooth) as MuJoCo's warmstart() does.
+// All warps of a CTA walk the phases together: the step is ~200 KB of straight-line code, far more
+// than the instruction cache holds, so keeping the CTA inside one phase at a time lets every fetched
+// line serve all of its warps. (Every tile of the CTA executes every phase of every substep.)
+#ifndef MYO_LOCKSTEP_WARPS
+#define MYO_LOCKSTEP_WARPS 0      // 0: the whole CTA walks the phases together; k: groups of k warps do (named barriers)
+#endif
+MYO_DI void lockstep_sync() {
+#if defined(MYO_EMUL) || MYO_LOCKSTEP_WARPS == 0
+  __syncthreads();
+#else
+  const unsigned nw = blockDim.x >> 5;
+  if (nw % MYO_LOCKSTEP_WARPS) { __syncthreads(); return; }
+  const unsigned group = (threadIdx.x >> 5) / MYO_LOCKSTEP_WARPS;
+  asm volatile("bar.sync %0, %1;" ::"r"(1u + group), "r"(32u * MYO_LOCKSTEP_WARPS) : "memory");
+#endif
+}
+#define MYO_CTA_SYNC lockstep_sync();
+// which of the eight phase boundaries of a substep carry the CTA barrier (bit i = boundary before phase i in the order
+// tree_forward, mass_bias, tendon, collision, constraints, actuation, solve, integrate). Worlds are independent, so the
+// barriers are a performance device only (instruction-cache sharing); see DESIGN.md for the measured choices.
+#ifndef MYO_SYNC_MASK
+#define MYO_SYNC_MASK 0xFF
+#endif
+#define MYO_SYNC(i) if ((MYO_SYNC_MASK >> (i)) & 1) lockstep_sync();
+
+// Optional (MYO_NEWTON_LOCKSTEP=1): the Newton iterations of a CTA's worlds in lock step too - barriers between Hessian build,
+// factorisation and line search, a CTA-wide vote ending the loop when no world iterates. Measured 3 % SLOWER than letting
+// each world iterate freely inside the phase (28.5 vs 27.7 ms per 32768-world step at steady state), so it is off.
+#ifndef MYO_NEWTON_LOCKSTEP
+#define MYO_NEWTON_LOCKSTEP 0
+#endif
+MYO_DI bool cta_any(bool v) {
+#if defined(MYO_EMUL)
+  return v;
+#else
+  return __syncthreads_or(v ? 1 : 0) != 0;
+#endif
+}
 template <int G>
 MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
   MYO_M
@@ -1372,11 +1410,12 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
   float* a = SF(o_qacc); float* qcon = SF(o_qcon);
   const float* as = SF(o_qaccs); const float* fs = SF(o_smooth);
   float* rows = SF(o_row);
-  if (nefc == 0) {
+  bool active = nefc > 0;
+  if (!active) {
     for (int i = c.lane; i < nv; i += G) { a[i] = as[i]; SF(o_warm)[i] = as[i]; qcon[i] = 0.f; }
     if (c.lane == 0) misc[MI_ITER] = 0;
     c.tile.sync();
-    return;
+    if (!MYO_NEWTON_LOCKSTEP) return;
   }
   float* Ma = SF(o_Ma); float* grad = SF(o_grad); float* p = SF(o_p); float* Mp = SF(o_Mp);
   // constraint rows in registers for the reductions and the line search: lane owns rows lane, lane + G, ...
@@ -1391,7 +1430,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
   // (fast) starts from qacc_warmstart without evaluating qacc_smooth at all - the minimiser of the convex cost does not
   // depend on the starting point, and skipping M^-1 f_smooth and one pass over the rows saves ~8 % of a substep; only a
   // non-finite warm start falls back to qacc_smooth.
-  {
+  if (active) {
     const float* w = SF(o_warm);
     bool use_smooth;
     if (fast) {
@@ -1427,19 +1466,25 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
   int iter = 0;
   MYO_PH_BEGIN
   float prev_step = 3.0e38f;
-  for (; iter < m.solver_iter; iter++) {
-    MYO_PH_RESTART newton_system<G>(mslot, c); MYO_PH(11)
-    float g2 = 0.f, amax = 0.f;
-    for (int i = c.lane; i < nv; i += G) { g2 += grad[i] * grad[i]; amax = fmaxf(amax, fabsf(a[i])); }
-    g2 = tile_sum<G>(c, g2);
-    amax = tile_max<G>(c, amax);
-    if (sqrtf(g2) * scale < m.solver_tol) break;
-    chol_factor_solve<G>(mslot, c, m.o_H, m.o_p, nv); MYO_PH(12)
+  for (int it = 0; it < m.solver_iter; it++) {
+    if (MYO_NEWTON_LOCKSTEP) { if (!cta_any(active)) break; }
+    else if (!active) break;
+    if (active) {
+      MYO_PH_RESTART newton_system<G>(mslot, c); MYO_PH(11)
+      float g2 = 0.f;
+      for (int i = c.lane; i < nv; i += G) g2 += grad[i] * grad[i];
+      g2 = tile_sum<G>(c, g2);
+      if (sqrtf(g2) * scale < m.solver_tol) active = false;
+    }
+    if (MYO_NEWTON_LOCKSTEP) lockstep_sync();
+    if (active) { chol_factor_solve<G>(mslot, c, m.o_H, m.o_p, nv); MYO_PH(12) }
+    if (MYO_NEWTON_LOCKSTEP) lockstep_sync();
+    if (active) {
     rows_dot<G>(mslot, c, m.o_p, R_JP, false, false);
     mul_M<G>(mslot, c, m.o_M, m.o_p, m.o_Mp);
-    float pMp = 0.f, gp = 0.f, pmax = 0.f;
-    for (int i = c.lane; i < nv; i += G) { pMp += p[i] * Mp[i]; gp += (Ma[i] - fs[i]) * p[i]; pmax = fmaxf(pmax, fabsf(p[i])); }
-    pMp = tile_sum<G>(c, pMp); gp = tile_sum<G>(c, gp); pmax = tile_max<G>(c, pmax);
+    float pMp = 0.f, gp = 0.f, pmax = 0.f, amax = 0.f;
+    for (int i = c.lane; i < nv; i += G) { pMp += p[i] * Mp[i]; gp += (Ma[i] - fs[i]) * p[i]; pmax = fmaxf(pmax, fabsf(p[i])); amax = fmaxf(amax, fabsf(a[i])); }
+    pMp = tile_sum<G>(c, pMp); gp = tile_sum<G>(c, gp); pmax = tile_max<G>(c, pmax); amax = tile_max<G>(c, amax);
     float rD[RMAX], rJ[RMAX], rP[RMAX];
 #pragma unroll
     for (int q = 0; q < RMAX; q++) {
@@ -1481,16 +1526,19 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
     changed = c.tile.ballot(changed != 0) != 0u;
     for (int i = c.lane; i < nv; i += G) { a[i] += alpha * p[i]; Ma[i] += alpha * Mp[i]; }
     c.tile.sync();
-    if (!changed && fabsf(alpha - 1.f) <= 1e-3f) { iter++; break; }
+    iter++;
+    if (!changed && fabsf(alpha - 1.f) <= 1e-3f) active = false;
 #ifdef MYO_SOLVER_DEBUG
-    if (iter > 8) printf("it %d gnorm*scale %.3e alpha %.6f pmax %.3e amax %.3e gp %.3e pMp %.3e nefc %d\n", iter, sqrtf(g2) * scale, alpha, pmax, amax, gp, pMp, nefc);
+    if (iter > 9) printf("it %d alpha %.6f pmax %.3e amax %.3e gp %.3e pMp %.3e nefc %d\n", iter, alpha, pmax, amax, gp, pMp, nefc);
 #endif
     // fp32 termination: the Newton step is at the rounding floor of qacc (quadratic convergence makes
     // the remaining error far smaller than the last step), or it stopped shrinking (noise-level cycling)
     const float step = alpha * pmax, aref_mag = fmaxf(1.f, amax);
-    if (step <= 2e-5f * aref_mag || (iter > 0 && step >= 0.5f * prev_step && step <= 1e-3f * aref_mag)) { iter++; break; }
+    if (step <= 2e-5f * aref_mag || (iter > 1 && step >= 0.5f * prev_step && step <= 1e-3f * aref_mag)) active = false;
     prev_step = step;
+    }
   }
+  if (nefc == 0) return;
   // final forces at the solution (jar is current)
   for (int i = c.lane; i < nv; i += G) { qcon[i] = 0.f; SF(o_warm)[i] = a[i]; }
   c.tile.sync();
@@ -1499,6 +1547,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
   c.tile.sync();
 }
 
+// ------------------------------------------------------------------------------------------------
 // a10.9 mj_Euler (implicit in joint damping) + mj_advance
 template <int G>
 MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
@@ -1540,47 +1589,29 @@ MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
   c.tile.sync();
 }
 
-// All warps of a CTA walk the phases together: the step is ~200 KB of straight-line code, far more
-// than the instruction cache holds, so keeping the CTA inside one phase at a time lets every fetched
-// line serve all of its warps. (Every tile of the CTA executes every phase of every substep.)
-#ifndef MYO_LOCKSTEP_WARPS
-#define MYO_LOCKSTEP_WARPS 0      // 0: the whole CTA walks the phases together; k: groups of k warps do (named barriers)
-#endif
-MYO_DI void lockstep_sync() {
-#if defined(MYO_EMUL) || MYO_LOCKSTEP_WARPS == 0
-  __syncthreads();
-#else
-  const unsigned nw = blockDim.x >> 5;
-  if (nw % MYO_LOCKSTEP_WARPS) { __syncthreads(); return; }
-  const unsigned group = (threadIdx.x >> 5) / MYO_LOCKSTEP_WARPS;
-  asm volatile("bar.sync %0, %1;" ::"r"(1u + group), "r"(32u * MYO_LOCKSTEP_WARPS) : "memory");
-#endif
-}
-#define MYO_CTA_SYNC lockstep_sync();
-
 // one full mj_step on the world in scratch
 template <int G>
 MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_M
   MYO_PH_BEGIN
-  MYO_CTA_SYNC phase_tree_forward<G>(mslot, c, true); MYO_PH(0)
+  MYO_SYNC(0) phase_tree_forward<G>(mslot, c, true); MYO_PH(0)
   MYO_PH(2)
-  MYO_CTA_SYNC phase_mass_bias<G>(mslot, c); MYO_PH(3)
+  MYO_SYNC(1) phase_mass_bias<G>(mslot, c); MYO_PH(3)
   // the velocity-stage temporaries are dead from here on: the tendon phase reuses their scratch (with the Hessian's)
-  MYO_CTA_SYNC phase_tendon<G>(mslot, c, status); MYO_PH(1)
-  MYO_CTA_SYNC phase_collision<G>(mslot, c, status); MYO_PH(5)
-  MYO_CTA_SYNC phase_constraints<G>(mslot, c, status); MYO_PH(6)
-  MYO_CTA_SYNC phase_actuation<G>(mslot, c); MYO_PH(7)
+  MYO_SYNC(2) phase_tendon<G>(mslot, c, status); MYO_PH(1)
+  MYO_SYNC(3) phase_collision<G>(mslot, c, status); MYO_PH(5)
+  MYO_SYNC(4) phase_constraints<G>(mslot, c, status); MYO_PH(6)
+  MYO_SYNC(5) phase_actuation<G>(mslot, c); MYO_PH(7)
   if (!fast || SI(o_misc)[MI_NEFC] == 0) solve_M_dense<G>(mslot, c, m.o_qaccs, 0.f);   // qacc_smooth (see phase_solve)
   MYO_PH(8)
-  MYO_CTA_SYNC phase_solve<G>(mslot, c, fast); MYO_PH(9)
+  MYO_SYNC(6) phase_solve<G>(mslot, c, fast); MYO_PH(9)
 }
 template <int G>
 MYO_PHASE void mj_step_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_M
   mj_forward_dev<G>(mslot, c, status, fast);
   MYO_PH_BEGIN
-  MYO_CTA_SYNC MYO_PH(15) phase_integrate<G>(mslot, c); MYO_PH(10)
+  MYO_SYNC(7) MYO_PH(15) phase_integrate<G>(mslot, c); MYO_PH(10)
 }
 
 }  // namespace myo

@@ -5,7 +5,7 @@ import torch
 from myochallenge_b200 import BatchSim, Model, _capi
 from myochallenge_b200.assets import asset_path
 
-def run(path, kind, n, steps=20):
+def run(path, kind, n, steps=20, spinup=3):
     m = Model(asset_path(path))
     cfg = m.default_task_cfg(kind)
     if kind == _capi.TASK_BAODING:
@@ -13,7 +13,7 @@ def run(path, kind, n, steps=20):
     sim = BatchSim(m, n, cfg, device="cuda:0", seed=0)
     sim.reset()
     a = torch.rand(n, sim.nu, device="cuda:0") * 2 - 1
-    for _ in range(3):
+    for _ in range(spinup):
         sim.step(a)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -30,13 +30,14 @@ if __name__ == "__main__":
     ap.add_argument("--model", default="all")
     ap.add_argument("--n", type=int, default=0)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--spinup", type=int, default=3, help="untimed steps first (150+: steady-state episode phases)")
     ap.add_argument("--lib", default="", help="alternate build of the library (development experiments)")
     args = ap.parse_args()
     if args.lib:
         _capi._LIB = _capi.bind(args.lib)
     if args.model in ("all", "finger"):
         for n in ([args.n] if args.n else [4096, 65536]):
-            run("finger/myo_finger_v0.mjb", _capi.TASK_POSE, n, args.steps)
+            run("finger/myo_finger_v0.mjb", _capi.TASK_POSE, n, args.steps, args.spinup)
     if args.model in ("all", "hand"):
         for n in ([args.n] if args.n else [4096, 32768]):
-            run("hand/myo_hand_baoding.mjb", _capi.TASK_BAODING, n, args.steps)
+            run("hand/myo_hand_baoding.mjb", _capi.TASK_BAODING, n, args.steps, args.spinup)
