@@ -290,6 +290,29 @@ class RecurrentPPO:
                 u.step_count = int(st["step"])
         return agent
 
+    def predict(self, observation, state=None, episode_start=None, deterministic: bool = False):
+        """``model.predict(obs, state=lstm_states, episode_start=..., deterministic=...)`` -> (actions clipped to the action space,
+        lstm_states), on device tensors of all worlds (observations already normalised unless the env's moments are attached)."""
+        obs = torch.as_tensor(observation, dtype=torch.float32, device=self.device)
+        n = obs.shape[0]
+        if state is None:
+            state = self.policy.initial_state(n)
+        if episode_start is None:
+            episode_start = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        es = torch.as_tensor(episode_start).to(self.device)
+        actions, _, _, state = self.policy.forward(obs, state, es, deterministic=deterministic)
+        return actions.clamp(-1.0, 1.0), state
+
+    def evaluate(self, n_episodes: int = 2000, deterministic: bool = True):
+        """The reference's evaluation loop (src/main_eval.py) over this agent's env; see ``evaluate.evaluate_policy``."""
+        from .evaluate import evaluate_policy
+        from .rollout import DeviceVecNormalize
+
+        norm = self.env if isinstance(self.env, DeviceVecNormalize) else None
+        out = evaluate_policy(self.policy, getattr(self.env, "venv", self.env), n_episodes, deterministic, norm)
+        self._state = None          # the env was reset by the evaluation: the next learn() starts from a fresh reset
+        return out
+
     def learn(self, total_timesteps: int, callback=None, **_ignored):
         if self._state is None:
             self._obs = self.env.reset_device()

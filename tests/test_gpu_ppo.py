@@ -239,3 +239,22 @@ def test_recurrent_ppo_save_load_round_trip(product_lib, tmp_path):
     agent.update.minibatch_grad(agent.buffer, idx); agent.update.adam_step()
     agent2.update.minibatch_grad(agent.buffer, idx); agent2.update.adam_step()
     assert torch.equal(agent.update.params, agent2.update.params)
+
+
+def test_evaluate_policy_counts_fixed_quota_per_world(product_lib):
+    """The reference's evaluation loop (src/main_eval.py:79-120) batched: every world contributes exactly its quota of episodes;
+    lengths respect the horizon; a horizon-limited, never-dropping setting gives length == horizon and drop_rate 0."""
+    from myochallenge_b200.envs import make_vec_env
+    from myochallenge_b200.evaluate import evaluate_policy
+
+    n = 96
+    env = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, device=DEV, seed=8, clip_actions=True, max_episode_steps=9, drop_th=-10.0)
+    pol = RecurrentPolicy(env.sim.nobs, env.sim.nu, lstm_hidden=64, pi=(32,), vf=(32,), max_batch=n, device=DEV)
+    pol.init_random(seed=0, log_std_init=-2.0)
+    out = evaluate_policy(pol, env, n_episodes=250, deterministic=True)
+    assert out["episodes"] == 3 * n                       # ceil(250 / 96) = 3 per world
+    assert out["mean_length"] == 9.0 and out["length_sem"] == 0.0 and out["drop_rate"] == 0.0
+    assert np.isfinite(out["mean_reward"]) and 0.0 <= out["score"] <= 1.0 and out["effort"] > 0
+    env2 = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, device=DEV, seed=8, clip_actions=True, max_episode_steps=200, drop_th=1.40)
+    out2 = evaluate_policy(pol, env2, n_episodes=n, deterministic=True)      # balls start at z ~ 1.44: a high drop threshold ends episodes early
+    assert out2["episodes"] == n and out2["mean_length"] < 200 and out2["drop_rate"] > 0.05
