@@ -20,7 +20,7 @@ namespace myo { void set_error(const std::string& msg); }
 namespace {
 
 constexpr int kMomThreads = 256;
-constexpr int kMomMaxCtas = 592;   // 4 x 148: partial count is bounded so the merge kernel stays one short loop
+constexpr int kMomMaxCtas = 148;   // one per SM: the merge walks the partials serially in fp64 (~0.15 us each), so their count is what the update costs
 
 #define RCK(call)                                                                 \
   do {                                                                            \

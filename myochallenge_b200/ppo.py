@@ -290,6 +290,12 @@ class RecurrentPPO:
                 u.step_count = int(st["step"])
         return agent
 
+    @staticmethod
+    def _world_size() -> int:
+        import torch.distributed as dist
+
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
     def predict(self, observation, state=None, episode_start=None, deterministic: bool = False):
         """``model.predict(obs, state=lstm_states, episode_start=..., deterministic=...)`` -> (actions clipped to the action space,
         lstm_states), on device tensors of all worlds (observations already normalised unless the env's moments are attached)."""
@@ -320,8 +326,13 @@ class RecurrentPPO:
             self._state = self.policy.initial_state(self.n_envs)
         start = self.num_timesteps
         while self.num_timesteps - start < total_timesteps:
+            norm = self.env if hasattr(self.env, "obs_rms") and hasattr(self.env.obs_rms, "sync") else None
+            base = (norm.obs_rms.state.clone(), norm.ret_rms.state.clone()) if norm is not None else None
             self._obs, self._starts = collect_rollouts(self.env, self.policy, self.buffer, self._state, self._obs, self._starts)
-            self.num_timesteps += self.n_steps * self.n_envs
+            if norm is not None:          # ranks saw different worlds: merge what each added to the running moments (no-op on one GPU)
+                norm.obs_rms.sync(base[0]); norm.ret_rms.sync(base[1])
+                norm._push_obs_norm()
+            self.num_timesteps += self.n_steps * self.n_envs * self._world_size()
             lr = None
             if self._lr_schedule is not None:
                 lr = self._lr_schedule(max(0.0, 1.0 - (self.num_timesteps - start) / float(total_timesteps)))
