@@ -199,7 +199,7 @@ def run_b200(args):
 
     env = make_vec_env(ENV_ID, n, device=dev, seed=rank_seed(args.seed, rank), weighted_reward_keys=RWD, clip_actions=True)
     sim = env.sim
-    pol = RecurrentPolicy(sim.nobs, sim.nu, lstm_hidden=256, pi=(256, 256), vf=(256, 256), max_batch=n, device=dev)
+    pol = RecurrentPolicy(sim.nobs, sim.nu, lstm_hidden=256, pi=(256, 256), vf=(256, 256), max_batch=n, device=dev, use_sde=args.use_sde)
     pol.init_random(seed=0, log_std_init=-2.0)             # same weights on every rank
     pol.seed(0x5EED + rank)
     stats = os.path.join(ROOT, "tests", "golden", "vecnormalize_baoding_step32.npz")
@@ -347,7 +347,7 @@ def run_b200(args):
         bw = min(n, args.ppo_batch_worlds)
         # phase-2 hyper-parameters of the reference (/root/reference/docs/summary.md:103-117), winning architecture
         agent = RecurrentPPO("MlpLstmPolicy", vn, n_steps=args.ppo_steps, batch_size=args.ppo_steps * bw, n_epochs=args.ppo_epochs,
-                             learning_rate=2.5e-5, clip_range=0.2, ent_coef=3e-5, max_grad_norm=0.8, gae_lambda=0.95, seed=0,
+                             learning_rate=2.5e-5, clip_range=0.2, ent_coef=3e-5, max_grad_norm=0.8, gae_lambda=0.95, seed=0, use_sde=args.use_sde,
                              policy_kwargs=dict(lstm_hidden_size=256, net_arch=[dict(pi=[256, 256], vf=[256, 256])], log_std_init=-2.0,
                                                 ortho_init=False, enable_critic_lstm=True))
         agent.policy.seed(0x5EED + rank)
@@ -413,7 +413,7 @@ def run_b200(args):
                                "random-init MlpLstmPolicy LSTM-256 + [256,256] actor/critic in the loop",
                    "worlds_per_gpu": n, "parallelism": f"worlds sharded over {world} GPU(s), no data-path collective",
                    "l2": "per-step working set (state + LSTM h/c + obs, ~190 MB at 32768 worlds) exceeds the 126 MB L2; no explicit flush",
-                   "spinup_steps": args.spinup, "steady_state": "episode phases mixed by an untimed spin-up of one horizon before warm-up",
+                   "use_sde": bool(args.use_sde), "spinup_steps": args.spinup, "steady_state": "episode phases mixed by an untimed spin-up of one horizon before warm-up",
                    "policy_ms": policy_ms, "world_kernel_ms": world_ms, "status_flags": status},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "sequential": seq_value,
@@ -447,6 +447,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spinup", type=int, default=200, help="untimed env steps before warm-up (one horizon: steady-state episode phases)")
+    ap.add_argument("--use-sde", action="store_true", help="generalised state-dependent exploration (the reference's winning runs train with use_sde=True)")
     ap.add_argument("--no-train", action="store_true", help="skip the whole-PPO-iteration leg")
     ap.add_argument("--ppo-steps", type=int, default=128, help="n_steps of the PPO iteration leg")
     ap.add_argument("--ppo-batch-worlds", type=int, default=2048, help="world sequences per minibatch")

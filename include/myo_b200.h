@@ -227,6 +227,8 @@ typedef struct myo_policy_cfg {
   int32_t obs_dim, act_dim, lstm_hidden;
   int32_t n_pi_layers, pi_layers[4];   /* mlp_extractor policy_net widths (ReLU) */
   int32_t n_vf_layers, vf_layers[4];
+  int32_t use_sde;                     /* generalised state-dependent exploration: log_std is [latent_dim][act_dim] (myo_ppo_*;
+                                          the rollout side is myo_sde_*; myo_policy_forward itself only produces the mean) */
 } myo_policy_cfg;
 int myo_policy_create(const myo_policy_cfg* cfg, int max_batch, int device, myo_policy** out);
 void myo_policy_destroy(myo_policy* p);
@@ -249,6 +251,21 @@ int myo_policy_set_obs_norm(myo_policy* p, const float* mean_dev, const float* v
  * counter-based stream keyed by (seed, world, forward-call counter); seed 0 restores the deterministic mean. */
 int myo_policy_seed(myo_policy* p, uint64_t seed);
 int64_t myo_policy_launch_count(const myo_policy* p);
+/* latent_dev: float[max_batch][latent_dim] (latent_dim = last mlp_extractor policy width) that every following
+ * myo_policy_forward fills with latent_pi, the input of action_net; NULL stops it. Without policy MLP layers latent_pi is
+ * the actor's new hidden state h[0] and nothing is written. */
+int myo_policy_set_latent_out(myo_policy* p, float* latent_dev);
+/* Generalised state-dependent exploration (SB3 StateDependentNoiseDistribution; `use_sde=True` in the reference's winning
+ * runs, /root/reference/docs/summary.md:86-117). log_std: float[latent_dim][act_dim].
+ * myo_sde_reset_noise  <- reset_noise / sample_weights: one exploration matrix per world, noise_mat[n][latent_dim][act_dim]
+ *                         (bf16 bits) = exp(log_std) * N(0,1), and std2[latent_dim][act_dim] = exp(2 log_std); counter-based
+ *                         draws keyed by (seed, world, epoch).
+ * myo_sde_sample       <- get_noise + log_prob: actions (holding the mean on entry) += latent . noise_mat[w];
+ *                         logp = sum_k log N(noise_k; 0, latent^2 . std2 + 1e-6). */
+int myo_sde_reset_noise(uint16_t* noise_mat_dev, float* std2_dev, const float* log_std_dev, int n, int latent_dim, int act_dim,
+                        uint64_t seed, uint32_t epoch, void* stream);
+int myo_sde_sample(const float* latent_dev, int latent_ld, const uint16_t* noise_mat_dev, const float* std2_dev, float* actions_dev,
+                   float* logp_dev, int n, int latent_dim, int act_dim, void* stream);
 
 /* ---- rollout side: VecNormalize running moments, reward scaling, GAE ------------ */
 /* Running moments as SB3's RunningMeanStd keeps them, on the device in fp64: state_dev = mean[d], var[d], count

@@ -65,6 +65,7 @@ class PolicyCfg(C.Structure):
         ("obs_dim", C.c_int32), ("act_dim", C.c_int32), ("lstm_hidden", C.c_int32),
         ("n_pi_layers", C.c_int32), ("pi_layers", C.c_int32 * 4),
         ("n_vf_layers", C.c_int32), ("vf_layers", C.c_int32 * 4),
+        ("use_sde", C.c_int32),
     ]
 
 
@@ -105,6 +106,9 @@ SIGNATURES = {
     "myo_policy_set_obs_norm": (_i, [_vp, _fp, _fp, C.c_float, C.c_float, _vp]),
     "myo_policy_seed": (_i, [_vp, C.c_uint64]),
     "myo_policy_launch_count": (C.c_int64, [_vp]),
+    "myo_policy_set_latent_out": (_i, [_vp, _fp]),
+    "myo_sde_reset_noise": (_i, [_vp, _fp, _fp, _i, _i, _i, C.c_uint64, C.c_uint32, _vp]),
+    "myo_sde_sample": (_i, [_fp, _i, _vp, _fp, _fp, _fp, _i, _i, _i, _vp]),
     "myo_running_moments_scratch": (_i, [_i, _i]),
     "myo_running_moments_update": (_i, [_vp, _fp, _i, _i, _vp, _fp, _fp, _vp]),
     "myo_running_moments_export": (_i, [_vp, _i, _fp, _fp, _vp]),

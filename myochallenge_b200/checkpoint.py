@@ -114,12 +114,13 @@ def architecture_of(state_dict) -> Dict[str, Any]:
         while f"mlp_extractor.{net}.{2 * l}.weight" in state_dict:
             w.append(state_dict[f"mlp_extractor.{net}.{2 * l}.weight"].shape[0]); l += 1
         widths[net] = tuple(w)
-    if tuple(state_dict["log_std"].shape) != (A,):
-        raise ValueError("log_std has shape %s: generalised state-dependent exploration (use_sde=True) policies are not built" %
-                         (tuple(state_dict["log_std"].shape),))
+    d_pi = widths["policy_net"][-1] if widths["policy_net"] else H
+    ls = tuple(state_dict["log_std"].shape)
+    if ls not in ((A,), (d_pi, A)):
+        raise ValueError("log_std has shape %s: expected (%d,) or, with use_sde=True, (%d, %d)" % (ls, A, d_pi, A))
     if "lstm_critic.weight_hh_l0" not in state_dict:
         raise ValueError("the checkpoint has no separate critic LSTM (enable_critic_lstm=False is not built)")
-    return dict(obs_dim=O, act_dim=A, lstm_hidden=H, pi=widths["policy_net"], vf=widths["value_net"])
+    return dict(obs_dim=O, act_dim=A, lstm_hidden=H, pi=widths["policy_net"], vf=widths["value_net"], use_sde=len(ls) == 2)
 
 
 def sb3_parameter_order(names):

@@ -78,6 +78,8 @@ struct FwdArgs {
   const float* obs_inv_std;
   float clip_obs;
   unsigned long long seed, step;   // seed != 0 and noise == null: sample with the in-kernel Philox stream
+  float* latent;                   // optional [n][latent_dim]: the actor's last MLP activation (latent_pi, the input of action_net)
+  int latent_dim;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -304,6 +306,11 @@ policy_forward_kernel(const __grid_constant__ FwdArgs a, const __grid_constant__
           float v[16];
 #pragma unroll
           for (int u = 0; u < 16; u++) v[u] = fmaxf(__uint_as_float(r[u]) + b[cb * 16 + u], 0.f);
+          if (a.latent && net == 0 && i == prog.n_ops - 2 && live) {      // latent_pi for state-dependent exploration (gSDE)
+            float4* dst = reinterpret_cast<float4*>(a.latent + (size_t)w * a.latent_dim + cb * 16);
+#pragma unroll
+            for (int q = 0; q < 4; q++) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          }
 #pragma unroll
           for (int q = 0; q < 2; q++) {
             uint4 p;
@@ -452,6 +459,57 @@ int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 }  // namespace
 
+// ---- generalised state-dependent exploration (SB3 StateDependentNoiseDistribution, use_sde=True) ---------------------
+// reset_noise: one exploration matrix per world, E[w][l][k] = exp(log_std[l][k]) * N(0, 1), kept in bf16; also the table
+// s2[l][k] = exp(2 log_std[l][k]) the variance needs. Counter-based draws keyed by (seed, world), counter (epoch, pair index).
+__global__ void sde_reset_noise_kernel(__nv_bfloat16* __restrict__ E, float* __restrict__ s2, const float* __restrict__ log_std, int n, int LA,
+                                       unsigned long long seed, unsigned int epoch) {
+  const int pairs = (LA + 1) / 2;
+  const long long total = (long long)n * pairs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(i / pairs), j = (int)(i - (long long)w * pairs);
+    float z0, z1;
+    philox_normal2(seed, (uint32_t)w, epoch, (uint32_t)j, &z0, &z1);
+    const int e = 2 * j;
+    E[(size_t)w * LA + e] = __float2bfloat16_rn(expf(log_std[e]) * z0);
+    if (e + 1 < LA) E[(size_t)w * LA + e + 1] = __float2bfloat16_rn(expf(log_std[e + 1]) * z1);
+  }
+  if (blockIdx.x == 0) for (int e = threadIdx.x; e < LA; e += blockDim.x) s2[e] = expf(2.f * log_std[e]);
+}
+
+// one warp per world: noise_k = sum_l latent_l E[w][l][k], variance_k = sum_l latent_l^2 s2[l][k] + 1e-6 (StateDependentNoiseDistribution.
+// get_noise / proba_distribution), action = mean + noise, log_prob = sum_k log N(noise_k; 0, variance_k). actions: mean in, action out.
+__global__ void sde_sample_kernel(const float* __restrict__ latent, int ld, const __nv_bfloat16* __restrict__ E, const float* __restrict__ s2,
+                                  float* __restrict__ actions, float* __restrict__ logp, int n, int L, int A) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n) return;
+  const __nv_bfloat16* Ew = E + (size_t)w * L * A;
+  const float* lat = latent + (size_t)w * ld;
+  float nz[2] = {0.f, 0.f}, var[2] = {0.f, 0.f};
+  for (int l = 0; l < L; l++) {
+    const float x = lat[l];
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      const int k = lane + 32 * q;
+      if (k < A) { nz[q] += x * __bfloat162float(Ew[l * A + k]); var[q] += x * x * s2[l * A + k]; }
+    }
+  }
+  float lp = 0.f;
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int k = lane + 32 * q;
+    if (k < A) {
+      const float v = var[q] + 1e-6f;
+      actions[(size_t)w * A + k] += nz[q];
+      lp += -0.5f * nz[q] * nz[q] / v - 0.5f * logf(v) - 0.9189385332046727f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) lp += __shfl_xor_sync(0xffffffffu, lp, o);
+  if (lane == 0 && logp) logp[w] = lp;
+}
+
 struct myo_policy {
   myo_policy_cfg cfg{};
   int device = 0, max_batch = 0, obs_pad = 0;
@@ -469,6 +527,7 @@ struct myo_policy {
   unsigned long long seed = 0, step = 0;
   int swap_lbo_sbo = 0;
   int64_t launches = 0;
+  float* latent_out = nullptr;   // caller-owned [max_batch][latent_dim], see myo_policy_set_latent_out
 };
 
 namespace {
@@ -652,6 +711,12 @@ int myo_policy_set_obs_norm(myo_policy* p, const float* mean_dev, const float* v
   return MYO_OK;
 }
 
+int myo_policy_set_latent_out(myo_policy* p, float* latent_dev) {
+  if (!p) { myo::set_error("null policy"); return MYO_E_ARG; }
+  p->latent_out = latent_dev;
+  return MYO_OK;
+}
+
 int myo_policy_seed(myo_policy* p, uint64_t seed) {
   if (!p) { myo::set_error("null policy"); return MYO_E_ARG; }
   p->seed = seed; p->step = 0;
@@ -674,9 +739,36 @@ int myo_policy_forward(myo_policy* p, int n, const float* obs_dev, float* h_dev,
   a.log_std = p->log_std;
   a.obs_mean = p->has_norm ? p->obs_mean : nullptr; a.obs_inv_std = p->has_norm ? p->obs_inv_std : nullptr; a.clip_obs = p->clip_obs;
   a.seed = p->seed; a.step = p->step++;
+  a.latent = (p->cfg.n_pi_layers > 0) ? p->latent_out : nullptr;
+  a.latent_dim = p->cfg.n_pi_layers > 0 ? p->cfg.pi_layers[p->cfg.n_pi_layers - 1] : p->cfg.lstm_hidden;
   dim3 grid((n + TILE_M - 1) / TILE_M, 2);
   policy_forward_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(a, p->prog[0], p->prog[1]);
   p->launches++;
+  PCK(cudaGetLastError());
+  return MYO_OK;
+}
+
+int myo_sde_reset_noise(uint16_t* noise_mat_dev, float* std2_dev, const float* log_std_dev, int n, int latent_dim, int act_dim, uint64_t seed,
+                        uint32_t epoch, void* stream) {
+  if (!noise_mat_dev || !std2_dev || !log_std_dev || n <= 0 || latent_dim <= 0 || act_dim <= 0) { myo::set_error("bad argument to myo_sde_reset_noise"); return MYO_E_ARG; }
+  const int LA = latent_dim * act_dim;
+  const long long total = (long long)n * ((LA + 1) / 2);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  sde_reset_noise_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<__nv_bfloat16*>(noise_mat_dev), std2_dev, log_std_dev, n, LA,
+                                                                                    seed, epoch);
+  PCK(cudaGetLastError());
+  return MYO_OK;
+}
+
+int myo_sde_sample(const float* latent_dev, int latent_ld, const uint16_t* noise_mat_dev, const float* std2_dev, float* actions_dev, float* logp_dev,
+                   int n, int latent_dim, int act_dim, void* stream) {
+  if (!latent_dev || !noise_mat_dev || !std2_dev || !actions_dev || n <= 0 || latent_dim <= 0 || act_dim <= 0 || act_dim > 64 || latent_ld < latent_dim) {
+    myo::set_error("bad argument to myo_sde_sample (act_dim <= 64)");
+    return MYO_E_ARG;
+  }
+  sde_sample_kernel<<<(n * 32 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(latent_dev, latent_ld, reinterpret_cast<const __nv_bfloat16*>(noise_mat_dev),
+                                                                                        std2_dev, actions_dev, logp_dev, n, latent_dim, act_dim);
   PCK(cudaGetLastError());
   return MYO_OK;
 }

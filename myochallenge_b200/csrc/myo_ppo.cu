@@ -229,8 +229,35 @@ __global__ void adv_stats_kernel(const float* __restrict__ adv, int64_t M, float
   }
 }
 
+// gSDE helpers: lat2 = latent^2 (operand of the variance GEMM), S2 = exp(2 log_std) zero-padded to [d][Ap]
+template <typename T>
+__global__ void square_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = from_op(x[i]);
+    y[i] = to_op<T>(v * v);
+  }
+}
+template <typename T>
+__global__ void sde_std2_kernel(const float* __restrict__ log_std, T* __restrict__ S2, int d, int A, int Ap) {
+  const int total = d * Ap;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int l = i / Ap, k = i - l * Ap;
+    S2[i] = to_op<T>(k < A ? expf(2.f * log_std[l * A + k]) : 0.f);
+  }
+}
+// dL/dlog_std[l][k] = dL/dS2[l][k] * 2 exp(2 log_std[l][k])
+__global__ void sde_logstd_grad_kernel(const float* __restrict__ dS2, const float* __restrict__ log_std, float* __restrict__ g, int d, int A, int Ap) {
+  const int total = d * A;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int l = i / A, k = i - l * A;
+    g[i] = dS2[l * Ap + k] * 2.f * expf(2.f * log_std[i]);
+  }
+}
+
 struct LossArgs {
   int64_t M; int A, Ap;
+  const float* var_raw;    // gSDE: [M][Ap] latent^2 . exp(2 log_std) (null: state-independent log_std[A])
+  float ent_coef;
   const float* mean_raw;   // [M][Ap] action_net output without bias
   const float* ba;         // action_net.bias
   const float* log_std;
@@ -241,7 +268,7 @@ struct LossArgs {
 // policy part: one warp per row. dMEAN[m][k] = g_m z_k / sigma_k, partial sums of dlog_std and the statistics.
 // part layout per CTA: [0] policy_loss [1] approx_kl [2] clip_fraction, [kStatSlots + k] dlog_std_k
 template <typename T>
-__global__ void policy_loss_kernel(LossArgs a, T* __restrict__ dMEAN, float* __restrict__ part) {
+__global__ void policy_loss_kernel(LossArgs a, T* __restrict__ dMEAN, T* __restrict__ Q, float* __restrict__ part) {
   extern __shared__ float sh[];      // [warps][kStatSlots + A]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int W = kStatSlots + a.A;
@@ -251,14 +278,24 @@ __global__ void policy_loss_kernel(LossArgs a, T* __restrict__ dMEAN, float* __r
   const float invM = 1.f / (float)a.M;
   const float amean = a.normalize_adv ? a.adv_stats[0] : 0.f, ainv = a.normalize_adv ? 1.f / (a.adv_stats[1] + 1e-8f) : 1.f;
   float pl = 0.f, kl = 0.f, cf = 0.f;
+  const bool sde = a.var_raw != nullptr;
+  float ent = 0.f;
   for (int64_t m = (int64_t)blockIdx.x * nw + wib; m < a.M; m += (int64_t)gridDim.x * nw) {
-    float lp = 0.f;
+    float lp = 0.f, en = 0.f;
     for (int k = lane; k < a.A; k += 32) {
-      const float ls = a.log_std[k];
-      const float z = (a.act[m * a.A + k] - (a.mean_raw[m * a.Ap + k] + a.ba[k])) * expf(-ls);
-      lp += -0.5f * z * z - ls - 0.9189385332046727f;
+      const float dlt = a.act[m * a.A + k] - (a.mean_raw[m * a.Ap + k] + a.ba[k]);
+      if (sde) {
+        const float v = a.var_raw[m * a.Ap + k] + 1e-6f;
+        lp += -0.5f * dlt * dlt / v - 0.5f * logf(v) - 0.9189385332046727f;
+        en += 1.4189385332046727f + 0.5f * logf(v);
+      } else {
+        const float ls = a.log_std[k];
+        const float z = dlt * expf(-ls);
+        lp += -0.5f * z * z - ls - 0.9189385332046727f;
+      }
     }
     lp = warp_sum(lp);
+    if (sde) ent += warp_sum(en);
     const float adv = (a.adv[m] - amean) * ainv;
     const float lr = lp - a.old_logp[m];
     const float ratio = expf(lr);
@@ -267,16 +304,25 @@ __global__ void policy_loss_kernel(LossArgs a, T* __restrict__ dMEAN, float* __r
     const float g = active ? -adv * ratio * invM : 0.f;
     pl -= fminf(u, v); kl += (ratio - 1.f) - lr; cf += fabsf(ratio - 1.f) > a.clip_range ? 1.f : 0.f;
     for (int k = lane; k < a.Ap; k += 32) {
-      float d = 0.f;
+      float d = 0.f, q = 0.f;
       if (k < a.A) {
-        const float is = expf(-a.log_std[k]);
-        const float z = (a.act[m * a.A + k] - (a.mean_raw[m * a.Ap + k] + a.ba[k])) * is;
-        d = g * z * is;
-        mine[kStatSlots + k] += g * (z * z - 1.f);
+        const float dlt = a.act[m * a.A + k] - (a.mean_raw[m * a.Ap + k] + a.ba[k]);
+        if (sde) {
+          const float iv = 1.f / (a.var_raw[m * a.Ap + k] + 1e-6f);
+          d = g * dlt * iv;
+          q = 0.5f * (g * (dlt * dlt * iv - 1.f) - a.ent_coef * invM) * iv;     // dL/dsigma^2: log-prob and entropy terms
+        } else {
+          const float is = expf(-a.log_std[k]);
+          const float z = dlt * is;
+          d = g * z * is;
+          mine[kStatSlots + k] += g * (z * z - 1.f);
+        }
       }
       dMEAN[m * a.Ap + k] = to_op<T>(d);
+      if (sde) Q[m * a.Ap + k] = to_op<T>(q);
     }
   }
+  if (lane == 0) mine[3] = ent;
   if (lane == 0) { mine[0] = pl; mine[1] = kl; mine[2] = cf; }
   __syncthreads();
   for (int k = threadIdx.x; k < W; k += blockDim.x) {
@@ -318,7 +364,7 @@ __global__ void value_loss_kernel(int64_t M, const float* __restrict__ vraw, con
 // merges the CTA partials in CTA order; writes the statistics and the log_std gradient
 __global__ void loss_finalize_kernel(const float* __restrict__ ppart, int pblocks, const float* __restrict__ vpart, int vblocks, int A, int64_t M,
                                      const float* __restrict__ log_std, const float* __restrict__ adv_stats, float ent_coef, float vf_coef,
-                                     float* __restrict__ stats, float* __restrict__ dlog_std) {
+                                     float* __restrict__ stats, float* __restrict__ dlog_std, int sde) {
   const int W = kStatSlots + A;
   __shared__ float s[kStatSlots];
   const float invM = 1.f / (float)M;
@@ -326,14 +372,15 @@ __global__ void loss_finalize_kernel(const float* __restrict__ ppart, int pblock
     float acc = 0.f;
     for (int b = 0; b < pblocks; b++) acc += ppart[(int64_t)b * W + k];
     if (k < kStatSlots) s[k] = acc;
-    else dlog_std[k - kStatSlots] = acc - ent_coef;      // d(-ent_coef * mean entropy) / dlog_std_k = -ent_coef
+    else if (!sde) dlog_std[k - kStatSlots] = acc - ent_coef;      // d(-ent_coef * mean entropy) / dlog_std_k = -ent_coef
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     float vl = 0.f;
     for (int b = 0; b < vblocks; b++) vl += vpart[b];
     float ent = 0.f;
-    for (int k = 0; k < A; k++) ent += 1.4189385332046727f + log_std[k];
+    if (sde) ent = s[3] * invM;       // per-sample entropies, summed by the loss kernel
+    else for (int k = 0; k < A; k++) ent += 1.4189385332046727f + log_std[k];
     const float pl = s[0] * invM, value_loss = vl * invM, entropy_loss = -ent;
     stats[0] = pl; stats[1] = value_loss; stats[2] = entropy_loss; stats[3] = s[1] * invM; stats[4] = s[2] * invM;
     stats[5] = pl + ent_coef * entropy_loss + vf_coef * value_loss;
@@ -406,8 +453,10 @@ struct GradKey {      // everything a captured graph bakes in
 
 struct myo_ppo {
   myo_policy_cfg cfg{};
-  int device = 0, precision = 1, maxT = 0, maxB = 0;
+  int device = 0, precision = 1, maxT = 0, maxB = 0, use_sde = 0;
   int O = 0, Op = 0, A = 0, Ap = 0, H = 0, Dmax = 0;
+  void *lat2 = nullptr, *S2 = nullptr, *Q = nullptr;      // gSDE: latent^2 [M][d], exp(2 log_std) [d][Ap], dL/dsigma^2 [M][Ap] (operand type)
+  float *var_raw = nullptr, *dS2 = nullptr;               //       latent^2 . S2 [M][Ap], dL/dS2 [d][Ap]
   int64_t n_params = 0, n_op = 0;
   int64_t o_log_std = 0;
   NetLayout net[2];
@@ -459,7 +508,10 @@ void build_layout(myo_ppo* p) {
     off += (numel + 7) / 8 * 8;
     return o;
   };
-  p->o_log_std = add("log_std", A);
+  {
+    const int d_pi = c.n_pi_layers ? c.pi_layers[c.n_pi_layers - 1] : H;
+    p->o_log_std = add("log_std", p->use_sde ? (int64_t)d_pi * A : A);
+  }
   const char* lstm_name[2] = {"lstm_actor", "lstm_critic"};
   for (int k = 0; k < 2; k++) {
     NetLayout& n = p->net[k];
@@ -585,10 +637,22 @@ int net_chain(myo_ppo* p, const GradArgs& a, int k, cudaStream_t st) {
   }
   RCK(gemm_nt(p, blas, M, n.head_np, d, in, d, wop + n.op_head, d, 0.f, nb.head_out, n.head_np));
   // ---- loss and its gradient at the head ----
+  const bool sde = k == 0 && p->use_sde;
+  if (sde) {       // variance of the state-dependent noise: latent^2 . exp(2 log_std)  (latent detached: learn_features=False)
+    square_kernel<T><<<blocks_for(M * d, 256), 256, 0, st>>>(in, static_cast<T*>(p->lat2), M * d);
+    sde_std2_kernel<T><<<blocks_for((int64_t)d * Ap, 256), 256, 0, st>>>(a.params + p->o_log_std, static_cast<T*>(p->S2), d, A, Ap);
+    p->launches += 2;
+    RCK(gemm_nn(p, blas, M, Ap, d, p->lat2, d, p->S2, Ap, p->var_raw, Ap));
+  }
   if (k == 0) {
-    LossArgs la{M, A, Ap, nb.head_out, a.params + n.head_b, a.params + p->o_log_std, p->act, p->ol, p->ad, p->adv_stats,
-                a.hp.clip_range, a.hp.normalize_advantage};
-    policy_loss_kernel<T><<<kLossBlocks, 256, sizeof(float) * 8 * (kStatSlots + A), st>>>(la, dhead, p->ppart);
+    LossArgs la{M, A, Ap, sde ? p->var_raw : nullptr, a.hp.ent_coef, nb.head_out, a.params + n.head_b, a.params + p->o_log_std, p->act, p->ol, p->ad,
+                p->adv_stats, a.hp.clip_range, a.hp.normalize_advantage};
+    policy_loss_kernel<T><<<kLossBlocks, 256, sizeof(float) * 8 * (kStatSlots + A), st>>>(la, dhead, static_cast<T*>(p->Q), p->ppart);
+    if (sde) {     // dL/dS2 = (latent^2)' . Q, then the chain rule through exp(2 log_std)
+      RCK(gemm_tn(p, blas, M, d, Ap, p->lat2, d, p->Q, Ap, p->dS2, Ap));
+      sde_logstd_grad_kernel<<<blocks_for((int64_t)d * A, 256), 256, 0, st>>>(p->dS2, a.params + p->o_log_std, a.grad + p->o_log_std, d, A, Ap);
+      p->launches++;
+    }
   } else {
     value_loss_kernel<T><<<kLossBlocks, 256, 0, st>>>(M, nb.head_out, a.params + n.head_b, p->ov, p->rt, a.hp.clip_range_vf, a.hp.vf_coef, dhead,
                                                        p->vpart);
@@ -659,7 +723,7 @@ int minibatch_issue(myo_ppo* p, const GradArgs& a, cudaStream_t st) {
   if (rc0) return rc0;
   if (rc) return rc;
   loss_finalize_kernel<<<1, 128, 0, st>>>(p->ppart, kLossBlocks, p->vpart, kLossBlocks, A, M, a.params + p->o_log_std, p->adv_stats, a.hp.ent_coef,
-                                          a.hp.vf_coef, a.stats, a.grad + p->o_log_std);
+                                          a.hp.vf_coef, a.stats, a.grad + p->o_log_std, p->use_sde);
   p->launches++;
   QCK(cudaGetLastError());
   return MYO_OK;
@@ -725,7 +789,7 @@ int myo_ppo_create(const myo_policy_cfg* cfg, int max_steps, int max_worlds, int
   for (int l = 0; l < cfg->n_vf_layers; l++) if (cfg->vf_layers[l] <= 0 || cfg->vf_layers[l] % 8) { myo::set_error("MLP widths must be multiples of 8"); return MYO_E_LIMIT; }
   QCK(cudaSetDevice(device));
   myo_ppo* p = new myo_ppo();
-  p->cfg = *cfg; p->device = device; p->precision = precision; p->maxT = max_steps; p->maxB = max_worlds;
+  p->cfg = *cfg; p->device = device; p->precision = precision; p->maxT = max_steps; p->maxB = max_worlds; p->use_sde = cfg->use_sde != 0;
   p->O = cfg->obs_dim; p->Op = round_up(cfg->obs_dim, 8); p->A = cfg->act_dim; p->Ap = round_up(cfg->act_dim, 8); p->H = cfg->lstm_hidden;
   p->Dmax = p->H;
   for (int l = 0; l < cfg->n_pi_layers; l++) p->Dmax = cfg->pi_layers[l] > p->Dmax ? cfg->pi_layers[l] : p->Dmax;
@@ -754,6 +818,10 @@ int myo_ppo_create(const myo_policy_cfg* cfg, int max_steps, int max_worlds, int
   A_(&p->ad, sizeof(float) * M); A_(&p->rt, sizeof(float) * M); A_(&p->adv_stats, sizeof(float) * 2);
   A_(&p->ppart, sizeof(float) * kLossBlocks * (kStatSlots + p->A)); A_(&p->vpart, sizeof(float) * kLossBlocks);
   A_(&p->npart, sizeof(double) * kNormBlocks);
+  if (p->use_sde) {
+    A_(&p->lat2, os * M * p->Dmax); A_(&p->S2, os * (size_t)p->Dmax * p->Ap); A_(&p->Q, os * M * p->Ap);
+    A_(&p->var_raw, sizeof(float) * M * p->Ap); A_(&p->dS2, sizeof(float) * (size_t)p->Dmax * p->Ap);
+  }
   if (rc) { myo_ppo_destroy(p); return rc; }
   for (int k = 0; k < 2; k++) {
     // an explicit workspace per handle: the two handles run concurrently, and cuBLAS must not allocate inside a graph capture

@@ -31,7 +31,7 @@ class RecurrentPolicy:
     ``action_net`` + state-independent ``log_std`` (DiagGaussian) and ``value_net``."""
 
     def __init__(self, obs_dim: int, act_dim: int, lstm_hidden: int = 256, pi: Sequence[int] = (256, 256),
-                 vf: Sequence[int] = (256, 256), max_batch: int = 32768, device="cuda:0", lib=None):
+                 vf: Sequence[int] = (256, 256), max_batch: int = 32768, device="cuda:0", lib=None, use_sde: bool = False):
         self._L = lib if lib is not None else _capi.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -46,16 +46,29 @@ class RecurrentPolicy:
             cfg.pi_layers[i] = wdt
         for i, wdt in enumerate(self.vf):
             cfg.vf_layers[i] = wdt
+        self.use_sde = bool(use_sde)
+        cfg.use_sde = int(self.use_sde)
         h = C.c_void_p()
         check(self._L, self._L.myo_policy_create(C.byref(cfg), int(max_batch), self.device.index or 0, C.byref(h)))
         self._h = h
         self.max_batch = int(max_batch)
         self._state: Dict[str, torch.Tensor] = {}
+        # generalised state-dependent exploration (use_sde=True): the kernel produces the mean and latent_pi; the noise
+        # latent_pi . E[w] with one exploration matrix per world and the log-prob come from myo_sde_sample
+        self.latent_dim = self.pi[-1] if self.pi else self.lstm_hidden
+        self._latent = self._noise_mat = self._std2 = None
+        self._noise_epoch, self._sde_seed = 0, 0x5DE
+        if self.use_sde:
+            if self.act_dim > 64:
+                raise ValueError("use_sde supports act_dim <= 64")
+            if self.pi:
+                self._latent = torch.zeros(self.max_batch, self.latent_dim, dtype=torch.float32, device=self.device)
+                check(self._L, self._L.myo_policy_set_latent_out(self._h, _ptr(self._latent)))
 
     # -- parameters ---------------------------------------------------------------------------
     def state_dict_shapes(self) -> Dict[str, Tuple[int, ...]]:
         H, O, A = self.lstm_hidden, self.obs_dim, self.act_dim
-        shp = {"log_std": (A,)}
+        shp = {"log_std": (self.latent_dim, A) if self.use_sde else (A,)}
         for net in ("lstm_actor", "lstm_critic"):
             shp[f"{net}.weight_ih_l0"] = (4 * H, O)
             shp[f"{net}.weight_hh_l0"] = (4 * H, H)
@@ -85,6 +98,9 @@ class RecurrentPolicy:
             if tuple(t.shape) != tuple(shape):
                 raise ValueError(f"{k}: expected shape {shape}, got {tuple(t.shape)}")
             self._state[k] = t
+            if k == "log_std" and self.use_sde:      # the kernel's own Gaussian head is unused: zero log_std, zero noise -> mean
+                t = torch.zeros(self.act_dim, dtype=torch.float32, device=self.device)
+                self._noise_mat = None                # exploration matrices follow log_std: resample before the next forward
             check(self._L, self._L.myo_policy_set_weight(self._h, k.encode(), _ptr(t), t.numel(), self._stream()))
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
@@ -121,7 +137,23 @@ class RecurrentPolicy:
             torch.cuda.current_stream(self.device).synchronize()   # m, v are temporaries: keep them alive until the copy ran
 
     def seed(self, seed: int) -> None:
-        check(self._L, self._L.myo_policy_seed(self._h, C.c_uint64(seed)))
+        self._sde_seed = int(seed) ^ 0x5DE5DE
+        if not self.use_sde:
+            check(self._L, self._L.myo_policy_seed(self._h, C.c_uint64(seed)))
+
+    def reset_noise(self, n_envs: Optional[int] = None) -> None:
+        """``policy.reset_noise(n_envs)``: draw one exploration matrix per world from the current ``log_std`` (SB3 calls it at the
+        start of every rollout and every ``sde_sample_freq`` steps)."""
+        if not self.use_sde:
+            return
+        n = self.max_batch if n_envs is None else int(n_envs)
+        L, A = self.latent_dim, self.act_dim
+        if self._noise_mat is None or self._noise_mat.shape[0] < n:
+            self._noise_mat = torch.empty(n, L, A, dtype=torch.bfloat16, device=self.device)
+            self._std2 = torch.empty(L, A, dtype=torch.float32, device=self.device)
+        self._noise_epoch += 1
+        check(self._L, self._L.myo_sde_reset_noise(_ptr(self._noise_mat), _ptr(self._std2), _ptr(self._state["log_std"]), n, L, A,
+                                                   C.c_uint64(self._sde_seed), C.c_uint32(self._noise_epoch), self._stream()))
 
     # -- forward ------------------------------------------------------------------------------
     def initial_state(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -146,13 +178,20 @@ class RecurrentPolicy:
             logp = torch.empty(n, dtype=torch.float32, device=self.device)
         else:
             actions, values, logp = out
+        if self.use_sde:
+            if noise is not None:
+                raise ValueError("use_sde: the noise is state dependent (latent_pi . exploration matrix); pass deterministic=True or nothing")
+            nz = None
+            deterministic_kernel = True
+        else:
+            deterministic_kernel = deterministic
         if deterministic:
             nz = None
         elif noise is not None:
             nz = noise.to(device=self.device, dtype=torch.float32).contiguous()
         else:
             nz = None   # in-kernel sampling when seed() was called, else the mean
-        if deterministic and noise is None:
+        if deterministic_kernel and noise is None:
             # the kernel samples only when a seed is set; make "deterministic" win over a seeded policy
             zero = getattr(self, "_zero_noise", None)
             if zero is None or zero.shape[0] < n:
@@ -161,6 +200,12 @@ class RecurrentPolicy:
             nz = zero[:n]
         check(self._L, self._L.myo_policy_forward(self._h, int(n), _ptr(obs), _ptr(h), _ptr(c), _ptr(es), _ptr(nz), _ptr(actions),
                                                   _ptr(values), _ptr(logp), self._stream()))
+        if self.use_sde and not deterministic:
+            if self._noise_mat is None or self._noise_mat.shape[0] < n:
+                self.reset_noise(max(n, self.max_batch if n <= self.max_batch else n))
+            lat = self._latent if self._latent is not None else h[0]
+            check(self._L, self._L.myo_sde_sample(_ptr(lat), int(lat.shape[1]), _ptr(self._noise_mat), _ptr(self._std2), _ptr(actions), _ptr(logp), int(n),
+                                                  self.latent_dim, self.act_dim, self._stream()))
         return actions, values, logp, (h, c)
 
     def predict_values(self, obs: torch.Tensor, lstm_states: Tuple[torch.Tensor, torch.Tensor], episode_starts: Optional[torch.Tensor] = None):

@@ -64,6 +64,7 @@ class PPOUpdate:
             cfg.pi_layers[i] = w
         for i, w in enumerate(policy.vf):
             cfg.vf_layers[i] = w
+        cfg.use_sde = int(getattr(policy, "use_sde", False))
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         h = C.c_void_p()
@@ -183,7 +184,7 @@ class RecurrentPPO:
 
     def __init__(self, policy="MlpLstmPolicy", env=None, learning_rate=3e-4, n_steps=128, batch_size=128, n_epochs=10, gamma=0.99,
                  gae_lambda=0.95, clip_range=0.2, clip_range_vf=None, normalize_advantage=True, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
-                 target_kl=None, policy_kwargs=None, seed=0, precision="bf16", device=None, **_ignored):
+                 target_kl=None, policy_kwargs=None, seed=0, precision="bf16", device=None, use_sde=False, sde_sample_freq=-1, **_ignored):
         if policy != "MlpLstmPolicy":
             raise ValueError("only MlpLstmPolicy is built (the policy every reference run uses)")
         if env is None:
@@ -196,7 +197,8 @@ class RecurrentPPO:
         arch = kw.get("net_arch", [dict(pi=[64, 64], vf=[64, 64])])
         arch = arch[0] if isinstance(arch, (list, tuple)) and arch and isinstance(arch[0], dict) else dict(pi=list(arch), vf=list(arch))
         self.policy = RecurrentPolicy(sim.nobs, sim.nu, kw.get("lstm_hidden_size", 256), tuple(arch.get("pi", ())), tuple(arch.get("vf", ())),
-                                      max_batch=venv.num_envs, device=self.device)
+                                      max_batch=venv.num_envs, device=self.device, use_sde=use_sde)
+        self.use_sde, self.sde_sample_freq = bool(use_sde), int(sde_sample_freq)
         self.policy.init_random(seed, log_std_init=kw.get("log_std_init", 0.0))
         self.policy.seed(seed + 1)
         if callable(clip_range):           # SB3 accepts schedules of the remaining progress; the kernels take the value at 1.0
@@ -234,7 +236,7 @@ class RecurrentPPO:
                     n_epochs=self.n_epochs, gamma=self.gamma, gae_lambda=self.gae_lambda, ent_coef=u.hyper.ent_coef, vf_coef=u.hyper.vf_coef,
                     max_grad_norm=u.max_grad_norm, learning_rate=u.learning_rate, clip_range=u.hyper.clip_range,
                     clip_range_vf=None if u.hyper.clip_range_vf <= 0 else u.hyper.clip_range_vf, normalize_advantage=bool(u.hyper.normalize_advantage),
-                    target_kl=self.target_kl, use_sde=False, _n_updates=u.step_count,
+                    target_kl=self.target_kl, use_sde=self.use_sde, sde_sample_freq=self.sde_sample_freq, _n_updates=u.step_count,
                     policy_kwargs=dict(lstm_hidden_size=self.policy.lstm_hidden, net_arch=[dict(pi=list(self.policy.pi), vf=list(self.policy.vf))],
                                        enable_critic_lstm=True, ortho_init=False))
         # torch.optim.Adam state over the parameters in state-dict order, as policy.optimizer.pth holds it
@@ -272,7 +274,8 @@ class RecurrentPPO:
                     normalize_advantage=bool(num("normalize_advantage", True)), ent_coef=float(num("ent_coef", 0.0)), vf_coef=float(num("vf_coef", 0.5)),
                     max_grad_norm=float(num("max_grad_norm", 0.5)), target_kl=d.get("target_kl") if not isinstance(d.get("target_kl"), dict) else None,
                     policy_kwargs=dict(lstm_hidden_size=arch["lstm_hidden"], net_arch=[dict(pi=list(arch["pi"]), vf=list(arch["vf"]))]),
-                    seed=int(d["seed"]) if isinstance(d.get("seed"), int) else 0, precision=d.get("precision", "bf16"))
+                    seed=int(d["seed"]) if isinstance(d.get("seed"), int) else 0, precision=d.get("precision", "bf16"),
+                    use_sde=arch["use_sde"], sde_sample_freq=int(num("sde_sample_freq", -1)))
         agent.set_parameters(ck["state_dict"])
         agent.num_timesteps = int(d.get("num_timesteps", 0)) if not isinstance(d.get("num_timesteps"), dict) else 0
         opt = ck.get("optimizer")
@@ -328,7 +331,8 @@ class RecurrentPPO:
         while self.num_timesteps - start < total_timesteps:
             norm = self.env if hasattr(self.env, "obs_rms") and hasattr(self.env.obs_rms, "sync") else None
             base = (norm.obs_rms.state.clone(), norm.ret_rms.state.clone()) if norm is not None else None
-            self._obs, self._starts = collect_rollouts(self.env, self.policy, self.buffer, self._state, self._obs, self._starts)
+            self._obs, self._starts = collect_rollouts(self.env, self.policy, self.buffer, self._state, self._obs, self._starts,
+                                                               sde_sample_freq=self.sde_sample_freq)
             if norm is not None:          # ranks saw different worlds: merge what each added to the running moments (no-op on one GPU)
                 norm.obs_rms.sync(base[0]); norm.ret_rms.sync(base[1])
                 norm._push_obs_norm()

@@ -268,7 +268,7 @@ class RecurrentRolloutBuffer:
         self.launch_count += 1
 
 
-def collect_rollouts(env, policy, buffer: RecurrentRolloutBuffer, state, obs, episode_starts, clip_actions=True):
+def collect_rollouts(env, policy, buffer: RecurrentRolloutBuffer, state, obs, episode_starts, clip_actions=True, sde_sample_freq=-1):
     """``RecurrentPPO.collect_rollouts``: n_steps of policy forward -> env step -> buffer.add, with the TimeLimit
     bootstrap (reward += gamma * V(terminal_observation) for truncated worlds, values from the critic state the step
     ended in) and the final GAE pass. ``env``: MyoVecEnv or DeviceVecNormalize (device path); ``state`` = (h, c) as
@@ -276,9 +276,12 @@ def collect_rollouts(env, policy, buffer: RecurrentRolloutBuffer, state, obs, ep
     h, c = state
     buffer.reset()
     norm = env if isinstance(env, DeviceVecNormalize) else None
+    use_sde = getattr(policy, "use_sde", False)
     for t in range(buffer.n_steps):
         if t == 0:
             buffer.h0.copy_(h); buffer.c0.copy_(c)
+        if use_sde and (t == 0 or (sde_sample_freq > 0 and t % sde_sample_freq == 0)):
+            policy.reset_noise(obs.shape[0])          # RecurrentPPO.collect_rollouts: new exploration matrices
         actions, values, logp, _ = policy.forward(obs, (h, c), episode_starts)
         buffer.put_obs(obs, norm)
         env_actions = actions.clamp(-1.0, 1.0) if clip_actions else actions

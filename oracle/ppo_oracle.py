@@ -123,11 +123,20 @@ def evaluate_actions(mods, obs, actions, episode_starts, h0, c0):
     latent_vf = mods["value_net"](latents[1])
     mean = mods["action_net"](latent_pi)
     values = mods["value_net_head"](latent_vf).squeeze(-1)
-    log_std = mods["log_std"]
-    dist = torch.distributions.Normal(mean, torch.ones_like(mean) * log_std.exp())
+    dist = action_distribution(mods["log_std"], mean, latent_pi)
     log_prob = dist.log_prob(actions).sum(-1)
     entropy = dist.entropy().sum(-1)
     return values, log_prob, entropy
+
+
+def action_distribution(log_std, mean, latent_pi):
+    """DiagGaussianDistribution (log_std [A]) or StateDependentNoiseDistribution (use_sde=True: log_std [latent_dim][A],
+    full_std, use_expln=False, learn_features=False so the latent is detached, epsilon 1e-6; stable_baselines3/common/
+    distributions.py proba_distribution)."""
+    if log_std.dim() == 1:
+        return torch.distributions.Normal(mean, torch.ones_like(mean) * log_std.exp())
+    variance = (latent_pi.detach() ** 2) @ (log_std.exp() ** 2)
+    return torch.distributions.Normal(mean, torch.sqrt(variance + 1e-6))
 
 
 def ppo_loss(mods, obs, actions, episode_starts, old_values, old_log_prob, advantages, returns, h0, c0, clip_range=0.2,
@@ -230,7 +239,7 @@ def synthetic_batch(sd, T, B, seed=0, start_prob=0.1, dtype=np.float32):
     """A rollout-like minibatch consistent with the policy ``sd`` (old log-probs / values evaluated by the policy itself on
     perturbed parameters, so ratios are near but not equal to 1 and some are clipped)."""
     rng = np.random.default_rng(seed)
-    O = sd["lstm_actor.weight_ih_l0"].shape[1]; H = sd["lstm_actor.weight_hh_l0"].shape[1]; A = sd["log_std"].shape[0]
+    O = sd["lstm_actor.weight_ih_l0"].shape[1]; H = sd["lstm_actor.weight_hh_l0"].shape[1]; A = sd["action_net.weight"].shape[0]
     obs = rng.normal(0, 1, (T, B, O)).clip(-10, 10)
     es = rng.random((T, B)) < start_prob
     h0 = rng.normal(0, 0.3, (2, B, H)); c0 = rng.normal(0, 0.5, (2, B, H))
@@ -238,8 +247,9 @@ def synthetic_batch(sd, T, B, seed=0, start_prob=0.1, dtype=np.float32):
     with torch.no_grad():
         dummy = torch.zeros(T, B, A, dtype=torch.float64)
         v, _, _ = evaluate_actions(mods, torch.as_tensor(obs), dummy, es, torch.as_tensor(h0), torch.as_tensor(c0))
-        mean = mods["action_net"](mods["policy_net"](_latent(mods, "lstm_actor", obs, es, h0[0], c0[0])))
-    std = np.exp(np.asarray(sd["log_std"], np.float64))
+        latent_pi = mods["policy_net"](_latent(mods, "lstm_actor", obs, es, h0[0], c0[0]))
+        mean = mods["action_net"](latent_pi)
+        std = action_distribution(mods["log_std"], mean, latent_pi).scale.numpy()
     actions = mean.numpy() + std * rng.normal(0, 1, (T, B, A))
     z = (actions - mean.numpy()) / std
     logp = (-0.5 * z * z - np.log(std) - 0.5 * math.log(2 * math.pi)).sum(-1)

@@ -30,7 +30,7 @@ def test_reads_the_reference_checkpoint_and_agrees_with_the_golden_fixture():
     assert list(c["state_dict"]) == ck.sb3_parameter_order(list(c["state_dict"]))        # the order SB3 itself wrote
     for k, v in sd.items():
         assert torch.equal(c["state_dict"][k], v), k
-    assert ck.architecture_of(c["state_dict"]) == dict(obs_dim=86, act_dim=39, lstm_hidden=128, pi=(), vf=())
+    assert ck.architecture_of(c["state_dict"]) == dict(obs_dim=86, act_dim=39, lstm_hidden=128, pi=(), vf=(), use_sde=False)
     d = c["data"]
     assert d["n_steps"] == 256 and d["batch_size"] == 128 and d["n_epochs"] == 10 and d["use_sde"] is False
     assert d["policy_kwargs"]["lstm_hidden_size"] == 128 and d["policy_kwargs"]["enable_critic_lstm"] is True

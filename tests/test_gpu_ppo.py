@@ -30,8 +30,8 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _setup(O, A, H, pi, vf, T, B, n_envs, seed, precision, sd=None, start_prob=0.15, **hyper):
-    pol = RecurrentPolicy(O, A, lstm_hidden=H, pi=pi, vf=vf, max_batch=64, device=DEV)
+def _setup(O, A, H, pi, vf, T, B, n_envs, seed, precision, sd=None, start_prob=0.15, use_sde=False, **hyper):
+    pol = RecurrentPolicy(O, A, lstm_hidden=H, pi=pi, vf=vf, max_batch=64, device=DEV, use_sde=use_sde)
     if sd is None:
         sd = pol.init_random(seed=seed, log_std_init=-0.7)
     else:
@@ -258,3 +258,82 @@ def test_evaluate_policy_counts_fixed_quota_per_world(product_lib):
     env2 = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, device=DEV, seed=8, clip_actions=True, max_episode_steps=200, drop_th=1.40)
     out2 = evaluate_policy(pol, env2, n_episodes=n, deterministic=True)      # balls start at z ~ 1.44: a high drop threshold ends episodes early
     assert out2["episodes"] == n and out2["mean_length"] < 200 and out2["drop_rate"] > 0.05
+
+
+# ---- generalised state-dependent exploration (use_sde=True, the winning runs' setting: /root/reference/docs/summary.md:86-117) ----
+def test_sde_sampling_matches_the_distribution(product_lib):
+    """myo_sde_reset_noise / myo_sde_sample against StateDependentNoiseDistribution: action = mean + latent . E[w] with the stored
+    exploration matrices, log_prob = log N(action; mean, sqrt(latent^2 . exp(log_std)^2 + 1e-6)); E ~ exp(log_std) * N(0, 1)."""
+    n, H, A = 512, 64, 39
+    pol = RecurrentPolicy(86, A, lstm_hidden=H, pi=(32,), vf=(), max_batch=n, device=DEV, use_sde=True)
+    sd = pol.init_random(seed=2, log_std_init=-1.5)
+    assert tuple(sd["log_std"].shape) == (32, A)
+    g = torch.Generator().manual_seed(0)
+    obs = torch.randn(n, 86, generator=g).to(DEV)
+    starts = torch.ones(n, dtype=torch.uint8, device=DEV)
+    h, c = pol.initial_state(n)
+    mean, v0, _, _ = pol.forward(obs, (h, c), starts, deterministic=True)
+    mean = mean.clone()
+    pol.seed(11); pol.reset_noise(n)
+    h, c = pol.initial_state(n)
+    act, v1, logp, _ = pol.forward(obs, (h, c), starts)
+    lat = pol._latent[:n].double(); E = pol._noise_mat[:n].double(); ls = pol.state_dict()["log_std"].double()
+    noise = torch.bmm(lat.unsqueeze(1), E).squeeze(1)
+    assert torch.allclose((act - mean).double(), noise, rtol=1e-4, atol=1e-5) and torch.equal(v0, v1)
+    var = (lat ** 2) @ (ls.exp() ** 2) + 1e-6
+    ref_lp = torch.distributions.Normal(mean.double(), var.sqrt()).log_prob(act.double()).sum(1)
+    assert torch.allclose(logp.double(), ref_lp, rtol=1e-4, atol=1e-3)
+    z = (E / ls.exp()).flatten()                           # the draws behind the matrices: standard normal (bf16 storage: 2^-9 relative)
+    assert abs(float(z.mean())) < 5e-3 and abs(float(z.std()) - 1.0) < 5e-3
+    pol.reset_noise(n)
+    assert not torch.equal(E, pol._noise_mat[:n].double())   # a new epoch draws new matrices
+
+
+@pytest.mark.parametrize("pi,vf,precision", [((32,), (48, 16), "fp32"), ((), (), "fp32"), ((256, 256), (256, 256), "bf16")])
+def test_sde_gradient_matches_oracle(product_lib, pi, vf, precision):
+    O, A, H, T, B, n_envs = (86, 39, 256, 6, 33, 40) if precision == "bf16" else (17, 5, 64, 10, 9, 12)
+    hyper = dict(clip_range=0.2, ent_coef=0.01, vf_coef=0.7, normalize_advantage=True)
+    pol = RecurrentPolicy(O, A, lstm_hidden=H, pi=pi, vf=vf, max_batch=64, device=DEV, use_sde=True)
+    sd = pol.init_random(seed=5, log_std_init=-1.0)
+    sd["log_std"] = sd["log_std"] + 0.3 * torch.randn(sd["log_std"].shape, generator=torch.Generator().manual_seed(1))
+    pol, upd, buf, idx, sd64, batch = _setup(O, A, H, pi, vf, T, B, n_envs, 9, precision, sd=sd, use_sde=True, **hyper)
+    stats = upd.minibatch_grad(buf, idx).cpu().numpy()
+    ref_grads, ref_stats = ppo_oracle.gradients(sd64, batch, **hyper)
+    got = upd.grad_dict()
+    assert tuple(got["log_std"].shape) == (pi[-1] if pi else H, A)
+    for i, k in enumerate(STAT_NAMES[:6]):
+        tol = (2e-5 + 1e-4 * abs(ref_stats[k])) if precision == "fp32" else (2e-2 + 5e-2 * abs(ref_stats[k]))
+        assert abs(stats[i] - ref_stats[k]) <= tol, (k, stats[i], ref_stats[k])
+    for k, r in ref_grads.items():
+        gk = got[k].cpu().double().flatten(); rk = r.flatten()
+        if precision == "fp32":
+            assert float((gk - rk).abs().max()) <= 2e-4 * float(rk.abs().max()) + 1e-7, (k, float((gk - rk).abs().max()), float(rk.abs().max()))
+        else:
+            cos = float(torch.dot(gk, rk) / (gk.norm() * rk.norm() + 1e-30))
+            assert cos >= 0.98 and 0.9 <= float(gk.norm() / rk.norm()) <= 1.1, (k, cos, float(gk.norm() / rk.norm()))
+
+
+def test_sde_recurrent_ppo_is_on_policy_and_learns(product_lib):
+    """RecurrentPPO(use_sde=True) end to end on Baoding: before the first optimiser step the update reproduces the rollout's
+    log-probs (approx_kl <= 2e-3, clip_fraction <= 0.02), then two iterations run."""
+    from myochallenge_b200.envs import make_vec_env
+    from myochallenge_b200.ppo import RecurrentPPO
+    from myochallenge_b200.rollout import DeviceVecNormalize, collect_rollouts
+
+    n, T = 256, 16
+    env = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, device=DEV, seed=5, clip_actions=True, max_episode_steps=7)
+    vn = DeviceVecNormalize(env, gamma=0.99)
+    agent = RecurrentPPO("MlpLstmPolicy", vn, n_steps=T, batch_size=T * 64, n_epochs=2, learning_rate=1e-4, ent_coef=0.001, use_sde=True,
+                         policy_kwargs=dict(lstm_hidden_size=64, net_arch=[dict(pi=[64], vf=[64])], log_std_init=-2.0), seed=1)
+    agent._obs = vn.reset_device().clone()
+    agent._starts = torch.ones(n, dtype=torch.uint8, device=DEV)
+    agent._state = agent.policy.initial_state(n)
+    agent._obs, agent._starts = collect_rollouts(vn, agent.policy, agent.buffer, agent._state, agent._obs, agent._starts)
+    acts = agent.buffer.actions
+    assert float(acts.std()) > 1e-3 and torch.isfinite(agent.buffer.log_probs).all()
+    stats = agent.update.minibatch_grad(agent.buffer, torch.arange(64, dtype=torch.int32, device=DEV)).cpu().numpy()
+    assert stats[3] <= 2e-3 and stats[4] <= 0.02, stats
+    before = agent.update.state_dict()["log_std"].clone()
+    agent.learn(total_timesteps=2 * n * T)
+    assert len(agent.logs) == 2 and all(np.isfinite(l["train/loss"]) for l in agent.logs)
+    assert not torch.equal(before, agent.update.state_dict()["log_std"]) and tuple(before.shape) == (64, 39)
