@@ -38,8 +38,8 @@ constexpr int MAX_N = 256;
 constexpr int STAGE_BYTES = MAX_N * CHUNK_K * 2;  // 16 KB
 constexpr int MAX_OPS = 12;
 constexpr int THREADS = 192;
-constexpr int MAX_K1 = 96 + 256;                  // padded obs + hidden
-constexpr int A1_BYTES = TILE_M * MAX_K1 * 2;     // 90112
+constexpr int MAX_K1 = 128 + 256;                 // padded obs (hand pose: 108, die: 103) + hidden
+constexpr int A1_BYTES = TILE_M * MAX_K1 * 2;     // 98304
 constexpr int HB_BYTES = TILE_M * 256 * 2;        // 65536
 constexpr int SMEM_BYTES = A1_BYTES + HB_BYTES + STAGES * STAGE_BYTES + 256;
 
@@ -643,7 +643,7 @@ int myo_policy_create(const myo_policy_cfg* cfg, int max_batch, int device, myo_
   }
   const int H = cfg->lstm_hidden;
   if (H <= 0 || H % 64 || H > 256) { myo::set_error("lstm_hidden must be 64, 128, 192 or 256"); return MYO_E_LIMIT; }
-  if (cfg->obs_dim <= 0 || cfg->obs_dim > 96) { myo::set_error("obs_dim must be in 1..96"); return MYO_E_LIMIT; }
+  if (cfg->obs_dim <= 0 || cfg->obs_dim > 128) { myo::set_error("obs_dim must be in 1..128"); return MYO_E_LIMIT; }
   if (cfg->act_dim <= 0 || cfg->act_dim > 256) { myo::set_error("act_dim must be in 1..256"); return MYO_E_LIMIT; }
   if (cfg->n_pi_layers < 0 || cfg->n_pi_layers > 4 || cfg->n_vf_layers < 0 || cfg->n_vf_layers > 4) { myo::set_error("at most 4 MLP layers per head"); return MYO_E_LIMIT; }
   for (int l = 0; l < cfg->n_pi_layers; l++) if (cfg->pi_layers[l] <= 0 || cfg->pi_layers[l] % 16 || cfg->pi_layers[l] > 256) { myo::set_error("MLP widths must be multiples of 16 up to 256"); return MYO_E_LIMIT; }

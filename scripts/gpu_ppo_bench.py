@@ -13,13 +13,14 @@ ap.add_argument("--batch-worlds", type=int, default=2048)
 ap.add_argument("--epochs", type=int, default=10)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--precision", default="bf16")
+ap.add_argument("--use-sde", action="store_true")
 ap.add_argument("--minibatches", type=int, default=0, help="time only this many minibatch steps (0: full train())")
 args = ap.parse_args()
 dev = "cuda:0"
 env = make_vec_env("CustomMyoChallengeBaodingP2-v1", args.n, device=dev, seed=0, clip_actions=True)
 vn = DeviceVecNormalize(env, gamma=0.99)
 agent = RecurrentPPO("MlpLstmPolicy", vn, n_steps=args.steps, batch_size=args.steps * args.batch_worlds, n_epochs=args.epochs, learning_rate=2.5e-5,
-                     clip_range=0.2, ent_coef=3e-5, max_grad_norm=0.8, gae_lambda=0.95, precision=args.precision,
+                     clip_range=0.2, ent_coef=3e-5, max_grad_norm=0.8, gae_lambda=0.95, precision=args.precision, use_sde=args.use_sde,
                      policy_kwargs=dict(lstm_hidden_size=256, net_arch=[dict(pi=[256, 256], vf=[256, 256])], log_std_init=-2.0))
 agent._obs = vn.reset_device().clone()
 agent._starts = torch.ones(args.n, dtype=torch.uint8, device=dev)
@@ -30,6 +31,9 @@ for it in range(args.iters):
     e0.record()
     agent._obs, agent._starts = collect_rollouts(vn, agent.policy, agent.buffer, agent._state, agent._obs, agent._starts)
     e1.record()
+    first = agent.update.minibatch_grad(agent.buffer, torch.arange(args.batch_worlds, dtype=torch.int32, device=dev)).tolist()
+    print("   first minibatch before any step of this iteration: approx_kl %.5f clip_fraction %.5f policy_loss %.5f" % (first[3], first[4], first[0]),
+          "| action std", float(agent.buffer.actions.std()), flush=True)
     if args.minibatches:
         idx = torch.randperm(args.n)[: args.batch_worlds].to(dev, dtype=torch.int32)
         for _ in range(args.minibatches):

@@ -72,6 +72,31 @@ def test_random_init_matches_fp32_reference(product_lib, n, H, pi, vf):
     _close(a2, ra2, 8e-2, 3e-2)
 
 
+@pytest.mark.parametrize("obs_dim,act_dim,H,pi,vf", [(108, 39, 256, (256, 256), (256, 256)),      # hand pose (BASELINE configs[2]): obs 108
+                                                     (103, 39, 128, (64,), (64,)),                 # die reorient obs 103
+                                                     (17, 5, 64, (64, 64), (64, 64)),              # finger (configs[1]): obs 17, 5 muscles
+                                                     (9, 6, 64, (), ())])                          # elbow (configs[0]): obs 9, K = 16 + 64 ends in a half chunk
+def test_other_observation_sizes(product_lib, obs_dim, act_dim, H, pi, vf):
+    n = 200
+    pol = RecurrentPolicy(obs_dim, act_dim, lstm_hidden=H, pi=pi, vf=vf, max_batch=256, device=DEV, lib=product_lib)
+    sd = {k: t.to(DEV) for k, t in pol.init_random(seed=4).items()}
+    g = torch.Generator(device="cpu").manual_seed(5)
+    obs = (torch.randn(n, obs_dim, generator=g) * 2).clamp(-10, 10).to(DEV)
+    h0 = (torch.rand(2, n, H, generator=g) * 2 - 1).to(DEV)
+    c0 = (torch.randn(2, n, H, generator=g) * 2).to(DEV)
+    starts = (torch.rand(n, generator=g) < 0.3).float().to(DEV)
+    noise = torch.randn(n, act_dim, generator=g).to(DEV)
+    ra, rv, rlp, rh, rc = torch_reference_forward(sd, obs, h0, c0, starts, noise, pi, vf)
+    h, c = h0.clone(), c0.clone()
+    a, v, lp, _ = pol.forward(obs, (h, c), starts, noise=noise)
+    torch.cuda.synchronize()
+    _close(h, rh, 5e-2, 0, 3e-3)
+    _close(c, rc, 5e-2, 2e-2, 3e-3)
+    _close(a, ra, 5e-2, 2e-2)
+    _close(v, rv, 5e-2, 2e-2)
+    assert torch.allclose(lp, rlp, atol=1e-3, rtol=1e-5)
+
+
 def test_in_kernel_sampling_statistics(product_lib):
     """seed() switches on the in-kernel Philox/Box-Muller noise: (action - mean) / std must be ~N(0,1), differ
     between calls, and be reproducible for the same (seed, call index)."""

@@ -337,3 +337,27 @@ def test_sde_recurrent_ppo_is_on_policy_and_learns(product_lib):
     agent.learn(total_timesteps=2 * n * T)
     assert len(agent.logs) == 2 and all(np.isfinite(l["train/loss"]) for l in agent.logs)
     assert not torch.equal(before, agent.update.state_dict()["log_std"]) and tuple(before.shape) == (64, 39)
+
+
+@pytest.mark.parametrize("env_id,n,H", [("CustomMyoElbowPoseRandom-v0", 64, 64), ("CustomMyoFingerPoseRandom-v0", 512, 64), ("CustomMyoHandPoseRandom-v0", 256, 128)])
+def test_recurrent_ppo_on_the_pose_configs(product_lib, env_id, n, H):
+    """BASELINE configs[0..2] (elbow, finger, hand pose) through the same loop: rollout + update run, the first minibatch is on
+    policy, episodes end by the horizon (100)."""
+    from myochallenge_b200.envs import make_vec_env
+    from myochallenge_b200.ppo import RecurrentPPO
+    from myochallenge_b200.rollout import DeviceVecNormalize, collect_rollouts
+
+    T = 12
+    env = make_vec_env(env_id, n, device=DEV, seed=1, clip_actions=True, max_episode_steps=10)
+    vn = DeviceVecNormalize(env, gamma=0.99)
+    agent = RecurrentPPO("MlpLstmPolicy", vn, n_steps=T, batch_size=T * (n // 2), n_epochs=1, learning_rate=1e-4,
+                         policy_kwargs=dict(lstm_hidden_size=H, net_arch=[dict(pi=[64], vf=[64])], log_std_init=-1.0), seed=3)
+    agent._obs = vn.reset_device().clone()
+    agent._starts = torch.ones(n, dtype=torch.uint8, device=DEV)
+    agent._state = agent.policy.initial_state(n)
+    agent._obs, agent._starts = collect_rollouts(vn, agent.policy, agent.buffer, agent._state, agent._obs, agent._starts)
+    assert float(agent.buffer.episode_starts[10].float().mean()) > 0.9      # horizon 10: (nearly) every world restarts at step 10 (pose envs may end earlier: far_th)
+    stats = agent.update.minibatch_grad(agent.buffer, torch.arange(n // 2, dtype=torch.int32, device=DEV)).cpu().numpy()
+    assert stats[3] <= 2e-3 and stats[4] <= 0.02, stats
+    agent.learn(total_timesteps=n * T)
+    assert np.isfinite(agent.logs[-1]["train/loss"]) and agent.logs[-1]["train/n_updates"] == 2
