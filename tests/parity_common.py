@@ -153,3 +153,82 @@ def B_pose_target(obs0, om):
     """pose target recovered from the reset observation: pose_err + qpos"""
     nq, nv = om.nq, om.nv
     return obs0[nq + nv: 2 * nq + nv].astype(np.float64) + obs0[:nq].astype(np.float64)
+
+
+def check_episode_returns(lib, device, n, steps, seed=5, min_same_length=0.9, ks_alpha=0.05):
+    """north_star: "multi-step episode return distributions must be statistically indistinguishable on fixed seeds".
+    Baoding P2 worlds with the full reset randomisation (task, start angle, radii, period, ball mass / size / friction) are
+    rolled for `steps` env steps under seeded random actions (held for 5 steps); the oracle (fp64) replays every world from the
+    same reset state with the same per-world parameters and actions, and the reference's reward / termination are evaluated on
+    its state (targets are sites without dynamics: their positions are taken from the product's observations). Compared:
+    per-world episode length (first drop, else `steps`), per-world return, and the two return samples by a Kolmogorov-Smirnov
+    test. fp32 vs fp64 trajectories of a contact-rich system drift apart slowly, so lengths must agree for >= 90 % of the
+    worlds and returns of the agreeing worlds to 1 % (+0.05 absolute), not bit for bit."""
+    from scipy import stats as sps
+    import torch
+
+    path = HAND_BAODING_PATH()
+    model, cfg, B = make_batch(lib, path, _capi.TASK_BAODING, n, device, auto_reset=0, task_choice_random=1, randomize_physics=1,
+                               max_episode_steps=steps + 1)
+    for k, w in enumerate((5.0, 5.0, 0.0, 1.0, 0.0, 5.0, 0.0)):      # the winning curriculum's reward weights
+        cfg.rwd_weight[k] = w
+    _, _, B = (model, cfg, sim.BatchSim(model, n, cfg, device=device, seed=seed))
+    B.reset()
+    q0, v0, a0, _ = [t.cpu().numpy().astype(np.float64) for t in B.get_state()]
+    mass = [B.get_param(_capi.PARAM_BODY_MASS, cfg.ball_body[k]).cpu().numpy().reshape(n) for k in range(2)]
+    size = [B.get_param(_capi.PARAM_GEOM_SIZE, cfg.ball_geom[k]).cpu().numpy().reshape(n, 3) for k in range(2)]
+    fric = [B.get_param(_capi.PARAM_GEOM_FRICTION, cfg.ball_geom[k]).cpu().numpy().reshape(n, 3) for k in range(2)]
+    rng = np.random.default_rng(seed)
+    acts, tgt, rews, dones = [], [], [], []
+    a = None
+    for t in range(steps):
+        if t % 5 == 0:
+            a = rng.uniform(-1, 1, (n, B.nu)).astype(np.float32)
+        obs, rew, done, _ = B.step(torch.as_tensor(a).to(device))
+        acts.append(a.copy()); tgt.append(obs[:, 35:41].cpu().numpy().astype(np.float64)); rews.append(rew.cpu().numpy().copy()); dones.append(done.cpu().numpy().astype(bool))
+    rews, dones = np.array(rews), np.array(dones)
+    first = np.where(dones.any(0), dones.argmax(0), steps - 1)          # step index of the first drop (or the last step)
+    g_len = first + 1
+    g_ret = np.array([rews[: first[w] + 1, w].sum() for w in range(n)])
+    om, od = oracle.load(path)
+    nominal = (np.array(om.body_mass).copy(), np.array(om.geom_size).copy(), np.array(om.geom_friction).copy())
+    o_len, o_ret = np.zeros(n, int), np.zeros(n)
+    for w in range(n):
+        om.body_mass[:] = nominal[0]; om.geom_size[:] = nominal[1]; om.geom_friction[:] = nominal[2]
+        for k in range(2):
+            om.body_mass[cfg.ball_body[k]] = mass[k][w]
+            om.geom_size[cfg.ball_geom[k]] = size[k][w]
+            om.geom_friction[cfg.ball_geom[k]] = fric[k][w]
+        od.reset()
+        od.qpos[:] = q0[w]; od.qvel[:] = v0[w]; od.act[:] = a0[w]
+        ret, length = 0.0, steps
+        for t in range(steps):
+            od.ctrl[:] = 1.0 / (1.0 + np.exp(-5.0 * (acts[t][w].astype(np.float64) - 0.5)))
+            od.step(cfg.frame_skip)
+            od.call("o_kinematics")
+            o1, o2 = np.array(od.site_xpos[cfg.ball_site[0]]), np.array(od.site_xpos[cfg.ball_site[1]])
+            t1, t2 = tgt[t][w, :3], tgt[t][w, 3:]
+            d1, d2 = np.linalg.norm(t1 - o1), np.linalg.norm(t2 - o2)
+            fall = (o1[2] < cfg.drop_th) or (o2[2] < cfg.drop_th)
+            terms = [-d1, -d2, -np.linalg.norm(od.act) / om.na, float(not fall), -(d1 + d2),
+                     float(d1 < cfg.proximity_th and d2 < cfg.proximity_th and not fall), float(fall)]
+            ret += sum(cfg.rwd_weight[k] * terms[k] for k in range(7))
+            if fall:
+                length = t + 1
+                break
+        o_len[w], o_ret[w] = length, ret
+    om.body_mass[:] = nominal[0]; om.geom_size[:] = nominal[1]; om.geom_friction[:] = nominal[2]
+    same = g_len == o_len
+    assert same.mean() >= min_same_length, f"episode lengths agree for {same.mean():.2%} of the worlds: {g_len[~same]} vs {o_len[~same]}"
+    np.testing.assert_allclose(g_ret[same], o_ret[same], rtol=1e-2, atol=5e-2)
+    if n >= 32:
+        ks = sps.ks_2samp(g_ret, o_ret)
+        assert ks.pvalue > ks_alpha, f"return distributions differ: KS p = {ks.pvalue:.3f}"
+        kl = sps.ks_2samp(g_len, o_len)
+        assert kl.pvalue > ks_alpha, f"episode-length distributions differ: KS p = {kl.pvalue:.3f}"
+    return dict(same_length=float(same.mean()), dropped=float((g_len < steps).mean()), mean_return=(float(g_ret.mean()), float(o_ret.mean())))
+
+
+def HAND_BAODING_PATH():
+    from conftest import HAND_BAODING
+    return HAND_BAODING

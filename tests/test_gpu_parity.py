@@ -29,6 +29,14 @@ def test_env_step(product_lib, name, path, kind, n):
     pc.check_env_step_matches_mj_steps(product_lib, DEV, path, kind, 8)
 
 
+def test_episode_return_distribution_matches_oracle(product_lib):
+    """north_star's multi-step bar: 128 fully randomised Baoding worlds, 40 env steps (400 mj_steps) under seeded random actions,
+    against the fp64 oracle replaying every world: episode lengths, returns, and a KS test on the two return samples."""
+    out = pc.check_episode_returns(product_lib, DEV, 128, 40)
+    assert out["dropped"] > 0.05, out            # the sample contains early terminations (drops), not just full-length episodes
+    print(out)
+
+
 def test_lane_width_invariance(product_lib, monkeypatch):
     """The tile width only changes which lane does the work and the order of the tile-wide reductions:
     8-, 16- and 32-lane runs of the same worlds agree to fp32 rounding (1e-5 relative after 5 substeps)."""
