@@ -131,6 +131,10 @@ typedef struct myo_task_cfg {
   int32_t balls_overlap;        /* 0: after RSI the start angles are re-drawn uniformly (:634-638) */
   float beta_init_angle[2];     /* (a, b) of np_random.beta; a <= 0: off. Used only with limit_init_angle (:504-520) */
   float beta_ball_size[2], beta_ball_mass[2];   /* (:563-573, :590-600) */
+  /* ---- phase-1 env CustomBaodingEnv.reset (/root/reference/src/envs/baoding.py:146-215): start angles 3pi/4 (+ the RSI
+   *      phase, drawn whenever enable_rsi), ball placement gated by rsi_probability, then noise on balls / palm / fingers ---- */
+  int32_t p1_reset;
+  float noise_palm, noise_balls;
 } myo_task_cfg;
 
 const char* myo_last_error(void);

@@ -50,6 +50,7 @@ class TaskCfg(C.Structure):
         ("clip_actions", C.c_int32),
         ("enable_rsi", C.c_int32), ("rsi_probability", C.c_float), ("balls_overlap", C.c_int32),
         ("beta_init_angle", C.c_float * 2), ("beta_ball_size", C.c_float * 2), ("beta_ball_mass", C.c_float * 2),
+        ("p1_reset", C.c_int32), ("noise_palm", C.c_float), ("noise_balls", C.c_float),
     ]
 
 

@@ -112,29 +112,51 @@ __global__ void gather_state_kernel(int B, int H, const int32_t* __restrict__ id
   C0[i] = keep[b] * c0[src];
 }
 
+// four consecutive elements at once (H is a multiple of 8, rows are 16-byte aligned)
+__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+__device__ __forceinline__ void store4(bf16* p, float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  uint2 v;
+  v.x = *reinterpret_cast<uint32_t*>(&lo); v.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 add4(float4 a, float4 b, float4 c) { return make_float4(a.x + b.x + c.x, a.y + b.y + c.y, a.z + b.z + c.z, a.w + b.w + c.w); }
+
 // ---- LSTM cell, step t of the sequence forward (torch gate order i f g o) -------------------------------------------
 // G[t]: x W_ih^T + h_prev W_hh^T (no bias yet) -> activated gates in place; Cs[t] = c_t; Hs[t] = h_t;
-// HP[t+1] = keep_{t+1} h_t (operand of the next recurrent GEMM)
+// HP[t+1] = keep_{t+1} h_t (operand of the next recurrent GEMM). A thread owns four consecutive units of one world.
 template <typename T>
 __global__ void lstm_cell_fwd_kernel(int t, int Tn, int B, int H, float* __restrict__ G, const float* __restrict__ bih, const float* __restrict__ bhh,
                                      const float* __restrict__ keep, const float* __restrict__ C0, float* __restrict__ Cs,
                                      T* __restrict__ Hs, T* __restrict__ HP) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * H) return;
-  const int b = i / H, j = i - b * H;
+  const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int H4 = H >> 2;
+  if (i4 >= B * H4) return;
+  const int b = i4 / H4, j = (i4 - b * H4) << 2;
   const int64_t m = (int64_t)t * B + b;
   float* g = G + m * 4 * H;
-  const float gi = sigmoidf_(g[j] + bih[j] + bhh[j]);
-  const float gf = sigmoidf_(g[H + j] + bih[H + j] + bhh[H + j]);
-  const float gg = tanhf(g[2 * H + j] + bih[2 * H + j] + bhh[2 * H + j]);
-  const float go = sigmoidf_(g[3 * H + j] + bih[3 * H + j] + bhh[3 * H + j]);
-  const float cp = t == 0 ? C0[i] : keep[m] * Cs[(m - B) * H + j];
-  const float c = gf * cp + gi * gg;
-  const float h = go * tanhf(c);
-  g[j] = gi; g[H + j] = gf; g[2 * H + j] = gg; g[3 * H + j] = go;
-  Cs[m * H + j] = c;
-  Hs[m * H + j] = to_op<T>(h);
-  if (t + 1 < Tn) HP[(m + B) * H + j] = to_op<T>(keep[m + B] * h);
+  const float4 pi = add4(ld4(g + j), ld4(bih + j), ld4(bhh + j));
+  const float4 pf = add4(ld4(g + H + j), ld4(bih + H + j), ld4(bhh + H + j));
+  const float4 pg = add4(ld4(g + 2 * H + j), ld4(bih + 2 * H + j), ld4(bhh + 2 * H + j));
+  const float4 po = add4(ld4(g + 3 * H + j), ld4(bih + 3 * H + j), ld4(bhh + 3 * H + j));
+  float4 cp = t == 0 ? ld4(C0 + (int64_t)b * H + j) : ld4(Cs + (m - B) * H + j);
+  if (t > 0) { const float k = keep[m]; cp.x *= k; cp.y *= k; cp.z *= k; cp.w *= k; }
+  const float kn = t + 1 < Tn ? keep[m + B] : 0.f;
+  float gi[4] = {pi.x, pi.y, pi.z, pi.w}, gf[4] = {pf.x, pf.y, pf.z, pf.w}, gg[4] = {pg.x, pg.y, pg.z, pg.w}, go[4] = {po.x, po.y, po.z, po.w};
+  const float cpv[4] = {cp.x, cp.y, cp.z, cp.w};
+  float c[4], h[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    gi[q] = sigmoidf_(gi[q]); gf[q] = sigmoidf_(gf[q]); gg[q] = tanhf(gg[q]); go[q] = sigmoidf_(go[q]);
+    c[q] = gf[q] * cpv[q] + gi[q] * gg[q];
+    h[q] = go[q] * tanhf(c[q]);
+  }
+  store4(g + j, gi[0], gi[1], gi[2], gi[3]); store4(g + H + j, gf[0], gf[1], gf[2], gf[3]);
+  store4(g + 2 * H + j, gg[0], gg[1], gg[2], gg[3]); store4(g + 3 * H + j, go[0], go[1], go[2], go[3]);
+  store4(Cs + m * H + j, c[0], c[1], c[2], c[3]);
+  store4(Hs + m * H + j, h[0], h[1], h[2], h[3]);
+  if (t + 1 < Tn) store4(HP + (m + B) * H + j, kn * h[0], kn * h[1], kn * h[2], kn * h[3]);
 }
 
 // step t of the backward recurrence. dHs: dL/dh_t from the layers above; dh_carry = dG_{t+1} W_hh (not yet masked);
@@ -143,35 +165,64 @@ template <typename T>
 __global__ void lstm_cell_bwd_kernel(int t, int Tn, int B, int H, const float* __restrict__ G, const float* __restrict__ keep,
                                      const float* __restrict__ C0, const float* __restrict__ Cs, const float* __restrict__ dHs,
                                      const float* __restrict__ dh_carry, float* __restrict__ dc_carry, T* __restrict__ dG) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * H) return;
-  const int b = i / H, j = i - b * H;
-  const int64_t m = (int64_t)t * B + b;
+  const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int H4 = H >> 2;
+  if (i4 >= B * H4) return;
+  const int b = i4 / H4, j = (i4 - b * H4) << 2;
+  const int64_t m = (int64_t)t * B + b, bo = (int64_t)b * H + j;
   const float* g = G + m * 4 * H;
-  const float gi = g[j], gf = g[H + j], gg = g[2 * H + j], go = g[3 * H + j];
-  float dh = dHs[m * H + j], dc = 0.f;
-  if (t + 1 < Tn) { dh += keep[m + B] * dh_carry[i]; dc = dc_carry[i]; }
-  const float tc = tanhf(Cs[m * H + j]);
-  dc += dh * go * (1.f - tc * tc);
-  const float cp = t == 0 ? C0[i] : keep[m] * Cs[(m - B) * H + j];
+  const float4 vi = ld4(g + j), vf = ld4(g + H + j), vg = ld4(g + 2 * H + j), vo = ld4(g + 3 * H + j);
+  const float4 vdh = ld4(dHs + m * H + j), vc = ld4(Cs + m * H + j);
+  float4 vcar = make_float4(0.f, 0.f, 0.f, 0.f), vdc = vcar;
+  float kn = 0.f;
+  if (t + 1 < Tn) { vcar = ld4(dh_carry + bo); vdc = ld4(dc_carry + bo); kn = keep[m + B]; }
+  float4 vcp = t == 0 ? ld4(C0 + bo) : ld4(Cs + (m - B) * H + j);
+  const float k = keep[m];
+  if (t > 0) { vcp.x *= k; vcp.y *= k; vcp.z *= k; vcp.w *= k; }
+  const float gi[4] = {vi.x, vi.y, vi.z, vi.w}, gf[4] = {vf.x, vf.y, vf.z, vf.w}, gg[4] = {vg.x, vg.y, vg.z, vg.w}, go[4] = {vo.x, vo.y, vo.z, vo.w};
+  const float dhs[4] = {vdh.x, vdh.y, vdh.z, vdh.w}, cs[4] = {vc.x, vc.y, vc.z, vc.w}, car[4] = {vcar.x, vcar.y, vcar.z, vcar.w};
+  const float dcs[4] = {vdc.x, vdc.y, vdc.z, vdc.w}, cp[4] = {vcp.x, vcp.y, vcp.z, vcp.w};
+  float di[4], df[4], dg[4], dO[4], dcn[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const float dh = dhs[q] + kn * car[q];
+    const float tc = tanhf(cs[q]);
+    const float dc = dcs[q] + dh * go[q] * (1.f - tc * tc);
+    di[q] = dc * gg[q] * gi[q] * (1.f - gi[q]);
+    df[q] = dc * cp[q] * gf[q] * (1.f - gf[q]);
+    dg[q] = dc * gi[q] * (1.f - gg[q] * gg[q]);
+    dO[q] = dh * tc * go[q] * (1.f - go[q]);
+    dcn[q] = dc * gf[q] * k;
+  }
   T* d = dG + m * 4 * H;
-  d[j] = to_op<T>(dc * gg * gi * (1.f - gi));
-  d[H + j] = to_op<T>(dc * cp * gf * (1.f - gf));
-  d[2 * H + j] = to_op<T>(dc * gi * (1.f - gg * gg));
-  d[3 * H + j] = to_op<T>(dh * tc * go * (1.f - go));
-  dc_carry[i] = dc * gf * keep[m];
+  store4(d + j, di[0], di[1], di[2], di[3]); store4(d + H + j, df[0], df[1], df[2], df[3]);
+  store4(d + 2 * H + j, dg[0], dg[1], dg[2], dg[3]); store4(d + 3 * H + j, dO[0], dO[1], dO[2], dO[3]);
+  store4(dc_carry + bo, dcn[0], dcn[1], dcn[2], dcn[3]);
 }
 
 // ---- MLP glue ----------------------------------------------------------------------------------------------------------
+// four elements per thread (widths are multiples of 8, buffers 16-byte aligned)
 template <typename T>
 __global__ void bias_relu_kernel(const float* __restrict__ Z, const float* __restrict__ bias, T* __restrict__ A, int64_t total, int W) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    A[i] = to_op<T>(fmaxf(Z[i] + bias[i % W], 0.f));
+  const int64_t n4 = total >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 z = ld4(Z + 4 * i), bb = ld4(bias + (4 * i) % W);
+    store4(A + 4 * i, fmaxf(z.x + bb.x, 0.f), fmaxf(z.y + bb.y, 0.f), fmaxf(z.z + bb.z, 0.f), fmaxf(z.w + bb.w, 0.f));
+  }
+}
+__device__ __forceinline__ float4 ld4op(const float* p) { return ld4(p); }
+__device__ __forceinline__ float4 ld4op(const bf16* p) {
+  const uint2 v = *reinterpret_cast<const uint2*>(p);
+  const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&v.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+  return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
 }
 template <typename T>
 __global__ void relu_bwd_kernel(const float* __restrict__ dA, const T* __restrict__ A, T* __restrict__ dZ, int64_t total) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
-    dZ[i] = to_op<T>(from_op(A[i]) > 0.f ? dA[i] : 0.f);
+  const int64_t n4 = total >> 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 d = ld4(dA + 4 * i), a = ld4op(A + 4 * i);
+    store4(dZ + 4 * i, a.x > 0.f ? d.x : 0.f, a.y > 0.f ? d.y : 0.f, a.z > 0.f ? d.z : 0.f, a.w > 0.f ? d.w : 0.f);
+  }
 }
 
 // column sums of Y[M][ld] (first N columns) -> part[chunk][N], then out[N] (and out2[N] if given): two stages, fixed order
@@ -616,9 +667,9 @@ int net_chain(myo_ppo* p, const GradArgs& a, int k, cudaStream_t st) {
   T* wop = static_cast<T*>(p->wop);
   T* X = static_cast<T*>(p->X); T* dG = static_cast<T*>(nb.dG); T* Hs = static_cast<T*>(nb.Hs); T* HP = static_cast<T*>(nb.HP);
   T* dZ = static_cast<T*>(nb.dZ); T* dhead = static_cast<T*>(nb.dhead);
-  const int cell_blocks = (B * H + 255) / 256;
+  const int cell_blocks = (B * (H / 4) + 255) / 256;
   // ---- forward over the sequences ----
-  gather_state_kernel<T><<<cell_blocks, 256, 0, st>>>(B, H, p->idx, a.h0 + (int64_t)k * a.n * H, a.c0 + (int64_t)k * a.n * H, p->keep, HP, nb.C0);
+  gather_state_kernel<T><<<(B * H + 255) / 256, 256, 0, st>>>(B, H, p->idx, a.h0 + (int64_t)k * a.n * H, a.c0 + (int64_t)k * a.n * H, p->keep, HP, nb.C0);
   p->launches++;
   RCK(gemm_nt(p, blas, M, 4 * H, Op, X, Op, wop + n.op_wih, Op, 0.f, nb.G, 4 * H));
   for (int t = 0; t < Tn; t++) {
@@ -631,7 +682,7 @@ int net_chain(myo_ppo* p, const GradArgs& a, int k, cudaStream_t st) {
   for (int l = 0; l < n.nl; l++) {
     T* Aout = static_cast<T*>(nb.Al[l]);
     RCK(gemm_nt(p, blas, M, n.width[l], d, in, d, wop + n.op_w[l], d, 0.f, nb.T1, n.width[l]));
-    bias_relu_kernel<T><<<blocks_for(M * n.width[l], 256), 256, 0, st>>>(nb.T1, a.params + n.b[l], Aout, M * n.width[l], n.width[l]);
+    bias_relu_kernel<T><<<blocks_for(M * n.width[l] / 4, 256), 256, 0, st>>>(nb.T1, a.params + n.b[l], Aout, M * n.width[l], n.width[l]);
     p->launches++;
     in = Aout; d = n.width[l];
   }
@@ -669,7 +720,7 @@ int net_chain(myo_ppo* p, const GradArgs& a, int k, cudaStream_t st) {
     const T* Aout = static_cast<const T*>(nb.Al[l]);
     const T* inl = l > 0 ? static_cast<const T*>(nb.Al[l - 1]) : Hs;
     const int din = l > 0 ? n.width[l - 1] : H;
-    relu_bwd_kernel<T><<<blocks_for(M * n.width[l], 256), 256, 0, st>>>(nb.T1, Aout, dZ, M * n.width[l]);
+    relu_bwd_kernel<T><<<blocks_for(M * n.width[l] / 4, 256), 256, 0, st>>>(nb.T1, Aout, dZ, M * n.width[l]);
     p->launches++;
     RCK(gemm_tn(p, blas, M, n.width[l], din, dZ, n.width[l], inl, din, a.grad + n.w[l], din));
     RCK(colsum<T>(p, nb.cpart, dZ, M, n.width[l], n.width[l], a.grad + n.b[l], nullptr, st));

@@ -182,7 +182,28 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
     Philox rng;
     rng.init(b.seed, (uint32_t)w, (uint32_t)episode);
     ti[TI_EPISODE] = episode; ti[TI_ELAPSED] = 0;
-    if (t.kind == MYO_TASK_BAODING) {
+    if (t.kind == MYO_TASK_BAODING && t.p1_reset) {
+      // CustomBaodingEnv.reset (phase 1, /root/reference/src/envs/baoding.py:146-215)
+      ti[TI_TASK] = t.task_choice_random ? min(2, (int)(rng.uniform() * 3.f)) : t.fixed_task;      // sample_task
+      const float phase = t.enable_rsi ? rng.uniform(-kPi, kPi) : 0.f;
+      tf[TF_ANGLE1] = 0.75f * kPi + phase; tf[TF_ANGLE2] = -0.25f * kPi + phase;
+      tf[TF_XR] = rng.uniform(t.goal_xrange[0], t.goal_xrange[1]);
+      tf[TF_YR] = rng.uniform(t.goal_yrange[0], t.goal_yrange[1]);
+      tf[TF_PERIOD] = rng.uniform(t.goal_time_period[0], t.goal_time_period[1]);
+      ti[TI_FLAGS] = 0;
+      if (t.enable_rsi && rng.uniform() < t.rsi_probability) {      // self.step(zeros) + balls onto the targets (closed form, see below)
+        ti[TI_FLAGS] = 1;
+        if (ti[TI_TASK] == MYO_BAODING_CW || ti[TI_TASK] == MYO_BAODING_CCW) {
+#pragma unroll
+          for (int k = 0; k < 2; k++) {
+            float sn, cs;
+            sincosf(tf[TF_ANGLE1 + k], &sn, &cs);
+            const int slot = m.s_pos_slot[t.target_site[k]];
+            if (slot >= 0) { c.wpp(m)[slot] = tf[TF_XR] * cs + t.center_pos[0]; c.wpp(m)[slot + 1] = tf[TF_YR] * sn + t.center_pos[1]; }
+          }
+        }
+      }
+    } else if (t.kind == MYO_TASK_BAODING) {
       float a1;
       if (t.task_choice_random) {
         ti[TI_TASK] = min(2, (int)(rng.uniform() * 3.f));
@@ -324,6 +345,30 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         if (dyn == 3) a = clipf(a, 0.f, 1.f);
       }
       SF(o_act)[ai] = a;
+    }
+    c.tile.sync();
+  }
+  if (t.kind == MYO_TASK_BAODING && t.p1_reset && (t.noise_balls > 0.f || t.noise_palm > 0.f || t.noise_fingers > 0.f) && m.nq - 14 >= 23) {
+    if (c.lane == 0) {     // phase-1 noise, applied after the RSI ball placement as the reference orders it (:196-210)
+      Philox rng;
+      rng.init(b.seed ^ 0x9E3779B97F4A7C15ull, (uint32_t)w, (uint32_t)ti[TI_EPISODE]);
+      if (t.noise_balls > 0.f)
+        for (int k = 0; k < 2; k++) for (int e = 0; e < 3; e++) qpos[t.ball_qposadr[k] + e] += rng.uniform(-t.noise_balls, t.noise_balls);
+      if (t.noise_palm > 0.f) {       // _add_noise_to_palm_position
+        qpos[0] = rng.uniform(-0.5f * kPi, -0.5f * kPi + kPi / 18.f * t.noise_palm);
+        qpos[1] = rng.uniform(-kPi / 18.f * t.noise_palm, kPi / 18.f * t.noise_palm);
+        qpos[2] = rng.uniform(-kPi / 18.f * t.noise_palm, kPi / 18.f * t.noise_palm);
+      }
+      if (t.noise_fingers > 0.f) {    // phase-1 _add_noise_to_finger_positions: thumb 3..6, flexions, abductions - one draw per group
+        const float th = rng.uniform(-kPi / 18.f * t.noise_fingers, kPi / 18.f * t.noise_fingers);
+        qpos[3] = th; qpos[4] = th; qpos[5] = th; qpos[6] = th;
+        const float fl = rng.uniform(0.f, kPi / 6.f * t.noise_fingers);
+        const int idx[12] = {7, 9, 10, 11, 13, 14, 15, 17, 18, 19, 21, 22};
+#pragma unroll
+        for (int k = 0; k < 12; k++) qpos[idx[k]] = fl;
+        const float ab = rng.uniform(-kPi / 36.f * t.noise_fingers, kPi / 36.f * t.noise_fingers);
+        qpos[8] = ab; qpos[12] = ab; qpos[16] = ab; qpos[20] = ab;
+      }
     }
     c.tile.sync();
   }

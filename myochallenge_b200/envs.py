@@ -125,10 +125,24 @@ def make_task_cfg(model: Model, env_id: str, **overrides) -> _capi.TaskCfg:
         fc = kw.pop("obj_friction_change", (0.2, 0.001, 0.00002))
         for i in range(3):
             cfg.obj_friction_change[i] = float(fc[i])
-        task_choice = kw.pop("task_choice", "fixed")
-        if task_choice not in ("fixed", "random"):
-            raise ValueError(f"task_choice must be 'fixed' or 'random', got {task_choice!r}")
-        cfg.task_choice_random = int(task_choice == "random")
+        cfg.p1_reset = int(reg.get("phase", 2) == 1)
+        if cfg.p1_reset:        # CustomBaodingEnv._setup: task=None | "cw" | "ccw" | "random" (sample_task, :285-296)
+            task = kw.pop("task", None)
+            if task not in (None, "cw", "ccw", "random"):
+                raise ValueError("Unknown task for baoding: ", task)
+            cfg.task_choice_random = int(task == "random")
+            if task in ("cw", "ccw"):
+                cfg.fixed_task = 1 if task == "cw" else 2
+            cfg.noise_palm = float(kw.pop("noise_palm", 0.0))
+            cfg.noise_balls = float(kw.pop("noise_balls", 0.0))
+            for name, v in (("noise_palm", cfg.noise_palm), ("noise_fingers", float(kw.get("noise_fingers", 0.0)))):
+                if not 0 <= v <= 1:
+                    raise AssertionError(f"{name} must be between 0 and 1")
+        else:
+            task_choice = kw.pop("task_choice", "fixed")
+            if task_choice not in ("fixed", "random"):
+                raise ValueError(f"task_choice must be 'fixed' or 'random', got {task_choice!r}")
+            cfg.task_choice_random = int(task_choice == "random")
         cfg.randomize_physics = int(reg.get("phase", 2) == 2)     # P1's reset keeps the nominal balls
         cfg.overlap_probability = float(kw.pop("overlap_probability", 0.0))
         cfg.balls_overlap = int(bool(kw.pop("balls_overlap", False)))    # read only inside the RSI branch (/root/reference/src/envs/baoding.py:634)

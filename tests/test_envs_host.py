@@ -161,3 +161,24 @@ def test_two_rank_moment_merge_gloo():
         np.testing.assert_allclose(var, ref.var, rtol=1e-10)
         assert count == pytest.approx(ref.count)
     assert res[0][4] != res[1][4]                    # ranks draw from disjoint world streams
+
+
+def test_every_curriculum_step_maps_to_a_task_cfg(product_lib):
+    """The reference's 32 training steps (config.json of each, packaged as data) all translate into the device task configuration:
+    no knob of the winning curriculum is rejected or silently dropped."""
+    from myochallenge_b200 import curriculum
+
+    steps = curriculum.load()
+    assert len(steps) == 32 and steps[0]["step"].startswith("01_") and steps[-1]["step"].startswith("32_")
+    m = Model(asset_path("hand/myo_hand_baoding.mjb"), lib=product_lib)
+    cfgs = {s["step"][:2]: curriculum.task_cfg(s, m) for s in steps}
+    c01, c04, c06, c15, c18, c23, c32 = (cfgs[k] for k in ("01", "04", "06", "15", "18", "23", "32"))
+    assert c01.p1_reset == 1 and c01.enable_rsi == 1 and c01.rsi_probability == 1.0 and c01.goal_time_period[0] > 1e30      # static targets
+    assert c04.p1_reset == 1 and c04.task_choice_random == 1 and c04.rsi_probability == pytest.approx(0.9) and c04.drop_th == pytest.approx(1.3)
+    assert c06.enable_rsi == 0 and tuple(c06.goal_time_period) == (10.0, 10.0)
+    assert c15.p1_reset == 0 and c15.overlap_probability == pytest.approx(0.9)
+    assert c18.limit_init_angle == pytest.approx(np.pi / 3, rel=1e-3)
+    assert c23.noise_fingers == pytest.approx(0.2) and c23.randomize_physics == 1
+    assert c32.limit_init_angle == pytest.approx(np.pi) and list(c32.rwd_weight)[:7] == [5, 5, 0, 1, 0, 5, 0]
+    with pytest.raises(ValueError):
+        make_task_cfg(m, "CustomMyoChallengeBaodingP1-v1", task="sideways")

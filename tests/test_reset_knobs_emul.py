@@ -113,3 +113,30 @@ def test_beta_init_angle(emul_lib):
     assert 800 < n < 1200                                # two of three tasks rotate
     z = (phase + np.pi) / (2 * np.pi)
     assert abs(z.mean() - 0.5) < 4 * np.sqrt(0.05 / n) and abs(z.var() - 0.05) < 0.01       # beta(2, 2): mean 1/2, var 1/20
+
+
+def test_phase1_reset(emul_lib):
+    """CustomBaodingEnv.reset (phase 1, /root/reference/src/envs/baoding.py:146-215): start angles 3 pi / 4 and - pi / 4 (+ the RSI phase),
+    ball placement gated by rsi_probability, then noise on the balls / palm / fingers."""
+    n = 400
+    m = Model(HAND_BAODING, lib=emul_lib)
+    P1 = "CustomMyoChallengeBaodingP1-v1"
+    # plain P1 (task None = CCW): after the first step the targets sit at 3 pi / 4 (goal[0] = 0)
+    sim = BatchSim(m, 8, make_task_cfg(m, P1), device="cpu", seed=2)
+    sim.reset()
+    o = sim.step(torch.zeros(8, sim.nu))[0].numpy()
+    np.testing.assert_allclose(_target_angle(o), 0.75 * np.pi, atol=3e-4)
+    # RSI with probability 0.5 + noises
+    cfg = make_task_cfg(m, P1, task="random", enable_rsi=True, rsi_probability=0.5, noise_palm=1.0, noise_fingers=0.5, noise_balls=0.002, drop_th=1.3)
+    sim = BatchSim(m, n, cfg, device="cpu", seed=3)
+    obs = sim.reset().numpy()
+    q = sim.get_state()[0].numpy()
+    assert (q[:, 0] >= -np.pi / 2 - 1e-6).all() and (q[:, 0] <= -np.pi / 2 + np.pi / 18 + 1e-6).all() and q[:, 0].std() > 0.02     # palm noise
+    assert (np.abs(q[:, 1:3]) <= np.pi / 18 + 1e-6).all()
+    assert np.allclose(q[:, 3], q[:, 6]) and (np.abs(q[:, 3]) <= np.pi / 36 + 1e-6).all()                       # thumb: one draw, noise 0.5
+    assert np.allclose(q[:, 7], q[:, 22]) and (q[:, 7] >= 0).all() and (q[:, 7] <= np.pi / 12 + 1e-6).all()     # flexions
+    assert np.allclose(q[:, 8], q[:, 20]) and (np.abs(q[:, 8]) <= np.pi / 72 + 1e-6).all()                      # abductions
+    err = np.abs(obs[:, [41, 42, 44, 45]]).max(1)                      # ball-target xy error: RSI worlds are within the ball noise
+    on_target = err <= 0.002 + 1e-5
+    assert 0.4 < on_target.mean() < 0.6
+    assert (obs[on_target][:, 47:] > 0).all() and (obs[~on_target][:, 47:] == 0).all()      # activations only after the in-reset step
