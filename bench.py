@@ -229,7 +229,21 @@ def run_b200(args):
     # its episode (balls resting on the palm, few contacts); episodes end at random times (drop / TimeLimit), and only after
     # ~one horizon are the episode phases - and with them contact counts and Newton iterations per substep - mixed as they
     # are for the rest of a training run. Timing the first steps would overstate throughput by ~20 %.
-    for _ in range(args.spinup):
+    # With a policy that rarely drops the balls nearly every episode runs the full horizon, so worlds that start together stay
+    # in phase for ever (all 32768 would truncate on the same step); the spin-up therefore staggers them - world w is reset
+    # once, at spin-up step w mod horizon - so that any timed window averages over the phases of an episode.
+    horizon = int(env.cfg.max_episode_steps)
+    widx = torch.arange(n, device=dev)
+
+    def stagger(sim_, t, starts_):
+        if horizon > 0 and t < horizon:
+            mask = (widx[: sim_.n] % horizon) == t
+            sim_.reset(mask)
+            return torch.maximum(starts_, mask.to(torch.uint8))
+        return starts_
+
+    for t in range(args.spinup):
+        starts = stagger(sim, t, starts)
         step_device()
     for _ in range(args.warmup):
         step_device()
@@ -312,7 +326,8 @@ def run_b200(args):
         with torch.cuda.stream(strm[k]):
             b = hb[k]
             o = halves[k].reset_device()
-            for _ in range(args.spinup):                                   # same steady state as the device-resident loop
+            for t in range(args.spinup):                                   # same steady state as the device-resident loop
+                b["starts"] = stagger(halves[k].sim, t, b["starts"])
                 a_, _, _, _ = pol.forward(o, b["state"], b["starts"], out=b["out"])
                 o, _, dn_, _ = halves[k].step_device(a_)
                 b["starts"] = dn_.clone()
@@ -413,7 +428,7 @@ def run_b200(args):
                                "random-init MlpLstmPolicy LSTM-256 + [256,256] actor/critic in the loop",
                    "worlds_per_gpu": n, "parallelism": f"worlds sharded over {world} GPU(s), no data-path collective",
                    "l2": "per-step working set (state + LSTM h/c + obs, ~190 MB at 32768 worlds) exceeds the 126 MB L2; no explicit flush",
-                   "use_sde": bool(args.use_sde), "spinup_steps": args.spinup, "steady_state": "episode phases mixed by an untimed spin-up of one horizon before warm-up",
+                   "use_sde": bool(args.use_sde), "spinup_steps": args.spinup, "steady_state": "untimed spin-up of one horizon before warm-up, worlds' episode phases staggered uniformly over the horizon",
                    "policy_ms": policy_ms, "world_kernel_ms": world_ms, "status_flags": status},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "sequential": seq_value,
