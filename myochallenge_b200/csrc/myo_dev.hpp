@@ -133,6 +133,8 @@ struct BatchPtrs {
   int *task_i, *status;
   float* dump;   // [n][scratch_words] written by forward / mj_step mode (may be null)
   unsigned long long seed;
+  const int* order;   // optional [n_alloc]: slot -> world, worlds grouped by their recent constraint count (null: identity)
+  int* work;          // [n_alloc]: constraint rows of the world's last substep (the grouping key for the next step)
 };
 
 enum { TI_ELAPSED = 0, TI_EPISODE = 1, TI_TASK = 2, TI_FLAGS = 3, TI_WORDS = 4 };

@@ -6,6 +6,9 @@
 // all in one launch. HBM is touched once per env step: state + per-world parameters in (float4,
 // world-major rows so a tile reads one contiguous row), state + obs/reward/flags out.
 #include <cuda_runtime.h>
+#ifndef MYO_EMUL
+#include <cub/device/device_radix_sort.cuh>
+#endif
 
 #include <algorithm>
 #include <cstdio>
@@ -117,6 +120,7 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
   if (c.lane == 0) {
     misc[MI_STATUS] = status;
     if (status && io) atomicOr(b.status, status);
+    if (a.mode == MODE_ENV_STEP && b.work) b.work[w] = io ? misc[MI_NEFC] : 0x7fff;      // padding worlds sort to the end
   }
   store_world<G>(mslot, c, b, w, true);
   if (b.dump && a.mode != MODE_ENV_STEP) {
@@ -151,7 +155,8 @@ __global__ void __launch_bounds__(kThreads) world_kernel(int mslot, const __grid
   c.soff = m.tab_words + tid * m.scratch_words;
   // state arrays are padded to a multiple of wpc worlds, so every tile of a CTA runs the same number of
   // iterations (the phases contain CTA-wide barriers); padding worlds are stepped but have no I/O
-  for (int w = blockIdx.x * wpc + tid; w < b.n_alloc; w += gridDim.x * wpc) {
+  for (int slot = blockIdx.x * wpc + tid; slot < b.n_alloc; slot += gridDim.x * wpc) {
+    const int w = b.order ? b.order[slot] : slot;
     run_world<G>(mslot, t, b, a, c, w);
     c.tile.sync();
   }
@@ -289,6 +294,13 @@ struct myo_batch {
   int grid = 0, threads = myo::kThreads, smem = 0, regs = 0, wpc = 0, tab_bytes = 0;
   int64_t launches = 0;
   std::vector<void*> allocs;
+  // world grouping: after every env step the worlds are sorted by the constraint rows of their last substep, and the next
+  // step walks them in that order, so the 14 worlds that share a CTA (and its phase barriers) carry similar loads
+  bool sort_worlds = false;
+  int *order[2] = {nullptr, nullptr}, *iota = nullptr, *keys_out = nullptr;
+  void* sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  int cur_order = -1;      // index of the order the next step uses (-1: identity)
 };
 
 namespace {
@@ -464,6 +476,25 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
       (rc = dev_alloc(b, &b->p.task_i, n * myo::TI_WORDS)) || (rc = dev_alloc(b, &b->p.status, 4)))
     return fail(rc);
   b->p.dump = nullptr;
+  b->p.order = nullptr; b->p.work = nullptr;
+#ifndef MYO_EMUL
+  {
+    const char* e = getenv("MYO_SORT_WORLDS");
+    b->sort_worlds = e ? atoi(e) != 0 : (b->p.n_alloc >= 4 * b->wpc * 148);      // worth it only when every SM sees several groups
+    if (b->sort_worlds) {
+      if ((rc = dev_alloc(b, &b->p.work, n)) || (rc = dev_alloc(b, &b->order[0], n)) || (rc = dev_alloc(b, &b->order[1], n)) ||
+          (rc = dev_alloc(b, &b->iota, n)) || (rc = dev_alloc(b, &b->keys_out, n)))
+        return fail(rc);
+      std::vector<int> io(n);
+      for (size_t i = 0; i < n; i++) io[i] = (int)i;
+      if (cudaMemcpy(b->iota, io.data(), n * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { myo::set_error("cudaMemcpy(iota) failed"); return fail(MYO_E_CUDA); }
+      cub::DeviceRadixSort::SortPairs(nullptr, b->sort_tmp_bytes, b->p.work, b->keys_out, b->iota, b->order[0], (int)n, 0, 15);
+      char* tmp = nullptr;
+      if ((rc = dev_alloc(b, &tmp, b->sort_tmp_bytes))) return fail(rc);
+      b->sort_tmp = tmp;
+    }
+  }
+#endif
   MYO_LAUNCH(myo::init_worlds_kernel, (b->p.n_alloc + 127) / 128, 128, b->tab_bytes, (cudaStream_t)0, dm, b->p, cfg->fixed_task);
   b->launches++;
   if (cudaDeviceSynchronize() != cudaSuccess) { myo::set_error("world initialisation failed"); return fail(MYO_E_CUDA); }
@@ -515,7 +546,22 @@ int myo_batch_step(myo_batch* b, const float* actions_dev, float* obs_dev, float
   a.mode = myo::MODE_ENV_STEP; a.nsub = b->cfg.frame_skip > 0 ? b->cfg.frame_skip : 1;
   a.in = actions_dev; a.obs = obs_dev; a.reward = reward_dev; a.done = done_dev; a.truncated = truncated_dev;
   a.terminal_obs = terminal_obs_dev; a.info = info_dev;
-  return launch(b, a, stream);
+  b->p.order = (b->sort_worlds && b->cur_order >= 0) ? b->order[b->cur_order] : nullptr;
+  int rc = launch(b, a, stream);
+  b->p.order = nullptr;
+  if (rc || !b->sort_worlds) return rc;
+#ifndef MYO_EMUL
+  // grouping for the next step: stable radix sort of (rows of the last substep, world); keys fit 15 bits
+  const int nxt = b->cur_order == 0 ? 1 : 0;
+  if (cub::DeviceRadixSort::SortPairs(b->sort_tmp, b->sort_tmp_bytes, b->p.work, b->keys_out, b->iota, b->order[nxt], b->p.n_alloc, 0, 15,
+                                      static_cast<cudaStream_t>(stream)) != cudaSuccess) {
+    myo::set_error("world grouping sort failed");
+    return MYO_E_CUDA;
+  }
+  b->launches++;
+  b->cur_order = nxt;
+#endif
+  return MYO_OK;
 }
 
 static int ensure_dump(myo_batch* b) {

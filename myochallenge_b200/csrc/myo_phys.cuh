@@ -1395,6 +1395,9 @@ MYO_DI void lockstep_sync() {
 #ifndef MYO_NEWTON_LOCKSTEP
 #define MYO_NEWTON_LOCKSTEP 0
 #endif
+#ifndef MYO_NEWTON_STEP_TOL
+#define MYO_NEWTON_STEP_TOL 2e-5f      // last Newton step relative to max(1, |qacc|_inf) below which the solve stops (fp32 floor)
+#endif
 MYO_DI bool cta_any(bool v) {
 #if defined(MYO_EMUL)
   return v;
@@ -1534,7 +1537,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
     // fp32 termination: the Newton step is at the rounding floor of qacc (quadratic convergence makes
     // the remaining error far smaller than the last step), or it stopped shrinking (noise-level cycling)
     const float step = alpha * pmax, aref_mag = fmaxf(1.f, amax);
-    if (step <= 2e-5f * aref_mag || (iter > 1 && step >= 0.5f * prev_step && step <= 1e-3f * aref_mag)) active = false;
+    if (step <= MYO_NEWTON_STEP_TOL * aref_mag || (iter > 1 && step >= 0.5f * prev_step && step <= 1e-3f * aref_mag)) active = false;
     prev_step = step;
     }
   }
