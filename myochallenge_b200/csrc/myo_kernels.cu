@@ -120,7 +120,7 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
   if (c.lane == 0) {
     misc[MI_STATUS] = status;
     if (status && io) atomicOr(b.status, status);
-    if (a.mode == MODE_ENV_STEP && b.work) b.work[w] = io ? misc[MI_NEFC] : 0x7fff;      // padding worlds sort to the end
+    if (a.mode == MODE_ENV_STEP && b.work) b.work[w] = io ? 0x7ffe - misc[MI_NEFC] : 0x7fff;      // heavy worlds first (the partial last wave of CTAs gets the light ones), padding worlds last
   }
   store_world<G>(mslot, c, b, w, true);
   if (b.dump && a.mode != MODE_ENV_STEP) {
