@@ -322,7 +322,21 @@ class RecurrentPPO:
         self._state = None          # the env was reset by the evaluation: the next learn() starts from a fresh reset
         return out
 
-    def learn(self, total_timesteps: int, callback=None, **_ignored):
+    def learn(self, total_timesteps: int, callback=None, reset_num_timesteps: bool = True, **_ignored):
+        """``agent.learn(total_timesteps, callback=[...], reset_num_timesteps=True)`` (/root/reference/src/train/trainer.py:67-71).
+        ``callback``: None, a plain ``callback(agent, log) -> bool``, a ``callbacks.BaseCallback`` or a list of them."""
+        from .callbacks import BaseCallback, CallbackList
+
+        cb = None
+        if isinstance(callback, (list, tuple)):
+            cb = CallbackList(list(callback))
+        elif isinstance(callback, BaseCallback):
+            cb = callback
+        if cb is not None:
+            cb.init_callback(self)
+            cb.on_training_start()
+        if reset_num_timesteps:
+            self.num_timesteps = 0
         if self._state is None:
             self._obs = self.env.reset_device()
             self._starts = torch.ones(self.n_envs, dtype=torch.uint8, device=self.device)
@@ -344,6 +358,15 @@ class RecurrentPPO:
             log["time/total_timesteps"] = self.num_timesteps
             log["rollout/reward_mean"] = float(self.buffer.rewards.mean())
             self.logs.append(log)
-            if callback is not None and callback(self, log) is False:
+            if cb is not None:
+                if not cb.on_rollout_end(self.n_steps, log):
+                    break
+            elif callback is not None and callback(self, log) is False:
                 break
+            if self._state is None:        # a callback evaluated on the training env and reset it
+                self._obs = self.env.reset_device()
+                self._starts = torch.ones(self.n_envs, dtype=torch.uint8, device=self.device)
+                self._state = self.policy.initial_state(self.n_envs)
+        if cb is not None:
+            cb.on_training_end()
         return self

@@ -361,3 +361,42 @@ def test_recurrent_ppo_on_the_pose_configs(product_lib, env_id, n, H):
     assert stats[3] <= 2e-3 and stats[4] <= 0.02, stats
     agent.learn(total_timesteps=n * T)
     assert np.isfinite(agent.logs[-1]["train/loss"]) and agent.logs[-1]["train/n_updates"] == 2
+
+
+def test_sb3_style_callbacks(product_lib, tmp_path):
+    """``agent.learn(total_timesteps, callback=[EvalCallback(...), CheckpointCallback(...)], reset_num_timesteps=True)`` as
+    /root/reference/src/main_baoding.py:84-125 calls it: checkpoints (zip + VecNormalize pickle) appear when a multiple of save_freq is
+    crossed, evaluations.npz grows every eval_freq calls, the best model is kept, and training continues from a fresh reset afterwards."""
+    from myochallenge_b200.callbacks import BaseCallback, CheckpointCallback, EvalCallback
+    from myochallenge_b200.envs import make_vec_env
+    from myochallenge_b200.ppo import RecurrentPPO
+    from myochallenge_b200.rollout import DeviceVecNormalize
+
+    n, T = 64, 8
+    env = make_vec_env("CustomMyoChallengeBaodingP2-v1", n, device=DEV, seed=2, clip_actions=True, max_episode_steps=6)
+    vn = DeviceVecNormalize(env, gamma=0.99)
+    eval_env = DeviceVecNormalize(make_vec_env("CustomMyoChallengeBaodingP2-v1", 32, device=DEV, seed=9, clip_actions=True, max_episode_steps=6), gamma=0.99,
+                                  training=False, norm_reward=False)
+    agent = RecurrentPPO("MlpLstmPolicy", vn, n_steps=T, batch_size=T * 32, n_epochs=1, learning_rate=1e-4,
+                         policy_kwargs=dict(lstm_hidden_size=64, net_arch=[dict(pi=[32], vf=[32])], log_std_init=-2.0), seed=1)
+
+    class Count(BaseCallback):
+        def _on_step(self):
+            self.seen = getattr(self, "seen", 0) + 1
+            return True
+
+    new_best = Count()
+    cbs = [EvalCallback(eval_env, callback_on_new_best=new_best, n_eval_episodes=40, eval_freq=16, log_path=str(tmp_path), best_model_save_path=str(tmp_path),
+                        deterministic=True, verbose=0),
+           CheckpointCallback(save_freq=24, save_path=str(tmp_path), save_vecnormalize="True")]
+    agent.learn(total_timesteps=6 * n * T, callback=cbs, reset_num_timesteps=True)          # 6 rollouts = 48 calls
+    assert len(agent.logs) == 6 and agent.num_timesteps == 6 * n * T
+    zips = sorted(f for f in os.listdir(tmp_path) if f.startswith("rl_model_") and f.endswith(".zip"))
+    pkls = sorted(f for f in os.listdir(tmp_path) if f.startswith("rl_model_vecnormalize_"))
+    assert len(zips) == 2 and len(pkls) == 2 and zips[0] == f"rl_model_{3 * n * T}_steps.zip"      # calls 24 and 48
+    ev = np.load(os.path.join(tmp_path, "evaluations.npz"))
+    assert list(ev["timesteps"]) == [2 * n * T, 4 * n * T, 6 * n * T] and ev["results"].shape == (3, 1) and ev["ep_lengths"].max() <= 6
+    assert os.path.exists(os.path.join(tmp_path, "best_model.zip")) and new_best.seen >= 1
+    assert "eval/mean_reward" in agent.logs[1] and "eval/mean_reward" not in agent.logs[0]
+    agent2 = RecurrentPPO.load(os.path.join(tmp_path, zips[-1]), env=vn)
+    assert torch.equal(agent2.update.params, agent.update.params)
