@@ -200,7 +200,7 @@ class RecurrentPPO:
                                       max_batch=venv.num_envs, device=self.device, use_sde=use_sde)
         self.use_sde, self.sde_sample_freq = bool(use_sde), int(sde_sample_freq)
         self.policy.init_random(seed, log_std_init=kw.get("log_std_init", 0.0))
-        self.policy.seed(seed + 1)
+        self.policy.seed(seed + 1 + 7919 * self._rank())       # same weights on every rank, different action noise
         if callable(clip_range):           # SB3 accepts schedules of the remaining progress; the kernels take the value at 1.0
             clip_range = float(clip_range(1.0))
         if callable(clip_range_vf):
@@ -292,6 +292,12 @@ class RecurrentPPO:
                 u.exp_avg[o: o + n].copy_(st["exp_avg"].reshape(-1)); u.exp_avg_sq[o: o + n].copy_(st["exp_avg_sq"].reshape(-1))
                 u.step_count = int(st["step"])
         return agent
+
+    @staticmethod
+    def _rank() -> int:
+        import torch.distributed as dist
+
+        return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
 
     @staticmethod
     def _world_size() -> int:
