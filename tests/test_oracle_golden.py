@@ -109,3 +109,26 @@ def test_energy_is_conserved_without_dissipation():
         ke_max = max(ke_max, 0.5 * d.qvel @ M @ d.qvel)
     assert ke_max > 1e-4                                # something moved
     assert abs(energy() - e0) < 0.05 * ke_max           # semi-implicit Euler drift stays a few % of the exchange
+
+
+def test_lengthrange_brackets_the_tendon_lengths_over_the_joint_box():
+    """SURVEY.md 8c (weaker fixture): MuJoCo stored ``actuator_lengthrange`` = the shortest / longest muscle length it reached by
+    simulation (pulling each muscle until equilibrium, so slightly past the soft joint limits and not necessarily at the global
+    extremum over the other joints). The oracle's tendon path over the whole joint box (corners + 3000 random poses, i.e. with
+    the sphere / cylinder wraps and pulleys engaged far from qpos0) must reproduce those extremes: within 1.5 % of each bound."""
+    import itertools
+
+    m, d = oracle.load(FINGER)
+    lr = np.array(m.actuator_lengthrange).reshape(-1, 2)
+    jr = np.array(m.jnt_range).reshape(-1, 2)
+    rng = np.random.default_rng(0)
+    pts = [np.array(c) for c in itertools.product(*[(a, b) for a, b in jr])] + [rng.uniform(jr[:, 0], jr[:, 1]) for _ in range(3000)]
+    mn, mx = np.full(lr.shape[0], np.inf), np.full(lr.shape[0], -np.inf)
+    for q in pts:
+        d.qpos[:] = q
+        d.call("o_fwd_position")
+        L = np.array(d.actuator_length)
+        mn, mx = np.minimum(mn, L), np.maximum(mx, L)
+    np.testing.assert_allclose(mn, lr[:, 0], rtol=1.5e-2)
+    np.testing.assert_allclose(mx, lr[:, 1], rtol=1.5e-2)
+    assert np.abs(mn[1:] / lr[1:, 0] - 1).max() < 5e-4        # four of the five lower bounds are reproduced to 0.05 %
