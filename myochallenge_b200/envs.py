@@ -121,7 +121,8 @@ def make_task_cfg(model: Model, env_id: str, **overrides) -> _capi.TaskCfg:
         for name, default in (("goal_time_period", (5, 5)), ("goal_xrange", (0.025, 0.025)), ("goal_yrange", (0.028, 0.028)),
                               ("obj_size_range", (0.018, 0.024)), ("obj_mass_range", (0.030, 0.300))):
             lo, hi = kw.pop(name, default)
-            getattr(cfg, name)[0], getattr(cfg, name)[1] = float(lo), float(hi)
+            # the curriculum's first step holds the targets still with goal_time_period = 1e100: keep it finite in fp32
+            getattr(cfg, name)[0], getattr(cfg, name)[1] = min(float(lo), 1e30), min(float(hi), 1e30)
         fc = kw.pop("obj_friction_change", (0.2, 0.001, 0.00002))
         for i in range(3):
             cfg.obj_friction_change[i] = float(fc[i])

@@ -173,7 +173,7 @@ def test_every_curriculum_step_maps_to_a_task_cfg(product_lib):
     m = Model(asset_path("hand/myo_hand_baoding.mjb"), lib=product_lib)
     cfgs = {s["step"][:2]: curriculum.task_cfg(s, m) for s in steps}
     c01, c04, c06, c15, c18, c23, c32 = (cfgs[k] for k in ("01", "04", "06", "15", "18", "23", "32"))
-    assert c01.p1_reset == 1 and c01.enable_rsi == 1 and c01.rsi_probability == 1.0 and c01.goal_time_period[0] > 1e30      # static targets
+    assert c01.p1_reset == 1 and c01.enable_rsi == 1 and c01.rsi_probability == 1.0 and 1e29 < c01.goal_time_period[0] < 3e38 and c01.goal_time_period[1] == c01.goal_time_period[0]      # static targets, finite in fp32
     assert c04.p1_reset == 1 and c04.task_choice_random == 1 and c04.rsi_probability == pytest.approx(0.9) and c04.drop_th == pytest.approx(1.3)
     assert c06.enable_rsi == 0 and tuple(c06.goal_time_period) == (10.0, 10.0)
     assert c15.p1_reset == 0 and c15.overlap_probability == pytest.approx(0.9)

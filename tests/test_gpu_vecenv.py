@@ -107,3 +107,32 @@ def test_rsi_and_beta_reset_matches_host_emulation(product_lib, emul_lib):
     obs = outs[0][0]
     on_target = np.abs(obs[:, 41:43]).max(1) < 1e-6
     assert 0.5 < on_target.mean() < 0.9            # rsi_probability 0.7
+
+
+def test_phase1_reset_and_curriculum_steps_on_gpu(product_lib, emul_lib):
+    """The phase-1 env's reset (RSI gate, ball / palm / finger noise, task selector) on the GPU against the host build of the same
+    sources, and a few steps of the packaged 32-step curriculum created through the factory and stepped."""
+    from conftest import HAND_BAODING
+    from myochallenge_b200 import curriculum
+    from myochallenge_b200.envs import make_task_cfg
+    from myochallenge_b200.sim import BatchSim, Model
+
+    n = 64
+    kw = dict(task="random", enable_rsi=True, rsi_probability=0.6, noise_palm=0.5, noise_fingers=0.3, noise_balls=0.001, drop_th=1.3)
+    outs = []
+    for lib, dev in ((product_lib, "cuda:0"), (emul_lib, "cpu")):
+        m = Model(HAND_BAODING, lib=lib)
+        sim = BatchSim(m, n, make_task_cfg(m, "CustomMyoChallengeBaodingP1-v1", **kw), device=dev, seed=4)
+        obs = sim.reset().cpu().numpy().copy()
+        o1 = sim.step(torch.zeros(n, sim.nu, device=dev))[0].cpu().numpy().copy()
+        outs.append((obs, o1))
+    for a, b in zip(*outs):
+        np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5)
+    steps = curriculum.load()
+    for k in (0, 3, 14, 22, 31):
+        env = EnvironmentFactory.create(steps[k]["env_name"], num_envs=32, seed=k, **steps[k]["config"])
+        obs = env.reset()
+        for _ in range(3):
+            obs, rew, done, infos = env.step(np.zeros((32, 39), np.float32))
+        assert obs.shape == (32, 86) and np.isfinite(obs).all() and np.isfinite(rew).all(), steps[k]["step"]
+        env.close()
