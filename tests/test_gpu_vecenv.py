@@ -129,10 +129,13 @@ def test_phase1_reset_and_curriculum_steps_on_gpu(product_lib, emul_lib):
     for a, b in zip(*outs):
         np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5)
     steps = curriculum.load()
-    for k in (0, 3, 14, 22, 31):
+    rng = np.random.default_rng(0)
+    for k in range(len(steps)):                       # all 32 steps of the winning curriculum
         env = EnvironmentFactory.create(steps[k]["env_name"], num_envs=32, seed=k, **steps[k]["config"])
         obs = env.reset()
-        for _ in range(3):
-            obs, rew, done, infos = env.step(np.zeros((32, 39), np.float32))
+        assert np.isfinite(obs).all(), steps[k]["step"]
+        for _ in range(12):
+            obs, rew, done, infos = env.step(rng.uniform(-1, 1, (32, 39)).astype(np.float32))
         assert obs.shape == (32, 86) and np.isfinite(obs).all() and np.isfinite(rew).all(), steps[k]["step"]
+        assert env.sim.status() & 8 == 0, steps[k]["step"]          # no non-finite state
         env.close()
