@@ -182,3 +182,26 @@ def test_every_curriculum_step_maps_to_a_task_cfg(product_lib):
     assert c32.limit_init_angle == pytest.approx(np.pi) and list(c32.rwd_weight)[:7] == [5, 5, 0, 1, 0, 5, 0]
     with pytest.raises(ValueError):
         make_task_cfg(m, "CustomMyoChallengeBaodingP1-v1", task="sideways")
+
+
+def test_host_vecnormalize_save_load_round_trip(tmp_path):
+    """``VecNormalize.load(path, venv)`` / ``.save(path)`` of the host-array class (the reference: src/main_eval.py:65-67,
+    src/train/trainer.py:73-75): statistics and switches survive, including ``training = False`` as evaluation scripts set it."""
+    class Venv(_FakeVenv):
+        class _A:
+            shape = (39,)
+        action_space = _A()
+
+    g = np.load(os.path.join(GOLDEN, "vecnormalize_baoding_step32.npz"))
+    v = VecNormalize.from_moments(Venv(), g["obs_mean"], g["obs_var"], g["obs_count"], g["ret_mean"], g["ret_var"], g["ret_count"], training=False,
+                                  norm_reward=False)
+    p = str(tmp_path / "env.pkl")
+    v.save(p)
+    w = VecNormalize.load(p, Venv())
+    np.testing.assert_array_equal(w.obs_rms.mean, v.obs_rms.mean); np.testing.assert_array_equal(w.obs_rms.var, v.obs_rms.var)
+    assert w.obs_rms.count == v.obs_rms.count and w.ret_rms.var == v.ret_rms.var and (w.training, w.norm_obs, w.norm_reward) == (False, True, False)
+    obs = np.tile(g["obs_mean"], (3, 1)).astype(np.float32) + 0.01
+    np.testing.assert_array_equal(w.normalize_obs(obs), v.normalize_obs(obs))
+    if os.path.isdir("/root/reference/trained_models"):       # the reference's own pickle, read directly
+        ref = VecNormalize.load("/root/reference/trained_models/curriculum_steps_complete_baoding_winner/32_phase_2_smaller_rate_resume/env.pkl", Venv())
+        np.testing.assert_array_equal(ref.obs_rms.mean, g["obs_mean"]); assert ref.clip_obs == 10.0 and ref.gamma == 0.99
