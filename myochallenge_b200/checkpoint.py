@@ -34,7 +34,20 @@ import numpy as np
 import torch
 
 SB3_VERSION = "1.6.2"       # /root/reference/requirements.txt:135
-_SAFE_MODULES = ("numpy", "builtins", "collections", "copyreg", "_codecs", "torch")
+# Explicit (module, name) allowlist for unpickling foreign files: array / scalar reconstruction and plain containers
+# only. Everything else - including builtins such as eval / exec / getattr / __import__ - resolves to an inert _Bag.
+_SAFE_GLOBALS = {
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy", "float32"), ("numpy", "float64"), ("numpy", "int64"), ("numpy", "int32"),
+    ("numpy", "bool_"), ("numpy", "uint8"),
+    ("collections", "OrderedDict"), ("collections", "deque"), ("copyreg", "_reconstructor"), ("_codecs", "encode"),
+    ("builtins", "object"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"), ("builtins", "frozenset"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "bool"), ("builtins", "str"), ("builtins", "bytes"), ("builtins", "bytearray"),
+    ("builtins", "complex"), ("builtins", "slice"), ("builtins", "range"),
+    ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_parameter"), ("torch", "FloatStorage"), ("torch", "DoubleStorage"),
+    ("torch", "LongStorage"), ("torch", "device"), ("torch", "Size"),
+}
 
 
 class _Bag:
@@ -62,10 +75,12 @@ class RNNStates(tuple):
 
 class _Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
-        if module.split(".")[0] in _SAFE_MODULES:
+        if (module, name) in _SAFE_GLOBALS:
             return super().find_class(module, name)
         if name == "RNNStates":
             return RNNStates
+        if (module, name) == ("torch.storage", "_load_from_bytes"):      # tensors inside cloudpickled attributes
+            return lambda b: torch.load(io.BytesIO(b), map_location="cpu", weights_only=True)
         return type(name, (_Bag,), {"__module__": module})
 
 
@@ -86,14 +101,31 @@ def _decode_data(raw: Dict[str, Any]) -> Dict[str, Any]:
     return out
 
 
+def sb3_save_path(path: str) -> str:
+    """SB3's ``open_path`` in write mode: '.zip' is appended only when the path has no suffix at all (the reference's
+    trainer saves 'final_model.pkl', which stays 'final_model.pkl')."""
+    import os
+
+    return path + ".zip" if os.path.splitext(path)[1] == "" else path
+
+
+def sb3_load_path(path: str) -> str:
+    """SB3's ``open_path`` in read mode: the path as given if it exists, else with '.zip' appended."""
+    import os
+
+    if os.path.exists(path) or os.path.splitext(path)[1] != "":
+        return path
+    return path + ".zip"
+
+
 def load_sb3_zip(path: str) -> Dict[str, Any]:
     """-> dict(state_dict, data, optimizer (or None), version). ``data`` holds the constructor / training attributes
     (``policy_kwargs``, ``n_steps``, ``batch_size``, ``gamma``, ..., ``_last_obs``, ``_last_lstm_states``)."""
     with zipfile.ZipFile(path) as z:
         names = set(z.namelist())
-        sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu")
+        sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
         raw = json.loads(z.read("data")) if "data" in names else {}
-        opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu") if "policy.optimizer.pth" in names else None
+        opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu", weights_only=True) if "policy.optimizer.pth" in names else None
         ver = z.read("_stable_baselines3_version").decode().strip() if "_stable_baselines3_version" in names else None
     data = _decode_data(raw)
     pk = data.get("policy_kwargs")

@@ -74,7 +74,8 @@ class PPOUpdate:
         self.n_params = int(self._L.myo_ppo_param_count(h))
         f = dict(dtype=torch.float32, device=self.device)
         self.params = torch.zeros(self.n_params, **f)
-        self.grad = torch.zeros(self.n_params, **f)
+        self._bucket = torch.zeros(self.n_params + 1, **f)       # flat gradient + one slot for approx_kl (reduced with it)
+        self.grad = self._bucket[: self.n_params]
         self.exp_avg = torch.zeros(self.n_params, **f)
         self.exp_avg_sq = torch.zeros(self.n_params, **f)
         self.stats = torch.zeros(len(STAT_NAMES), **f)
@@ -121,7 +122,12 @@ class PPOUpdate:
             C.byref(self.hyper), _p(self.grad), _p(self.stats), self._stream()))
         return self.stats
 
-    def all_reduce_grad(self) -> float:
+    def all_reduce_grad(self, with_kl: bool = False) -> float:
+        """One collective per optimiser step. ``with_kl``: approx_kl of this rank's minibatch rides in the last slot of
+        the bucket, so every rank sees the same (mean) value and takes the same early-stop branch."""
+        if with_kl:
+            self._bucket[self.n_params] = self.stats[3]
+            return allreduce_flat(self._bucket)
         return allreduce_flat(self.grad)
 
     def adam_step(self, grad_scale: float = 1.0, learning_rate: Optional[float] = None):
@@ -145,10 +151,12 @@ class PPOUpdate:
             perm = torch.randperm(n, generator=generator, device="cpu").to(self.device, dtype=torch.int32)
             for s in range(0, n, self.batch_worlds):
                 self.minibatch_grad(buf, perm[s: s + self.batch_worlds])
-                if target_kl is not None and float(self.stats[3]) > 1.5 * target_kl:
+                scale = self.all_reduce_grad(with_kl=target_kl is not None)
+                # SB3 stops before the optimiser step of the offending minibatch; the test is on the rank-mean approx_kl
+                # (reduced with the gradient) so no rank leaves the loop while the others wait in the collective
+                if target_kl is not None and float(self._bucket[self.n_params]) * scale > 1.5 * target_kl:
                     stop = True
                     break
-                scale = self.all_reduce_grad()
                 self.adam_step(scale, learning_rate)
                 acc += self.stats
                 count += 1
@@ -247,7 +255,7 @@ class RecurrentPPO:
         opt = {"state": {i: {"step": torch.tensor(float(u.step_count)), "exp_avg": m[i], "exp_avg_sq": v[i]} for i in range(len(names))} if u.step_count else {},
                "param_groups": [{"lr": u.learning_rate, "betas": tuple(u.betas), "eps": u.adam_eps, "weight_decay": 0, "amsgrad": False,
                                  "params": list(range(len(names)))}]}
-        checkpoint.save_sb3_zip(path if path.endswith(".zip") else path + ".zip", self.get_parameters()["policy"], data, opt)
+        checkpoint.save_sb3_zip(checkpoint.sb3_save_path(path), self.get_parameters()["policy"], data, opt)
 
     @classmethod
     def load(cls, path: str, env=None, custom_objects=None, **kwargs):
@@ -256,7 +264,7 @@ class RecurrentPPO:
         moments from ``policy.optimizer.pth`` when present."""
         from . import checkpoint
 
-        ck = checkpoint.load_sb3_zip(path if path.endswith(".zip") else path + ".zip")
+        ck = checkpoint.load_sb3_zip(checkpoint.sb3_load_path(path))
         d = dict(ck["data"])
         d.update(custom_objects or {})
         d.update(kwargs)
@@ -343,13 +351,23 @@ class RecurrentPPO:
             cb.on_training_start()
         if reset_num_timesteps:
             self.num_timesteps = 0
-        if self._state is None:
+        norm = self.env if hasattr(self.env, "obs_rms") and hasattr(self.env.obs_rms, "sync") else None
+
+        def fresh_reset():
+            # reset_device() folds this rank's reset observations into obs_rms: merge them across ranks at once, so the
+            # state every rank enters the next interval with (the next ``base``) is the same everywhere
+            base = norm.obs_rms.state.clone() if norm is not None else None
             self._obs = self.env.reset_device()
+            if norm is not None:
+                norm.obs_rms.sync(base)
+                norm._push_obs_norm()
             self._starts = torch.ones(self.n_envs, dtype=torch.uint8, device=self.device)
             self._state = self.policy.initial_state(self.n_envs)
+
+        if self._state is None:
+            fresh_reset()
         start = self.num_timesteps
         while self.num_timesteps - start < total_timesteps:
-            norm = self.env if hasattr(self.env, "obs_rms") and hasattr(self.env.obs_rms, "sync") else None
             base = (norm.obs_rms.state.clone(), norm.ret_rms.state.clone()) if norm is not None else None
             self._obs, self._starts = collect_rollouts(self.env, self.policy, self.buffer, self._state, self._obs, self._starts,
                                                                sde_sample_freq=self.sde_sample_freq)
@@ -370,9 +388,7 @@ class RecurrentPPO:
             elif callback is not None and callback(self, log) is False:
                 break
             if self._state is None:        # a callback evaluated on the training env and reset it
-                self._obs = self.env.reset_device()
-                self._starts = torch.ones(self.n_envs, dtype=torch.uint8, device=self.device)
-                self._state = self.policy.initial_state(self.n_envs)
+                fresh_reset()
         if cb is not None:
             cb.on_training_end()
         return self

@@ -71,16 +71,20 @@ class DeviceRunningMeanStd:
     def count(self):
         return self.state[2 * self.d]
 
-    def sync(self, base: "DeviceRunningMeanStd | None" = None):
-        """Merge the moments of all ranks (each rank saw its own worlds). ``base``: the common state every rank started
-        the interval from (so it is counted once); without it the ranks' states are merged as independent samples."""
+    def sync(self, base: "torch.Tensor | None" = None):
+        """Merge the moments of all ranks (each rank saw its own worlds). ``base``: the state THIS rank started the
+        interval from; every rank contributes what it added since (its state minus its own base) and the contributions
+        are merged in rank order onto rank 0's base, so all ranks end with the same state even if their bases differed.
+        Without ``base`` the ranks' states are merged as independent samples. Stays on the device (no host round trip)."""
         import torch.distributed as dist
 
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
-        merged = merge_moment_states([t.cpu().numpy() for t in _all_gather(self.state)], self.d,
-                                     None if base is None else base.cpu().numpy())
-        self.state.copy_(torch.from_numpy(merged).to(self.device))
+        mine = self.state if base is None else torch.cat([self.state, base.to(self.state)])
+        got = torch.stack(_all_gather(mine))
+        n = 2 * self.d + 1
+        merged = merge_moment_states(got[:, :n], self.d, bases=None if base is None else got[:, n:])
+        self.state.copy_(merged)
         _capi.check(self._L, self._L.myo_running_moments_export(_p(self.state), self.d, _p(self.mean_f), _p(self.var_f), _stream_ptr(self.device)))
 
 
@@ -92,39 +96,51 @@ def _all_gather(t):
     return out
 
 
-def merge_moment_states(states, d, base=None):
-    """Chan merge, in rank order, of per-rank RunningMeanStd states [mean(d), var(d), count] (host, fp64). With ``base``
-    (the state all ranks started from) each rank contributes only what it added since: its state minus the base."""
+def merge_moment_states(states, d, base=None, bases=None):
+    """Chan merge, in rank order, of per-rank RunningMeanStd states [mean(d), var(d), count] (fp64; numpy arrays or
+    torch tensors on any device, result of the same kind). ``bases`` (one per rank) or ``base`` (shared): the state each
+    rank started the interval from - a rank then contributes only what it added since (its state minus ITS base), merged
+    onto rank 0's base; a rank whose base differs from rank 0's still contributes exactly its own additions, so every
+    rank computes the same result. Branch-free, so the device version never synchronises with the host."""
+    as_numpy = not torch.is_tensor(states) and not torch.is_tensor(states[0])
+    S = torch.stack([torch.as_tensor(np.asarray(s) if as_numpy else s, dtype=torch.float64) for s in states]) if not torch.is_tensor(states) else states
+    K = S.shape[0]
+    if bases is not None:
+        B = torch.stack([torch.as_tensor(np.asarray(b) if as_numpy else b, dtype=torch.float64) for b in bases]) if not torch.is_tensor(bases) else bases
+    elif base is not None:
+        B = torch.as_tensor(np.asarray(base) if as_numpy else base, dtype=torch.float64).to(S.device).expand(K, -1)
+    else:
+        B = None
+
     def split(s):
-        return s[:d].copy(), s[d: 2 * d].copy(), float(s[2 * d])
+        return s[:d], s[d: 2 * d], s[2 * d]
 
     def merge(a, b):
         (ma, va, na), (mb, vb, nb) = a, b
-        if nb <= 0:
-            return a
         tot = na + nb
+        safe = torch.clamp(tot, min=1e-300)
         delta = mb - ma
-        return ma + delta * nb / tot, (va * na + vb * nb + delta * delta * na * nb / tot) / tot, tot
+        return ma + delta * nb / safe, (va * na + vb * nb + delta * delta * na * nb / safe) / safe, tot
 
-    def subtract(s, b):      # inverse of merge: the batch that turns b into s
+    def subtract(s, b):      # inverse of merge: the batch that turns b into s (count 0 when nothing was added)
         (ms, vs, ns), (mb, vb, nb) = s, b
-        nx = ns - nb
-        if nx <= 0:
-            return ms, vs, 0.0
-        mx = (ms * ns - mb * nb) / nx
+        nx = torch.clamp(ns - nb, min=0.0)
+        safe = torch.clamp(nx, min=1e-300)
+        mx = torch.where(nx > 0, (ms * ns - mb * nb) / safe, ms)
         delta = mx - mb
-        vx = (vs * ns - vb * nb - delta * delta * nb * nx / ns) / nx
-        return mx, np.maximum(vx, 0.0), nx
+        vx = torch.where(nx > 0, (vs * ns - vb * nb - delta * delta * nb * nx / torch.clamp(ns, min=1e-300)) / safe, vs)
+        return mx, torch.clamp(vx, min=0.0), nx
 
-    acc = split(states[0]) if base is None else split(base)
-    for k, s in enumerate(states):
-        if base is None:
-            if k == 0:
-                continue
-            acc = merge(acc, split(s))
-        else:
-            acc = merge(acc, subtract(split(s), split(base)))
-    return np.concatenate([acc[0], acc[1], [acc[2]]])
+    if B is None:
+        acc = split(S[0])
+        for k in range(1, K):
+            acc = merge(acc, split(S[k]))
+    else:
+        acc = split(B[0])
+        for k in range(K):
+            acc = merge(acc, subtract(split(S[k]), split(B[k])))
+    out = torch.cat([acc[0], acc[1], acc[2].reshape(1)])
+    return out.numpy() if as_numpy else out
 
 
 class DeviceVecNormalize:

@@ -113,3 +113,31 @@ def test_vecnormalize_round_trip_names_sb3_classes(tmp_path):
     assert {"obs_rms", "ret_rms", "clip_obs", "clip_reward", "gamma", "epsilon", "training", "norm_obs", "norm_reward", "num_envs", "observation_space",
             "action_space", "old_obs", "old_reward", "norm_obs_keys"} <= set(v.__dict__) and "venv" not in v.__dict__
     assert v.observation_space.__dict__["_shape"] == (86,) and v.action_space.__dict__["high"].max() == 1.0
+
+
+def test_unpickler_does_not_resolve_builtins_or_os(tmp_path):
+    """the loader must not hand out eval / exec / os.system: a crafted pickle gets inert stand-ins."""
+    import pickle
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("echo pwned > %s" % (tmp_path / "pwned"),))
+
+    class Evil2:
+        def __reduce__(self):
+            return (eval, ("__import__('os').getcwd()",))
+
+    for obj in (Evil(), Evil2()):
+        out = ck._loads(pickle.dumps(obj))
+        assert isinstance(out, ck._Bag)
+    assert not (tmp_path / "pwned").exists()
+
+
+def test_save_and_load_paths_follow_sb3_open_path(tmp_path):
+    assert ck.sb3_save_path("a/final_model.pkl") == "a/final_model.pkl"       # the reference's trainer.save name
+    assert ck.sb3_save_path("a/rl_model_100_steps") == "a/rl_model_100_steps.zip"
+    p = tmp_path / "final_model.pkl"
+    p.write_bytes(b"x")
+    assert ck.sb3_load_path(str(p)) == str(p)
+    assert ck.sb3_load_path(str(tmp_path / "model")) == str(tmp_path / "model") + ".zip"

@@ -135,3 +135,78 @@ def test_two_rank_rollout_moment_sync_gloo():
         np.testing.assert_allclose(merged[:3], ref.mean, rtol=1e-11)
         np.testing.assert_allclose(merged[3:6], ref.var, rtol=1e-9)
         assert merged[6] == pytest.approx(ref.count)
+
+
+def test_merge_with_per_rank_bases_is_rank_consistent_and_exact():
+    """ranks whose bases differ (each folded its own reset observations in before the base was
+    taken) must still end with one common state, and it must not drift when the merge is repeated rollout after rollout."""
+    from myochallenge_b200.rollout import merge_moment_states
+
+    rng = np.random.default_rng(5)
+    d, K = 3, 4
+
+    def state(r):
+        return np.concatenate([r.mean, r.var, [r.count]])
+
+    ranks = []
+    for k in range(K):
+        r = ro.RunningMeanStd(shape=(d,))
+        r.update(rng.normal(k, 1 + k, (8, d)))           # rank-specific reset batch: bases differ
+        ranks.append(r)
+    spread = []
+    for it in range(8):
+        bases = [state(r) for r in ranks]
+        batches = [rng.normal(0.5 * k, 2.0, (32, d)) for k in range(K)]
+        for r, b in zip(ranks, batches):
+            r.update(b)
+        states = [state(r) for r in ranks]
+        merged = [merge_moment_states(states, d, bases=bases) for _ in range(K)]      # what each rank computes
+        for m in merged[1:]:
+            np.testing.assert_array_equal(m, merged[0])
+        # exact: rank 0's base + every rank's batch of this interval
+        ref = ro.RunningMeanStd(shape=(d,))
+        ref.mean, ref.var, ref.count = bases[0][:d].copy(), bases[0][d:2 * d].copy(), bases[0][2 * d]
+        ref.update(np.concatenate(batches))
+        np.testing.assert_allclose(merged[0][:d], ref.mean, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(merged[0][d:2 * d], ref.var, rtol=1e-8)
+        assert merged[0][2 * d] == pytest.approx(ref.count)
+        for r in ranks:
+            r.mean, r.var, r.count = merged[0][:d].copy(), merged[0][d:2 * d].copy(), float(merged[0][2 * d])
+        spread.append(float(np.abs(merged[0][:d]).max()))
+    assert max(spread) < 5.0 and np.isfinite(spread).all()          # the r1 formula reached 2e3 here
+
+
+def _sync3_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from myochallenge_b200.rollout import _all_gather, merge_moment_states
+
+    rng = np.random.default_rng(100 + rank)
+    r = ro.RunningMeanStd(shape=(2,))
+    r.update(rng.normal(rank, 1, (5, 2)))                 # per-rank reset observations: a different base on every rank
+    out = []
+    for it in range(3):
+        base = torch.from_numpy(np.concatenate([r.mean, r.var, [r.count]]))
+        r.update(rng.normal(0, 1, (16, 2)))
+        mine = torch.cat([torch.from_numpy(np.concatenate([r.mean, r.var, [r.count]])), base])
+        got = torch.stack(_all_gather(mine))
+        m = merge_moment_states(got[:, :5], 2, bases=got[:, 5:]).numpy()
+        r.mean, r.var, r.count = m[:2].copy(), m[2:4].copy(), float(m[4])
+        out.append(m)
+    q.put((rank, np.stack(out)))
+    dist.destroy_process_group()
+
+
+def test_three_rank_sync_with_different_bases_gloo():
+    ctx = mp.get_context("spawn")
+    q, port = ctx.Queue(), _free_port()
+    ps = [ctx.Process(target=_sync3_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(timeout=60)
+    for _, m in res[1:]:
+        np.testing.assert_array_equal(m, res[0][1])          # every rank holds the same moments after every sync
+    counts = res[0][1][:, 4]
+    np.testing.assert_allclose(np.diff(counts), 48.0)          # 3 ranks x 16 samples per interval, nothing double counted
