@@ -176,6 +176,17 @@ int myo_batch_get_state(myo_batch* b, float* qpos_dev, float* qvel_dev, float* a
 /* values_dev: float[n_worlds][ncomp] for override slot (kind, id) declared in the task cfg */
 int myo_batch_set_param(myo_batch* b, int kind, int id, const float* values_dev, void* stream);
 int myo_batch_get_param(myo_batch* b, int kind, int id, float* values_dev, void* stream);
+/* Per-world task state - what the reference keeps as attributes of each env object between steps
+ * (/root/reference/src/envs/baoding.py:519-557: which_task, ball_{1,2}_starting_angle, x_radius, y_radius, the goal
+ * trajectory's time period, counter; /root/reference/src/envs/reorient.py:207-212: pos_dist, rot_dist of the last step).
+ *   ti_dev int32[n_worlds][MYO_TASK_STATE_I]: elapsed steps (TimeLimit), episode index (RNG key), task (0 hold, 1 cw, 2 ccw),
+ *                                             flags (bit 0: counter = elapsed + 1, the RSI reset's in-reset step)
+ *   tf_dev float[n_worlds][MYO_TASK_STATE_F]: start angle 1, start angle 2, x_radius, y_radius, time period, pos_dist, rot_dist, -
+ * Either pointer may be NULL. pose_target_dev float[n_worlds][nq]: the pose task's target_jnt_value. */
+#define MYO_TASK_STATE_I 4
+#define MYO_TASK_STATE_F 8
+int myo_batch_get_task_state(myo_batch* b, int32_t* ti_dev, float* tf_dev, float* pose_target_dev, void* stream);
+int myo_batch_set_task_state(myo_batch* b, const int32_t* ti_dev, const float* tf_dev, const float* pose_target_dev, void* stream);
 /* one env step for every world. actions[n,nu] in [-1,1]; obs[n,nobs]; reward[n]; done[n] (env
  * termination OR time limit, as SB3 sees it); truncated[n] (TimeLimit.truncated);
  * terminal_obs[n,nobs] (written for worlds that finished; may be NULL); info[n,MYO_INFO_TERMS]

@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmyo_b200.so")
 
 MYO_MAX_OVERRIDE = 4
 MYO_INFO_TERMS = 8
+TASK_STATE_I, TASK_STATE_F = 4, 8
 TASK_NONE, TASK_POSE, TASK_BAODING = 0, 1, 2
 PARAM_BODY_MASS, PARAM_GEOM_SIZE, PARAM_GEOM_FRICTION, PARAM_SITE_POS = 0, 1, 2, 3
 
@@ -93,6 +94,8 @@ SIGNATURES = {
     "myo_batch_get_state": (_i, [_vp, _fp, _fp, _fp, _fp, _vp]),
     "myo_batch_set_param": (_i, [_vp, _i, _i, _fp, _vp]),
     "myo_batch_get_param": (_i, [_vp, _i, _i, _fp, _vp]),
+    "myo_batch_get_task_state": (_i, [_vp, _vp, _fp, _fp, _vp]),
+    "myo_batch_set_task_state": (_i, [_vp, _vp, _fp, _fp, _vp]),
     "myo_batch_step": (_i, [_vp, _fp, _fp, _fp, _vp, _vp, _fp, _fp, _vp]),
     "myo_batch_mj_step": (_i, [_vp, _fp, _i, _vp]),
     "myo_batch_forward": (_i, [_vp, _fp, _vp]),

@@ -14,6 +14,8 @@ constexpr int CON_WORDS = 24;   // scratch words per contact record
 constexpr int SEG_WORDS = 8;    // table words per tendon segment record
 constexpr int SEG_OUT = 9;      // scratch words per tendon segment result: length, KT moment-arm slots
 constexpr int ROW_WORDS = 4;    // scratch words per constraint row (one float4)
+constexpr int kFastRows = 96;           // constraint rows of the fast layout: 32 limit rows + 4 x 16 contacts
+constexpr int kSoloRowsPerLane = 10;    // rows per lane the full-capacity (one world per CTA) kernel keeps in registers
 
 enum { J_FREE = 0, J_BALL = 1, J_SLIDE = 2, J_HINGE = 3 };
 enum { G_PLANE = 0, G_SPHERE = 2, G_CAPSULE = 3, G_ELLIPSOID = 4, G_CYLINDER = 5, G_BOX = 6 };
@@ -134,6 +136,9 @@ struct BatchPtrs {
   float* dump;   // [n][scratch_words] written by forward / mj_step mode (may be null)
   unsigned long long seed;
   const int* order;   // optional [n_alloc]: slot -> world, worlds grouped by their recent constraint count (null: identity)
+  // worlds the fast kernel hands to the full-capacity kernel of the same env step (see myo_kernels.cu): world index | kind << 30
+  int* redo_list;     // [n_alloc]
+  int* redo_count;    // [1]
   int* work;          // [n_alloc]: constraint rows of the world's last substep (the grouping key for the next step)
 };
 
@@ -142,7 +147,8 @@ enum { TF_ANGLE1 = 0, TF_ANGLE2 = 1, TF_XR = 2, TF_YR = 3, TF_PERIOD = 4, TF_WOR
 // o_misc scratch words
 enum { MI_NLIM = 0, MI_NCON = 1, MI_NEFC = 2, MI_ITER = 3, MI_STATUS = 4, MI_ONE = 5 /*float 1*/, MI_WORDS = 8 };
 
-enum StepMode { MODE_ENV_STEP = 0, MODE_MJ_STEP = 1, MODE_FORWARD = 2, MODE_GET_OBS = 3, MODE_RESET = 4 };
+enum StepMode { MODE_ENV_STEP = 0, MODE_MJ_STEP = 1, MODE_FORWARD = 2, MODE_GET_OBS = 3, MODE_RESET = 4, MODE_REDO = 5 };
+enum { REDO_STEP = 0, REDO_RESET = 1 };      // kinds of redo-list entries
 
 struct StepArgs {
   int mode, nsub;

@@ -40,8 +40,22 @@ namespace myo {
 
 constexpr int kThreads = 448;   // up to 14 one-warp worlds per CTA (register cap 144)
 
-template <int G>
-__device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G>& c, int w) {
+// hand world w to the full-capacity kernel of this env step
+MYO_DI void redo_push(const BatchPtrs& b, int w, int kind) {
+#ifdef MYO_EMUL
+  const int k = (*b.redo_count)++;
+#else
+  const int k = atomicAdd(b.redo_count, 1);
+#endif
+  b.redo_list[k] = w | (kind << 30);
+}
+
+// One world, one env step / reset / test hook. SOLO: the CTA holds this world only (full-capacity layout), so phases may be
+// called conditionally; otherwise every tile of the CTA must reach the same phase barriers and anything that needs extra
+// physics (a reset with reference-state initialisation) or more room (more contacts / limit rows than the fast layout
+// holds) is handed to the SOLO kernel through the redo list.
+template <int G, int RMAX, bool SOLO>
+__device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G>& c, int w, int kind) {
   MYO_M
   int status = 0;
   int* ti = b.task_i + (size_t)w * TI_WORDS;
@@ -50,10 +64,11 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
   int* misc = SI(o_misc);
   const bool io = w < b.n_worlds;                    // padding worlds never touch caller buffers
   const int wi = io ? w : b.n_worlds - 1;
-  if (a.mode == MODE_RESET) {
-    if (a.mask && !a.mask[wi]) return;
+  const bool redo_reset = a.mode == MODE_REDO && kind == REDO_RESET;
+  if (a.mode == MODE_RESET || redo_reset) {
+    if (a.mode == MODE_RESET && a.mask && !a.mask[wi]) return;
     load_world<G>(mslot, c, b, w);
-    task_reset<G>(mslot, t, c, b, w, ti, tf, ptarget);
+    task_reset<G, RMAX, SOLO>(mslot, t, c, b, w, ti, tf, ptarget);
     if (c.lane == 0) b.time[w] = 0.f;
     if (a.obs && io) {
       phase_tree_forward<G>(mslot, c, false);
@@ -74,22 +89,47 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
   if (a.mode == MODE_FORWARD || a.mode == MODE_MJ_STEP) {
     for (int i = c.lane; i < m.nu; i += G) SF(o_ctrl)[i] = a.in ? a.in[(size_t)wi * m.nu + i] : 0.f;
     c.tile.sync();
-    if (a.mode == MODE_FORWARD) mj_forward_dev<G>(mslot, c, &status, false);
+    if (a.mode == MODE_FORWARD) mj_forward_dev<G, RMAX>(mslot, c, &status, false);
     else {
-      for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(mslot, c, &status, false);
+      for (int s = 0; s < a.nsub; s++) mj_step_dev<G, RMAX>(mslot, c, &status, false);
       if (c.lane == 0) b.time[w] += (float)a.nsub * m.timestep;
     }
-  } else {   // MODE_ENV_STEP
+  } else {   // MODE_ENV_STEP (or its repetition with full capacities)
     if (t.kind == MYO_TASK_BAODING) baoding_targets<G>(mslot, t, c, ti, tf);
     task_action<G>(mslot, t, c, a.in + (size_t)wi * m.nu);
     c.tile.sync();
-    for (int s = 0; s < a.nsub; s++) mj_step_dev<G>(mslot, c, &status, true);
+    for (int s = 0; s < a.nsub; s++) mj_step_dev<G, RMAX>(mslot, c, &status, true);
+    if (!SOLO && b.redo_list) {
+      // outgrew the fast layout in some substep: nothing of this attempt is kept, the full-capacity kernel steps the world again
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) status |= c.tile.shfl_xor(status, o);
+      if (status & (ST_CON_OVERFLOW | ST_EFC_OVERFLOW)) {
+        if (c.lane == 0 && io) redo_push(b, w, REDO_STEP);
+        if (c.lane == 0 && b.work) b.work[w] = io ? 0 : 0x7fff;
+        if (io) return;
+        status &= ~(ST_CON_OVERFLOW | ST_EFC_OVERFLOW);
+      }
+    }
     // get_obs: kinematics at the post-step state (MyoSuite get_obs -> sim.forward)
     phase_tree_forward<G>(mslot, c, false);
     task_obs<G>(mslot, t, c, ptarget);
     float info[MYO_INFO_TERMS], reward;
     bool env_done;
     task_reward<G>(mslot, t, c, info, &reward, &env_done);
+    // a world whose state left the finite range ends its episode here (MuJoCo would warn and reset the data): the reset
+    // below keeps NaNs out of the running moments downstream
+    bool bad = false;
+    for (int i = c.lane; i < m.nq; i += G) bad |= !isfinite(SF(o_qpos)[i]);
+    for (int i = c.lane; i < m.nv; i += G) bad |= !isfinite(SF(o_qvel)[i]);
+    bad = c.tile.ballot(bad) != 0u;
+    if (bad) {
+      status |= ST_NONFINITE; env_done = true; reward = 0.f;
+#pragma unroll
+      for (int k = 0; k < MYO_INFO_TERMS; k++) info[k] = 0.f;
+      info[6] = 1.f;
+      for (int i = c.lane; i < m.nobs; i += G) SF(o_obs)[i] = 0.f;
+      c.tile.sync();
+    }
     const int elapsed = ti[TI_ELAPSED] + 1;
     const bool limit = t.max_episode_steps > 0 && elapsed >= t.max_episode_steps;
     const bool done = env_done || limit;
@@ -106,10 +146,16 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
     if (a.info && io) for (int k = c.lane; k < MYO_INFO_TERMS; k += G) a.info[(size_t)w * MYO_INFO_TERMS + k] = info[k];
     if (done && t.auto_reset) {
       if (a.terminal_obs && io) for (int i = c.lane; i < m.nobs; i += G) a.terminal_obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
-      task_reset<G>(mslot, t, c, b, w, ti, tf, ptarget);
-      if (c.lane == 0) b.time[w] = 0.f;
-      phase_tree_forward<G>(mslot, c, false);
-      task_obs<G>(mslot, t, c, ptarget);
+      if (!SOLO && reset_needs_physics(t)) {
+        // the reset runs an env step of its own (reference-state initialisation): done by the SOLO kernel, which also writes
+        // the first observation of the new episode; the terminal state is stored as it is
+        if (c.lane == 0 && io) redo_push(b, w, REDO_RESET);
+      } else {
+        task_reset<G, RMAX, SOLO>(mslot, t, c, b, w, ti, tf, ptarget);
+        if (c.lane == 0) b.time[w] = 0.f;
+        phase_tree_forward<G>(mslot, c, false);
+        task_obs<G>(mslot, t, c, ptarget);
+      }
     }
     if (io) for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
   }
@@ -120,10 +166,10 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
   if (c.lane == 0) {
     misc[MI_STATUS] = status;
     if (status && io) atomicOr(b.status, status);
-    if (a.mode == MODE_ENV_STEP && b.work) b.work[w] = io ? 0x7ffe - misc[MI_NEFC] : 0x7fff;      // heavy worlds first (the partial last wave of CTAs gets the light ones), padding worlds last
+    if ((a.mode == MODE_ENV_STEP || a.mode == MODE_REDO) && b.work) b.work[w] = io ? 0x7ffe - min(misc[MI_NEFC], 0x7ffe) : 0x7fff;      // heavy worlds first (the partial last wave of CTAs gets the light ones), padding worlds last
   }
   store_world<G>(mslot, c, b, w, true);
-  if (b.dump && a.mode != MODE_ENV_STEP) {
+  if (b.dump && (a.mode == MODE_FORWARD || a.mode == MODE_MJ_STEP)) {
     c.tile.sync();
     float* out = b.dump + (size_t)w * m.scratch_words;
     for (int i = c.lane; i < m.scratch_words; i += G) out[i] = c.sp()[i];
@@ -153,11 +199,35 @@ __global__ void __launch_bounds__(kThreads) world_kernel(int mslot, const __grid
   const int wpc = blockDim.x / G;
   const int tid = threadIdx.x / G;
   c.soff = m.tab_words + tid * m.scratch_words;
+  constexpr int RMAX = kFastRows / G > 0 ? kFastRows / G : 1;
   // state arrays are padded to a multiple of wpc worlds, so every tile of a CTA runs the same number of
   // iterations (the phases contain CTA-wide barriers); padding worlds are stepped but have no I/O
   for (int slot = blockIdx.x * wpc + tid; slot < b.n_alloc; slot += gridDim.x * wpc) {
     const int w = b.order ? b.order[slot] : slot;
-    run_world<G>(mslot, t, b, a, c, w);
+    run_world<G, RMAX, false>(mslot, t, b, a, c, w, 0);
+    c.tile.sync();
+  }
+}
+
+// Full-capacity kernel: ONE world per CTA (a single tile), scratch laid out with MuJoCo's own capacities (nconmax contacts,
+// njmax rows). It serves the redo list of an env step (worlds that outgrew the fast layout; resets that run physics), explicit
+// resets of tasks whose reset runs physics, and the parity hooks (forward / mj_step with stage dumps).
+template <int G>
+__global__ void __launch_bounds__(G < 32 ? 32 : G) solo_kernel(int mslot, const __grid_constant__ myo_task_cfg t,
+                                                             const __grid_constant__ BatchPtrs b, const __grid_constant__ StepArgs a) {
+  MYO_M
+  const int count = a.mode == MODE_REDO ? *b.redo_count : b.n_worlds;
+  if ((int)blockIdx.x >= count) return;
+  stage_tables(m);
+  cg::thread_block block = cg::this_thread_block();
+  cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
+  Ctx<G> c(tile);
+  c.soff = m.tab_words;
+  constexpr int RMAX = G == 1 ? kSoloRowsPerLane * 32 : kSoloRowsPerLane;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    int w = i, kind = 0;
+    if (a.mode == MODE_REDO) { const int e = b.redo_list[i]; w = e & 0x3fffffff; kind = e >> 30; }
+    run_world<G, RMAX, true>(mslot, t, b, a, c, w, kind);
     c.tile.sync();
   }
 }
@@ -290,8 +360,10 @@ struct myo_batch {
   myo::PackedModel pm;
   myo_task_cfg cfg;
   myo::BatchPtrs p{};
-  int device = 0, n = 0, slot = -1;
+  int device = 0, n = 0, slot = -1, slot_full = -1;
   int grid = 0, threads = myo::kThreads, smem = 0, regs = 0, wpc = 0, tab_bytes = 0;
+  int solo_grid = 0, solo_smem = 0, solo_regs = 0;
+  bool use_redo = false;       // env steps are followed by the full-capacity pass over the redo list
   int64_t launches = 0;
   std::vector<void*> allocs;
   // world grouping: after every env step the worlds are sorted by the constraint rows of their last substep, and the next
@@ -328,24 +400,30 @@ template <class T> int dev_alloc(myo_batch* b, T** p, size_t count) {
 // constant-memory model slots, per device
 std::mutex g_slot_mu;
 bool g_slot_busy[64][kModelSlots];
-int acquire_slot(myo_batch* b) {
+int acquire_slot(myo_batch* b) {      // two descriptors per batch: the fast layout and the full-capacity one
   std::lock_guard<std::mutex> lk(g_slot_mu);
   const int d = b->device & 63;
-  for (int s = 0; s < kModelSlots; s++)
-    if (!g_slot_busy[d][s]) { g_slot_busy[d][s] = true; b->slot = s; return MYO_OK; }
-  set_error("too many live batches on one device (16 model slots in constant memory)");
-  return MYO_E_LIMIT;
+  int got[2] = {-1, -1}, k = 0;
+  for (int s = 0; s < kModelSlots && k < 2; s++)
+    if (!g_slot_busy[d][s]) got[k++] = s;
+  if (k < 2) { set_error("too many live batches on one device (16 model slots in constant memory, two per batch)"); return MYO_E_LIMIT; }
+  g_slot_busy[d][got[0]] = g_slot_busy[d][got[1]] = true;
+  b->slot = got[0]; b->slot_full = got[1];
+  return MYO_OK;
 }
 void release_slot(myo_batch* b) {
   std::lock_guard<std::mutex> lk(g_slot_mu);
   if (b->slot >= 0) g_slot_busy[b->device & 63][b->slot] = false;
-  b->slot = -1;
+  if (b->slot_full >= 0) g_slot_busy[b->device & 63][b->slot_full] = false;
+  b->slot = b->slot_full = -1;
 }
 int upload_slot(myo_batch* b) {
 #ifdef MYO_EMUL
   c_models[b->slot] = b->pm.dm;
+  c_models[b->slot_full] = b->pm.dm_full;
 #else
   CK(cudaMemcpyToSymbol(c_models, &b->pm.dm, sizeof(DevModel), (size_t)b->slot * sizeof(DevModel)));
+  CK(cudaMemcpyToSymbol(c_models, &b->pm.dm_full, sizeof(DevModel), (size_t)b->slot_full * sizeof(DevModel)));
 #endif
   return MYO_OK;
 }
@@ -356,11 +434,27 @@ template <int G> int launch_world(myo_batch* b, const StepArgs& a, cudaStream_t 
   CK(cudaGetLastError());
   return MYO_OK;
 }
+template <int G> int launch_solo(myo_batch* b, const StepArgs& a, cudaStream_t st) {
+  const int want = a.mode == MODE_REDO ? b->solo_grid : std::min(b->n, b->solo_grid);
+  MYO_LAUNCH(solo_kernel<G>, std::max(1, want), G, b->solo_smem, st, b->slot_full, b->cfg, b->p, a);
+  b->launches++;
+  CK(cudaGetLastError());
+  return MYO_OK;
+}
+// fast kernel (many worlds per CTA, fast capacities)
 int launch(myo_batch* b, const StepArgs& a, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(b->device));
   int rc = MYO_OK;
   MYO_LANES_CASES(b, launch_world, b, a, st)
+  return rc;
+}
+// full-capacity kernel (one world per CTA)
+int launch_full(myo_batch* b, const StepArgs& a, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(b->device));
+  int rc = MYO_OK;
+  MYO_LANES_CASES(b, launch_solo, b, a, st)
   return rc;
 }
 template <int G> int configure(myo_batch* b) {
@@ -390,6 +484,17 @@ template <int G> int configure(myo_batch* b) {
   if (per_sm < 1) per_sm = 1;
   const int need = (b->n + wpc - 1) / wpc;
   b->grid = std::max(1, std::min(need, prop.multiProcessorCount * per_sm));
+  // full-capacity kernel: one world per CTA
+  const size_t full_bytes = (size_t)b->pm.dm_full.scratch_words * sizeof(float);
+  if (tab_bytes + full_bytes > prop.sharedMemPerBlockOptin) { set_error("model tables + one full-capacity world exceed shared memory per CTA"); return MYO_E_LIMIT; }
+  b->solo_smem = (int)(tab_bytes + full_bytes);
+  CK(cudaFuncSetAttribute(solo_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, b->solo_smem));
+  cudaFuncAttributes fs;
+  CK(cudaFuncGetAttributes(&fs, solo_kernel<G>));
+  b->solo_regs = fs.numRegs;
+  int solo_per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&solo_per_sm, solo_kernel<G>, G, b->solo_smem));
+  b->solo_grid = prop.multiProcessorCount * std::max(1, solo_per_sm);
   return MYO_OK;
 }
 
@@ -463,6 +568,8 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
     return fail(MYO_E_CUDA);
   }
   b->pm.dm.g_tables = b->pm.d_tables;
+  b->pm.dm_full.g_tables = b->pm.d_tables;
+  b->pm.dm_full.tab_words = b->pm.dm.tab_words;
   MYO_LANES_CASES(b, configure, b)
   if (rc) return fail(rc);
   if ((rc = acquire_slot(b)) || (rc = upload_slot(b))) return fail(rc);
@@ -477,6 +584,17 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
     return fail(rc);
   b->p.dump = nullptr;
   b->p.order = nullptr; b->p.work = nullptr;
+  b->p.redo_list = nullptr; b->p.redo_count = nullptr;
+  {
+    // the full-capacity pass after every env step is needed when the fast layout is smaller than MuJoCo's capacities or
+    // when resets run physics (MYO_REDO=0 switches it off for experiments: overflowing worlds are then truncated + flagged)
+    const myo::DevModel& df = b->pm.dm_full;
+    bool want = df.ncon_max > dm.ncon_max || df.nlim_max > dm.nlim_max || df.nefc_max > dm.nefc_max || myo::reset_needs_physics(*cfg);
+    if (const char* e = getenv("MYO_REDO")) want = want && atoi(e) != 0;
+    b->use_redo = want;
+    if ((rc = dev_alloc(b, &b->p.redo_list, n)) || (rc = dev_alloc(b, &b->p.redo_count, 4))) return fail(rc);
+    if (!want) b->p.redo_list = nullptr;
+  }
 #ifndef MYO_EMUL
   {
     const char* e = getenv("MYO_SORT_WORLDS");
@@ -536,7 +654,8 @@ int myo_batch_reset(myo_batch* b, const uint8_t* mask_dev, float* obs_dev, void*
   if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
   myo::StepArgs a{};
   a.mode = myo::MODE_RESET; a.mask = mask_dev; a.obs = obs_dev;
-  return launch(b, a, stream);
+  // a reset that runs physics (reference-state initialisation) is the full-capacity kernel's job
+  return myo::reset_needs_physics(b->cfg) ? launch_full(b, a, stream) : launch(b, a, stream);
 }
 
 int myo_batch_step(myo_batch* b, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
@@ -547,8 +666,13 @@ int myo_batch_step(myo_batch* b, const float* actions_dev, float* obs_dev, float
   a.in = actions_dev; a.obs = obs_dev; a.reward = reward_dev; a.done = done_dev; a.truncated = truncated_dev;
   a.terminal_obs = terminal_obs_dev; a.info = info_dev;
   b->p.order = (b->sort_worlds && b->cur_order >= 0) ? b->order[b->cur_order] : nullptr;
+  if (b->use_redo) CK(cudaMemsetAsync(b->p.redo_count, 0, sizeof(int), static_cast<cudaStream_t>(stream)));
   int rc = launch(b, a, stream);
   b->p.order = nullptr;
+  if (!rc && b->use_redo) {      // worlds the fast kernel could not finish: same step, full capacities, one world per CTA
+    a.mode = myo::MODE_REDO;
+    rc = launch_full(b, a, stream);
+  }
   if (rc || !b->sort_worlds) return rc;
 #ifndef MYO_EMUL
   // grouping for the next step: stable radix sort of (rows of the last substep, world); keys fit 15 bits
@@ -564,9 +688,9 @@ int myo_batch_step(myo_batch* b, const float* actions_dev, float* obs_dev, float
   return MYO_OK;
 }
 
-static int ensure_dump(myo_batch* b) {
+static int ensure_dump(myo_batch* b) {      // the parity hooks run in the full-capacity layout
   if (b->p.dump) return MYO_OK;
-  return dev_alloc(b, &b->p.dump, (size_t)b->p.n_alloc * b->pm.dm.scratch_words);
+  return dev_alloc(b, &b->p.dump, (size_t)b->p.n_alloc * b->pm.dm_full.scratch_words);
 }
 
 int myo_batch_mj_step(myo_batch* b, const float* ctrl_dev, int nsub, void* stream) {
@@ -575,7 +699,7 @@ int myo_batch_mj_step(myo_batch* b, const float* ctrl_dev, int nsub, void* strea
   if (rc) return rc;
   myo::StepArgs a{};
   a.mode = myo::MODE_MJ_STEP; a.nsub = nsub; a.in = ctrl_dev;
-  return launch(b, a, stream);
+  return launch_full(b, a, stream);
 }
 
 int myo_batch_forward(myo_batch* b, const float* ctrl_dev, void* stream) {
@@ -584,7 +708,7 @@ int myo_batch_forward(myo_batch* b, const float* ctrl_dev, void* stream) {
   if (rc) return rc;
   myo::StepArgs a{};
   a.mode = myo::MODE_FORWARD; a.in = ctrl_dev;
-  return launch(b, a, stream);
+  return launch_full(b, a, stream);
 }
 
 int myo_batch_get_obs(myo_batch* b, float* obs_dev, void* stream) {
@@ -627,6 +751,26 @@ int myo_batch_get_state(myo_batch* b, float* qpos_dev, float* qvel_dev, float* a
   return MYO_OK;
 }
 
+int myo_batch_get_task_state(myo_batch* b, int32_t* ti_dev, float* tf_dev, float* pose_target_dev, void* stream) {
+  if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
+  static_assert(myo::TI_WORDS == MYO_TASK_STATE_I && myo::TF_WORDS == MYO_TASK_STATE_F, "task state layout");
+  CK(cudaSetDevice(b->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ti_dev) CK(cudaMemcpyAsync(ti_dev, b->p.task_i, (size_t)b->n * myo::TI_WORDS * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (tf_dev) CK(cudaMemcpyAsync(tf_dev, b->p.task_f, (size_t)b->n * myo::TF_WORDS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (pose_target_dev) return repack(b, pose_target_dev, b->pm.dm.nq, 0, b->p.pose_target, b->pm.dm.nq4, 0, b->pm.dm.nq, stream);
+  return MYO_OK;
+}
+int myo_batch_set_task_state(myo_batch* b, const int32_t* ti_dev, const float* tf_dev, const float* pose_target_dev, void* stream) {
+  if (!b) { myo::set_error("null batch"); return MYO_E_ARG; }
+  CK(cudaSetDevice(b->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ti_dev) CK(cudaMemcpyAsync(b->p.task_i, ti_dev, (size_t)b->n * myo::TI_WORDS * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (tf_dev) CK(cudaMemcpyAsync(b->p.task_f, tf_dev, (size_t)b->n * myo::TF_WORDS * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (pose_target_dev) return repack(b, b->p.pose_target, b->pm.dm.nq4, 0, pose_target_dev, b->pm.dm.nq, 0, b->pm.dm.nq, stream);
+  return MYO_OK;
+}
+
 static const myo::PackedModel::Slot* find_slot(const myo_batch* b, int kind, int id) {
   for (const auto& s : b->pm.slots) if (s.kind == kind && s.id == id) return &s;
   return nullptr;
@@ -648,7 +792,7 @@ int myo_batch_get_param(myo_batch* b, int kind, int id, float* values_dev, void*
 
 int myo_batch_stage_dump(myo_batch* b, int stage, void* out_dev, int* width, void* stream) {
   if (!b || stage < 0 || stage >= MYO_STAGE_COUNT) { myo::set_error("bad stage"); return MYO_E_ARG; }
-  const myo::DevModel& d = b->pm.dm;
+  const myo::DevModel& d = b->pm.dm_full;
   int w = 0;
   switch (stage) {
     case MYO_STAGE_XPOS: w = 3 * d.nbody; break;

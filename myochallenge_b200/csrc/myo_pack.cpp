@@ -521,71 +521,90 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   }
 
   // ---------------------------------------------------------------- capacities + scratch layout
+  // Two layouts of the same tables: the FAST one (out.dm) keeps a world small enough that many share an SM - 16 contacts, 32
+  // limit rows - and the FULL one (out.dm_full) has MuJoCo's own capacities (nconmax contacts, njmax rows). A world that
+  // outgrows the fast layout during an env step is stepped again, from the same state, by the full-capacity kernel
+  // (myo_kernels.cu: redo list), so the capacities are a performance knob, never a change of results.
   int nlim = 0;
-  for (int j = 0; j < njnt; j++) if (jlimited[j] && (jtype[j] == J_HINGE || jtype[j] == J_SLIDE)) nlim++;
+  for (int j = 0; j < njnt; j++) if (jlimited[j] && (jtype[j] == J_HINGE || jtype[j] == J_SLIDE)) nlim += 2;
   d.any_tendon_limit = 0;
-  { std::vector<int> tl = ivec(m, "tendon_limited"); for (int t = 0; t < ntendon; t++) if (tl[t]) { nlim++; d.any_tendon_limit = 1; } }
-  d.nlim_max = std::max(1, std::min(nlim, 32));
-  d.ncon_max = std::max(1, std::min(d.npair, 16));
-  d.nefc_max = d.nlim_max + 4 * d.ncon_max;
+  { std::vector<int> tl = ivec(m, "tendon_limited"); for (int t = 0; t < ntendon; t++) if (tl[t]) { nlim += 2; d.any_tendon_limit = 1; } }
   if (nv > 64) { status = MYO_E_LIMIT; return "nv exceeds the dense solver limit (64)"; }
   out.lanes = nv <= 8 ? 8 : (nv <= 16 ? 16 : 32);
   if (const char* ov = getenv("MYO_LANES")) {   // development override of the tile width (8, 16 or 32)
     const int g = atoi(ov);
     if (g == 8 || g == 16 || g == 32) out.lanes = g;
   }
-
-  int off = 0;
-  auto take = [&](int words) { int o = off; off += pad4(std::max(words, 1)); return o; };
-  d.o_qpos = take(nq); d.o_qvel = take(nv); d.o_act = take(na); d.o_ctrl = take(nu); d.o_warm = take(nv);
-  d.o_wparam = take(d.nparam4);
-  d.o_xpos = take(3 * nbody); d.o_xmat = take(9 * nbody); d.o_xipos = take(3 * nbody);
-  d.o_cdof = take(6 * nv);
-  d.o_M = take(nM);
-  d.o_tenL = take(ntendon); d.o_tenV = take(ntendon); d.o_tenJ = take(ntendon * KT); d.o_actF = take(nu);
-  d.o_bias = take(nv); d.o_passive = take(nv); d.o_qact = take(nv); d.o_smooth = take(nv); d.o_qaccs = take(nv);
-  d.o_qacc = take(nv); d.o_qcon = take(nv); d.o_actdot = take(na);
-  // solver vectors; the observation (assembled after the last substep, when they are dead) shares their words
   {
-    const int a0 = off;
-    d.o_grad = take(nv); d.o_p = take(nv); d.o_Mp = take(nv); d.o_Ma = take(nv);
-    d.o_obs = a0;
-    off = a0 + std::max(off - a0, pad4(d.nobs));
-  }
-  d.o_misc = take(MI_WORDS);
-  // velocity-stage temporaries and the composite inertias are dead once M and qfrc_bias exist; the Newton Hessian
-  // (and the tendon phase's per-segment results) reuse their words
-  {
-    const int a0 = off;
-    d.o_cdofdot = take(6 * nv); d.o_cfrc = take(6 * nbody);
-    d.o_cinert = take(10 * nbody);
-    const int tmp_words = off - a0;
-    d.o_H = a0;
-    // dense Hessian, lower triangle by rows: rows 4a..4a+3 have the same length, ((a + 1) | 1) float4s (odd, so the four
-    // rows of a group start on different banks); one more row (pad4(nv) words) for the right-hand side
     d.nd = 0;
     for (int i = 0; i < nv; i++) if (!dsimple[i]) d.nd = i + 1;
+    // dense Hessian, lower triangle by rows: rows 4a..4a+3 have the same length, ((a + 1) | 1) float4s (odd, so the four
+    // rows of a group start on different banks); one more row (pad4(nv) words) for the right-hand side
     const int n4 = pad4(nv);
     std::vector<int> roff(n4 + 1, 0);
     int hw = 0;
     for (int i = 0; i < n4; i++) { roff[i] = hw; hw += 4 * ((i / 4 + 1) | 1); }
-    roff[n4] = hw; hw += n4;
+    roff[n4] = hw;
     B.I(d.h_roff, roff);
     // (a, b), a >= b, of pair e = a (a + 1) / 2 + b for the contact blocks of the Hessian: a | b << 8
     std::vector<int> pair_ab;
     for (int a = 0; a < KS; a++) for (int b2 = 0; b2 <= a; b2++) pair_ab.push_back(a | (b2 << 8));
     B.I(d.pair_ab, pair_ab);
-    off = a0 + std::max(tmp_words, hw);
-    // limit / contact / row records follow directly: the tendon phase runs before they are rebuilt, so its per-segment
-    // results may run on from the Hessian's words into theirs
-    d.o_lim = take(d.nlim_max * LIM_WORDS); d.o_con = take(d.ncon_max * CON_WORDS); d.o_row = take(d.nefc_max * ROW_WORDS);
-    off = std::max(off, a0 + pad4(d.nseg * SEG_OUT));
   }
-  // world stride: tiles of one warp land on different banks
-  if (out.lanes < 32) { while (off % 32 != out.lanes) off += 4; }
-  else if (off % 32 == 0) off += 4;
-  d.scratch_words = off;
+  int ncon_fast = 16, nlim_fast = 32;
+  if (const char* ov = getenv("MYO_NCON_CAP")) { const int v = atoi(ov); if (v >= 1 && v <= 16) ncon_fast = v; }     // development: fast-layout capacities
+  if (const char* ov = getenv("MYO_NLIM_CAP")) { const int v = atoi(ov); if (v >= 1 && v <= 32) nlim_fast = v; }
   B.finish();
+  const int njmax = std::max(1, m.sz("njmax")), nconmax = std::max(1, m.sz("nconmax"));
+  auto layout = [&](DevModel& dd, int nlim_cap, int ncon_cap, int nefc_cap) {
+    dd.nlim_max = std::max(1, std::min(nlim, nlim_cap));
+    dd.ncon_max = std::max(1, std::min(dd.npair, ncon_cap));
+    dd.nefc_max = std::min(dd.nlim_max + 4 * dd.ncon_max, nefc_cap);
+    int off = 0;
+    auto take = [&](int words) { int o = off; off += pad4(std::max(words, 1)); return o; };
+    dd.o_qpos = take(nq); dd.o_qvel = take(nv); dd.o_act = take(na); dd.o_ctrl = take(nu); dd.o_warm = take(nv);
+    dd.o_wparam = take(dd.nparam4);
+    dd.o_xpos = take(3 * nbody); dd.o_xmat = take(9 * nbody); dd.o_xipos = take(3 * nbody);
+    dd.o_cdof = take(6 * nv);
+    dd.o_M = take(nM);
+    dd.o_tenL = take(ntendon); dd.o_tenV = take(ntendon); dd.o_tenJ = take(ntendon * KT); dd.o_actF = take(nu);
+    dd.o_bias = take(nv); dd.o_passive = take(nv); dd.o_qact = take(nv); dd.o_smooth = take(nv); dd.o_qaccs = take(nv);
+    dd.o_qacc = take(nv); dd.o_qcon = take(nv); dd.o_actdot = take(na);
+    // solver vectors; the observation (assembled after the last substep, when they are dead) shares their words
+    {
+      const int a0 = off;
+      dd.o_grad = take(nv); dd.o_p = take(nv); dd.o_Mp = take(nv); dd.o_Ma = take(nv);
+      dd.o_obs = a0;
+      off = a0 + std::max(off - a0, pad4(dd.nobs));
+    }
+    dd.o_misc = take(MI_WORDS);
+    // velocity-stage temporaries and the composite inertias are dead once M and qfrc_bias exist; the Newton Hessian
+    // (and the tendon phase's per-segment results) reuse their words
+    {
+      const int a0 = off;
+      dd.o_cdofdot = take(6 * nv); dd.o_cfrc = take(6 * nbody);
+      dd.o_cinert = take(10 * nbody);
+      const int tmp_words = off - a0;
+      dd.o_H = a0;
+      const int n4 = pad4(nv);
+      int hw = 0;
+      for (int i = 0; i < n4; i++) hw += 4 * ((i / 4 + 1) | 1);
+      hw += n4;
+      off = a0 + std::max(tmp_words, hw);
+      // limit / contact / row records follow directly: the tendon phase runs before they are rebuilt, so its per-segment
+      // results may run on from the Hessian's words into theirs
+      dd.o_lim = take(dd.nlim_max * LIM_WORDS); dd.o_con = take(dd.ncon_max * CON_WORDS); dd.o_row = take(dd.nefc_max * ROW_WORDS);
+      off = std::max(off, a0 + pad4(dd.nseg * SEG_OUT));
+    }
+    // world stride: tiles of one warp land on different banks
+    if (out.lanes < 32) { while (off % 32 != out.lanes) off += 4; }
+    else if (off % 32 == 0) off += 4;
+    dd.scratch_words = off;
+  };
+  layout(d, nlim_fast, ncon_fast, nlim_fast + 4 * ncon_fast);
+  out.dm_full = d;
+  // full capacities, bounded by what the solo kernel keeps in registers per lane (kSoloRowsPerLane rows)
+  layout(out.dm_full, njmax, nconmax, std::min(njmax, kSoloRowsPerLane * out.lanes));
   status = MYO_OK;
   return "";
 }

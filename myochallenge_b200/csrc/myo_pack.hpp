@@ -10,7 +10,8 @@
 namespace myo {
 
 struct PackedModel {
-  DevModel dm{};                 // tables are word offsets into the table block
+  DevModel dm{};                 // tables are word offsets into the table block; scratch layout with the FAST capacities
+  DevModel dm_full{};            // same tables, scratch layout with MuJoCo's own capacities (nconmax contacts, njmax rows)
   std::vector<int> ibuf;         // all int tables, concatenated
   std::vector<float> fbuf;       // all float tables, concatenated
   std::vector<TabF*> ffix;       // float tables: offsets get shifted by ibuf.size() once packing is done

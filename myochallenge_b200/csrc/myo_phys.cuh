@@ -1405,7 +1405,7 @@ MYO_DI bool cta_any(bool v) {
   return __syncthreads_or(v ? 1 : 0) != 0;
 #endif
 }
-template <int G>
+template <int G, int RMAX>
 MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
   MYO_M
   int* misc = SI(o_misc);
@@ -1422,7 +1422,7 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
   }
   float* Ma = SF(o_Ma); float* grad = SF(o_grad); float* p = SF(o_p); float* Mp = SF(o_Mp);
   // constraint rows in registers for the reductions and the line search: lane owns rows lane, lane + G, ...
-  constexpr int RMAX = 96 / G > 0 ? 96 / G : 1;     // nefc_max <= 32 + 4 * 16 (pack_model)
+  // RMAX rows per lane: nefc_max <= RMAX * G (pack_model: kFastRows for the fast layout, kSoloRowsPerLane * G for the full one)
   auto row_cost = [&](int field) {
     float part = 0.f;
     for (int r = c.lane; r < nefc; r += G) { const float* row = rows + r * ROW_WORDS; const float j = row[field]; if (j < 0.f) part += 0.5f * row[R_D] * j * j; }
@@ -1593,7 +1593,7 @@ MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
 }
 
 // one full mj_step on the world in scratch
-template <int G>
+template <int G, int RMAX>
 MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_M
   MYO_PH_BEGIN
@@ -1607,12 +1607,12 @@ MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_SYNC(5) phase_actuation<G>(mslot, c); MYO_PH(7)
   if (!fast || SI(o_misc)[MI_NEFC] == 0) solve_M_dense<G>(mslot, c, m.o_qaccs, 0.f);   // qacc_smooth (see phase_solve)
   MYO_PH(8)
-  MYO_SYNC(6) phase_solve<G>(mslot, c, fast); MYO_PH(9)
+  MYO_SYNC(6) phase_solve<G, RMAX>(mslot, c, fast); MYO_PH(9)
 }
-template <int G>
+template <int G, int RMAX>
 MYO_PHASE void mj_step_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_M
-  mj_forward_dev<G>(mslot, c, status, fast);
+  mj_forward_dev<G, RMAX>(mslot, c, status, fast);
   MYO_PH_BEGIN
   MYO_SYNC(7) MYO_PH(15) phase_integrate<G>(mslot, c); MYO_PH(10)
 }

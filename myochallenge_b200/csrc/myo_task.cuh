@@ -42,11 +42,11 @@ MYO_PHASE void store_world(int mslot, Ctx<G>& c, const BatchPtrs& b, int w, bool
 // BaseV0.step: muscle actuators with normalize_act get ctrl = 1/(1+exp(-5(a-0.5))); other actuators
 // are de-normalised linearly into ctrlrange (MyoSuite Robot.normalize_actions).
 template <int G>
-MYO_PHASE void task_action(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float* a) {
+MYO_PHASE void task_action(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float* a) {      // a == nullptr: the zero action
   MYO_M
   float* ctrl = SF(o_ctrl);
   for (int i = c.lane; i < m.nu; i += G) {
-    float u = a[i];
+    float u = a ? a[i] : 0.f;
     if (t.clip_actions) u = clipf(u, -1.f, 1.f);
     if (t.normalize_act) {
       if (m.a_dyntype[i] == 3) u = 1.f / (1.f + expf(-5.f * (u - 0.5f)));
@@ -163,14 +163,19 @@ MYO_PHASE void task_reward(int mslot, const myo_task_cfg& t, Ctx<G>& c, float* i
   *reward = dense; *done = dn;
 }
 
+// does this task's reset run physics (the reference's RSI branch calls self.step(zeros) inside reset())? Such resets are only
+// performed by the one-world-per-CTA kernel (SOLO), which may call the substep phases conditionally.
+inline __host__ __device__ bool reset_needs_physics(const myo_task_cfg& t) { return t.kind == MYO_TASK_BAODING && t.enable_rsi != 0; }
+
 // env.reset(): sample the task's reset distribution with a counter-based RNG keyed by
 // (seed, world, episode) and write the initial state into scratch.
-template <int G>
+template <int G, int RMAX, bool SOLO>
 MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const BatchPtrs& b, int w, int* ti,
                            float* tf, float* pose_target) {
   MYO_M
   float* qpos = SF(o_qpos);
   const int episode = ti[TI_EPISODE] + 1;
+  float nf_th = 0.f, nf_fl = 0.f;      // phase-2 finger noise (lane 0), applied after the RSI branch as the reference orders it
   c.tile.sync();
   if (!(t.kind == MYO_TASK_POSE && t.reset_type == 0)) {   // reset_type "none" keeps the last state
     for (int i = c.lane; i < m.nq; i += G) qpos[i] = m.init_qpos[i];
@@ -216,8 +221,12 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         }
         else a1 = rng.uniform(0.f, 2.f * kPi);
       } else {
+        // task_choice "fixed": the start angles are drawn ONCE per env object, in _setup (:326-331), and reset() never touches
+        // them again: one draw per world, the same in every episode
         ti[TI_TASK] = t.fixed_task;
-        a1 = (rng.uniform() < t.overlap_probability) ? 0.75f * kPi : 0.25f * kPi;
+        Philox once;
+        once.init(b.seed ^ 0xD1B54A32D192ED03ull, (uint32_t)w, 0u);
+        a1 = (once.uniform() < t.overlap_probability) ? 0.75f * kPi : 0.25f * kPi;
       }
       tf[TF_ANGLE1] = a1; tf[TF_ANGLE2] = a1 - kPi;
       tf[TF_XR] = rng.uniform(t.goal_xrange[0], t.goal_xrange[1]);
@@ -262,10 +271,9 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         }
       }
       // RSI (/root/reference/src/envs/baoding.py:606-638): new start angles, one env.step(zeros) on the freshly reset env,
-      // then the balls are put on the targets that step placed. What survives the final set_state(qpos, qvel) is: the
-      // target site positions (moved only for the rotation tasks, a7), self.counter = 1, and the muscle activations
-      // after one zero-action env step (set_state restores qpos / qvel only). All three are closed-form, so no physics
-      // step is run here: the kinematics pass below only reads the target sites' world positions.
+      // then the balls are put on the targets' world xy as that step's observation shows them, and set_state(qpos, qvel)
+      // restores the hand pose and zero velocities (activations, time and the warm start keep what the step left). The
+      // targets ride on the palm, which sags a little during the step, so the step is really run (below, SOLO kernel).
       ti[TI_FLAGS] = 0;
       if (t.enable_rsi && rng.uniform() < t.rsi_probability) {
         ti[TI_FLAGS] = 1;
@@ -284,12 +292,8 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         if (!t.balls_overlap) { tf[TF_ANGLE1] = rng.uniform(0.f, 2.f * kPi); tf[TF_ANGLE2] = tf[TF_ANGLE1] - kPi; }
       }
       if (t.noise_fingers > 0.f && m.nq - 14 >= 23) {   // _add_noise_to_finger_positions: one draw per group
-        const float th = rng.uniform(-kPi / 18.f * t.noise_fingers, kPi / 18.f * t.noise_fingers);
-        qpos[4] = th; qpos[5] = th; qpos[6] = th;
-        const float fl = rng.uniform(0.f, kPi / 6.f * t.noise_fingers);
-        const int idx[12] = {7, 9, 10, 11, 13, 14, 15, 17, 18, 19, 21, 22};
-#pragma unroll
-        for (int k = 0; k < 12; k++) qpos[idx[k]] = fl;
+        nf_th = rng.uniform(-kPi / 18.f * t.noise_fingers, kPi / 18.f * t.noise_fingers);
+        nf_fl = rng.uniform(0.f, kPi / 6.f * t.noise_fingers);
       }
     } else if (t.kind == MYO_TASK_POSE) {
       // update_target: sample target_jnt_value inside target_jnt_range, then get_target_pose scales the
@@ -311,40 +315,36 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
     }
   }
   c.tile.sync();
-  if (t.kind == MYO_TASK_BAODING && t.enable_rsi && (ti[TI_FLAGS] & 1)) {
-    phase_tree_forward<G>(mslot, c, false);
-    if (c.lane == 0) {
+  if constexpr (SOLO) {
+    if (t.kind == MYO_TASK_BAODING && t.enable_rsi && (ti[TI_FLAGS] & 1)) {
+      // self.step(np.zeros(nu)): the target sites already sit at goal[0] + the RSI angles (rotation tasks), the zero action
+      // goes through BaseV0.step's remap, Robot.step runs frame_skip substeps, get_obs -> sim.forward
+      task_action<G>(mslot, t, c, nullptr);
+      c.tile.sync();
+      int st = 0;
+      for (int sub = 0; sub < t.frame_skip; sub++) mj_step_dev<G, RMAX>(mslot, c, &st, true);
+      phase_tree_forward<G>(mslot, c, false);
+      float g[2][3];
 #pragma unroll
-      for (int k = 0; k < 2; k++) {      // qpos[23,24] = obs[35,36]; qpos[30,31] = obs[38,39] (:627-631): ball xy <- target xy
-        float g[3];
-        site_world(m, c.sp(), c.wpp(m), t.target_site[k], g);
-        qpos[t.ball_qposadr[k]] = g[0]; qpos[t.ball_qposadr[k] + 1] = g[1];
+      for (int k = 0; k < 2; k++) site_world(m, c.sp(), c.wpp(m), t.target_site[k], g[k]);
+      c.tile.sync();
+      // qpos = init_qpos.copy(); qpos[23, 24] = obs[35, 36]; qpos[30, 31] = obs[38, 39]; set_state(qpos, init_qvel) (:627-632)
+      for (int i = c.lane; i < m.nq; i += G) qpos[i] = m.init_qpos[i];
+      for (int i = c.lane; i < m.nv; i += G) SF(o_qvel)[i] = 0.f;
+      c.tile.sync();
+      if (c.lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 2; k++) { qpos[t.ball_qposadr[k]] = g[k][0]; qpos[t.ball_qposadr[k] + 1] = g[k][1]; }
       }
+      c.tile.sync();
     }
-    // data.act after env.step(zeros): ctrl = remap(0) held for frame_skip substeps of the activation dynamics (mj_fwdActuation +
-    // mj_Euler's act += h act_dot, muscle activations clamped to [0, 1]), starting from act = 0
-    for (int i = c.lane; i < m.nu; i += G) {
-      const int ai = i - (m.nu - m.na);
-      if (ai < 0) continue;
-      const int dyn = m.a_dyntype[i];
-      const float lo = (m.g_tables + m.a_ctrlrange.off)[2 * i], hi = (m.g_tables + m.a_ctrlrange.off)[2 * i + 1];
-      float u = 0.f;
-      if (t.normalize_act) u = dyn == 3 ? 1.f / (1.f + expf(2.5f)) : 0.5f * (lo + hi);
-      if (m.a_ctrllimited[i]) u = clipf(u, lo, hi);
-      const float* dp = m.g_tables + m.a_dynprm.off + 3 * i;
-      float a = 0.f;
-      for (int s = 0; s < t.frame_skip; s++) {
-        float adot = 0.f;
-        if (dyn == 3) {
-          const float uc = clipf(u, 0.f, 1.f), ac = clipf(a, 0.f, 1.f);
-          const float tau = (uc > a) ? dp[0] * (0.5f + 1.5f * ac) : dp[1] / (0.5f + 1.5f * ac);
-          adot = (uc - a) / fmaxf(kMinVal, tau);
-        } else if (dyn == 1) adot = u;
-        else if (dyn == 2) adot = (u - a) / fmaxf(kMinVal, dp[0]);
-        a += m.timestep * adot;
-        if (dyn == 3) a = clipf(a, 0.f, 1.f);
-      }
-      SF(o_act)[ai] = a;
+  }
+  if (t.kind == MYO_TASK_BAODING && !t.p1_reset && t.noise_fingers > 0.f && m.nq - 14 >= 23) {
+    if (c.lane == 0) {
+      qpos[4] = nf_th; qpos[5] = nf_th; qpos[6] = nf_th;
+      const int idx[12] = {7, 9, 10, 11, 13, 14, 15, 17, 18, 19, 21, 22};
+#pragma unroll
+      for (int k = 0; k < 12; k++) qpos[idx[k]] = nf_fl;
     }
     c.tile.sync();
   }

@@ -187,6 +187,23 @@ class BatchSim:
         check(self._L, self._L.myo_batch_get_param(self._h, int(kind), int(obj_id), _ptr(v), self._stream()))
         return v
 
+    def get_task_state(self):
+        """Per-world task state (see ``myo_batch_get_task_state``): (ti int32[n, 4] = elapsed, episode, task, flags;
+        tf float32[n, 8] = angle1, angle2, x_radius, y_radius, period, pos_dist, rot_dist, -; pose target float32[n, nq])."""
+        ti = torch.empty(self.n, _capi.TASK_STATE_I, dtype=torch.int32, device=self.device)
+        tf = torch.empty(self.n, _capi.TASK_STATE_F, dtype=torch.float32, device=self.device)
+        pt = torch.empty(self.n, self.nq, dtype=torch.float32, device=self.device)
+        check(self._L, self._L.myo_batch_get_task_state(self._h, _ptr(ti), _ptr(tf), _ptr(pt), self._stream()))
+        return ti, tf, pt
+
+    def set_task_state(self, ti=None, tf=None, pose_target=None):
+        i = None if ti is None else torch.as_tensor(ti, device=self.device).to(torch.int32).contiguous()
+        f = None if tf is None else self._f32(tf, (self.n, _capi.TASK_STATE_F))
+        p = None if pose_target is None else self._f32(pose_target, (self.n, self.nq))
+        if i is not None and tuple(i.shape) != (self.n, _capi.TASK_STATE_I):
+            raise ValueError("ti must be [n, %d]" % _capi.TASK_STATE_I)
+        check(self._L, self._L.myo_batch_set_task_state(self._h, _ptr(i), _ptr(f), _ptr(p), self._stream()))
+
     def stage(self, name: str) -> torch.Tensor:
         """Per-component parity hook: a stage result of the last ``forward`` / ``mj_step`` substep."""
         sid = _capi.STAGES[name]

@@ -352,8 +352,26 @@ HAND_JOINTS = ['pro_sup', 'deviation', 'flexion', 'cmc_abduction', 'cmc_flexion'
 HAND_MUSCLES = ['ECRL', 'ECRB', 'ECU', 'FCR', 'FCU', 'PL', 'PT', 'PQ', 'FDS5', 'FDS4', 'FDS3', 'FDS2', 'FDP5', 'FDP4', 'FDP3',
                 'FDP2', 'EDC5', 'EDC4', 'EDC3', 'EDC2', 'EDM', 'EIP', 'EPL', 'EPB', 'FPL', 'APL', 'OP', 'RI2', 'LU_RB2', 'UI_UB2',
                 'RI3', 'LU_RB3', 'UI_UB3', 'RI4', 'LU_RB4', 'UI_UB4', 'RI5', 'LU_RB5', 'UI_UB5']
-P0 = np.array([-0.2415, -0.455, 1.415])          # wrist centre (design pose = palm up, pro_sup = -1.57)
-ORBIT_C = P0 + np.array([0.0, -0.055, 0.0])      # centre of the target orbit on the palm
+# The one MuJoCo-produced hand observation in the reference (trained_models/phase_1/phase1_final.zip:_last_original_obs, a
+# just-reset Baoding P1 env) pins where the balls start and where the target sites are in the world at the
+# initial pose: the stand-in is placed so that its reset observation reproduces those numbers (tests/test_envs_host.py).
+REF_BALL_POS = {1: np.array([-0.227, -0.511, 1.452]), 2: np.array([-0.256, -0.552, 1.442])}
+REF_TARGET_POS = {1: np.array([-0.21591, -0.51066, 1.44507]), 2: np.array([-0.25508, -0.54608, 1.45052])}
+P0 = np.array([-0.2357, -0.4734, 1.408])          # wrist centre (design pose = palm up, pro_sup = -1.57)
+ORBIT_C = P0 + np.array([0.0, -0.055, 0.0])      # centre of the palm under the target orbit
+
+
+def _rot_between(a, b):
+    """Smallest rotation matrix taking direction a onto direction b."""
+    a, b = _unit(a), _unit(b)
+    v, c = np.cross(a, b), float(np.dot(a, b))
+    K = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+    return np.eye(3) + K + K @ K / (1.0 + c)
+
+
+def _mat2quat(R):
+    w = np.sqrt(max(0.0, 1.0 + R[0, 0] + R[1, 1] + R[2, 2])) / 2.0
+    return np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
 
 
 def build_hand(balls: bool) -> mjb.MjbModel:
@@ -387,6 +405,7 @@ def build_hand(balls: bool) -> mjb.MjbModel:
     B.capsule("thumb_mc", "thumb_mc_g", t0, t1, 0.011); B.capsule("thumb_prox", "thumb_prox_g", t1, t2, 0.010)
     B.capsule("thumb_dist", "thumb_dist_g", t2, t3 - 0.006 * dt_, 0.009)
     B.site("thumb_dist", "THtip", t3)
+    B.site("world", "THtip_target", t3)        # PoseEnvV0 visualisation targets: <tip>_target, moved by update_target
     # fingers 2..5 (index .. little); rest pose tilted 15 degrees toward the palm
     tilt = np.deg2rad(15.0)
     df = np.array([0.0, -np.cos(tilt), np.sin(tilt)]); nf = np.array([0.0, np.sin(tilt), np.cos(tilt)])
@@ -408,6 +427,7 @@ def build_hand(balls: bool) -> mjb.MjbModel:
         B.capsule(f"prox{k}", f"prox{k}_g", p0, p1, 0.009); B.capsule(f"mid{k}", f"mid{k}_g", p1, p2, 0.008)
         B.capsule(f"dist{k}", f"dist{k}_g", p2, p3 - 0.005 * df, 0.007)
         B.site(f"dist{k}", tipname[k], p3)
+        B.site("world", tipname[k] + "_target", p3)
         # extensor wrapping cylinders at MCP (on the palm) and PIP (on the proximal phalanx), axis = flexion axis
         B.cylinder("palm", f"mcp{k}_wrap", p0, (1, 0, 0), 0.0075, 0.006)
         B.cylinder(f"prox{k}", f"pip{k}_wrap", p1, (1, 0, 0), 0.0060, 0.005)
@@ -484,26 +504,32 @@ def build_hand(balls: bool) -> mjb.MjbModel:
         B.plane("floor")
         # target sites live on a fixed frame rotated -90 deg about z w.r.t. the world (as the reference's
         # observations imply: local (x, y) -> world (y, -x)); centre_pos = (-0.0125, -0.07) maps onto ORBIT_C
-        for k, off in ((1, (0.0087, 0.0174)), (2, (-0.0203, -0.0236))):
-            c = ORBIT_C + np.array([off[0], off[1], 0.034])
+        for k in (1, 2):
+            c = REF_BALL_POS[k]
             B.body(f"ball{k}", "world", c, 0.043, (8.3248e-6,) * 3, simple=1)
             B.joint(f"ball{k}", f"ball{k}_free", FREE, limited=False)
             B.sphere(f"ball{k}", f"ball{k}", c, 0.022, contype=3, conaffinity=1)
             B.site(f"ball{k}", f"ball{k}_site", c)
-        B.body("target_frame", "world", ORBIT_C, 0.0, (0, 0, 0))
-        for k, ang in ((1, 0.75 * np.pi), (2, -0.25 * np.pi)):
-            B.site("target_frame", f"target{k}_site", ORBIT_C)   # position set below (rotated frame)
+        # The target sites ride on the palm ("desired_positions_wrt_palm" in BaodingEnvV1.step; the reference's obs_rms shows
+        # the targets' world z moving with the wrist: std 1 cm). They sit in a massless frame fixed to the palm whose pose is
+        # solved from the reference observation: local (x, y) = radius * (cos, sin)(start angle) + center_pos must land on
+        # REF_TARGET_POS at the initial pose. The frame is Rz(-90 deg) (local (x, y) -> world (y, -x)) followed by the
+        # smallest rotation that aligns the two sites' separation with the observed one.
+        B.body("target_frame", "palm", P0, 0.0, (0, 0, 0))
+        for k in (1, 2):
+            B.site("target_frame", f"target{k}_site", P0)   # position set below (rotated frame)
     m = B.compile()
     if balls:
-        # rotate the target frame by -90 deg about z: world = origin + Rz(-90) local
         tb = B.bid("target_frame")
-        m.arrays["body_quat"][tb] = [np.cos(-np.pi / 4), 0, 0, np.sin(-np.pi / 4)]
-        # local centre_pos must land on ORBIT_C: origin = ORBIT_C - Rz(-90) (cx, cy, 0) = ORBIT_C - (cy, -cx, 0)
         cx, cy = -0.0125, -0.07
-        m.arrays["body_pos"][tb] = ORBIT_C - np.array([cy, -cx, 0.0]) + np.array([0, 0, 0.030])
-        for k, ang in ((1, 0.75 * np.pi), (2, -0.25 * np.pi)):
-            s = m.name2id("site", f"target{k}_site")
-            m.arrays["site_pos"][s] = [0.025 * np.cos(ang) + cx, 0.028 * np.sin(ang) + cy, 0.0]
+        loc = {k: np.array([0.025 * np.cos(ang) + cx, 0.028 * np.sin(ang) + cy, 0.0]) for k, ang in ((1, 0.75 * np.pi), (2, -0.25 * np.pi))}
+        Rz = np.array([[0.0, 1.0, 0.0], [-1.0, 0.0, 0.0], [0.0, 0.0, 1.0]])
+        R = _rot_between(Rz @ (loc[2] - loc[1]), REF_TARGET_POS[2] - REF_TARGET_POS[1]) @ Rz
+        origin = 0.5 * (REF_TARGET_POS[1] + REF_TARGET_POS[2]) - R @ (0.5 * (loc[1] + loc[2]))
+        m.arrays["body_quat"][tb] = _mat2quat(R)
+        m.arrays["body_pos"][tb] = origin - P0          # the palm's frame is axis-aligned with origin P0 at the design pose
+        for k in (1, 2):
+            m.arrays["site_pos"][m.name2id("site", f"target{k}_site")] = loc[k]
     return finalize(m)
 
 
@@ -517,6 +543,7 @@ def build_elbow() -> mjb.MjbModel:
     B.joint("forearm", "r_elbow_flex", HINGE, (0, 1, 0), rng=(0.0, 2.27), damping=0.3, armature=0.01)
     B.capsule("forearm", "forearm_g", E, E + np.array([0, 0, -0.27]), 0.025, contype=0, conaffinity=0)
     B.site("forearm", "wrist", E + np.array([0, 0, -0.27]))
+    B.site("world", "wrist_target", E + np.array([0, 0, -0.27]))      # PoseEnvV0 visualisation target
     B.cylinder("humerus", "elbow_wrap", E, (0, 1, 0), 0.018, 0.03)
     B.site("humerus", "elbow_side_post", E + np.array([0.05, 0, 0.0]))
     specs = [("TRIlong", -1, 0.012, 800), ("TRIlat", -1, 0.0, 600), ("TRImed", -1, -0.012, 600),

@@ -29,3 +29,7 @@ def test_episode_returns_small(emul_lib):
     """Logic check of the multi-step return comparison on the host build (6 worlds, 10 env steps); the statistical version runs on the GPU."""
     out = pc.check_episode_returns(emul_lib, "cpu", 6, 10, min_same_length=0.8)
     assert out["same_length"] >= 0.8
+
+
+def test_more_contacts_than_the_fast_layout_holds(emul_lib):
+    pc.check_many_contacts(emul_lib, "cpu", n=6)

@@ -79,3 +79,9 @@ def test_full_size_properties(product_lib):
     o3, r3, _, _ = run(1000, 12)
     assert torch.equal(o1[:1000], o3) and torch.equal(r1[:1000], r3)            # worlds are independent
     assert st1 & 8 == 0                                                          # no non-finite state
+
+
+def test_more_contacts_than_the_fast_layout_holds(product_lib):
+    """Worlds with 17+ contacts: pairs bit-exact through the full-capacity parity hooks, and the env step (fast kernel + redo
+    pass) reproduces the oracle's step with no overflow reported."""
+    pc.check_many_contacts(product_lib, "cuda:0", n=32)
