@@ -525,10 +525,10 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   // limit rows - and the FULL one (out.dm_full) has MuJoCo's own capacities (nconmax contacts, njmax rows). A world that
   // outgrows the fast layout during an env step is stepped again, from the same state, by the full-capacity kernel
   // (myo_kernels.cu: redo list), so the capacities are a performance knob, never a change of results.
-  int nlim = 0;
-  for (int j = 0; j < njnt; j++) if (jlimited[j] && (jtype[j] == J_HINGE || jtype[j] == J_SLIDE)) nlim += 2;
+  int nlim = 0;      // limited joints + tendons; each can raise a row on either side (both at once only if its range is narrower than 2 x margin)
+  for (int j = 0; j < njnt; j++) if (jlimited[j] && (jtype[j] == J_HINGE || jtype[j] == J_SLIDE)) nlim++;
   d.any_tendon_limit = 0;
-  { std::vector<int> tl = ivec(m, "tendon_limited"); for (int t = 0; t < ntendon; t++) if (tl[t]) { nlim += 2; d.any_tendon_limit = 1; } }
+  { std::vector<int> tl = ivec(m, "tendon_limited"); for (int t = 0; t < ntendon; t++) if (tl[t]) { nlim++; d.any_tendon_limit = 1; } }
   if (nv > 64) { status = MYO_E_LIMIT; return "nv exceeds the dense solver limit (64)"; }
   out.lanes = nv <= 8 ? 8 : (nv <= 16 ? 16 : 32);
   if (const char* ov = getenv("MYO_LANES")) {   // development override of the tile width (8, 16 or 32)
@@ -556,8 +556,8 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   if (const char* ov = getenv("MYO_NLIM_CAP")) { const int v = atoi(ov); if (v >= 1 && v <= 32) nlim_fast = v; }
   B.finish();
   const int njmax = std::max(1, m.sz("njmax")), nconmax = std::max(1, m.sz("nconmax"));
-  auto layout = [&](DevModel& dd, int nlim_cap, int ncon_cap, int nefc_cap) {
-    dd.nlim_max = std::max(1, std::min(nlim, nlim_cap));
+  auto layout = [&](DevModel& dd, int nlim_sides, int nlim_cap, int ncon_cap, int nefc_cap) {
+    dd.nlim_max = std::max(1, std::min(nlim * nlim_sides, nlim_cap));
     dd.ncon_max = std::max(1, std::min(dd.npair, ncon_cap));
     dd.nefc_max = std::min(dd.nlim_max + 4 * dd.ncon_max, nefc_cap);
     int off = 0;
@@ -601,10 +601,10 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     else if (off % 32 == 0) off += 4;
     dd.scratch_words = off;
   };
-  layout(d, nlim_fast, ncon_fast, nlim_fast + 4 * ncon_fast);
+  layout(d, 1, nlim_fast, ncon_fast, nlim_fast + 4 * ncon_fast);
   out.dm_full = d;
   // full capacities, bounded by what the solo kernel keeps in registers per lane (kSoloRowsPerLane rows)
-  layout(out.dm_full, njmax, nconmax, std::min(njmax, kSoloRowsPerLane * out.lanes));
+  layout(out.dm_full, 2, njmax, nconmax, std::min(njmax, kSoloRowsPerLane * out.lanes));
   status = MYO_OK;
   return "";
 }

@@ -681,12 +681,96 @@ static int raw_sphere_sphere(double* dist, double* pos, double* frame, double ma
   addscl3(pos, pos1, dif, r1 + 0.5 * (*dist));
   return 1;
 }
+/* ---- capsule - box. NOT a restatement of MuJoCo's mjc_CapsuleBox (that source is not in the container and its case
+ * analysis cannot be reproduced from memory): an own closest-point collider, the same algorithm in the kernel
+ * (csrc/myo_phys.cuh capsule_box). The capsule is its core segment p(t) = c + t d, |t| <= h, in the box frame; the
+ * squared distance to the box f(t) = sum_i max(0, |c_i + t d_i| - s_i)^2 is convex and piecewise quadratic, so f' is
+ * monotone and piecewise linear with breakpoints where a coordinate crosses a face: the minimiser is found exactly
+ * by walking the sorted breakpoints. Contacts: if both end points of the segment are within reach of the box
+ * (capsule lying along a face) one contact per end point, else one contact at the closest point. */
+static double box_point_dist(const double* p, const double* s, double* q) {      /* q: closest point of the box to p */
+  double f = 0;
+  for (int i = 0; i < 3; i++) { q[i] = clip(p[i], -s[i], s[i]); f += (p[i] - q[i]) * (p[i] - q[i]); }
+  return sqrt(f);
+}
+static double seg_box_dfdt(const double* c, const double* d, const double* s, double t) {
+  double g = 0;
+  for (int i = 0; i < 3; i++) {
+    double x = c[i] + t * d[i], e = fabs(x) - s[i];
+    if (e > 0) g += 2 * e * (x > 0 ? d[i] : -d[i]);
+  }
+  return g;
+}
+static double seg_box_closest_t(const double* c, const double* d, double h, const double* s) {
+  double bp[8]; int nb = 0;
+  bp[nb++] = -h;
+  for (int i = 0; i < 3; i++) if (fabs(d[i]) > 1e-12) for (int sg = -1; sg <= 1; sg += 2) {
+    double t = (sg * s[i] - c[i]) / d[i];
+    if (t > -h && t < h) bp[nb++] = t;
+  }
+  bp[nb++] = h;
+  for (int i = 1; i < nb; i++) { double v = bp[i]; int j = i - 1; while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; j--; } bp[j + 1] = v; }
+  /* f' at every breakpoint (monotone): last negative, first positive, exact zeros in between form a flat stretch */
+  double g[8]; int lo = -1, hi = nb;
+  for (int k = 0; k < nb; k++) g[k] = seg_box_dfdt(c, d, s, bp[k]);
+  for (int k = 0; k < nb; k++) if (g[k] < 0) lo = k;
+  for (int k = nb - 1; k >= 0; k--) if (g[k] > 0) hi = k;
+  if (hi == 0) return bp[0];
+  if (lo == nb - 1) return bp[nb - 1];
+  if (hi == lo + 1) return bp[lo] + (bp[hi] - bp[lo]) * (-g[lo]) / (g[hi] - g[lo]);
+  return 0.5 * (bp[lo + 1] + bp[hi - 1]);
+}
+/* one contact between the capsule's point p (box frame) and the box; returns 0 when out of reach */
+static int capsule_box_point(const double* p, const double* s, double r, double margin, double* dist, double* pos_b, double* nrm_b) {
+  double q[3];
+  double dd = box_point_dist(p, s, q);
+  if (dd > r + margin) return 0;
+  if (dd > 1e-10) {      /* outside: normal from the capsule toward the box */
+    for (int i = 0; i < 3; i++) nrm_b[i] = (q[i] - p[i]) / dd;
+    *dist = dd - r;
+  } else {               /* the core segment is inside the box: leave through the nearest face */
+    int ax = 0; double best = 1e300;
+    for (int i = 0; i < 3; i++) { double dep = s[i] - fabs(p[i]); if (dep < best) { best = dep; ax = i; } }
+    nrm_b[0] = nrm_b[1] = nrm_b[2] = 0;
+    nrm_b[ax] = p[ax] > 0 ? -1 : 1;
+    *dist = -best - r;
+  }
+  for (int i = 0; i < 3; i++) pos_b[i] = p[i] + nrm_b[i] * (r + 0.5 * (*dist));
+  return 1;
+}
+/* capsule (pos pc, axis = column 2 of Rc, radius r, half length h) vs box (pos pb, frame Rb, half sizes s):
+ * up to two contacts (dist, world pos, world normal capsule -> box) */
+static int capsule_box(double margin, const double* pc, const double* Rc, double r, double h, const double* pb, const double* Rb,
+                       const double* s, double* dist, double* pos, double* nrm) {
+  double ax[3] = { Rc[2], Rc[5], Rc[8] }, dif[3], c[3], d[3];
+  sub3(dif, pc, pb); mulmatTvec3(c, Rb, dif); mulmatTvec3(d, Rb, ax);
+  double pe[2][3], de[2], pb2[2][3], nb2[2][3]; int he[2];
+  for (int e = 0; e < 2; e++) {
+    double t = e ? h : -h;
+    for (int i = 0; i < 3; i++) pe[e][i] = c[i] + t * d[i];
+    he[e] = capsule_box_point(pe[e], s, r, margin, &de[e], pb2[e], nb2[e]);
+  }
+  int n = 0;
+  if (he[0] && he[1]) {
+    for (int e = 0; e < 2; e++) { dist[n] = de[e]; mulmatvec3(pos + 3*n, Rb, pb2[e]); add3(pos + 3*n, pos + 3*n, pb); mulmatvec3(nrm + 3*n, Rb, nb2[e]); n++; }
+    return n;
+  }
+  double t = seg_box_closest_t(c, d, h, s), p[3], posb[3], nrmb[3];
+  for (int i = 0; i < 3; i++) p[i] = c[i] + t * d[i];
+  if (capsule_box_point(p, s, r, margin, &dist[0], posb, nrmb)) {
+    mulmatvec3(pos, Rb, posb); add3(pos, pos, pb); mulmatvec3(nrm, Rb, nrmb);
+    n = 1;
+  }
+  return n;
+}
+
+/* returns the number of candidate contacts written (dist / pos / frame normal per contact), -1 for an unsupported pair */
 static int collide_pair(const OModel* m, const OData* d, int g1, int g2, double margin, double* dist, double* pos, double* frame) {
   int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
   const double *p1 = d->geom_xpos + 3*g1, *p2 = d->geom_xpos + 3*g2;
   const double *R1 = d->geom_xmat + 9*g1, *R2 = d->geom_xmat + 9*g2;
   const double *s1 = m->geom_size + 3*g1, *s2 = m->geom_size + 3*g2;
-  zero(frame, 9);
+  zero(frame, 18);
   if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) return raw_sphere_sphere(dist, pos, frame, margin, p1, s1[0], p2, s2[0]);
   if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) {
     double axis[3] = { R2[2], R2[5], R2[8] }, vec[3];
@@ -704,6 +788,12 @@ static int collide_pair(const OModel* m, const OData* d, int g1, int g2, double 
     cpy(frame, nrm, 3);
     addscl3(pos, p2, nrm, -(*dist)/2 - s2[0]);
     return 1;
+  }
+  if (t1 == GEOM_CAPSULE && t2 == GEOM_BOX) {
+    double nrm[6];
+    int n = capsule_box(margin, p1, R1, s1[0], s1[1], p2, R2, s2, dist, pos, nrm);
+    for (int k = 0; k < n; k++) cpy(frame + 9*k, nrm + 3*k, 3);
+    return n;
   }
   if (t1 == GEOM_PLANE && t2 == GEOM_CAPSULE) return -1;   /* never in range for shipped models */
   return -1; /* unsupported pair type */
@@ -737,10 +827,12 @@ void o_collision(const OModel* m, OData* d) {
           sub3(dif, d->geom_xpos + 3*g2, d->geom_xpos + 3*g1);
           if (dot3(dif, nrm) > margin + rb2) continue;
         }
-        double dist, pos[3], frame[9];
-        int r = collide_pair(m, d, g1, g2, margin, &dist, pos, frame);
+        double dists[2], poss[6], frames[18];
+        int r = collide_pair(m, d, g1, g2, margin, dists, poss, frames);
         if (r < 0) { d->unsupported_pairs++; continue; }
-        if (!r || dist >= margin) continue;
+        for (int kc = 0; kc < r; kc++) {
+        double dist = dists[kc]; double* pos = poss + 3*kc; double* frame = frames + 9*kc;
+        if (dist >= margin) continue;
         if (d->ncon >= m->nconmax) { d->warn_overflow++; continue; }
         int c = d->ncon++;
         make_frame(frame);
@@ -768,6 +860,7 @@ void o_collision(const OModel* m, OData* d) {
         }
         double* f5 = d->contact_friction + 5*c;
         f5[0] = fri[0]; f5[1] = fri[0]; f5[2] = fri[1]; f5[3] = fri[2]; f5[4] = fri[2];
+        }
       }
   }
 }

@@ -73,10 +73,11 @@ def test_p2_reset_distribution(product_lib):
         assert 0.03 <= mass.min() and mass.max() <= 0.3 and abs(mass.mean() - 0.165) < 0.01
         assert 0.018 <= size.min() and size.max() <= 0.024 and abs(size.mean() - 0.021) < 3e-4
         assert 0.8 <= fri[:, 0].min() and fri[:, 0].max() <= 1.2 and fri[:, 0].std() > 0.1
-    # targets move only for cw / ccw: after one step a third of the worlds keep their target (hold)
-    o0 = env.sim.get_obs().cpu().numpy().copy()
-    o1, _, _, _ = env.step(np.zeros((n, 39), np.float32))
-    moved = np.abs(o1[:, 35:37] - o0[:, 35:37]).max(1) > 1e-7
+    # the target sites (positions in their body frame) move only for cw / ccw: after one step a third of the worlds keep theirs (hold)
+    s0 = sim.get_param(_capi.PARAM_SITE_POS, cfg.target_site[0]).cpu().numpy().copy()
+    env.step(np.zeros((n, 39), np.float32))
+    s1 = sim.get_param(_capi.PARAM_SITE_POS, cfg.target_site[0]).cpu().numpy()
+    moved = np.abs(s1[:, :2] - s0[:, :2]).max(1) > 1e-7
     assert 0.6 < moved.mean() < 0.73
     env.close()
 
@@ -105,7 +106,7 @@ def test_rsi_and_beta_reset_matches_host_emulation(product_lib, emul_lib):
     for a, b in zip(*outs):
         np.testing.assert_allclose(a, b, rtol=2e-5, atol=2e-5)
     obs = outs[0][0]
-    on_target = np.abs(obs[:, 41:43]).max(1) < 1e-6
+    on_target = np.abs(obs[:, 41:43]).max(1) < 1e-3       # the in-reset step leaves the palm-mounted targets a fraction of a millimetre off
     assert 0.5 < on_target.mean() < 0.9            # rsi_probability 0.7
 
 
