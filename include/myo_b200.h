@@ -66,7 +66,7 @@ typedef enum {
   MYO_E_LIMIT = -6     /* model exceeds a compiled-in capacity */
 } myo_status;
 
-typedef enum { MYO_TASK_NONE = 0, MYO_TASK_POSE = 1, MYO_TASK_BAODING = 2 } myo_task_kind;
+typedef enum { MYO_TASK_NONE = 0, MYO_TASK_POSE = 1, MYO_TASK_BAODING = 2, MYO_TASK_REORIENT = 3 } myo_task_kind;
 
 /* Baoding `Task` enum values (MyoSuite baoding_v1.Task; 0 = hold, see
  * /root/reference/src/envs/baoding.py:287-294, /root/reference/src/models/classifier.py:116) */
@@ -77,11 +77,14 @@ typedef enum {
   MYO_PARAM_BODY_MASS = 0,     /* 1 float  */
   MYO_PARAM_GEOM_SIZE = 1,     /* 3 floats */
   MYO_PARAM_GEOM_FRICTION = 2, /* 3 floats */
-  MYO_PARAM_SITE_POS = 3       /* 3 floats */
+  MYO_PARAM_SITE_POS = 3,      /* 3 floats */
+  MYO_PARAM_BODY_POS = 4,      /* 3 floats: body_pos (frame in the parent) */
+  MYO_PARAM_BODY_MAT = 5       /* 9 floats: rotation matrix of body_quat, row major */
 } myo_param_kind;
 
 #define MYO_MAX_OVERRIDE 4
-#define MYO_INFO_TERMS 8
+#define MYO_INFO_TERMS 12
+#define MYO_MAX_ROT_RANGES 4
 
 /* Task / env configuration: the kwargs of the gym registrations plus the curriculum knobs of
  * CustomBaodingP2Env._setup (/root/reference/src/envs/baoding.py:300-401) and
@@ -94,9 +97,10 @@ typedef struct myo_task_cfg {
   int32_t auto_reset;           /* SubprocVecEnv worker semantics: reset inside step on done */
   int32_t solver_iterations;    /* Newton iteration cap per mj_step (<=0: model's opt.iterations) */
   float solver_tolerance;       /* <=0: model's opt.tolerance */
-  /* reward weights, in the order written to info[]:
-   *  baoding: pos_dist_1 pos_dist_2 act_reg alive sparse solved done  (7 used)
-   *  pose   : pose bonus penalty act_reg sparse solved done           (7 used) */
+  /* reward weights, in the order written to info[] (slot 7 always carries the dense reward):
+   *  baoding : pos_dist_1 pos_dist_2 act_reg alive sparse solved done dense
+   *  pose    : pose bonus penalty act_reg sparse solved done dense
+   *  reorient: pos_dist rot_dist act_reg alive sparse solved done dense pos_dist_diff rot_dist_diff */
   float rwd_weight[MYO_INFO_TERMS];
   /* ---- baoding ---- */
   float drop_th, proximity_th;
@@ -112,7 +116,7 @@ typedef struct myo_task_cfg {
   int32_t ball_qposadr[2], ball_dofadr[2];
   /* ---- pose ---- */
   float pose_thd, far_th, target_distance;
-  int32_t reset_type;           /* 0 none, 1 init, 2 random */
+  int32_t reset_type;           /* 0 none, 1 init, 2 random, 3 sds */
   int32_t target_type;          /* 0 fixed, 1 generate */
   int32_t n_target_jnt;         /* <=0: target_jnt_value given for all nq */
   int32_t target_jnt_ids[64];
@@ -135,6 +139,23 @@ typedef struct myo_task_cfg {
    *      phase, drawn whenever enable_rsi), ball placement gated by rsi_probability, then noise on balls / palm / fingers ---- */
   int32_t p1_reset;
   float noise_palm, noise_balls;
+  /* ---- die reorientation: CustomReorientEnv._setup / reset (/root/reference/src/envs/reorient.py:58-196) on MyoSuite's
+   *      ReorientEnvV0. drop_th and obj_friction_change above are shared with the baoding block. ---- */
+  float goal_pos[2], goal_rot[2];          /* ranges of the goal position / Euler-angle offsets */
+  float obj_size_change;                   /* die (and target) half sizes +- this much, one draw per reset */
+  float pos_th, rot_th;
+  int32_t n_goal_rot[3];                   /* goal_rot_x / _y / _z: optional lists of (low, high) ranges, one picked per reset */
+  float goal_rot_axis[3][MYO_MAX_ROT_RANGES][2];
+  int32_t object_body, goal_body, object_site, goal_site;   /* "Object", "target", "object_o", "target_o" */
+  int32_t object_geom0, object_ngeom;      /* geoms of the Object body: the last three scale in all half sizes, earlier ones in size[1] */
+  int32_t object_qposadr, object_dofadr;
+  float goal_init_pos[3], goal_obj_offset[3];   /* target_o at the initial pose; target_o - object_o there (visualisation offset) */
+  int32_t n_ovr_bodypose, ovr_bodypose[MYO_MAX_OVERRIDE];   /* bodies whose body_pos / body_quat are per-world (the goal body) */
+  /* ---- pose curriculum knobs of CustomPoseEnv (/root/reference/src/envs/pose.py:55-66, 88-95) ---- */
+  float sds_distance;           /* reset_type 3 ("sds"): qpos = (1 - sds_distance) target + sds_distance init_qpos */
+  int32_t weight_body;          /* >= 0: body_mass[weight_body] ~ U(weight_range) per reset, geom_size[weight_geom][0] = 0.01 + 2.5 w / 100 */
+  int32_t weight_geom;
+  float weight_range[2];
 } myo_task_cfg;
 
 const char* myo_last_error(void);

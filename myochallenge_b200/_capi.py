@@ -12,10 +12,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmyo_b200.so")
 
 MYO_MAX_OVERRIDE = 4
-MYO_INFO_TERMS = 8
+MYO_INFO_TERMS = 12
+MYO_MAX_ROT_RANGES = 4
 TASK_STATE_I, TASK_STATE_F = 4, 8
-TASK_NONE, TASK_POSE, TASK_BAODING = 0, 1, 2
-PARAM_BODY_MASS, PARAM_GEOM_SIZE, PARAM_GEOM_FRICTION, PARAM_SITE_POS = 0, 1, 2, 3
+TASK_NONE, TASK_POSE, TASK_BAODING, TASK_REORIENT = 0, 1, 2, 3
+PARAM_BODY_MASS, PARAM_GEOM_SIZE, PARAM_GEOM_FRICTION, PARAM_SITE_POS, PARAM_BODY_POS, PARAM_BODY_MAT = 0, 1, 2, 3, 4, 5
+PARAM_NCOMP = {0: 1, 1: 3, 2: 3, 3: 3, 4: 3, 5: 9}
 
 STAGES = {
     "xpos": 0, "xmat": 1, "site_xpos": 2, "ten_length": 3, "ten_J": 4, "qM": 5, "qfrc_bias": 6,
@@ -52,6 +54,13 @@ class TaskCfg(C.Structure):
         ("enable_rsi", C.c_int32), ("rsi_probability", C.c_float), ("balls_overlap", C.c_int32),
         ("beta_init_angle", C.c_float * 2), ("beta_ball_size", C.c_float * 2), ("beta_ball_mass", C.c_float * 2),
         ("p1_reset", C.c_int32), ("noise_palm", C.c_float), ("noise_balls", C.c_float),
+        ("goal_pos", C.c_float * 2), ("goal_rot", C.c_float * 2), ("obj_size_change", C.c_float), ("pos_th", C.c_float), ("rot_th", C.c_float),
+        ("n_goal_rot", C.c_int32 * 3), ("goal_rot_axis", ((C.c_float * 2) * MYO_MAX_ROT_RANGES) * 3),
+        ("object_body", C.c_int32), ("goal_body", C.c_int32), ("object_site", C.c_int32), ("goal_site", C.c_int32),
+        ("object_geom0", C.c_int32), ("object_ngeom", C.c_int32), ("object_qposadr", C.c_int32), ("object_dofadr", C.c_int32),
+        ("goal_init_pos", C.c_float * 3), ("goal_obj_offset", C.c_float * 3),
+        ("n_ovr_bodypose", C.c_int32), ("ovr_bodypose", C.c_int32 * MYO_MAX_OVERRIDE),
+        ("sds_distance", C.c_float), ("weight_body", C.c_int32), ("weight_geom", C.c_int32), ("weight_range", C.c_float * 2),
     ]
 
 

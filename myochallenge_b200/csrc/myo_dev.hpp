@@ -76,7 +76,7 @@ struct DevModel {
   float solver_tol, timestep, gravity[3], inv_sqrt_impratio, meaninertia;
   int any_damping, any_tendon_passive, any_joint_spring, any_tendon_limit;
   // body tables
-  TabI b_parent, b_root, b_jntadr, b_jntnum, b_dofadr, b_dofnum, b_nchain, b_chain, b_mass_slot,
+  TabI b_parent, b_root, b_jntadr, b_jntnum, b_dofadr, b_dofnum, b_nchain, b_chain, b_mass_slot, b_pose_slot,
       b_sameframe, lvl_adr, lvl_body, b_subadr, b_sub;
   TabF b_pos, b_mat, b_ipos, b_imat, b_mass, b_inertia, b_invweight0;
   // joints
@@ -143,7 +143,7 @@ struct BatchPtrs {
 };
 
 enum { TI_ELAPSED = 0, TI_EPISODE = 1, TI_TASK = 2, TI_FLAGS = 3, TI_WORDS = 4 };
-enum { TF_ANGLE1 = 0, TF_ANGLE2 = 1, TF_XR = 2, TF_YR = 3, TF_PERIOD = 4, TF_WORDS = 8 };
+enum { TF_ANGLE1 = 0, TF_ANGLE2 = 1, TF_XR = 2, TF_YR = 3, TF_PERIOD = 4, TF_POSDIST = 5, TF_ROTDIST = 6, TF_WORDS = 8 };
 // o_misc scratch words
 enum { MI_NLIM = 0, MI_NCON = 1, MI_NEFC = 2, MI_ITER = 3, MI_STATUS = 4, MI_ONE = 5 /*float 1*/, MI_WORDS = 8 };
 

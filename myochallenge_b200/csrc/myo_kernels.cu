@@ -115,7 +115,7 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
     task_obs<G>(mslot, t, c, ptarget);
     float info[MYO_INFO_TERMS], reward;
     bool env_done;
-    task_reward<G>(mslot, t, c, info, &reward, &env_done);
+    task_reward<G>(mslot, t, c, tf, info, &reward, &env_done);
     // a world whose state left the finite range ends its episode here (MuJoCo would warn and reset the data): the reset
     // below keeps NaNs out of the running moments downstream
     bool bad = false;
@@ -509,6 +509,7 @@ int myo_task_cfg_default(const myo_model* mh, int kind, myo_task_cfg* cfg) {
   cfg->kind = kind; cfg->frame_skip = 10; cfg->max_episode_steps = kind == MYO_TASK_BAODING ? 200 : 100;
   cfg->normalize_act = 1; cfg->auto_reset = 1;
   cfg->solver_iterations = 0; cfg->solver_tolerance = 0.f;
+  cfg->weight_body = -1; cfg->weight_geom = -1;
   if (kind == MYO_TASK_BAODING) {
     // BaodingEnvV1.DEFAULT_RWD_KEYS_AND_WEIGHTS (pos_dist 5/5, alive 0, act_reg 0), /root/reference/src/envs/baoding.py:16-22
     cfg->rwd_weight[0] = 5.f; cfg->rwd_weight[1] = 5.f;
@@ -536,11 +537,62 @@ int myo_task_cfg_default(const myo_model* mh, int kind, myo_task_cfg* cfg) {
     cfg->n_ovr_body = 2; cfg->ovr_body[0] = cfg->ball_body[0]; cfg->ovr_body[1] = cfg->ball_body[1];
     cfg->n_ovr_geom = 2; cfg->ovr_geom[0] = cfg->ball_geom[0]; cfg->ovr_geom[1] = cfg->ball_geom[1];
     cfg->n_ovr_site = 2; cfg->ovr_site[0] = cfg->target_site[0]; cfg->ovr_site[1] = cfg->target_site[1];
+  } else if (kind == MYO_TASK_REORIENT) {
+    // ReorientEnvV0.DEFAULT_RWD_KEYS_AND_WEIGHTS (pos_dist 100, rot_dist 1) and CustomReorientEnv._setup's defaults
+    // (/root/reference/src/envs/reorient.py:58-125); frame_skip 5, horizon 150 come from the registrations (src/envs/__init__.py:26-55)
+    cfg->frame_skip = 5; cfg->max_episode_steps = 150;
+    cfg->rwd_weight[0] = 100.f; cfg->rwd_weight[1] = 1.f;
+    cfg->goal_pos[0] = cfg->goal_pos[1] = 0.f; cfg->goal_rot[0] = cfg->goal_rot[1] = 0.785f;
+    cfg->pos_th = 0.025f; cfg->rot_th = 0.262f; cfg->drop_th = 0.2f;
+    cfg->object_body = m.name2id("body", "Object"); cfg->goal_body = m.name2id("body", "target");
+    cfg->object_site = m.name2id("site", "object_o"); cfg->goal_site = m.name2id("site", "target_o");
+    if (cfg->object_body < 0 || cfg->goal_body < 0 || cfg->object_site < 0 || cfg->goal_site < 0) {
+      myo::set_error("model lacks the reorient names: bodies Object / target, sites object_o / target_o");
+      return MYO_E_ARG;
+    }
+    const int ob = cfg->object_body, gb = cfg->goal_body;
+    cfg->object_geom0 = m.i("body_geomadr")[ob]; cfg->object_ngeom = m.i("body_geomnum")[ob];
+    if (cfg->object_ngeom < 3 || cfg->object_ngeom > MYO_MAX_OVERRIDE) {
+      myo::set_error("the Object body must carry 3 or 4 geoms (the reference's reset scales the last three as boxes)");
+      return MYO_E_LIMIT;
+    }
+    const int j = m.i("body_jntadr")[ob];
+    if (m.i("body_jntnum")[ob] != 1 || m.i("jnt_type")[j] != 0) { myo::set_error("the Object body must hang on a free joint"); return MYO_E_ARG; }
+    cfg->object_qposadr = m.i("jnt_qposadr")[j]; cfg->object_dofadr = m.i("jnt_dofadr")[j];
+    const double* sq = m.d("site_quat");
+    for (int sid : {cfg->object_site, cfg->goal_site})
+      if (sq[4 * sid] < 1.0 - 1e-9) { myo::set_error("object_o / target_o must share their bodies' frames (identity site_quat)"); return MYO_E_UNSUPPORTED; }
+    if (m.i("body_parentid")[gb] != 0 || m.i("body_jntnum")[gb] != 0) { myo::set_error("the target body must be fixed to the world"); return MYO_E_UNSUPPORTED; }
+    // goal_init_pos = site_xpos[target_o], goal_obj_offset = target_o - object_o, both at the model's qpos0 (the env reads them
+    // right after MujocoEnv.__init__'s sim.forward(), reorient.py:88-92)
+    const double* bp = m.d("body_pos") + 3 * gb; const double* bq = m.d("body_quat") + 4 * gb;
+    const double* sp = m.d("site_pos"); const double* q0 = m.d("qpos0") + cfg->object_qposadr;
+    auto rot = [](const double* q, const double* v, double* o) {
+      const double w = q[0], x = q[1], y = q[2], z = q[3];
+      const double R[9] = {w*w + x*x - y*y - z*z, 2*(x*y - w*z), 2*(x*z + w*y), 2*(x*y + w*z), w*w - x*x + y*y - z*z, 2*(y*z - w*x),
+                           2*(x*z - w*y), 2*(y*z + w*x), w*w - x*x - y*y + z*z};
+      for (int r = 0; r < 3; r++) o[r] = R[3*r] * v[0] + R[3*r + 1] * v[1] + R[3*r + 2] * v[2];
+    };
+    double tg[3], oo[3];
+    rot(bq, sp + 3 * cfg->goal_site, tg);
+    rot(q0 + 3, sp + 3 * cfg->object_site, oo);
+    for (int e = 0; e < 3; e++) {
+      tg[e] += bp[e]; oo[e] += q0[e];
+      cfg->goal_init_pos[e] = (float)tg[e]; cfg->goal_obj_offset[e] = (float)(tg[e] - oo[e]);
+    }
+    cfg->n_ovr_geom = cfg->object_ngeom;
+    for (int k = 0; k < cfg->object_ngeom; k++) {
+      cfg->ovr_geom[k] = cfg->object_geom0 + k;
+      const double* gp = m.d("geom_pos") + 3 * (cfg->object_geom0 + k);
+      if (gp[0] != 0.0 || gp[1] != 0.0 || gp[2] != 0.0) { myo::set_error("die geoms away from the body origin (per-world geom_pos) are not supported"); return MYO_E_UNSUPPORTED; }
+    }
+    cfg->n_ovr_bodypose = 1; cfg->ovr_bodypose[0] = gb;
   } else if (kind == MYO_TASK_POSE) {
     // PoseEnvV0.DEFAULT_RWD_KEYS_AND_WEIGHTS: pose 1, bonus 4, penalty 50, act_reg 1 (order: pose bonus penalty act_reg)
     cfg->rwd_weight[0] = 1.f; cfg->rwd_weight[1] = 4.f; cfg->rwd_weight[2] = 50.f; cfg->rwd_weight[3] = 1.f;
     cfg->pose_thd = 0.35f; cfg->far_th = 4.f * 3.14159265358979f / 2.f; cfg->target_distance = 1.f;
     cfg->reset_type = 1; cfg->target_type = 1;
+    cfg->weight_body = -1; cfg->weight_geom = -1;
   }
   return MYO_OK;
 }

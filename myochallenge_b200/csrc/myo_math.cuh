@@ -176,4 +176,28 @@ struct Philox {
   }
 };
 
+// MyoSuite utils/quat_math.py conventions (from mujoco-worldgen's rotations.py): extrinsic xyz Euler angles
+MYO_DI void euler2quat(float* q, const float* e) {
+  const float ai = 0.5f * e[2], aj = -0.5f * e[1], ak = 0.5f * e[0];
+  float si, ci, sj, cj, sk, ck;
+  sincosf(ai, &si, &ci); sincosf(aj, &sj, &cj); sincosf(ak, &sk, &ck);
+  const float cc = ci * ck, cs = ci * sk, sc = si * ck, ss = si * sk;
+  q[0] = cj * cc + sj * ss;
+  q[3] = cj * sc - sj * cs;
+  q[2] = -(cj * ss + sj * cc);
+  q[1] = cj * cs - sj * sc;
+}
+MYO_DI void mat2euler(float* e, const float* R) {      // R row major
+  const float cy = sqrtf(R[8] * R[8] + R[5] * R[5]);
+  if (cy > 4.f * 1.1920929e-7f) {
+    e[2] = -atan2f(R[1], R[0]);
+    e[1] = -atan2f(-R[2], cy);
+    e[0] = -atan2f(R[5], R[8]);
+  } else {
+    e[2] = -atan2f(-R[3], R[4]);
+    e[1] = -atan2f(-R[2], cy);
+    e[0] = 0.f;
+  }
+}
+
 }  // namespace myo

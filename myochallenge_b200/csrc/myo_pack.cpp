@@ -181,7 +181,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   d.ndlevel = ndlevel;
 
   // ---------------------------------------------------------------- override slots
-  std::vector<int> mass_slot(nbody, -1), size_slot(ngeom, -1), fri_slot(ngeom, -1), spos_slot(nsite, -1);
+  std::vector<int> mass_slot(nbody, -1), pose_slot(nbody, -1), size_slot(ngeom, -1), fri_slot(ngeom, -1), spos_slot(nsite, -1);
   {
     int np = 0;
     const double* bm = m.d("body_mass"); const double* gs = m.d("geom_size"); const double* gf = m.d("geom_friction");
@@ -209,13 +209,24 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
       for (int e = 0; e < 3; e++) out.param0.push_back((float)sp[3 * s + e]);
       np += 3;
     }
+    for (int k = 0; k < cfg.n_ovr_bodypose && k < MYO_MAX_OVERRIDE; k++) {      // body_pos (3) followed by the matrix of body_quat (9)
+      int b = cfg.ovr_bodypose[k];
+      if (b <= 0 || b >= nbody) { status = MYO_E_ARG; return "override body (pose) id out of range"; }
+      pose_slot[b] = np; out.slots.push_back({MYO_PARAM_BODY_POS, b, np, 3}); out.slots.push_back({MYO_PARAM_BODY_MAT, b, np + 3, 9});
+      const double* bp = m.d("body_pos") + 3 * b;
+      for (int e = 0; e < 3; e++) out.param0.push_back((float)bp[e]);
+      float R[9];
+      quat2mat_h(m.d("body_quat") + 4 * b, R);
+      for (int e = 0; e < 9; e++) out.param0.push_back(R[e]);
+      np += 12;
+    }
     d.nparam = np; d.nparam4 = pad4(std::max(np, 1));
     out.param0.resize(d.nparam4, 0.f);
   }
 
   B.I(d.b_parent, parent); B.I(d.b_root, rootid); B.I(d.b_jntadr, jntadr); B.I(d.b_jntnum, jntnum);
   B.I(d.b_dofadr, dofadr); B.I(d.b_dofnum, dofnum); B.I(d.b_nchain, nchain); B.I(d.b_chain, chain);
-  B.I(d.b_mass_slot, mass_slot); B.I(d.b_sameframe, sameframe);
+  B.I(d.b_mass_slot, mass_slot); B.I(d.b_pose_slot, pose_slot); B.I(d.b_sameframe, sameframe);
   B.I(d.lvl_adr, lvl_adr); B.I(d.lvl_body, lvl_body);
   {   // subtree of every body (itself first, then its descendants in body order): composite inertia / force sums
     std::vector<int> subadr(nbody + 1, 0), sub;
@@ -288,8 +299,12 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
         if (!((gcontype[g1] & gconaff[g2]) || (gcontype[g2] & gconaff[g1]))) continue;
         const int t1 = gtype[g1], t2 = gtype[g2];
         const bool sup = (t1 == G_SPHERE && t2 == G_SPHERE) || (t1 == G_SPHERE && t2 == G_CAPSULE) ||
-                         (t1 == G_PLANE && t2 == G_SPHERE);
+                         (t1 == G_PLANE && t2 == G_SPHERE) || (t1 == G_CAPSULE && t2 == G_BOX);
         p_g1.push_back(g1); p_g2.push_back(g2); p_sup.push_back(sup ? 1 : 0);
+        if (t1 == G_CAPSULE && t2 == G_BOX) {      // up to two contacts: the pair is listed twice, p_supported = 1 + contact number
+          p_sup.back() = 1;
+          p_g1.push_back(g1); p_g2.push_back(g2); p_sup.push_back(2);
+        }
       }
   }
   d.npair = (int)p_g1.size();
@@ -506,6 +521,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   // ---------------------------------------------------------------- task-dependent sizes
   if (cfg.kind == MYO_TASK_BAODING) d.nobs = (nq - 14) + 24 + na;
   else if (cfg.kind == MYO_TASK_POSE) d.nobs = nq + nv + nq + na;
+  else if (cfg.kind == MYO_TASK_REORIENT) d.nobs = (nq - 7) + (nv - 6) + 18 + na;
   else d.nobs = nq + nv + na;
   d.nobs4 = pad4(d.nobs);
   {
@@ -515,6 +531,10 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     if (cfg.kind == MYO_TASK_BAODING) {   // CustomBaodingP2Env._setup: init_qpos[:-14] = 0; init_qpos[0] = -1.57
       for (int k = 0; k < nq - 14; k++) out.init_qpos[k] = 0.f;
       out.init_qpos[0] = -1.57f;
+    }
+    if (cfg.kind == MYO_TASK_REORIENT) {   // CustomReorientEnv._setup: init_qpos[:-7] = 0; init_qpos[0] = -1.5 (/root/reference/src/envs/reorient.py:123-124)
+      for (int k = 0; k < nq - 7; k++) out.init_qpos[k] = 0.f;
+      out.init_qpos[0] = -1.5f;
     }
     B.F(d.init_qpos, out.init_qpos);
     B.F(d.param0, out.param0);

@@ -97,9 +97,16 @@ MYO_PHASE void body_local_pose(int mslot, Ctx<G>& c, int b) {
     normalize4(q);
     quat2mat(R, q);
   } else {
+    const int ps = m.b_pose_slot[b];      // per-world body_pos / body_quat (the reorient goal body)
+    if (ps >= 0) {
+      cpy3(pos, c.wpp(m) + ps);
 #pragma unroll
-    for (int k = 0; k < 9; k++) R[k] = m.b_mat[9 * b + k];
-    cpy3(pos, m.b_pos + 3 * b);
+      for (int k = 0; k < 9; k++) R[k] = c.wpp(m)[ps + 3 + k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) R[k] = m.b_mat[9 * b + k];
+      cpy3(pos, m.b_pos + 3 * b);
+    }
     for (int j = jadr; j < jadr + jnum; j++) {
       const int qa = m.j_qposadr[j], da = m.j_dofadr[j];
       const float dq = qpos[qa] - m.j_qpos0[j];
@@ -685,6 +692,97 @@ MYO_DI bool sphere_sphere(float margin, const float* p1, float r1, const float* 
   return true;
 }
 
+// ---- capsule - box: own closest-point collider (NOT MuJoCo's mjc_CapsuleBox; see oracle/myo_oracle.c capsule_box, the same
+// algorithm in fp64). Capsule core segment p(t) = c + t d, |t| <= h, in the box frame; f(t) = sum_i max(0, |c_i + t d_i| - s_i)^2
+// is convex piecewise quadratic: walk the sorted breakpoints of its piecewise-linear derivative.
+MYO_DI float seg_box_dfdt(const float* c, const float* d, const float* s, float t) {
+  float g = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float x = c[i] + t * d[i], e = fabsf(x) - s[i];
+    if (e > 0.f) g += 2.f * e * (x > 0.f ? d[i] : -d[i]);
+  }
+  return g;
+}
+MYO_DI float seg_box_closest_t(const float* c, const float* d, float h, const float* s) {
+  float bp[8];
+  int nb = 0;
+  bp[nb++] = -h;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (fabsf(d[i]) > 1e-12f) {
+#pragma unroll
+      for (int sg = -1; sg <= 1; sg += 2) {
+        const float t = ((float)sg * s[i] - c[i]) / d[i];
+        if (t > -h && t < h) bp[nb++] = t;
+      }
+    }
+  bp[nb++] = h;
+  for (int i = 1; i < nb; i++) { const float v = bp[i]; int j = i - 1; while (j >= 0 && bp[j] > v) { bp[j + 1] = bp[j]; j--; } bp[j + 1] = v; }
+  float g[8];
+  int lo = -1, hi = nb;
+  for (int k = 0; k < nb; k++) g[k] = seg_box_dfdt(c, d, s, bp[k]);
+  for (int k = 0; k < nb; k++) if (g[k] < 0.f) lo = k;
+  for (int k = nb - 1; k >= 0; k--) if (g[k] > 0.f) hi = k;
+  if (hi == 0) return bp[0];
+  if (lo == nb - 1) return bp[nb - 1];
+  if (hi == lo + 1) return bp[lo] + (bp[hi] - bp[lo]) * (-g[lo]) / (g[hi] - g[lo]);
+  return 0.5f * (bp[lo + 1] + bp[hi - 1]);
+}
+// one contact between the capsule's point p (box frame) and the box: dist, position and normal (capsule -> box) in the box frame
+MYO_DI bool capsule_box_point(const float* p, const float* s, float r, float margin, float* dist, float* pos_b, float* nrm_b) {
+  float q[3], f = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { q[i] = clipf(p[i], -s[i], s[i]); f += (p[i] - q[i]) * (p[i] - q[i]); }
+  const float dd = sqrtf(f);
+  if (dd > r + margin) return false;
+  if (dd > 1e-10f) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) nrm_b[i] = (q[i] - p[i]) / dd;
+    *dist = dd - r;
+  } else {      // core segment inside the box: leave through the nearest face
+    int ax = 0;
+    float best = 3.0e38f;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const float dep = s[i] - fabsf(p[i]); if (dep < best) { best = dep; ax = i; } }
+    nrm_b[0] = nrm_b[1] = nrm_b[2] = 0.f;
+    nrm_b[ax] = p[ax] > 0.f ? -1.f : 1.f;
+    *dist = -best - r;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) pos_b[i] = p[i] + nrm_b[i] * (r + 0.5f * (*dist));
+  return true;
+}
+// contact number `sub` (0 or 1) of capsule (pc, axis, r, h) vs box (pb, Rb, s): both end points within reach -> one contact per end
+// point, else a single contact at the closest point of the core segment
+MYO_PHASE bool capsule_box(int sub, float margin, const float* pc, const float* axis, float r, float h, const float* pb, const float* Rb,
+                            const float* s, float* dist, float* pos, float* nrm) {
+  float dif[3], c[3], d[3];
+  sub3(dif, pc, pb); mulmatTvec3(c, Rb, dif); mulmatTvec3(d, Rb, axis);
+  float pe[2][3], de[2], pb2[2][3], nb2[2][3];
+  bool he[2];
+#pragma unroll
+  for (int e = 0; e < 2; e++) {
+    const float t = e ? h : -h;
+#pragma unroll
+    for (int i = 0; i < 3; i++) pe[e][i] = c[i] + t * d[i];
+    he[e] = capsule_box_point(pe[e], s, r, margin, &de[e], pb2[e], nb2[e]);
+  }
+  float posb[3], nrmb[3];
+  if (he[0] && he[1]) {
+    *dist = de[sub];
+    cpy3(posb, pb2[sub]); cpy3(nrmb, nb2[sub]);
+  } else {
+    if (sub) return false;
+    const float t = seg_box_closest_t(c, d, h, s);
+    float p[3] = {c[0] + t * d[0], c[1] + t * d[1], c[2] + t * d[2]};
+    if (!capsule_box_point(p, s, r, margin, dist, posb, nrmb)) return false;
+  }
+  mulmatvec3(pos, Rb, posb); add3(pos, pos, pb);
+  mulmatvec3(nrm, Rb, nrmb);
+  return true;
+}
+
 template <int G>
 MYO_PHASE void phase_collision(int mslot, Ctx<G>& c, int* status) {
   MYO_M
@@ -723,6 +821,16 @@ MYO_PHASE void phase_collision(int mslot, Ctx<G>& c, int* status) {
           if (m.g_size_slot[g1] >= 0) s1 = c.wpp(m)[m.g_size_slot[g1]];
           if (m.g_size_slot[g2] >= 0) s2 = c.wpp(m)[m.g_size_slot[g2]];
           if (t1 == G_SPHERE && t2 == G_SPHERE) hit = sphere_sphere(margin, p1, s1, p2, s2, &dist, pos, nrm);
+          else if (t1 == G_CAPSULE && t2 == G_BOX) {
+            float ax[3], Rb[9], sz[3];
+            geom_world_zaxis(m, c.sp(), g1, ax);
+            mulmat3(Rb, SF(o_xmat) + 9 * m.g_body[g2], m.g_mat + 9 * g2);
+            float half = m.g_size[3 * g1 + 1];
+            if (m.g_size_slot[g1] >= 0) half = c.wpp(m)[m.g_size_slot[g1] + 1];
+#pragma unroll
+            for (int e = 0; e < 3; e++) sz[e] = (m.g_size_slot[g2] >= 0) ? c.wpp(m)[m.g_size_slot[g2] + e] : m.g_size[3 * g2 + e];
+            hit = capsule_box(m.p_supported[p] - 1, margin, p1, ax, s1, half, p2, Rb, sz, &dist, pos, nrm);
+          }
           else if (t1 == G_SPHERE && t2 == G_CAPSULE) {
             float ax[3], v[3];
             geom_world_zaxis(m, c.sp(), g2, ax);

@@ -113,6 +113,24 @@ MYO_PHASE void task_obs(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float
     for (int i = c.lane; i < m.nq; i += G) { obs[i] = qpos[i]; obs[m.nq + m.nv + i] = pose_target[i] - qpos[i]; }
     for (int i = c.lane; i < m.nv; i += G) obs[m.nq + i] = qvel[i] * m.frame_dt;
     for (int i = c.lane; i < m.na; i += G) obs[2 * m.nq + m.nv + i] = act[i];
+  } else if (t.kind == MYO_TASK_REORIENT) {
+    // ReorientEnvV0.get_obs_dict: hand_qpos | hand_qvel * dt | obj_pos | goal_pos | pos_err | obj_rot | goal_rot | rot_err | act
+    const int nh = m.nq - 7, nhv = m.nv - 6, o0 = nh + nhv;
+    for (int i = c.lane; i < nh; i += G) obs[i] = qpos[i];
+    for (int i = c.lane; i < nhv; i += G) obs[nh + i] = qvel[i] * m.frame_dt;
+    for (int i = c.lane; i < m.na; i += G) obs[o0 + 18 + i] = act[i];
+    if (c.lane == 0) {
+      float po[3], pg[3], eo[3], eg[3];
+      site_world(m, c.sp(), c.wpp(m), t.object_site, po);
+      site_world(m, c.sp(), c.wpp(m), t.goal_site, pg);
+      mat2euler(eo, SF(o_xmat) + 9 * m.s_body[t.object_site]);      // the sites share their bodies' frames (checked on the host)
+      mat2euler(eg, SF(o_xmat) + 9 * m.s_body[t.goal_site]);
+#pragma unroll
+      for (int e = 0; e < 3; e++) {
+        obs[o0 + e] = po[e]; obs[o0 + 3 + e] = pg[e]; obs[o0 + 6 + e] = pg[e] - po[e] - t.goal_obj_offset[e];
+        obs[o0 + 9 + e] = eo[e]; obs[o0 + 12 + e] = eg[e]; obs[o0 + 15 + e] = eg[e] - eo[e];
+      }
+    }
   } else {
     for (int i = c.lane; i < m.nq; i += G) obs[i] = qpos[i];
     for (int i = c.lane; i < m.nv; i += G) obs[m.nq + i] = qvel[i];
@@ -123,7 +141,7 @@ MYO_PHASE void task_obs(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float
 
 // reward terms + dense reward + termination from the observation in scratch. info: MYO_INFO_TERMS floats.
 template <int G>
-MYO_PHASE void task_reward(int mslot, const myo_task_cfg& t, Ctx<G>& c, float* info, float* reward, bool* done) {
+MYO_PHASE void task_reward(int mslot, const myo_task_cfg& t, Ctx<G>& c, float* tf, float* info, float* reward, bool* done) {
   MYO_M
   const float* obs = SF(o_obs); const float* act = SF(o_act);
   float a2 = 0.f;
@@ -153,10 +171,23 @@ MYO_PHASE void task_reward(int mslot, const myo_task_cfg& t, Ctx<G>& c, float* i
     term[3] = -act_mag; term[4] = -dist; term[5] = dist < t.pose_thd ? 1.f : 0.f;
     term[6] = dist > t.far_th ? 1.f : 0.f;
     dn = dist > t.far_th;
+  } else if (t.kind == MYO_TASK_REORIENT) {
+    // CustomReorientEnv.get_reward_dict (/root/reference/src/envs/reorient.py:11-56): distances, their decrease since the last
+    // step (self.pos_dist / self.rot_dist, refreshed in step() and reset()), drop = pos_dist > drop_th
+    const int o0 = (m.nq - 7) + (m.nv - 6);
+    const float pd = norm3(obs + o0 + 6), rd = norm3(obs + o0 + 15);
+    const bool drop = pd > t.drop_th;
+    term[0] = -pd; term[1] = -rd; term[2] = -act_mag; term[3] = drop ? 0.f : 1.f; term[4] = -rd - 10.f * pd;
+    term[5] = (pd < t.pos_th && rd < t.rot_th && !drop) ? 1.f : 0.f;
+    term[6] = drop ? 1.f : 0.f;
+    term[8] = tf[TF_POSDIST] - pd; term[9] = tf[TF_ROTDIST] - rd;
+    dn = drop;
+    c.tile.sync();
+    if (c.lane == 0) { tf[TF_POSDIST] = pd; tf[TF_ROTDIST] = rd; }      // step(): self.pos_dist / self.rot_dist <- this step's
   }
   float dense = 0.f;
 #pragma unroll
-  for (int k = 0; k < 7; k++) dense += t.rwd_weight[k] * term[k];
+  for (int k = 0; k < MYO_INFO_TERMS; k++) if (k != 7) dense += t.rwd_weight[k] * term[k];
   term[7] = dense;
 #pragma unroll
   for (int k = 0; k < MYO_INFO_TERMS; k++) info[k] = term[k];
@@ -295,7 +326,49 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         nf_th = rng.uniform(-kPi / 18.f * t.noise_fingers, kPi / 18.f * t.noise_fingers);
         nf_fl = rng.uniform(0.f, kPi / 6.f * t.noise_fingers);
       }
+    } else if (t.kind == MYO_TASK_REORIENT) {
+      // CustomReorientEnv.reset (/root/reference/src/envs/reorient.py:127-178): goal position, goal orientation (set_orientation,
+      // :180-205), die friction, one size offset for die and target. The RSI branch only edits body_pos / body_quat of the
+      // free-jointed die, which MuJoCo's kinematics never reads (a free body's pose is its qpos): it changes nothing.
+      const int ps = m.b_pose_slot[t.goal_body];
+      if (ps >= 0) {
+        for (int e = 0; e < 3; e++) c.wpp(m)[ps + e] = t.goal_init_pos[e] + rng.uniform(t.goal_pos[0], t.goal_pos[1]);
+        float lo[3], hi[3];
+        for (int ax = 0; ax < 3; ax++) {      // the three range choices first, then the three angles (the reference's draw order)
+          lo[ax] = t.goal_rot[0]; hi[ax] = t.goal_rot[1];
+          if (t.n_goal_rot[ax] > 0) {
+            const int k = min(t.n_goal_rot[ax] - 1, (int)(rng.uniform() * (float)t.n_goal_rot[ax]));
+            lo[ax] = t.goal_rot_axis[ax][k][0]; hi[ax] = t.goal_rot_axis[ax][k][1];
+          }
+        }
+        float eul[3], q[4], R[9];
+        for (int ax = 0; ax < 3; ax++) eul[ax] = rng.uniform(lo[ax], hi[ax]);
+        euler2quat(q, eul);
+        quat2mat(R, q);
+        for (int e = 0; e < 9; e++) c.wpp(m)[ps + 3 + e] = R[e];
+      }
+      for (int k = 0; k < t.object_ngeom; k++) {
+        const int g = t.object_geom0 + k, fs = m.g_fri_slot[g];
+        for (int e = 0; e < 3; e++) {
+          const float nominal = m.g_friction[3 * g + e];
+          const float v = rng.uniform(nominal - t.obj_friction_change[e], nominal + t.obj_friction_change[e]);
+          if (fs >= 0) c.wpp(m)[fs + e] = v;
+        }
+      }
+      const float del = rng.uniform(-t.obj_size_change, t.obj_size_change);
+      for (int k = 0; k < t.object_ngeom; k++) {
+        const int g = t.object_geom0 + k, ss = m.g_size_slot[g];
+        if (ss < 0) continue;
+        const bool slab = k >= t.object_ngeom - 3;       // the last three geoms grow in every half size, earlier ones in size[1]
+        for (int e = 0; e < 3; e++) c.wpp(m)[ss + e] = m.g_size[3 * g + e] + ((slab || e == 1) ? del : 0.f);
+      }
     } else if (t.kind == MYO_TASK_POSE) {
+      if (t.weight_body >= 0) {      // CustomPoseEnv.reset: a new weight, and the size of its first geom with it (pose.py:55-66)
+        const float wgt = rng.uniform(t.weight_range[0], t.weight_range[1]);
+        const int ms = m.b_mass_slot[t.weight_body], ss = t.weight_geom >= 0 ? m.g_size_slot[t.weight_geom] : -1;
+        if (ms >= 0) c.wpp(m)[ms] = wgt;
+        if (ss >= 0) c.wpp(m)[ss] = 0.01f + 2.5f * wgt / 100.f;
+      }
       // update_target: sample target_jnt_value inside target_jnt_range, then get_target_pose scales the
       // distance from init_qpos by target_distance
       for (int i = 0; i < m.nq; i++) pose_target[i] = (t.n_target_jnt > 0) ? 0.f : t.target_jnt_value[i];
@@ -307,6 +380,9 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         }
       }
       for (int i = 0; i < m.nq; i++) pose_target[i] = m.init_qpos[i] + t.target_distance * (pose_target[i] - m.init_qpos[i]);
+      if (t.reset_type == 3) {   // "sds": start between the target and the initial pose (pose.py:88-95)
+        for (int i = 0; i < m.nq; i++) qpos[i] = (1.f - t.sds_distance) * pose_target[i] + t.sds_distance * m.init_qpos[i];
+      }
       if (t.reset_type == 2) {   // "random": uniform inside jnt_range for every joint
         for (int j = 0; j < m.njnt; j++)
           if (m.j_type[j] == J_HINGE || m.j_type[j] == J_SLIDE)
@@ -369,6 +445,15 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
         const float ab = rng.uniform(-kPi / 36.f * t.noise_fingers, kPi / 36.f * t.noise_fingers);
         qpos[8] = ab; qpos[12] = ab; qpos[16] = ab; qpos[20] = ab;
       }
+    }
+    c.tile.sync();
+  }
+  if (t.kind == MYO_TASK_REORIENT) {      // reset(): self.pos_dist / self.rot_dist from the reset observation (reorient.py:176-177)
+    phase_tree_forward<G>(mslot, c, false);
+    task_obs<G>(mslot, t, c, pose_target);
+    if (c.lane == 0) {
+      const int o0 = (m.nq - 7) + (m.nv - 6);
+      tf[TF_POSDIST] = norm3(SF(o_obs) + o0 + 6); tf[TF_ROTDIST] = norm3(SF(o_obs) + o0 + 15);
     }
     c.tile.sync();
   }

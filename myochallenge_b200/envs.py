@@ -18,7 +18,7 @@ import numpy as np
 from . import _capi
 from .assets import asset_path
 from .sim import Model
-from .vec_env import BAODING_KEYS, POSE_KEYS, MyoVecEnv
+from .vec_env import BAODING_KEYS, POSE_KEYS, REORIENT_KEYS, MyoVecEnv
 
 _JNT_HAND = ['pro_sup', 'deviation', 'flexion', 'cmc_abduction', 'cmc_flexion', 'mp_flexion', 'ip_flexion', 'mcp2_flexion',
              'mcp2_abduction', 'pm2_flexion', 'md2_flexion', 'mcp3_flexion', 'mcp3_abduction', 'pm3_flexion', 'md3_flexion',
@@ -47,6 +47,12 @@ REGISTRY: Dict[str, Dict[str, Any]] = {
                                                        goal_yrange=(0.022, 0.032), obj_size_range=(0.018, 0.024),
                                                        obj_mass_range=(0.030, 0.300), obj_friction_change=(0.2, 0.001, 0.00002),
                                                        task_choice="random")),
+    # die reorientation   [REF src/envs/__init__.py:26-55]
+    "CustomMyoChallengeDieReorientP1-v0": dict(kind=_capi.TASK_REORIENT, model="hand/myo_hand_die.mjb", horizon=150,
+                                               kwargs=dict(normalize_act=True, frame_skip=5, goal_pos=(-.010, .010), goal_rot=(-1.57, 1.57))),
+    "CustomMyoChallengeDieReorientP2-v0": dict(kind=_capi.TASK_REORIENT, model="hand/myo_hand_die.mjb", horizon=150,
+                                               kwargs=dict(normalize_act=True, frame_skip=5, goal_pos=(-.020, .020), goal_rot=(-3.14, 3.14),
+                                                           obj_size_change=0.007, obj_friction_change=(0.2, 0.001, 0.00002))),
     "CustomMyoElbowPoseFixed-v0": dict(kind=_capi.TASK_POSE, model="arm/myo_elbow_1dof6muscles.mjb", horizon=100,
                                        kwargs=dict(target_jnt_range={"r_elbow_flex": (2, 2)}, normalize_act=True, pose_thd=.175, reset_type="random")),
     "CustomMyoElbowPoseRandom-v0": dict(kind=_capi.TASK_POSE, model="arm/myo_elbow_1dof6muscles.mjb", horizon=100,
@@ -85,10 +91,11 @@ FACTORY_NAMES = {
     "CustomMyoElbowPoseFixed": "CustomMyoElbowPoseFixed-v0", "CustomMyoElbowPoseRandom": "CustomMyoElbowPoseRandom-v0",
     "CustomMyoFingerPoseFixed": "CustomMyoFingerPoseFixed-v0", "CustomMyoFingerPoseRandom": "CustomMyoFingerPoseRandom-v0",
     "CustomMyoHandPoseFixed": "CustomMyoHandPoseFixed-v0", "CustomMyoHandPoseRandom": "CustomMyoHandPoseRandom-v0",
+    "CustomMyoReorientP1": "CustomMyoChallengeDieReorientP1-v0", "CustomMyoReorientP2": "CustomMyoChallengeDieReorientP2-v0",
 }
-# names the reference factory knows whose models / task kernels are outside this build (die, pen, key-turn, reach, mixture)
-UNSUPPORTED = {"MyoFingerReachFixed", "MyoFingerReachRandom", "MyoHandKeyTurnFixed", "MyoHandKeyTurnRandom", "CustomMyoReorientP1",
-               "CustomMyoReorientP2", "MixtureModelBaodingEnv", "CustomMyoPenTwirlRandom"}
+# names the reference factory knows whose models / task kernels are outside this build (pen, key-turn, reach, mixture)
+UNSUPPORTED = {"MyoFingerReachFixed", "MyoFingerReachRandom", "MyoHandKeyTurnFixed", "MyoHandKeyTurnRandom",
+               "MixtureModelBaodingEnv", "CustomMyoPenTwirlRandom"}
 
 
 def _weights(cfg, keys, weighted_reward_keys):
@@ -109,7 +116,7 @@ def make_task_cfg(model: Model, env_id: str, **overrides) -> _capi.TaskCfg:
     kw.update(overrides)
     cfg = model.default_task_cfg(reg["kind"])
     cfg.max_episode_steps = int(kw.pop("max_episode_steps", reg["horizon"]))
-    cfg.frame_skip = int(kw.pop("frame_skip", 10))
+    cfg.frame_skip = int(kw.pop("frame_skip", 5 if reg["kind"] == _capi.TASK_REORIENT else 10))
     cfg.normalize_act = int(bool(kw.pop("normalize_act", True)))
     cfg.auto_reset = int(bool(kw.pop("auto_reset", True)))
     cfg.clip_actions = int(bool(kw.pop("clip_actions", False)))
@@ -158,15 +165,42 @@ def make_task_cfg(model: Model, env_id: str, **overrides) -> _capi.TaskCfg:
                 if len(v) != 2 or min(v) <= 0:
                     raise ValueError(f"{k} must be the (a, b) > 0 of a beta distribution, got {v!r}")
                 getattr(cfg, k)[0], getattr(cfg, k)[1] = float(v[0]), float(v[1])
+    elif reg["kind"] == _capi.TASK_REORIENT:
+        # CustomReorientEnv._setup (/root/reference/src/envs/reorient.py:58-125)
+        if "weighted_reward_keys" in kw:
+            _weights(cfg, REORIENT_KEYS, kw.pop("weighted_reward_keys"))
+        for name, default in (("goal_pos", (0.0, 0.0)), ("goal_rot", (0.785, 0.785))):
+            lo, hi = kw.pop(name, default)
+            getattr(cfg, name)[0], getattr(cfg, name)[1] = float(lo), float(hi)
+        cfg.obj_size_change = float(kw.pop("obj_size_change", 0.0))
+        fc = kw.pop("obj_friction_change", (0, 0, 0))
+        for i in range(3):
+            cfg.obj_friction_change[i] = float(fc[i])
+        cfg.pos_th, cfg.rot_th, cfg.drop_th = float(kw.pop("pos_th", 0.025)), float(kw.pop("rot_th", 0.262)), float(kw.pop("drop_th", 0.200))
+        for ax, name in enumerate(("goal_rot_x", "goal_rot_y", "goal_rot_z")):
+            ranges = kw.pop(name, None)
+            if ranges is not None:
+                if not 0 < len(ranges) <= _capi.MYO_MAX_ROT_RANGES:
+                    raise ValueError(f"{name}: between 1 and {_capi.MYO_MAX_ROT_RANGES} (low, high) ranges")
+                cfg.n_goal_rot[ax] = len(ranges)
+                for k, (lo, hi) in enumerate(ranges):
+                    cfg.goal_rot_axis[ax][k][0], cfg.goal_rot_axis[ax][k][1] = float(lo), float(hi)
+        # enable_rsi / rsi_distance_*: the reference's RSI branch only rewrites body_pos / body_quat of the free-jointed die, which
+        # MuJoCo's kinematics never reads (a free body's pose is its qpos), so these knobs change nothing there - nor here
+        for k in ("enable_rsi", "rsi_distance_pos", "rsi_distance_rot"):
+            kw.pop(k, None)
     else:
         if "weighted_reward_keys" in kw:
             _weights(cfg, POSE_KEYS, kw.pop("weighted_reward_keys"))
         cfg.pose_thd = float(kw.pop("pose_thd", 0.35))
         cfg.target_distance = float(kw.pop("target_distance", 1.0))
         rt = kw.pop("reset_type", "init")
-        if rt not in ("none", "init", "random"):
-            raise NotImplementedError(f"reset_type {rt!r}")
-        cfg.reset_type = {"none": 0, "init": 1, "random": 2}[rt]
+        if rt is None:
+            rt = "none"
+        if rt not in ("none", "init", "random", "sds"):
+            raise ValueError(f"Reset Type not found: {rt!r}")
+        cfg.reset_type = {"none": 0, "init": 1, "random": 2, "sds": 3}[rt]
+        cfg.sds_distance = float(kw.pop("sds_distance", 0) or 0)
         tt = kw.pop("target_type", "generate")
         if tt not in ("generate", "fixed"):
             raise NotImplementedError(f"target_type {tt!r}")
@@ -184,10 +218,19 @@ def make_task_cfg(model: Model, env_id: str, **overrides) -> _capi.TaskCfg:
             cfg.n_target_jnt = 0
             for i, v in enumerate(np.asarray(val, float).reshape(-1)):
                 cfg.target_jnt_value[i] = float(v)
-        for k in ("viz_site_targets", "weight_bodyname", "weight_range", "sds_distance"):
-            v = kw.pop(k, None)
-            if k in ("weight_bodyname", "weight_range", "sds_distance") and v:
-                raise NotImplementedError(f"{k}={v!r} is not part of the device reset yet")
+        kw.pop("viz_site_targets", None)
+        kw.pop("sds_distance", None)
+        wb, wr = kw.pop("weight_bodyname", None), kw.pop("weight_range", None)
+        if wb is not None:       # CustomPoseEnv.reset: body_mass[bid] ~ U(weight_range); geom_size[body_geomadr[bid]][0] follows (pose.py:55-66)
+            if wr is None or len(wr) != 2:
+                raise ValueError("weight_bodyname needs weight_range=(low, high)")
+            bid = model.name2id("body", wb)
+            gid = int(model.array("body_geomadr")[bid])
+            cfg.weight_body, cfg.weight_geom = bid, gid
+            cfg.weight_range[0], cfg.weight_range[1] = float(wr[0]), float(wr[1])
+            cfg.n_ovr_body, cfg.ovr_body[0] = 1, bid
+            if gid >= 0:
+                cfg.n_ovr_geom, cfg.ovr_geom[0] = 1, gid
     kw.pop("model_path", None)
     kw.pop("obs_keys", None)
     if kw:

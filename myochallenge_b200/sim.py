@@ -177,12 +177,12 @@ class BatchSim:
         check(self._L, self._L.myo_batch_set_state(self._h, _ptr(q), _ptr(v), _ptr(a), _ptr(t), self._stream()))
 
     def set_param(self, kind: int, obj_id: int, values):
-        ncomp = 1 if kind == _capi.PARAM_BODY_MASS else 3
+        ncomp = _capi.PARAM_NCOMP[int(kind)]
         v = self._f32(values, (self.n, ncomp))
         check(self._L, self._L.myo_batch_set_param(self._h, int(kind), int(obj_id), _ptr(v), self._stream()))
 
     def get_param(self, kind: int, obj_id: int) -> torch.Tensor:
-        ncomp = 1 if kind == _capi.PARAM_BODY_MASS else 3
+        ncomp = _capi.PARAM_NCOMP[int(kind)]
         v = torch.empty(self.n, ncomp, dtype=torch.float32, device=self.device)
         check(self._L, self._L.myo_batch_get_param(self._h, int(kind), int(obj_id), _ptr(v), self._stream()))
         return v

@@ -59,7 +59,7 @@ class LazyInfos(Sequence):
         if isinstance(i, slice):
             return [self[j] for j in range(*i.indices(len(self)))]
         row = self._info[i]
-        rwd = {k: float(row[j]) for j, k in enumerate(self._keys)}
+        rwd = {k: float(row[j]) for j, k in enumerate(self._keys) if k != "dense"}
         d: Dict[str, Any] = dict(rwd)
         d["rwd_dict"] = rwd
         d["rwd_dense"] = float(row[7])
@@ -73,6 +73,8 @@ class LazyInfos(Sequence):
 
 BAODING_KEYS = ("pos_dist_1", "pos_dist_2", "act_reg", "alive", "sparse", "solved", "done")
 POSE_KEYS = ("pose", "bonus", "penalty", "act_reg", "sparse", "solved", "done")
+# CustomReorientEnv.get_reward_dict (/root/reference/src/envs/reorient.py:21-46); slot 7 is the dense reward in every task
+REORIENT_KEYS = ("pos_dist", "rot_dist", "act_reg", "alive", "sparse", "solved", "done", "dense", "pos_dist_diff", "rot_dist_diff")
 
 
 class MyoVecEnv:
@@ -85,7 +87,7 @@ class MyoVecEnv:
         self.cfg = cfg
         self.observation_space = Box(-10.0, 10.0, (self.sim.nobs,), np.float32)
         self.action_space = Box(-1.0, 1.0, (self.sim.nu,), np.float32)
-        self._keys = BAODING_KEYS if cfg.kind == _capi.TASK_BAODING else POSE_KEYS
+        self._keys = {_capi.TASK_BAODING: BAODING_KEYS, _capi.TASK_REORIENT: REORIENT_KEYS}.get(cfg.kind, POSE_KEYS)
         n, pin = self.num_envs, self.device.type == "cuda"
         self._h_act = torch.zeros(n, self.sim.nu, dtype=torch.float32, pin_memory=pin)
         self._h_obs = torch.zeros(n, self.sim.nobs, dtype=torch.float32, pin_memory=pin)

@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TEMPLATE = os.path.join(ROOT, "myochallenge_b200", "assets", "finger", "myo_finger_v0.mjb")
 
 FREE, SLIDE, HINGE = 0, 2, 3
-PLANE, SPHERE, CAPSULE, CYLINDER = 0, 2, 3, 5
+PLANE, SPHERE, CAPSULE, CYLINDER, BOX = 0, 2, 3, 5, 6
 W_PULLEY, W_SITE, W_SPHERE, W_CYL = 2, 3, 4, 5
 
 
@@ -101,6 +101,12 @@ class Builder:
         o = self.bodies[self.bid(body)]["origin"]
         self.geoms.append(dict(name=name, body=self.bid(body), type=SPHERE, size=(radius, 0, 0), pos=np.asarray(center, float) - o,
                                quat=np.array([1.0, 0, 0, 0]), contype=contype, conaffinity=conaffinity, rbound=radius))
+
+    def box(self, body, name, center, half, contype=0, conaffinity=0):
+        o = self.bodies[self.bid(body)]["origin"]
+        half = np.asarray(half, float)
+        self.geoms.append(dict(name=name, body=self.bid(body), type=BOX, size=tuple(half), pos=np.asarray(center, float) - o,
+                               quat=np.array([1.0, 0, 0, 0]), contype=contype, conaffinity=conaffinity, rbound=float(np.linalg.norm(half))))
 
     def cylinder(self, body, name, center, axis, radius, halflen):
         """Wrapping cylinder (never collides)."""
@@ -374,7 +380,9 @@ def _mat2quat(R):
     return np.array([w, (R[2, 1] - R[1, 2]) / (4 * w), (R[0, 2] - R[2, 0]) / (4 * w), (R[1, 0] - R[0, 1]) / (4 * w)])
 
 
-def build_hand(balls: bool) -> mjb.MjbModel:
+def build_hand(kind: str) -> mjb.MjbModel:
+    """kind: 'pose' (hand only), 'baoding' (+ two balls and the target sites), 'die' (+ the die and its target)."""
+    balls = kind == "baoding"
     B = Builder()
     P = lambda x, y, z: P0 + np.array([x, y, z], float)
     B.body("forearm", "world", P(0, 0.25, 0), 1.0, (4e-3, 4e-4, 4e-3))
@@ -518,6 +526,25 @@ def build_hand(balls: bool) -> mjb.MjbModel:
         B.body("target_frame", "palm", P0, 0.0, (0, 0, 0))
         for k in (1, 2):
             B.site("target_frame", f"target{k}_site", P0)   # position set below (rotated frame)
+    if kind == "die":
+        # Die: the reference's reset (/root/reference/src/envs/reorient.py:100-160) treats the LAST THREE geoms of body "Object" as
+        # boxes that grow / shrink with obj_size_change in all three half sizes (earlier geoms, if any, only in size[1]): here
+        # the die is exactly three mutually orthogonal slabs whose union is a cube with bevelled edges. The target die is a
+        # non-colliding copy on the body "target" (moved / turned by reset through body_pos / body_quat), shown offset from
+        # the hand: goal_obj_offset = target_o - object_o at the initial pose.
+        h, k = 0.015, 0.012
+        c = ORBIT_C + np.array([0.0, 0.0, 0.038])
+        mass = 0.05
+        B.body("Object", "world", c, mass, (mass * (2 * h) ** 2 / 6.0,) * 3, simple=1)
+        B.joint("Object", "OBJT_free", FREE, limited=False)
+        for nm, half in (("dice_z", (h, h, k)), ("dice_y", (h, k, h)), ("dice_x", (k, h, h))):
+            B.box("Object", nm, c, half, contype=3, conaffinity=1)
+        B.site("Object", "object_o", c)
+        tc = c + np.array([0.0, 0.0, 0.15])
+        B.body("target", "world", tc, 0.0, (0, 0, 0))
+        B.box("target", "target_dice", tc, (h, h, h))
+        B.site("target", "target_o", tc)
+        B.site("target", "target_ball", tc + np.array([0.0, 0.0, 0.03]))
     m = B.compile()
     if balls:
         tb = B.bid("target_frame")
@@ -565,8 +592,8 @@ def main():
     out = os.path.join(ROOT, "myochallenge_b200", "assets")
     os.makedirs(os.path.join(out, "hand"), exist_ok=True)
     os.makedirs(os.path.join(out, "arm"), exist_ok=True)
-    for rel, m in (("hand/myo_hand_baoding.mjb", build_hand(True)), ("hand/myo_hand_pose.mjb", build_hand(False)),
-                   ("arm/myo_elbow_1dof6muscles.mjb", build_elbow())):
+    for rel, m in (("hand/myo_hand_baoding.mjb", build_hand("baoding")), ("hand/myo_hand_pose.mjb", build_hand("pose")),
+                   ("hand/myo_hand_die.mjb", build_hand("die")), ("arm/myo_elbow_1dof6muscles.mjb", build_elbow())):
         raw = mjb.dump(m)
         with open(os.path.join(out, rel), "wb") as f:
             f.write(raw)

@@ -18,6 +18,7 @@ MOTOR_FINGER = os.path.join(ASSETS, "finger", "motor_finger_v0.mjb")
 MYO_LOAD = os.path.join(ASSETS, "basic", "myo_load.mjb")
 HAND_BAODING = os.path.join(ASSETS, "hand", "myo_hand_baoding.mjb")
 HAND_POSE = os.path.join(ASSETS, "hand", "myo_hand_pose.mjb")
+HAND_DIE = os.path.join(ASSETS, "hand", "myo_hand_die.mjb")
 ELBOW = os.path.join(ASSETS, "arm", "myo_elbow_1dof6muscles.mjb")
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
@@ -64,6 +65,9 @@ def random_states(model_path, n, seed, steps=(5, 120), ctrl_hi=0.6):
     if om.nq == 37:      # baoding: reference init pose (/root/reference/src/envs/baoding.py:400-401)
         init[:23] = 0
         init[0] = -1.57
+    if om.nq == 30:      # die: reference init pose (/root/reference/src/envs/reorient.py:123-124)
+        init[:23] = 0
+        init[0] = -1.5
     for _ in range(n):
         od.reset()
         od.qpos[:] = init

@@ -35,6 +35,7 @@ from myosuite.envs.myo.myochallenge.baoding_v1 import Task  # noqa: E402
 M_RESET = 256
 BAODING_TERMS = ("pos_dist_1", "pos_dist_2", "act_reg", "alive", "sparse", "solved", "done", "dense")
 POSE_TERMS = ("pose", "bonus", "penalty", "act_reg", "sparse", "solved", "done", "dense")
+REORIENT_TERMS = ("pos_dist", "rot_dist", "act_reg", "alive", "sparse", "solved", "done", "dense", "pos_dist_diff", "rot_dist_diff")
 
 
 def seed_all(env, s):
@@ -66,6 +67,18 @@ def baoding_snapshot(u):
                 qpos=np.array(d.qpos), qvel=np.array(d.qvel), act=np.array(d.act))
 
 
+def reorient_snapshot(u):
+    m, d = u.sim.model, u.sim.data
+    g0, gn = u.object_gid0, u.object_gidn
+    return dict(goal_pos=np.array(m.body_pos[u.goal_bid]), goal_quat=np.array(m.body_quat[u.goal_bid]), die_size=np.array(m.geom_size[g0:gn]),
+                die_fric=np.array(m.geom_friction[g0:gn]), pos_dist=float(u.pos_dist), rot_dist=float(u.rot_dist),
+                qpos=np.array(d.qpos), qvel=np.array(d.qvel), act=np.array(d.act))
+
+
+def env_kind(u):
+    return "baoding" if hasattr(u, "which_task") else ("reorient" if hasattr(u, "goal_bid") else "pose")
+
+
 def stack(snaps):
     return {k: np.array([s[k] for s in snaps]) for k in snaps[0]}
 
@@ -87,18 +100,29 @@ def reset_samples(env_name, config, n, seed, instances=1):
     if seed is not None:
         seed_all(env, seed)
     out = []
-    if hasattr(u, "which_task"):
+    if env_kind(u) == "baoding":
         instrument(u)
         for _ in range(n):
             obs = env.reset()
             s = baoding_snapshot(u)
             s["obs"] = np.array(obs)
             out.append(s)
+    elif env_kind(u) == "reorient":
+        for _ in range(n):
+            obs = env.reset()
+            s = reorient_snapshot(u)
+            s["obs"] = np.array(obs)
+            out.append(s)
     else:
         for _ in range(n):
             obs = env.reset()
-            out.append(dict(target=np.array(u.target_jnt_value, float), qpos=np.array(u.sim.data.qpos), qvel=np.array(u.sim.data.qvel),
-                            act=np.array(u.sim.data.act), obs=np.array(obs)))
+            rec = dict(target=np.array(u.target_jnt_value, float), qpos=np.array(u.sim.data.qpos), qvel=np.array(u.sim.data.qvel),
+                       act=np.array(u.sim.data.act), obs=np.array(obs))
+            if u.weight_bodyname is not None:
+                bid = u.sim.model.body_name2id(u.weight_bodyname)
+                rec["weight_mass"] = float(u.sim.model.body_mass[bid])
+                rec["weight_size0"] = float(u.sim.model.geom_size[u.sim.model.body_geomadr[bid]][0])
+            out.append(rec)
     return stack(out)
 
 
@@ -108,10 +132,11 @@ def step_cases(env_name, config, n_cases, seed, every=3, horizon=40):
     u = env.unwrapped
     seed_all(env, seed)
     rng = np.random.RandomState(seed + 1)
-    baoding = hasattr(u, "which_task")
+    kind = env_kind(u)
+    baoding = kind == "baoding"
     if baoding:
         instrument(u)
-    terms = BAODING_TERMS if baoding else POSE_TERMS
+    terms = dict(baoding=BAODING_TERMS, pose=POSE_TERMS, reorient=REORIENT_TERMS)[kind]
     cases = []
     while len(cases) < n_cases:
         env.reset()
@@ -119,13 +144,14 @@ def step_cases(env_name, config, n_cases, seed, every=3, horizon=40):
         for t in range(horizon):
             if t % 5 == 0:
                 a = rng.uniform(-1, 1, u.sim.model.nu)
-            pre = baoding_snapshot(u) if baoding else dict(target=np.array(u.target_jnt_value, float), qpos=np.array(u.sim.data.qpos),
-                                                           qvel=np.array(u.sim.data.qvel), act=np.array(u.sim.data.act))
+            pre = baoding_snapshot(u) if baoding else (reorient_snapshot(u) if kind == "reorient" else
+                                                       dict(target=np.array(u.target_jnt_value, float), qpos=np.array(u.sim.data.qpos),
+                                                            qvel=np.array(u.sim.data.qvel), act=np.array(u.sim.data.act)))
             obs, rew, done, info = env.step(a)
             if t % every == 0 or done:
                 c = {"pre_" + k: v for k, v in pre.items()}
                 c.update(action=np.array(a), obs=np.array(obs), reward=float(rew), done=bool(info["done"]),
-                         terms=np.array([float(info["rwd_dict"][k]) for k in terms]), post_qpos=np.array(u.sim.data.qpos),
+                         terms=np.array([float(np.squeeze(info["rwd_dict"][k])) for k in terms]), post_qpos=np.array(u.sim.data.qpos),
                          post_qvel=np.array(u.sim.data.qvel), post_act=np.array(u.sim.data.act))
                 if baoding:
                     c["post_counter"] = u.counter
@@ -158,7 +184,13 @@ def main():
              ("finger_random", "CustomMyoFingerPoseRandom", {}), ("finger_fixed", "CustomMyoFingerPoseFixed", {}),
              ("elbow_random", "CustomMyoElbowPoseRandom", {}), ("hand_random", "CustomMyoHandPoseRandom", {}),
              ("hand_fixed", "CustomMyoHandPoseFixed", {}),
-             ("finger_distance", "CustomMyoFingerPoseRandom", dict(target_distance=0.4, reset_type="init"))]
+             ("finger_distance", "CustomMyoFingerPoseRandom", dict(target_distance=0.4, reset_type="init")),
+             ("elbow_sds", "CustomMyoElbowPoseRandom", dict(reset_type="sds", sds_distance=0.3, target_distance=0.6, weight_bodyname=None, weight_range=None)),
+             ("finger_sds0", "CustomMyoFingerPoseRandom", dict(reset_type="sds", sds_distance=0, weight_bodyname=None, weight_range=None)),
+             ("elbow_weight", "CustomMyoElbowPoseRandom", dict(weight_bodyname="forearm", weight_range=(0.5, 2.0))),
+             ("die_p1", "CustomMyoReorientP1", {}), ("die_p2", "CustomMyoReorientP2", {}),
+             ("die_axes", "CustomMyoReorientP2", dict(goal_rot_x=[(-0.5, 0.5), (1.0, 1.2)], goal_rot_z=[(0.0, 0.0)], enable_rsi=True,
+                                                      rsi_distance_pos=0.5, rsi_distance_rot=0.5))]
     for tag, name, cfg in extra:
         put("reset", tag, name, cfg, reset_samples(name, cfg, M_RESET, 500 + len(meta["reset"]), instances=32 if tag == "p2_fixed_task" else 1))
         print("reset", tag, flush=True)
@@ -167,7 +199,11 @@ def main():
                  ("p1_cur02", cur[1]["env_name"], cur[1]["config"], 48),
                  ("p2_drop", "CustomMyoBaodingBallsP2", dict(drop_th=1.436, proximity_th=0.03), 48),
                  ("finger_random", "CustomMyoFingerPoseRandom", {}, 48), ("elbow_random", "CustomMyoElbowPoseRandom", {}, 32),
-                 ("hand_random", "CustomMyoHandPoseRandom", {}, 32)]
+                 ("hand_random", "CustomMyoHandPoseRandom", {}, 32),
+                 ("die_p2", "CustomMyoReorientP2", {}, 64),
+                 ("die_drop", "CustomMyoReorientP2", dict(drop_th=0.03, pos_th=0.05, rot_th=3.0,
+                                                          weighted_reward_keys=dict(pos_dist=1.0, rot_dist=0.2, pos_dist_diff=100.0, rot_dist_diff=10.0,
+                                                                                    alive=1.0, act_reg=0.5, solved=2.0, done=-3.0, sparse=0.1)), 48)]
     for tag, name, cfg, n in step_sets:
         put("step", tag, name, cfg, step_cases(name, cfg, n, 900 + len(meta["step"])))
         print("step", tag, flush=True)

@@ -2,12 +2,13 @@
 world (tests/emul), against the oracle. The GPU run of the same checks is tests/test_gpu_parity.py."""
 import pytest
 
-from conftest import ELBOW, FINGER, HAND_BAODING, HAND_POSE
+from conftest import ELBOW, FINGER, HAND_BAODING, HAND_DIE, HAND_POSE
 from myochallenge_b200 import _capi
 import parity_common as pc
 
 CASES = [("elbow", ELBOW, _capi.TASK_POSE, 8), ("finger", FINGER, _capi.TASK_POSE, 24),
-         ("hand_pose", HAND_POSE, _capi.TASK_POSE, 6), ("baoding", HAND_BAODING, _capi.TASK_BAODING, 10)]
+         ("hand_pose", HAND_POSE, _capi.TASK_POSE, 6), ("baoding", HAND_BAODING, _capi.TASK_BAODING, 10),
+         ("die", HAND_DIE, _capi.TASK_REORIENT, 10)]
 
 
 @pytest.mark.parametrize("name,path,kind,n", CASES, ids=[c[0] for c in CASES])

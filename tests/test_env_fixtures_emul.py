@@ -4,9 +4,9 @@ import pytest
 
 import env_fixture_checks as fx
 
-STEP_TAGS = ["p2_default", "p2_cur32", "p2_rsi", "p1_cur02", "p2_drop", "finger_random", "elbow_random", "hand_random"]
+STEP_TAGS = ["p2_default", "p2_cur32", "p2_rsi", "p1_cur02", "p2_drop", "finger_random", "elbow_random", "hand_random", "die_p2", "die_drop"]
 RESET_TAGS_CPU = ["cur02", "cur17", "cur26", "cur32", "p2_default", "p1_default", "p2_knobs", "p2_fixed_task", "p1_noise", "finger_random",
-                  "finger_fixed", "elbow_random", "hand_random", "hand_fixed", "finger_distance"]
+                  "finger_fixed", "elbow_random", "hand_random", "hand_fixed", "finger_distance", "die_p1", "die_p2", "die_axes", "elbow_sds", "finger_sds0", "elbow_weight"]
 
 
 @pytest.mark.parametrize("tag", STEP_TAGS)

@@ -71,6 +71,17 @@ def test_pose_registrations(product_lib):
     e = Model(asset_path("arm/myo_elbow_1dof6muscles.mjb"), lib=product_lib)
     cfg = make_task_cfg(e, "myoElbowPose1D6MRandom-v0")
     assert cfg.n_target_jnt == 1 and cfg.pose_thd == pytest.approx(0.175)
+    # the kwargs of the reference's pose mains (/root/reference/src/main_pose_elbow.py:30-43): reset_type "sds"
+    cfg = make_task_cfg(e, "CustomMyoElbowPoseRandom-v0", reset_type="sds", sds_distance=0.3, weight_bodyname=None, weight_range=None, target_distance=0.5)
+    assert cfg.reset_type == 3 and cfg.sds_distance == pytest.approx(0.3) and cfg.weight_body == -1
+    cfg = make_task_cfg(e, "CustomMyoElbowPoseRandom-v0", weight_bodyname="forearm", weight_range=(0.5, 2.0))
+    assert cfg.weight_body == e.name2id("body", "forearm") and cfg.n_ovr_body == 1 and cfg.n_ovr_geom == 1
+    # die reorientation registrations (/root/reference/src/envs/__init__.py:26-55)
+    d = Model(asset_path("hand/myo_hand_die.mjb"), lib=product_lib)
+    cfg = make_task_cfg(d, "CustomMyoChallengeDieReorientP2-v0", goal_rot_x=[(-0.5, 0.5), (1.0, 1.2)])
+    assert cfg.kind == _capi.TASK_REORIENT and cfg.frame_skip == 5 and cfg.max_episode_steps == 150 and cfg.object_ngeom == 3
+    assert cfg.obj_size_change == pytest.approx(0.007) and cfg.n_goal_rot[0] == 2 and cfg.goal_rot_axis[0][1][1] == pytest.approx(1.2)
+    assert tuple(cfg.rwd_weight)[:2] == (100.0, 1.0) and cfg.n_ovr_bodypose == 1
 
 
 def test_factory_names_and_errors():
@@ -78,7 +89,7 @@ def test_factory_names_and_errors():
     with pytest.raises(ValueError):
         EnvironmentFactory.create("NoSuchEnv")
     with pytest.raises(NotImplementedError):
-        EnvironmentFactory.create("CustomMyoReorientP2")
+        EnvironmentFactory.create("CustomMyoPenTwirlRandom")
     with pytest.raises(_capi.MyoError):           # no CPU path: creating worlds without a GPU fails loudly
         if torch.cuda.is_available():
             raise _capi.MyoError("gpu present")

@@ -9,7 +9,7 @@ from test_env_fixtures_emul import STEP_TAGS
 pytestmark = pytest.mark.gpu
 
 RESET_TAGS = ["cur%02d" % i for i in range(1, 33)] + ["p2_default", "p1_default", "p2_knobs", "p2_fixed_task", "p1_noise", "finger_random",
-                                                       "finger_fixed", "elbow_random", "hand_random", "hand_fixed", "finger_distance"]
+                                                       "finger_fixed", "elbow_random", "hand_random", "hand_fixed", "finger_distance", "die_p1", "die_p2", "die_axes", "elbow_sds", "finger_sds0", "elbow_weight"]
 
 
 @pytest.mark.parametrize("tag", STEP_TAGS)

@@ -4,14 +4,15 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ELBOW, FINGER, HAND_BAODING, HAND_POSE
+from conftest import ELBOW, FINGER, HAND_BAODING, HAND_DIE, HAND_POSE
 from myochallenge_b200 import _capi
 import parity_common as pc
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 CASES = [("elbow", ELBOW, _capi.TASK_POSE, 16), ("finger", FINGER, _capi.TASK_POSE, 64),
-         ("hand_pose", HAND_POSE, _capi.TASK_POSE, 16), ("baoding", HAND_BAODING, _capi.TASK_BAODING, 32)]
+         ("hand_pose", HAND_POSE, _capi.TASK_POSE, 16), ("baoding", HAND_BAODING, _capi.TASK_BAODING, 32),
+         ("die", HAND_DIE, _capi.TASK_REORIENT, 32)]
 
 
 @pytest.mark.parametrize("name,path,kind,n", CASES, ids=[c[0] for c in CASES])
