@@ -258,6 +258,10 @@ int myo_batch_status(myo_batch* b, int* flags, void* stream);
 /* number of kernel launches issued on behalf of this batch since creation */
 int64_t myo_batch_launch_count(const myo_batch* b);
 
+/* Measured FP32 FMA throughput of the device (TFLOP/s, 2 flops per FMA; a few ms): the denominator of bench.py's compute
+ * roofline - the world kernel is FP32-issue / latency bound, not HBM bound. */
+int myo_fp32_fma_peak(int device, double* tflops);
+
 /* ---- recurrent policy forward (sb3-contrib MlpLstmPolicy, separate actor/critic LSTMs) ------ */
 typedef struct myo_policy_cfg {
   int32_t obs_dim, act_dim, lstm_hidden;

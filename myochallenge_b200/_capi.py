@@ -112,6 +112,7 @@ SIGNATURES = {
     "myo_batch_stage_dump": (_i, [_vp, _i, _vp, _ip, _vp]),
     "myo_batch_status": (_i, [_vp, _ip, _vp]),
     "myo_batch_launch_count": (C.c_int64, [_vp]),
+    "myo_fp32_fma_peak": (_i, [_i, C.POINTER(C.c_double)]),
     "myo_policy_create": (_i, [C.POINTER(PolicyCfg), _i, _i, C.POINTER(_vp)]),
     "myo_policy_destroy": (None, [_vp]),
     "myo_policy_set_weight": (_i, [_vp, _cp, _fp, C.c_int64, _vp]),

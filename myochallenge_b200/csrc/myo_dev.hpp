@@ -137,8 +137,13 @@ struct BatchPtrs {
   unsigned long long seed;
   const int* order;   // optional [n_alloc]: slot -> world, worlds grouped by their recent constraint count (null: identity)
   // worlds the fast kernel hands to the full-capacity kernel of the same env step (see myo_kernels.cu): world index | kind << 30
-  int* redo_list;     // [n_alloc]
+  int* redo_list;     // [n_alloc], -1 = not written yet
   int* redo_count;    // [1]
+  // dynamic scheduling of the env step (fast kernel): [0] next group of worlds, [1] groups finished, [2] redo entries taken.
+  // CTAs fetch groups until none is left, then serve the redo list with the full-capacity layout, heavy_per_cta worlds at a
+  // time in the CTA's own shared memory - the redone worlds ride in the slack of the last wave instead of a pass of their own
+  int* sched;
+  int heavy_per_cta;
   int* work;          // [n_alloc]: constraint rows of the world's last substep (the grouping key for the next step)
 };
 

@@ -47,7 +47,11 @@ MYO_DI void redo_push(const BatchPtrs& b, int w, int kind) {
 #else
   const int k = atomicAdd(b.redo_count, 1);
 #endif
+#ifdef MYO_EMUL
   b.redo_list[k] = w | (kind << 30);
+#else
+  *reinterpret_cast<volatile int*>(b.redo_list + k) = w | (kind << 30);      // consumers wait for the slot to turn non-negative
+#endif
 }
 
 // One world, one env step / reset / test hook. SOLO: the CTA holds this world only (full-capacity layout), so phases may be
@@ -58,6 +62,7 @@ template <int G, int RMAX, bool SOLO>
 __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G>& c, int w, int kind) {
   MYO_M
   int status = 0;
+  bool deferred_reset = false;
   int* ti = b.task_i + (size_t)w * TI_WORDS;
   float* tf = b.task_f + (size_t)w * TF_WORDS;
   float* ptarget = b.pose_target + (size_t)w * m.nq4;
@@ -89,16 +94,16 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
   if (a.mode == MODE_FORWARD || a.mode == MODE_MJ_STEP) {
     for (int i = c.lane; i < m.nu; i += G) SF(o_ctrl)[i] = a.in ? a.in[(size_t)wi * m.nu + i] : 0.f;
     c.tile.sync();
-    if (a.mode == MODE_FORWARD) mj_forward_dev<G, RMAX>(mslot, c, &status, false);
+    if (a.mode == MODE_FORWARD) mj_forward_dev<G, RMAX, !SOLO>(mslot, c, &status, false);
     else {
-      for (int s = 0; s < a.nsub; s++) mj_step_dev<G, RMAX>(mslot, c, &status, false);
+      for (int s = 0; s < a.nsub; s++) mj_step_dev<G, RMAX, !SOLO>(mslot, c, &status, false);
       if (c.lane == 0) b.time[w] += (float)a.nsub * m.timestep;
     }
   } else {   // MODE_ENV_STEP (or its repetition with full capacities)
     if (t.kind == MYO_TASK_BAODING) baoding_targets<G>(mslot, t, c, ti, tf);
     task_action<G>(mslot, t, c, a.in + (size_t)wi * m.nu);
     c.tile.sync();
-    for (int s = 0; s < a.nsub; s++) mj_step_dev<G, RMAX>(mslot, c, &status, true);
+    for (int s = 0; s < a.nsub; s++) mj_step_dev<G, RMAX, !SOLO>(mslot, c, &status, true);
     if (!SOLO && b.redo_list) {
       // outgrew the fast layout in some substep: nothing of this attempt is kept, the full-capacity kernel steps the world again
 #pragma unroll
@@ -147,9 +152,10 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
     if (done && t.auto_reset) {
       if (a.terminal_obs && io) for (int i = c.lane; i < m.nobs; i += G) a.terminal_obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
       if (!SOLO && reset_needs_physics(t)) {
-        // the reset runs an env step of its own (reference-state initialisation): done by the SOLO kernel, which also writes
-        // the first observation of the new episode; the terminal state is stored as it is
-        if (c.lane == 0 && io) redo_push(b, w, REDO_RESET);
+        // the reset runs an env step of its own (reference-state initialisation): done by a full-capacity pass, which also
+        // writes the first observation of the new episode; the terminal state is stored as it is and the world is handed
+        // over after that store (end of this function)
+        deferred_reset = io;
       } else {
         task_reset<G, RMAX, SOLO>(mslot, t, c, b, w, ti, tf, ptarget);
         if (c.lane == 0) b.time[w] = 0.f;
@@ -157,7 +163,7 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
         task_obs<G>(mslot, t, c, ptarget);
       }
     }
-    if (io) for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
+    if (io && !deferred_reset) for (int i = c.lane; i < m.nobs; i += G) a.obs[(size_t)w * m.nobs + i] = SF(o_obs)[i];
   }
   // status flags
   for (int i = c.lane; i < m.nq; i += G) if (!isfinite(SF(o_qpos)[i])) status |= ST_NONFINITE;
@@ -169,6 +175,15 @@ __device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, 
     if ((a.mode == MODE_ENV_STEP || a.mode == MODE_REDO) && b.work) b.work[w] = io ? 0x7ffe - min(misc[MI_NEFC], 0x7ffe) : 0x7fff;      // heavy worlds first (the partial last wave of CTAs gets the light ones), padding worlds last
   }
   store_world<G>(mslot, c, b, w, true);
+  if (deferred_reset) {
+    c.tile.sync();
+    if (c.lane == 0) {
+#ifndef MYO_EMUL
+      __threadfence();
+#endif
+      redo_push(b, w, REDO_RESET);
+    }
+  }
   if (b.dump && (a.mode == MODE_FORWARD || a.mode == MODE_MJ_STEP)) {
     c.tile.sync();
     float* out = b.dump + (size_t)w * m.scratch_words;
@@ -188,8 +203,12 @@ __device__ void stage_tables(const DevModel& m) {
 #endif
 }
 
+#ifndef MYO_EMUL
+MYO_DI int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+#endif
+
 template <int G>
-__global__ void __launch_bounds__(kThreads) world_kernel(int mslot, const __grid_constant__ myo_task_cfg t,
+__global__ void __launch_bounds__(kThreads) world_kernel(int mslot, int mslot_full, const __grid_constant__ myo_task_cfg t,
                                                         const __grid_constant__ BatchPtrs b, const __grid_constant__ StepArgs a) {
   MYO_M
   stage_tables(m);
@@ -200,6 +219,69 @@ __global__ void __launch_bounds__(kThreads) world_kernel(int mslot, const __grid
   const int tid = threadIdx.x / G;
   c.soff = m.tab_words + tid * m.scratch_words;
   constexpr int RMAX = kFastRows / G > 0 ? kFastRows / G : 1;
+#ifndef MYO_EMUL
+  if (b.sched && a.mode == MODE_ENV_STEP) {
+    // Env step with dynamic scheduling: groups of wpc worlds (in the sorted order: heavy worlds first) are fetched from a
+    // global counter; when none is left the CTA serves the redo list - worlds that outgrew the fast layout, resets that run
+    // physics - with the full-capacity layout in its own shared memory. Overflows come from the heavy groups at the front,
+    // so the list is complete long before the last (light) groups finish and the redone worlds fill the slack of the last wave.
+    __shared__ int s_pick[3];
+    const int ngroups = b.n_alloc / wpc;
+    const DevModel& mf = c_models[mslot_full];
+    constexpr int RFULL = kSoloRowsPerLane;
+    bool exhausted = false;      // (thread 0) no group of worlds is left in the queue
+    for (;;) {
+      if (threadIdx.x == 0) {
+        // what next: a full-capacity batch as soon as enough redo entries wait (so that work spreads over the whole launch and
+        // not into a tail), else the next group of worlds, else - queue empty - whatever the redo list still holds
+        int kind = 2, idx = 0, cnt = 0;
+        for (;;) {
+          if (b.redo_list) {
+            const int avail = ld_volatile(b.redo_count), taken = ld_volatile(&b.sched[2]);
+            if (taken < avail && (exhausted || avail - taken >= b.heavy_per_cta)) {
+              const int want = min(taken + b.heavy_per_cta, avail);
+              if (atomicCAS(&b.sched[2], taken, want) == taken) { kind = 1; idx = taken; cnt = want - taken; break; }
+              continue;
+            }
+          }
+          if (!exhausted) {
+            const int g = atomicAdd(&b.sched[0], 1);
+            if (g < ngroups) { kind = 0; idx = g; break; }
+            exhausted = true;
+            continue;
+          }
+          if (!b.redo_list) break;
+          if (ld_volatile(&b.sched[1]) >= ngroups) {      // every group has finished: the list cannot grow any more
+            if (ld_volatile(&b.sched[2]) >= ld_volatile(b.redo_count)) break;
+            continue;
+          }
+          __nanosleep(1000);
+        }
+        s_pick[0] = kind; s_pick[1] = idx; s_pick[2] = cnt;
+      }
+      __syncthreads();
+      const int kind = s_pick[0], idx = s_pick[1], cnt = s_pick[2];
+      __syncthreads();
+      if (kind == 2) break;
+      if (kind == 0) {
+        const int slot = idx * wpc + tid;
+        run_world<G, RMAX, false>(mslot, t, b, a, c, b.order ? b.order[slot] : slot, 0);
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(&b.sched[1], 1); }
+      } else if (tid < cnt) {
+        int e;
+        while ((e = ld_volatile(b.redo_list + idx + tid)) < 0) __nanosleep(200);      // reserved but not written yet
+        __threadfence();
+        Ctx<G> ch(tile);
+        ch.soff = m.tab_words + tid * mf.scratch_words;
+        StepArgs ar = a;
+        ar.mode = MODE_REDO;
+        run_world<G, RFULL, true>(mslot_full, t, b, ar, ch, e & 0x3fffffff, e >> 30);
+      }
+    }
+    return;
+  }
+#endif
   // state arrays are padded to a multiple of wpc worlds, so every tile of a CTA runs the same number of
   // iterations (the phases contain CTA-wide barriers); padding worlds are stepped but have no I/O
   for (int slot = blockIdx.x * wpc + tid; slot < b.n_alloc; slot += gridDim.x * wpc) {
@@ -363,7 +445,9 @@ struct myo_batch {
   int device = 0, n = 0, slot = -1, slot_full = -1;
   int grid = 0, threads = myo::kThreads, smem = 0, regs = 0, wpc = 0, tab_bytes = 0;
   int solo_grid = 0, solo_smem = 0, solo_regs = 0;
-  bool use_redo = false;       // env steps are followed by the full-capacity pass over the redo list
+  bool use_redo = false;       // worlds the fast layout cannot finish are redone with full capacities within the same env step
+  bool dyn_sched = false;      // ... inside the fast kernel (dynamic scheduling); false: by a separate pass of the solo kernel
+  int* sched_dev = nullptr;
   int64_t launches = 0;
   std::vector<void*> allocs;
   // world grouping: after every env step the worlds are sorted by the constraint rows of their last substep, and the next
@@ -429,7 +513,7 @@ int upload_slot(myo_batch* b) {
 }
 
 template <int G> int launch_world(myo_batch* b, const StepArgs& a, cudaStream_t st) {
-  MYO_LAUNCH(world_kernel<G>, b->grid, b->threads, b->smem, st, b->slot, b->cfg, b->p, a);
+  MYO_LAUNCH(world_kernel<G>, b->grid, b->threads, b->smem, st, b->slot, b->slot_full, b->cfg, b->p, a);
   b->launches++;
   CK(cudaGetLastError());
   return MYO_OK;
@@ -644,8 +728,17 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
     bool want = df.ncon_max > dm.ncon_max || df.nlim_max > dm.nlim_max || df.nefc_max > dm.nefc_max || myo::reset_needs_physics(*cfg);
     if (const char* e = getenv("MYO_REDO")) want = want && atoi(e) != 0;
     b->use_redo = want;
-    if ((rc = dev_alloc(b, &b->p.redo_list, n)) || (rc = dev_alloc(b, &b->p.redo_count, 4))) return fail(rc);
+    if ((rc = dev_alloc(b, &b->p.redo_list, n)) || (rc = dev_alloc(b, &b->p.redo_count, 4)) || (rc = dev_alloc(b, &b->p.sched, 4))) return fail(rc);
     if (!want) b->p.redo_list = nullptr;
+    b->p.heavy_per_cta = std::max(1, std::min(b->wpc, (int)((b->smem - b->tab_bytes) / ((size_t)df.scratch_words * sizeof(float)))));
+#ifdef MYO_EMUL
+    b->dyn_sched = false;
+#else
+    b->dyn_sched = true;
+    if (const char* e = getenv("MYO_DYN_SCHED")) b->dyn_sched = atoi(e) != 0;      // 0: static striding + a separate full-capacity pass
+#endif
+    b->sched_dev = b->p.sched;
+    if (!b->dyn_sched) b->p.sched = nullptr;
   }
 #ifndef MYO_EMUL
   {
@@ -718,10 +811,15 @@ int myo_batch_step(myo_batch* b, const float* actions_dev, float* obs_dev, float
   a.in = actions_dev; a.obs = obs_dev; a.reward = reward_dev; a.done = done_dev; a.truncated = truncated_dev;
   a.terminal_obs = terminal_obs_dev; a.info = info_dev;
   b->p.order = (b->sort_worlds && b->cur_order >= 0) ? b->order[b->cur_order] : nullptr;
-  if (b->use_redo) CK(cudaMemsetAsync(b->p.redo_count, 0, sizeof(int), static_cast<cudaStream_t>(stream)));
+  cudaStream_t st_ = static_cast<cudaStream_t>(stream);
+  if (b->use_redo) {
+    CK(cudaMemsetAsync(b->p.redo_count, 0, sizeof(int), st_));
+    if (b->dyn_sched) CK(cudaMemsetAsync(b->p.redo_list, 0xFF, (size_t)b->p.n_alloc * sizeof(int), st_));
+  }
+  if (b->dyn_sched) CK(cudaMemsetAsync(b->sched_dev, 0, 4 * sizeof(int), st_));
   int rc = launch(b, a, stream);
   b->p.order = nullptr;
-  if (!rc && b->use_redo) {      // worlds the fast kernel could not finish: same step, full capacities, one world per CTA
+  if (!rc && b->use_redo && !b->dyn_sched) {      // worlds the fast kernel could not finish: same step, full capacities, one world per CTA
     a.mode = myo::MODE_REDO;
     rc = launch_full(b, a, stream);
   }

@@ -759,6 +759,9 @@ MYO_PHASE bool capsule_box(int sub, float margin, const float* pc, const float* 
                             const float* s, float* dist, float* pos, float* nrm) {
   float dif[3], c[3], d[3];
   sub3(dif, pc, pb); mulmatTvec3(c, Rb, dif); mulmatTvec3(d, Rb, axis);
+  // conservative early out (never drops a contact): the segment's extent along each box axis against the face plus reach
+#pragma unroll
+  for (int i = 0; i < 3; i++) if (fabsf(c[i]) - fabsf(d[i]) * h > s[i] + r + margin) return false;
   float pe[2][3], de[2], pb2[2][3], nb2[2][3];
   bool he[2];
 #pragma unroll
@@ -1495,7 +1498,7 @@ MYO_DI void lockstep_sync() {
 #ifndef MYO_SYNC_MASK
 #define MYO_SYNC_MASK 0xFF
 #endif
-#define MYO_SYNC(i) if ((MYO_SYNC_MASK >> (i)) & 1) lockstep_sync();
+#define MYO_SYNC(i) if (SYNC && ((MYO_SYNC_MASK >> (i)) & 1)) lockstep_sync();      // SYNC: template flag of the step functions
 
 // Optional (MYO_NEWTON_LOCKSTEP=1): the Newton iterations of a CTA's worlds in lock step too - barriers between Hessian build,
 // factorisation and line search, a CTA-wide vote ending the loop when no world iterates. Measured 3 % SLOWER than letting
@@ -1701,7 +1704,8 @@ MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
 }
 
 // one full mj_step on the world in scratch
-template <int G, int RMAX>
+// SYNC: the CTA's tiles walk the phases in lock step (fast kernel); false where tiles run on their own (full-capacity passes)
+template <int G, int RMAX, bool SYNC>
 MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_M
   MYO_PH_BEGIN
@@ -1717,10 +1721,10 @@ MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_PH(8)
   MYO_SYNC(6) phase_solve<G, RMAX>(mslot, c, fast); MYO_PH(9)
 }
-template <int G, int RMAX>
+template <int G, int RMAX, bool SYNC>
 MYO_PHASE void mj_step_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_M
-  mj_forward_dev<G, RMAX>(mslot, c, status, fast);
+  mj_forward_dev<G, RMAX, SYNC>(mslot, c, status, fast);
   MYO_PH_BEGIN
   MYO_SYNC(7) MYO_PH(15) phase_integrate<G>(mslot, c); MYO_PH(10)
 }

@@ -398,7 +398,7 @@ MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const Bat
       task_action<G>(mslot, t, c, nullptr);
       c.tile.sync();
       int st = 0;
-      for (int sub = 0; sub < t.frame_skip; sub++) mj_step_dev<G, RMAX>(mslot, c, &st, true);
+      for (int sub = 0; sub < t.frame_skip; sub++) mj_step_dev<G, RMAX, false>(mslot, c, &st, true);
       phase_tree_forward<G>(mslot, c, false);
       float g[2][3];
 #pragma unroll

@@ -529,16 +529,17 @@ def build_hand(kind: str) -> mjb.MjbModel:
     if kind == "die":
         # Die: the reference's reset (/root/reference/src/envs/reorient.py:100-160) treats the LAST THREE geoms of body "Object" as
         # boxes that grow / shrink with obj_size_change in all three half sizes (earlier geoms, if any, only in size[1]): here
-        # the die is exactly three mutually orthogonal slabs whose union is a cube with bevelled edges. The target die is a
-        # non-colliding copy on the body "target" (moved / turned by reset through body_pos / body_quat), shown offset from
-        # the hand: goal_obj_offset = target_o - object_o at the initial pose.
+        # the body carries exactly three boxes - the colliding cube and two thinner, non-colliding slabs inside it (face
+        # markings). The target die is a non-colliding copy on the body "target" (moved / turned by reset through body_pos /
+        # body_quat), shown offset from the hand: goal_obj_offset = target_o - object_o at the initial pose.
         h, k = 0.015, 0.012
         c = ORBIT_C + np.array([0.0, 0.0, 0.038])
         mass = 0.05
         B.body("Object", "world", c, mass, (mass * (2 * h) ** 2 / 6.0,) * 3, simple=1)
         B.joint("Object", "OBJT_free", FREE, limited=False)
-        for nm, half in (("dice_z", (h, h, k)), ("dice_y", (h, k, h)), ("dice_x", (k, h, h))):
-            B.box("Object", nm, c, half, contype=3, conaffinity=1)
+        B.box("Object", "dice", c, (h, h, h), contype=3, conaffinity=1)
+        for nm, half in (("dice_marks_y", (h, k, h)), ("dice_marks_x", (k, h, h))):
+            B.box("Object", nm, c, half)
         B.site("Object", "object_o", c)
         tc = c + np.array([0.0, 0.0, 0.15])
         B.body("target", "world", tc, 0.0, (0, 0, 0))

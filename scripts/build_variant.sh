@@ -6,4 +6,4 @@ C="$D/../myochallenge_b200/csrc"
 NAME="$1"; shift
 mkdir -p "$D/_prof"
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" \
-  -shared -o "$D/_prof/libmyo_$NAME.so" "$C/myo_model.cpp" "$C/myo_pack.cpp" "$C/myo_kernels.cu" "$C/myo_policy.cu" "$C/myo_rollout.cu" "$C/myo_ppo.cu" -lcudart -lcublas
+  -shared -o "$D/_prof/libmyo_$NAME.so" "$C/myo_model.cpp" "$C/myo_pack.cpp" "$C/myo_kernels.cu" "$C/myo_policy.cu" "$C/myo_rollout.cu" "$C/myo_ppo.cu" "$C/myo_util.cu" -lcudart -lcublas
