@@ -84,56 +84,86 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle (fp64 C restatement of the MuJoCo 2.1.0 step subset) on the host cores
-def cpu_env_steps_per_s(seconds: float, threads: int, frame_skip: int = 10, states=None):
-    """Steps a bounded sample of Baoding worlds with the oracle, one thread per core, `frame_skip` mj_steps per env
-    step under constant controls; returns (env-steps/s, sample description). ctypes releases the GIL per call."""
+# CPU arm: the oracle (fp64 C restatement of the MuJoCo 2.1.0 step subset) on the host cores, doing the SAME work per env step
+# as the product arm: recurrent policy forward (torch, CPU) -> action clip -> env step (target update, muscle remap, frame_skip
+# mj_steps, observation, reward, termination) -> reset of finished worlds. One Python thread per host core, 32 worlds per
+# thread per call (ctypes and torch release the GIL), oracle built -O3 -march=native on this machine, Newton tolerance at
+# MuJoCo's own default (1e-8).
+def cpu_env_steps_per_s(seconds: float, threads: int, frame_skip: int = 10, states=None, per: int = 32, with_policy: bool = True):
     import ctypes
 
     import numpy as np
+    import torch
 
     from myochallenge_b200.assets import asset_path
     from oracle import mjb, oracle
 
     path = asset_path("hand/myo_hand_baoding.mjb")
-    L = oracle.lib()
-    per = 4                                  # worlds per thread per call
+    L = oracle.lib(oracle.build_fast())
+    L.o_set_solver_tol(1e-8)
+    torch.set_num_threads(1)
     nw = threads * per
-    rng = np.random.default_rng(0)
     src = mjb.load(path)
     models = [oracle.OracleModel(src) for _ in range(threads)]
     datas = [oracle.OracleData(m) for m in models]
     m0 = models[0]
+    nobs = (m0.nq - 14) + 24 + m0.na
     q0r = np.array(m0.qpos0, np.float64).copy()
     q0r[:23] = 0.0
     q0r[0] = -1.57                             # reference init pose (/root/reference/src/envs/baoding.py:400-401)
     if states is None:
-        qpos = np.tile(q0r, (nw, 1))
-        qvel = np.zeros((nw, m0.nv))
-        act = np.zeros((nw, m0.na))
+        qpos = np.tile(q0r, (nw, 1)); qvel = np.zeros((nw, m0.nv)); act = np.zeros((nw, m0.na))
     else:
         qpos, qvel, act = [np.ascontiguousarray(np.resize(np.asarray(a, np.float64), (nw, a.shape[1]))) for a in states]
     warm = np.zeros((nw, m0.nv))
-    dp = ctypes.POINTER(ctypes.c_double)
+    obs = np.zeros((nw, nobs)); reward = np.zeros(nw); done = np.zeros(nw, np.int32)
+    rng0 = np.random.default_rng(0)
 
-    def ptr(a):
-        return a.ctypes.data_as(dp)
+    def new_task(k):      # CustomBaodingP2Env.reset with the P2 registration's ranges
+        a1 = rng0.uniform(0, 2 * np.pi, k)
+        return np.stack([rng0.integers(0, 3, k).astype(float), a1, a1 - np.pi, rng0.uniform(0.020, 0.030, k), rng0.uniform(0.022, 0.032, k),
+                         rng0.uniform(4, 6, k), np.zeros(k)], 1)
 
+    task = np.ascontiguousarray(new_task(nw))
+    ids = np.array([src.name2id("site", "ball1_site"), src.name2id("site", "ball2_site"), src.name2id("site", "target1_site"),
+                    src.name2id("site", "target2_site"), m0.nv - 12, m0.nv - 6], np.int32)
+    weights = np.array([5.0, 5.0, 0.0, 1.0, 0.0, 5.0, 0.0])      # the winning run's reward weights (RWD)
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int)
+
+    class Policy(torch.nn.Module):      # MlpLstmPolicy: LSTM-256 + [256, 256] for actor and critic, Gaussian head (log_std_init -2)
+        def __init__(self):
+            super().__init__()
+            self.la, self.lc = torch.nn.LSTMCell(nobs, 256), torch.nn.LSTMCell(nobs, 256)
+            self.pi = torch.nn.Sequential(torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, m0.nu))
+            self.vf = torch.nn.Sequential(torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 1))
+
+    torch.manual_seed(0)
+    pol = Policy().double()
     counts = [0] * threads
     stop = time.perf_counter() + seconds
 
     def work(t):
         lo, hi = t * per, (t + 1) * per
-        r = np.random.default_rng(t)
-        while time.perf_counter() < stop:
-            a = r.uniform(-1, 1, (nw, m0.nu))
-            ctrl = np.ascontiguousarray(1.0 / (1.0 + np.exp(-5.0 * (a - 0.5))))    # BaseV0.step muscle remap
-            L.o_batch_step(models[t]._p, datas[t]._p, lo, hi, frame_skip, ptr(qpos), ptr(qvel), ptr(act), ptr(warm), ptr(ctrl))
-            # worlds whose balls fell are reset, as the env would do
-            for w in range(lo, hi):
-                if not np.isfinite(qpos[w]).all() or qpos[w, 25] < 1.25 or qpos[w, 32] < 1.25:
-                    qpos[w] = q0r; qvel[w] = 0; act[w] = 0; warm[w] = 0
-            counts[t] += per
+        g = torch.Generator().manual_seed(t)
+        ha, ca, hc, cc = [torch.zeros(per, 256, dtype=torch.float64) for _ in range(4)]
+        action = np.zeros((nw, m0.nu))
+        with torch.no_grad():
+            while time.perf_counter() < stop:
+                if with_policy:
+                    o = torch.from_numpy(obs[lo:hi])
+                    ha, ca = pol.la(o, (ha, ca)); hc, cc = pol.lc(o, (hc, cc))
+                    mean, _value = pol.pi(ha), pol.vf(hc)
+                    action[lo:hi] = (mean + np.exp(-2.0) * torch.randn(per, m0.nu, generator=g, dtype=torch.float64)).clamp_(-1, 1).numpy()
+                else:
+                    action[lo:hi] = np.random.default_rng(counts[t]).uniform(-1, 1, (per, m0.nu))
+                L.o_batch_env_step(models[t]._p, datas[t]._p, lo, hi, frame_skip, qpos.ctypes.data_as(dp), qvel.ctypes.data_as(dp), act.ctypes.data_as(dp),
+                                   warm.ctypes.data_as(dp), action.ctypes.data_as(dp), task.ctypes.data_as(dp), ids.ctypes.data_as(ip),
+                                   weights.ctypes.data_as(dp), 1.25, 0.015, obs.ctypes.data_as(dp), reward.ctypes.data_as(dp), done.ctypes.data_as(ip))
+                for w in range(lo, hi):      # SubprocVecEnv worker: reset on done (or a non-finite state) / TimeLimit
+                    if done[w] or task[w, 6] >= 200 or not np.isfinite(qpos[w]).all():
+                        qpos[w] = q0r; qvel[w] = 0; act[w] = 0; warm[w] = 0; task[w] = new_task(1)[0]
+                        ha[w - lo] = 0; ca[w - lo] = 0; hc[w - lo] = 0; cc[w - lo] = 0
+                counts[t] += per
 
     t0 = time.perf_counter()
     ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
@@ -143,7 +173,9 @@ def cpu_env_steps_per_s(seconds: float, threads: int, frame_skip: int = 10, stat
         th.join()
     dt = time.perf_counter() - t0
     total = sum(counts)
-    return total / dt, f"{total} env steps ({frame_skip} mj_steps each, fp64 oracle) of {nw} Baoding worlds in {dt:.1f} s on {threads} threads; physics only, no policy"
+    what = "recurrent policy forward (torch CPU, fp64) + env step" if with_policy else "env step under uniform random actions"
+    return total / dt, (f"{total} env steps ({what}: targets, remap, {frame_skip} mj_steps, obs, reward, reset; fp64 oracle -O3 -march=native, Newton tol 1e-8) "
+                        f"of {nw} Baoding worlds in {dt:.1f} s on {threads} threads")
 
 
 def run_reference(args):
@@ -164,9 +196,11 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{ENV_ID}, host CPU path", "worlds_per_gpu": 0, "frame_skip": 10,
+        "config": {"workload": f"{ENV_ID} (BASELINE configs[4]) on the host cores: policy forward + env step per world, 32 worlds per thread", "worlds_per_gpu": 0, "frame_skip": 10,
                    "note": "MuJoCo/MyoSuite/SB3 are not installable offline (no wheels, no network): the reference's CPU path is "
-                           "represented by the fp64 C restatement of its mj_step subset (oracle/), one thread per host core"},
+                           "represented by the fp64 C restatement of its mj_step subset (oracle/, built -O3 -march=native here, Newton "
+                           "tolerance 1e-8 as MuJoCo's default), one thread per host core, with the same per-step work as the product arm "
+                           "(recurrent policy forward, targets, remap, obs, reward, resets)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -202,7 +236,7 @@ def run_b200(args):
     pol = RecurrentPolicy(sim.nobs, sim.nu, lstm_hidden=256, pi=(256, 256), vf=(256, 256), max_batch=n, device=dev, use_sde=args.use_sde)
     pol.init_random(seed=0, log_std_init=-2.0)             # same weights on every rank
     pol.seed(0x5EED + rank)
-    stats = os.path.join(ROOT, "tests", "golden", "vecnormalize_baoding_step32.npz")
+    stats = os.path.join(ROOT, "myochallenge_b200", "assets", "vecnormalize", "baoding_step32.npz")
     if os.path.exists(stats):                               # the reference's own running moments (fixture), applied as
         g = np.load(stats)                                  # VecNormalize.normalize_obs in the policy's input load
         pol.set_obs_norm(torch.from_numpy(g["obs_mean"]).float(), torch.from_numpy(g["obs_var"]).float(), float(g["epsilon"]), float(g["clip_obs"]))
@@ -421,6 +455,25 @@ def run_b200(args):
                 "algorithmic_bytes_per_env_step": b_env, "kernel_ms": world_ms, "kernel_share_of_step": world_ms / ms_per_step,
                 "note": "state stays in shared memory across the 10 substeps: the kernel is FP32-issue/latency bound, not HBM bound (DESIGN.md)"}
 
+    # ---- compute roofline: the bound that actually governs the world kernel (FP32 issue / latency) ------------
+    # FLOP and instruction counts per env step come from the committed ncu capture of this kernel (profiles/, per-launch
+    # counters divided by the worlds of the launch); the peak is measured live on this GPU (myo_fp32_fma_peak).
+    import ctypes as C
+    compute = None
+    cpath = os.path.join(ROOT, "profiles", "world_kernel_counters.json")
+    if os.path.exists(cpath):
+        cj = json.load(open(cpath))
+        pk = C.c_double()
+        _capi.check(_capi.lib(), _capi.lib().myo_fp32_fma_peak(local, C.byref(pk)))
+        flop = float(cj["fp32_flop_per_env_step"])
+        ach = flop * n / (world_ms * 1e-3) / 1e12
+        compute = {"kernel": roofline["kernel"], "bound": "fp32-issue", "achieved": ach, "peak": pk.value, "unit": "TFLOP/s", "frac": ach / pk.value if pk.value else None,
+                   "peak_source": "myo_fp32_fma_peak: FFMA microbenchmark run on this GPU just now (2 flop per FMA)",
+                   "fp32_flop_per_env_step": flop, "thread_inst_per_env_step": cj.get("thread_inst_per_env_step"),
+                   "warp_inst_per_env_step": cj.get("warp_inst_per_env_step"), "fp32_share_of_thread_inst": cj.get("fp32_share_of_thread_inst"),
+                   "issue_slot_utilisation_pct": cj.get("issue_active_pct"), "active_lanes_per_warp_inst": cj.get("lanes_per_inst"),
+                   "warps_per_sm": cj.get("warps_per_sm"), "counters_source": cj.get("source")}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 physics, bf16 x bf16 -> f32 policy GEMMs", "data": "synthetic",
@@ -434,7 +487,7 @@ def run_b200(args):
                 "sequential": seq_value,
                 "api": "MyoVecEnv.step_async/step_wait with numpy arrays + RecurrentPolicy.forward on H2D-copied observations; two half-size "
                        "envs stepped alternately on two streams (`sequential`: one env, every copy on the critical path)"},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "ppo_iteration": ppo,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "compute_roofline": compute, "ppo_iteration": ppo,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         q, v, a, _ = [x.double().cpu().numpy() for x in sim.get_state()]

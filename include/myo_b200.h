@@ -178,6 +178,10 @@ int myo_model_name2id(const myo_model* m, const char* group, const char* name);
 const char* myo_model_id2name(const myo_model* m, const char* group, int id);
 /* fills the baoding id fields of cfg (ball1/ball2 bodies, geoms, sites; target sites) by name */
 int myo_task_cfg_default(const myo_model* m, int kind, myo_task_cfg* cfg);
+/* Does this model run? MYO_OK, or MYO_E_UNSUPPORTED with EVERY blocking feature listed in `report` (one "- ..." line each;
+ * "~ ..." lines are advisory and do not block; report may be NULL) and in myo_last_error(): the answer a user needs for an out-of-band myo_hand_*.mjb
+ * (/root/reference/src/envs/__init__.py:17,29,44,62 bind models that are absent from the reference's repository). */
+int myo_model_check(const myo_model* m, char* report, size_t report_len);
 
 /* ---- batch (device) ------------------------------------------------------------------------ */
 int myo_batch_create(const myo_model* m, int n_worlds, int device, const myo_task_cfg* cfg, uint64_t seed,

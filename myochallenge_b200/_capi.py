@@ -93,6 +93,7 @@ SIGNATURES = {
     "myo_model_array": (_i, [_vp, _cp, C.POINTER(_vp), _ip, _ip, _ip]),
     "myo_model_name2id": (_i, [_vp, _cp, _cp]),
     "myo_model_id2name": (C.c_char_p, [_vp, _cp, _i]),
+    "myo_model_check": (_i, [_vp, C.c_char_p, C.c_size_t]),
     "myo_task_cfg_default": (_i, [_vp, _i, C.POINTER(TaskCfg)]),
     "myo_batch_create": (_i, [_vp, _i, _i, C.POINTER(TaskCfg), C.c_uint64, C.POINTER(_vp)]),
     "myo_batch_destroy": (None, [_vp]),

@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kThreads) world_kernel(int mslot, int mslot_fu
   const int tid = threadIdx.x / G;
   c.soff = m.tab_words + tid * m.scratch_words;
   constexpr int RMAX = kFastRows / G > 0 ? kFastRows / G : 1;
-#ifndef MYO_EMUL
+#if !defined(MYO_EMUL) && !defined(MYO_NO_HEAVY)
   if (b.sched && a.mode == MODE_ENV_STEP) {
     // Env step with dynamic scheduling: groups of wpc worlds (in the sorted order: heavy worlds first) are fetched from a
     // global counter; when none is left the CTA serves the redo list - worlds that outgrew the fast layout, resets that run
@@ -681,6 +681,14 @@ int myo_task_cfg_default(const myo_model* mh, int kind, myo_task_cfg* cfg) {
   return MYO_OK;
 }
 
+int myo_model_check(const myo_model* mh, char* report, size_t report_len) {
+  if (!mh) { myo::set_error("null model"); return MYO_E_ARG; }
+  const std::string r = myo::check_model(myo_model_host(mh));
+  if (report && report_len) { strncpy(report, r.c_str(), report_len - 1); report[report_len - 1] = 0; }
+  if (r.rfind("- ", 0) == 0 || r.find("\n- ") != std::string::npos) { myo::set_error("model is outside the supported subset:\n" + r); return MYO_E_UNSUPPORTED; }
+  return MYO_OK;      // "~ " lines, if any, are advisory
+}
+
 int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_task_cfg* cfg, uint64_t seed, myo_batch** out) {
   if (!mh || !cfg || !out || n_worlds <= 0) { myo::set_error("bad argument to myo_batch_create"); return MYO_E_ARG; }
   int ndev = 0;
@@ -731,7 +739,7 @@ int myo_batch_create(const myo_model* mh, int n_worlds, int device, const myo_ta
     if ((rc = dev_alloc(b, &b->p.redo_list, n)) || (rc = dev_alloc(b, &b->p.redo_count, 4)) || (rc = dev_alloc(b, &b->p.sched, 4))) return fail(rc);
     if (!want) b->p.redo_list = nullptr;
     b->p.heavy_per_cta = std::max(1, std::min(b->wpc, (int)((b->smem - b->tab_bytes) / ((size_t)df.scratch_words * sizeof(float)))));
-#ifdef MYO_EMUL
+#if defined(MYO_EMUL) || defined(MYO_NO_HEAVY)
     b->dyn_sched = false;
 #else
     b->dyn_sched = true;

@@ -94,7 +94,7 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
             nwrap = m.sz("nwrap"), nM = m.sz("nM");
   if (nv <= 0 || nbody <= 1) return "model has no degrees of freedom";
   if (m.sz("neq") > 0) return "equality constraints are outside the supported subset";
-  if (m.sz("npair") > 0 || m.sz("nexclude") > 0) return "explicit contact pairs / excludes are outside the supported subset";
+  if (m.sz("npair") > 0) return "explicit contact pairs (<contact><pair>) are outside the supported subset";
   if (na != 0 && na != nu) return "models mixing stateful and stateless actuators are outside the supported subset";
   if ((int)m.opt.at("integrator") != 0) return "only the Euler integrator is supported";
   if ((int)m.opt.at("cone") != 0) return "only pyramidal friction cones are supported";
@@ -286,12 +286,14 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
     B.F(d.g_margin, fvec(m, "geom_margin")); B.F(d.g_gap, fvec(m, "geom_gap"));
   }
   std::vector<int> p_g1, p_g2, p_sup;
+  std::vector<int> excl = m.sz("nexclude") > 0 ? ivec(m, "exclude_signature") : std::vector<int>();
   for (int b1 = 0; b1 < nbody; b1++) for (int b2 = b1 + 1; b2 < nbody; b2++) {
     if (!geomnum[b1] || !geomnum[b2]) continue;
     const int w1 = weld[b1], w2 = weld[b2];
     const int wp1 = weld[parent[w1]], wp2 = weld[parent[w2]];
     if (w1 == w2) continue;
     if (w1 != 0 && w2 != 0 && (w1 == wp2 || w2 == wp1)) continue;
+    if (std::find(excl.begin(), excl.end(), (b1 << 16) + b2) != excl.end()) continue;      // <contact><exclude body1 body2>
     for (int ga = geomadr[b1]; ga < geomadr[b1] + geomnum[b1]; ga++)
       for (int gb = geomadr[b2]; gb < geomadr[b2] + geomnum[b2]; gb++) {
         int g1 = ga, g2 = gb;
@@ -627,6 +629,60 @@ std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out
   layout(out.dm_full, 2, njmax, nconmax, std::min(njmax, kSoloRowsPerLane * out.lanes));
   status = MYO_OK;
   return "";
+}
+
+// Every feature of a model that keeps it outside the supported subset, one line each (empty: it runs). Unlike pack_model,
+// which stops at the first obstacle, this walks the whole model: a user holding the real myo_hand_*.mjb learns in one call
+// what stands between the file and the kernels.
+std::string check_model(const Model& m) {
+  std::string out;
+  auto add = [&](const std::string& line) { out += "- " + line + "\n"; };
+  const int nv = m.sz("nv"), nu = m.sz("nu"), na = m.sz("na"), nbody = m.sz("nbody"), njnt = m.sz("njnt"), ngeom = m.sz("ngeom"),
+            ntendon = m.sz("ntendon");
+  if (nv <= 0 || nbody <= 1) add("model has no degrees of freedom");
+  if (nv > 64) add("nv = " + std::to_string(nv) + " exceeds the dense solver limit (64)");
+  if (m.sz("neq") > 0) add(std::to_string(m.sz("neq")) + " equality constraint(s): not supported");
+  if (m.sz("npair") > 0) add(std::to_string(m.sz("npair")) + " explicit contact pair(s) (<contact><pair>): not supported (excludes are)");
+  if (na != 0 && na != nu) add("mix of stateful and stateless actuators (na = " + std::to_string(na) + ", nu = " + std::to_string(nu) + ")");
+  if ((int)m.opt.at("integrator") != 0) add("integrator is not Euler");
+  if ((int)m.opt.at("cone") != 0) add("elliptic friction cones (only pyramidal)");
+  std::vector<int> jtype = ivec(m, "jnt_type"), jbody = ivec(m, "jnt_bodyid"), jntnum = ivec(m, "body_jntnum");
+  int nball = 0;
+  for (int j = 0; j < njnt; j++) {
+    if (jtype[j] == J_BALL) nball++;
+    if (jtype[j] == J_FREE && jntnum[jbody[j]] != 1) add("free joint " + std::to_string(j) + " shares its body with other joints");
+  }
+  if (nball) add(std::to_string(nball) + " ball joint(s): not supported");
+  { int n = 0; const double* dl = m.d("dof_frictionloss"); for (int i = 0; i < nv; i++) if (dl[i] != 0) n++; if (n) add(std::to_string(n) + " dof(s) with frictionloss: not supported"); }
+  if (ntendon) { int n = 0; const double* tf = m.d("tendon_frictionloss"); for (int t = 0; t < ntendon; t++) if (tf[t] != 0) n++; if (n) add(std::to_string(n) + " tendon(s) with frictionloss: not supported"); }
+  if (nu) { std::vector<int> tr = ivec(m, "actuator_trntype"); int n = 0; for (int i = 0; i < nu; i++) if (tr[i] != 3) n++; if (n) add(std::to_string(n) + " actuator(s) not driven through a tendon (only tendon transmissions)"); }
+  if (m.sz("nwrap")) { std::vector<int> wt = ivec(m, "wrap_type"); int n = 0; for (int w : wt) if (w == 1) n++; if (n) add(std::to_string(n) + " fixed (joint) tendon term(s): only spatial tendons"); }
+  // colliding geom type pairs the narrow phase does not cover
+  std::vector<int> gtype = ivec(m, "geom_type"), gbody = ivec(m, "geom_bodyid"), ct = ivec(m, "geom_contype"), ca = ivec(m, "geom_conaffinity"),
+                   weld = ivec(m, "body_weldid"), parent = ivec(m, "body_parentid"), condim = ivec(m, "geom_condim");
+  static const char* tn[] = {"plane", "hfield", "sphere", "capsule", "ellipsoid", "cylinder", "box", "mesh"};
+  std::set<std::pair<int, int>> bad;
+  std::vector<int> excl = m.sz("nexclude") > 0 ? ivec(m, "exclude_signature") : std::vector<int>();
+  for (int g1 = 0; g1 < ngeom; g1++) for (int g2 = g1 + 1; g2 < ngeom; g2++) {
+    const int b1 = std::min(gbody[g1], gbody[g2]), b2 = std::max(gbody[g1], gbody[g2]);
+    if (b1 == b2) continue;
+    const int w1 = weld[b1], w2 = weld[b2];
+    if (w1 == w2 || (w1 != 0 && w2 != 0 && (w1 == weld[parent[w2]] || w2 == weld[parent[w1]]))) continue;
+    if (std::find(excl.begin(), excl.end(), (b1 << 16) + b2) != excl.end()) continue;
+    if (!((ct[g1] & ca[g2]) || (ct[g2] & ca[g1]))) continue;
+    const int t1 = std::min(gtype[g1], gtype[g2]), t2 = std::max(gtype[g1], gtype[g2]);
+    const bool sup = (t1 == G_SPHERE && t2 == G_SPHERE) || (t1 == G_SPHERE && t2 == G_CAPSULE) || (t1 == G_PLANE && t2 == G_SPHERE) ||
+                     (t1 == G_CAPSULE && t2 == G_BOX);
+    if (!sup) bad.insert({t1, t2});
+    const int dim = std::max(condim[g1], condim[g2]);
+    if (dim != 1 && dim != 3) bad.insert({100 + dim, 0});
+  }
+  // advisory ("~"): such pairs are accepted; a world in which one of them comes into broad-phase range raises status bit 0
+  for (auto& pr : bad) {
+    if (pr.first >= 100) out += "~ contact dimension " + std::to_string(pr.first - 100) + " between some geoms (rows are built for condim 1 and 3; others raise status bit 0 when they touch)\n";
+    else out += std::string("~ geom pair type ") + tn[pr.first & 7] + " - " + tn[pr.second & 7] + " can collide but has no narrow phase (have sphere-sphere, sphere-capsule, plane-sphere, capsule-box): status bit 0 if such a pair ever comes into range\n";
+  }
+  return out;
 }
 
 }  // namespace myo

@@ -26,5 +26,7 @@ struct PackedModel {
 
 // returns "" on success; status gets a myo_status code on failure
 std::string pack_model(const Model& m, const myo_task_cfg& cfg, PackedModel& out, int& status);
+// every unsupported feature of the model, one "- ..." line each; empty when the model is inside the supported subset
+std::string check_model(const Model& m);
 
 }  // namespace myo

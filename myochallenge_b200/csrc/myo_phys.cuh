@@ -832,7 +832,11 @@ MYO_PHASE void phase_collision(int mslot, Ctx<G>& c, int* status) {
             if (m.g_size_slot[g1] >= 0) half = c.wpp(m)[m.g_size_slot[g1] + 1];
 #pragma unroll
             for (int e = 0; e < 3; e++) sz[e] = (m.g_size_slot[g2] >= 0) ? c.wpp(m)[m.g_size_slot[g2] + e] : m.g_size[3 * g2 + e];
-            hit = capsule_box(m.p_supported[p] - 1, margin, p1, ax, s1, half, p2, Rb, sz, &dist, pos, nrm);
+            // (own output variables: handing &dist / pos / nrm to the noinline collider would park them in local memory for
+            // every pair type)
+            float bd, bp3[3], bn3[3];
+            hit = capsule_box(m.p_supported[p] - 1, margin, p1, ax, s1, half, p2, Rb, sz, &bd, bp3, bn3);
+            if (hit) { dist = bd; cpy3(pos, bp3); cpy3(nrm, bn3); }
           }
           else if (t1 == G_SPHERE && t2 == G_CAPSULE) {
             float ax[3], v[3];

@@ -60,6 +60,12 @@ class Model:
     def id2name(self, group: str, i: int) -> str:
         return self._L.myo_model_id2name(self._h, group.encode(), int(i)).decode()
 
+    def check(self) -> str:
+        """'' when the kernels can run this model, else one line per unsupported feature (``myo_model_check``)."""
+        buf = C.create_string_buffer(8192)
+        self._L.myo_model_check(self._h, buf, len(buf))
+        return buf.value.decode()
+
     def default_task_cfg(self, kind: int) -> TaskCfg:
         cfg = TaskCfg()
         check(self._L, self._L.myo_task_cfg_default(self._h, int(kind), C.byref(cfg)))

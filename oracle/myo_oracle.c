@@ -102,6 +102,7 @@ typedef struct OModel {
   double timestep, gravity[3], impratio;
   int cone, disableflags;
   double stat_meaninertia;
+  int nexclude; int* exclude_signature;      /* <contact><exclude>: (body1 << 16) + body2, body1 < body2 (mj_collision skips these body pairs) */
 #define X(T, n, c) T* n;
   MODEL_FIELDS(X)
 #undef X
@@ -157,7 +158,14 @@ OModel* o_model_new(const int* sz) {
 #undef X
   return m;
 }
+void o_model_set_excludes(OModel* m, int n, const int* sig) {
+  free(m->exclude_signature);
+  m->nexclude = n;
+  m->exclude_signature = (int*)calloc((size_t)(n > 0 ? n : 1), sizeof(int));
+  for (int i = 0; i < n; i++) m->exclude_signature[i] = sig[i];
+}
 void o_model_free(OModel* m) {
+  free(m->exclude_signature);
 #define X(T, n, c) free(m->n);
   MODEL_FIELDS(X)
 #undef X
@@ -809,6 +817,7 @@ void o_collision(const OModel* m, OData* d) {
     int wp1 = m->body_weldid[m->body_parentid[w1]], wp2 = m->body_weldid[m->body_parentid[w2]];
     if (w1 == w2) continue;
     if (w1 != 0 && w2 != 0 && (w1 == wp2 || w2 == wp1)) continue;
+    { int ex = 0; for (int e = 0; e < m->nexclude; e++) if (m->exclude_signature[e] == (b1 << 16) + b2) ex = 1; if (ex) continue; }
     for (int ga = m->body_geomadr[b1]; ga < m->body_geomadr[b1] + m->body_geomnum[b1]; ga++)
       for (int gb = m->body_geomadr[b2]; gb < m->body_geomadr[b2] + m->body_geomnum[b2]; gb++) {
         int g1 = ga, g2 = gb;
@@ -1155,17 +1164,19 @@ void o_fwd_actuation(const OModel* m, OData* d) {
  * norm of 1e-14 * scale so the oracle is the converged answer MuJoCo's Newton (tolerance 1e-8)
  * approximates. */
 static int cmp_double(const void* a, const void* b) { double x = *(const double*)a, y = *(const double*)b; return (x > y) - (x < y); }
+/* gradient tolerance of the Newton solve: 1e-14 (converged to rounding) for the parity tests; bench.py's CPU arm sets MuJoCo's
+ * own default, opt.tolerance = 1e-8, so that the baseline is not slower than the reference's solver would be */
+static double g_solver_tol = 1e-14;
+void o_set_solver_tol(double tol) { g_solver_tol = tol; }
+
 void o_fwd_constraint(const OModel* m, OData* d) {
   int nv = m->nv, ne = d->nefc;
   zero(d->qfrc_constraint, nv);
   d->solver_iter = 0;
   if (!ne) { cpy(d->qacc, d->qacc_smooth, nv); cpy(d->qacc_warmstart, d->qacc_smooth, nv); return; }
   double* a = d->qacc;
-  double* jar = (double*)malloc(sizeof(double)*ne); double* jp = (double*)malloc(sizeof(double)*ne);
-  double* grad = (double*)malloc(sizeof(double)*nv); double* p = (double*)malloc(sizeof(double)*nv);
-  double* Ma = (double*)malloc(sizeof(double)*nv); double* Mp = (double*)malloc(sizeof(double)*nv);
-  double* H = (double*)malloc(sizeof(double)*nv*nv); double* L = (double*)malloc(sizeof(double)*nv*nv);
-  double* bp = (double*)malloc(sizeof(double)*(ne + 1));
+  /* work arrays on the stack (nv <= 64, ne <= njmax): no allocator traffic in the solve */
+  double jar[ne], jp[ne], grad[nv], p[nv], Ma[nv], Mp[nv], H[nv*nv], L[nv*nv], bp[ne + 1];
   /* warm start: better of qacc_warmstart and qacc_smooth */
   double cost[2];
   for (int w = 0; w < 2; w++) {
@@ -1182,7 +1193,7 @@ void o_fwd_constraint(const OModel* m, OData* d) {
     for (int i = 0; i < nv; i++) { Ma[i] = dotn(d->Mdense + i*nv, a, nv); grad[i] = Ma[i] - d->qfrc_smooth[i]; }
     for (int r = 0; r < ne; r++) if (jar[r] < 0) for (int i = 0; i < nv; i++) grad[i] += d->efc_D[r]*jar[r]*d->efc_J[r*nv + i];
     double gn = sqrt(dotn(grad, grad, nv));
-    if (gn * scale < 1e-14) break;
+    if (gn * scale < g_solver_tol) break;
     d->solver_iter = it + 1;
     cpy(H, d->Mdense, nv*nv);
     for (int r = 0; r < ne; r++) if (jar[r] < 0) {
@@ -1219,7 +1230,6 @@ void o_fwd_constraint(const OModel* m, OData* d) {
     for (int i = 0; i < nv; i++) d->qfrc_constraint[i] += d->efc_J[r*nv + i] * d->efc_force[r];
   }
   cpy(d->qacc_warmstart, a, nv);
-  free(jar); free(jp); free(grad); free(p); free(Ma); free(Mp); free(H); free(L); free(bp);
 }
 
 /* ------------------------------------------------------------------ pipeline ------------- */
@@ -1248,16 +1258,15 @@ void o_forward(const OModel* m, OData* d) {
 void o_euler(const OModel* m, OData* d) {
   int nv = m->nv;
   double h = m->timestep;
-  double* qacc = (double*)malloc(sizeof(double)*nv);
+  double qacc[nv];
   int damp = 0;
   for (int i = 0; i < nv; i++) if (m->dof_damping[i] > 0) { damp = 1; break; }
   if (!damp) cpy(qacc, d->qacc, nv);
   else {
-    double* A = (double*)malloc(sizeof(double)*nv*nv); double* L = (double*)malloc(sizeof(double)*nv*nv);
+    double A[nv*nv], L[nv*nv];
     cpy(A, d->Mdense, nv*nv);
     for (int i = 0; i < nv; i++) { A[i*nv + i] += h * m->dof_damping[i]; qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i]; }
     chol_factor(L, A, nv); chol_solve(L, qacc, nv);
-    free(A); free(L);
   }
   for (int i = 0; i < m->na; i++) {
     int u = i + (m->nu - m->na);
@@ -1282,7 +1291,6 @@ void o_euler(const OModel* m, OData* d) {
     }
   }
   d->time += h;
-  free(qacc);
 }
 void o_step(const OModel* m, OData* d) { o_forward(m, d); o_euler(m, d); }
 void o_step_n(const OModel* m, OData* d, int n) { for (int i = 0; i < n; i++) o_step(m, d); }
@@ -1350,6 +1358,56 @@ void o_set_const(OModel* m, OData* d) {
 /* ------------------------------------------------------------------ batched CPU stepping -- */
 /* Used by bench.py's cpu_baseline / --impl reference arm: advance n independent worlds by
  * nsub substeps each; worlds [w0, w1) of caller-provided state arrays (double). */
+/* One Baoding env step for worlds [w0, w1) - the work a SubprocVecEnv worker does per step in the reference: BaodingEnvV1.step's
+ * target update, BaseV0.step's muscle remap, frame_skip mj_steps, get_obs (kinematics at the new state), the reward terms of
+ * CustomBaodingP2Env.get_reward_dict (/root/reference/src/envs/baoding.py:403-467) with the winning run's weights.
+ * task[w] = {which_task, angle1, angle2, x_radius, y_radius, period, counter}; ids = {ball1_site, ball2_site, target1_site,
+ * target2_site, ball1_dofadr, ball2_dofadr}. Used only by bench.py's CPU baseline legs. */
+void o_batch_env_step(OModel* m, OData* d, int w0, int w1, int nsub, double* qpos, double* qvel, double* act, double* warm,
+                      const double* action, double* task, const int* ids, const double* weights, double drop_th, double proximity_th,
+                      double* obs, double* reward, int* done) {
+  const double cx = -0.0125, cy = -0.07, dt = nsub * m->timestep;
+  const int nh = m->nq - 14, nobs = nh + 24 + m->na;
+  for (int w = w0; w < w1; w++) {
+    double* tk = task + 7*(size_t)w;
+    cpy(d->qpos, qpos + (size_t)w*m->nq, m->nq); cpy(d->qvel, qvel + (size_t)w*m->nv, m->nv);
+    cpy(d->act, act + (size_t)w*m->na, m->na); cpy(d->qacc_warmstart, warm + (size_t)w*m->nv, m->nv);
+    if (tk[0] > 0.5) {
+      const double sign = tk[0] < 1.5 ? -1.0 : 1.0, ang = sign * 2 * M_PI * (tk[6] * dt / tk[5]);
+      for (int k = 0; k < 2; k++) {
+        m->site_pos[3*ids[2 + k]] = tk[3] * cos(ang + tk[1 + k]) + cx;
+        m->site_pos[3*ids[2 + k] + 1] = tk[4] * sin(ang + tk[1 + k]) + cy;
+      }
+    }
+    tk[6] += 1;
+    for (int i = 0; i < m->nu; i++) d->ctrl[i] = 1.0 / (1.0 + exp(-5.0 * (action[(size_t)w*m->nu + i] - 0.5)));
+    for (int s = 0; s < nsub; s++) o_step(m, d);
+    o_kinematics(m, d);
+    double* o = obs + (size_t)w*nobs;
+    cpy(o, d->qpos, nh);
+    double d1 = 0, d2 = 0, a2 = 0;
+    for (int k = 0; k < 2; k++) {
+      const double* ob = d->site_xpos + 3*ids[k]; const double* tg = d->site_xpos + 3*ids[2 + k];
+      for (int e = 0; e < 3; e++) {
+        o[nh + 6*k + e] = ob[e]; o[nh + 6*k + 3 + e] = d->qvel[ids[4 + k] + e] * dt;
+        o[nh + 12 + 3*k + e] = tg[e]; o[nh + 18 + 3*k + e] = tg[e] - ob[e];
+        if (k == 0) d1 += (tg[e] - ob[e])*(tg[e] - ob[e]); else d2 += (tg[e] - ob[e])*(tg[e] - ob[e]);
+      }
+    }
+    cpy(o + nh + 24, d->act, m->na);
+    for (int i = 0; i < m->na; i++) a2 += d->act[i]*d->act[i];
+    d1 = sqrt(d1); d2 = sqrt(d2);
+    const int fall = d->site_xpos[3*ids[0] + 2] < drop_th || d->site_xpos[3*ids[1] + 2] < drop_th;
+    const double terms[7] = { -d1, -d2, -sqrt(a2) / m->na, fall ? 0.0 : 1.0, -(d1 + d2),
+                              (d1 < proximity_th && d2 < proximity_th && !fall) ? 1.0 : 0.0, fall ? 1.0 : 0.0 };
+    double r = 0;
+    for (int k = 0; k < 7; k++) r += weights[k] * terms[k];
+    reward[w] = r; done[w] = fall;
+    cpy(qpos + (size_t)w*m->nq, d->qpos, m->nq); cpy(qvel + (size_t)w*m->nv, d->qvel, m->nv);
+    cpy(act + (size_t)w*m->na, d->act, m->na); cpy(warm + (size_t)w*m->nv, d->qacc_warmstart, m->nv);
+  }
+}
+
 void o_batch_step(const OModel* m, OData* d, int w0, int w1, int nsub, double* qpos, double* qvel, double* act,
                   double* warm, const double* ctrl) {
   for (int w = w0; w < w1; w++) {

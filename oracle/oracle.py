@@ -26,13 +26,30 @@ def build(force: bool = False) -> str:
     return so
 
 
-def lib():
+def build_fast() -> str:
+    """bench.py's CPU baseline legs: the same source, -O3 -march=native, built ON the machine that runs it (into the system's
+    temporary directory, never shipped). Falls back to the strict build when no compiler is available."""
+    import tempfile
+
+    so = os.path.join(tempfile.gettempdir(), "libmyo_oracle_fast_%d.so" % os.getuid())
+    src = os.path.join(_HERE, "myo_oracle.c")
+    try:
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-std=gnu99", "-Wno-unused-function", "-shared", "-o", so, src, "-lm"])
+        return so
+    except Exception:
+        return build()
+
+
+def lib(path: str | None = None):
+    """``path``: load that build of the oracle instead of the strict one (first call only; bench.py's CPU legs)."""
     global _LIB
     if _LIB is None:
-        L = ctypes.CDLL(build())
+        L = ctypes.CDLL(path or build())
         vp, ip, cp, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)
         L.o_model_new.restype = vp; L.o_model_new.argtypes = [ip]
         L.o_model_free.argtypes = [vp]
+        L.o_model_set_excludes.argtypes = [vp, ctypes.c_int, ip]
         L.o_model_set_opt.argtypes = [vp, ctypes.c_double, dp, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double]
         L.o_model_field.restype = vp; L.o_model_field.argtypes = [vp, cp, ip, ip]
         L.o_data_new.restype = vp; L.o_data_new.argtypes = [vp]
@@ -48,6 +65,9 @@ def lib():
             getattr(L, f).argtypes = [vp, vp]; getattr(L, f).restype = None
         L.o_step_n.argtypes = [vp, vp, ctypes.c_int]
         L.o_batch_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp]
+        L.o_batch_env_step.argtypes = [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, dp, dp, ip, dp, ctypes.c_double,
+                                       ctypes.c_double, dp, dp, ip]
+        L.o_set_solver_tol.argtypes = [ctypes.c_double]
         L.o_muscle_gain.restype = ctypes.c_double; L.o_muscle_gain.argtypes = [ctypes.c_double, ctypes.c_double, dp, ctypes.c_double, dp]
         L.o_muscle_bias.restype = ctypes.c_double; L.o_muscle_bias.argtypes = [ctypes.c_double, dp, ctypes.c_double, dp]
         L.o_muscle_dynamics.restype = ctypes.c_double; L.o_muscle_dynamics.argtypes = [ctypes.c_double, ctypes.c_double, dp]
@@ -104,6 +124,9 @@ class OracleModel(_Fields):
         o = src.opt
         g = (ctypes.c_double * 3)(o["gravity0"], o["gravity1"], o["gravity2"])
         L.o_model_set_opt(self._p, o["timestep"], g, o["impratio"], o["cone"], o["disableflags"], src.stat["meaninertia"])
+        if s.get("nexclude", 0) > 0:
+            sig = np.ascontiguousarray(np.asarray(src.arrays["exclude_signature"]).reshape(-1), dtype=np.int32)
+            L.o_model_set_excludes(self._p, int(sig.size), sig.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
         for name, arr in src.arrays.items():
             v = self._get(name)
             if v is not None:

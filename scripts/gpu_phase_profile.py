@@ -11,7 +11,7 @@ from myochallenge_b200.assets import asset_path
 NAMES = ["tree_fwd", "tendon", "tree_bwd", "mass_bias", "factor", "collision", "constraints", "actuation", "solveM", "newton", "integrate", "  nt:hessian", "  nt:chol_factor", "  nt:chol_solve", "  nt:linesearch+dots", "barrier_pre_integrate"]
 
 def run(path, kind, n, steps=5, spinup=3):
-    m = Model(asset_path(path))
+    m = Model(os.path.join(os.environ["MYO_MODEL_DIR"], path) if os.environ.get("MYO_MODEL_DIR") else asset_path(path))
     cfg = m.default_task_cfg(kind)
     if kind == _capi.TASK_BAODING:
         cfg.task_choice_random = 1
@@ -38,6 +38,9 @@ def run(path, kind, n, steps=5, spinup=3):
         print(f"   {nm:12s} {buf[k]/sub:10.0f} cyc  {100*buf[k]/tot:5.1f}%")
 
 if __name__ == "__main__":
+    if os.environ.get("ONLY_HAND"):
+        run("hand/myo_hand_baoding.mjb", _capi.TASK_BAODING, 32768, spinup=int(os.environ.get("SPINUP", "150")))
+        sys.exit(0)
     run("finger/myo_finger_v0.mjb", _capi.TASK_POSE, 4096)
     hand = os.path.join(ROOT, "myochallenge_b200", "assets", "hand", "myo_hand_baoding.mjb")
     if os.path.exists(hand):

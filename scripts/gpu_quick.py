@@ -6,7 +6,7 @@ from myochallenge_b200 import BatchSim, Model, _capi
 from myochallenge_b200.assets import asset_path
 
 def run(path, kind, n, steps=20, spinup=3):
-    m = Model(asset_path(path))
+    m = Model(os.path.join(os.environ["MYO_MODEL_DIR"], path) if os.environ.get("MYO_MODEL_DIR") else asset_path(path))
     cfg = m.default_task_cfg(kind)
     if kind == _capi.TASK_BAODING:
         cfg.task_choice_random = 1
