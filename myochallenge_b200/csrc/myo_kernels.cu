@@ -58,8 +58,8 @@ MYO_DI void redo_push(const BatchPtrs& b, int w, int kind) {
 // called conditionally; otherwise every tile of the CTA must reach the same phase barriers and anything that needs extra
 // physics (a reset with reference-state initialisation) or more room (more contacts / limit rows than the fast layout
 // holds) is handed to the SOLO kernel through the redo list.
-template <int G, int RMAX, bool SOLO>
-__device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G>& c, int w, int kind) {
+template <int G, int RMAX, bool SOLO, int V>
+__device__ void run_world(int mslot, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, Ctx<G, V> c, int w, int kind) {
   MYO_M
   int status = 0;
   bool deferred_reset = false;
@@ -203,6 +203,19 @@ __device__ void stage_tables(const DevModel& m) {
 #endif
 }
 
+// the full-capacity pass of the fast kernel goes through one noinline call, so that its (large, cold) code does not take part
+// in the register allocation of the kernel body around the fast path
+template <int G>
+MYO_PHASE void heavy_world(int mslot_full, const myo_task_cfg& t, const BatchPtrs& b, const StepArgs& a, int soff, int entry) {
+  cg::thread_block block = cg::this_thread_block();
+  cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
+  Ctx<G, 1> ch(tile);
+  ch.soff = soff;
+  StepArgs ar = a;
+  ar.mode = MODE_REDO;
+  run_world<G, kSoloRowsPerLane, true>(mslot_full, t, b, ar, ch, entry & 0x3fffffff, entry >> 30);
+}
+
 #ifndef MYO_EMUL
 MYO_DI int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 #endif
@@ -214,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) world_kernel(int mslot, int mslot_fu
   stage_tables(m);
   cg::thread_block block = cg::this_thread_block();
   cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
-  Ctx<G> c(tile);
+  Ctx<G, 0> c(tile);
   const int wpc = blockDim.x / G;
   const int tid = threadIdx.x / G;
   c.soff = m.tab_words + tid * m.scratch_words;
@@ -272,11 +285,15 @@ __global__ void __launch_bounds__(kThreads) world_kernel(int mslot, int mslot_fu
         int e;
         while ((e = ld_volatile(b.redo_list + idx + tid)) < 0) __nanosleep(200);      // reserved but not written yet
         __threadfence();
-        Ctx<G> ch(tile);
+#ifdef MYO_HEAVY_INLINE
+        Ctx<G, 1> ch(tile);
         ch.soff = m.tab_words + tid * mf.scratch_words;
         StepArgs ar = a;
         ar.mode = MODE_REDO;
         run_world<G, RFULL, true>(mslot_full, t, b, ar, ch, e & 0x3fffffff, e >> 30);
+#else
+        heavy_world<G>(mslot_full, t, b, a, m.tab_words + tid * mf.scratch_words, e);
+#endif
       }
     }
     return;
@@ -303,7 +320,7 @@ __global__ void __launch_bounds__(G < 32 ? 32 : G) solo_kernel(int mslot, const 
   stage_tables(m);
   cg::thread_block block = cg::this_thread_block();
   cg::thread_block_tile<G> tile = cg::tiled_partition<G>(block);
-  Ctx<G> c(tile);
+  Ctx<G, 1> c(tile);
   c.soff = m.tab_words;
   constexpr int RMAX = G == 1 ? kSoloRowsPerLane * 32 : kSoloRowsPerLane;
   for (int i = blockIdx.x; i < count; i += gridDim.x) {

@@ -11,7 +11,10 @@
 namespace myo {
 namespace cg = cooperative_groups;
 
-template <int G>
+// V: code variant. The full-capacity passes instantiate every phase with V = 1, i.e. as separate functions, so that the register
+// conventions ptxas derives for the fast path's phases are not widened by the deeper call graph of those passes (measured:
+// sharing the functions cost the fast path 5 %).
+template <int G, int V = 0>
 struct Ctx {
   cg::thread_block_tile<G> tile;
   int lane;
@@ -30,12 +33,12 @@ struct Ctx {
 #define SI(field) (reinterpret_cast<int*>(MYO_SMEM_WORDS + c.soff + m.field))
 #define SO(off) (MYO_SMEM_WORDS + c.soff + (off))   // scratch word offset -> pointer (noinline phases take offsets, not pointers)
 
-template <int G> MYO_DI float tile_sum(const Ctx<G>& c, float v) {
+template <int G, int V> MYO_DI float tile_sum(const Ctx<G, V> c, float v) {
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) v += c.tile.shfl_xor(v, o);
   return v;
 }
-template <int G> MYO_DI float tile_max(const Ctx<G>& c, float v) {
+template <int G, int V> MYO_DI float tile_max(const Ctx<G, V> c, float v) {
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, c.tile.shfl_xor(v, o));
   return v;
@@ -83,8 +86,8 @@ MYO_DI void rodrigues(float* R, const float* a, float ang) {
   R[6] = t * a[0] * a[2] - sn * a[1]; R[7] = t * a[1] * a[2] + sn * a[0]; R[8] = cs + t * a[2] * a[2];
 }
 
-template <int G>
-MYO_PHASE void body_local_pose(int mslot, Ctx<G>& c, int b) {
+template <int G, int V>
+MYO_PHASE void body_local_pose(int mslot, Ctx<G, V> c, int b) {
   MYO_M
   const float* qpos = SF(o_qpos);
   float* cdof = SF(o_cdof);
@@ -135,8 +138,8 @@ MYO_PHASE void body_local_pose(int mslot, Ctx<G>& c, int b) {
   for (int k = 0; k < 9; k++) xm[k] = R[k];
 }
 
-template <int G>
-MYO_PHASE void phase_tree_forward(int mslot, Ctx<G>& c, bool dyn) {
+template <int G, int V>
+MYO_PHASE void phase_tree_forward(int mslot, Ctx<G, V> c, bool dyn) {
   MYO_M
   if (c.lane == 0) {
     float* xp = SF(o_xpos); float* xm = SF(o_xmat); float* xi = SF(o_xipos);
@@ -265,8 +268,8 @@ MYO_PHASE void phase_tree_forward(int mslot, Ctx<G>& c, bool dyn) {
 // a10.4 mj_crb + mj_rne backward + qfrc_bias, a lane per dof and no sweep up the tree: the lane adds the composite
 // inertia and the force of its body's subtree itself (host list b_sub), then forms its mass-matrix row in MuJoCo's
 // sparse dof_Madr layout (row i: i, parent(i), ...) and qfrc_bias_i = cdof_i . (subtree force).
-template <int G>
-MYO_PHASE void phase_mass_bias(int mslot, Ctx<G>& c) {
+template <int G, int V>
+MYO_PHASE void phase_mass_bias(int mslot, Ctx<G, V> c) {
   MYO_M
   const float* cdof = SF(o_cdof); const float* cin = SF(o_cinert); const float* cf = SF(o_cfrc);
   float* M = SF(o_M); float* bias = SF(o_bias);
@@ -314,8 +317,8 @@ MYO_PHASE void phase_mass_bias(int mslot, Ctx<G>& c) {
 }
 
 // y = M x (mj_mulM): a lane per row over the host-built list of the row's nonzeros (column | qM index << 8)
-template <int G>
-MYO_PHASE void mul_M(int mslot, Ctx<G>& c, int oM, int ox, int oy, bool sync = true) {
+template <int G, int V>
+MYO_PHASE void mul_M(int mslot, Ctx<G, V> c, int oM, int ox, int oy, bool sync = true) {
   MYO_M
   const float* M = SO(oM); const float* x = SO(ox); float* y = SO(oy);
   for (int i = c.lane; i < m.nv; i += G) {
@@ -332,6 +335,15 @@ MYO_PHASE void mul_M(int mslot, Ctx<G>& c, int oM, int ox, int oy, bool sync = t
   }
   if (sync) c.tile.sync();
 }
+
+// Helpers that take pointers to the caller's small arrays (points, frames, coefficient sets): as noinline functions those arrays
+// live in local memory and every call stores and reloads them (round-2 profile: 240 local loads + 90 local stores per world
+// and substep, 1.85 of 32 bytes used per sector). Inlined, they stay in registers. -DMYO_OUTLINE_HELPERS restores the calls.
+#ifdef MYO_OUTLINE_HELPERS
+#define MYO_HELPER MYO_PHASE
+#else
+#define MYO_HELPER MYO_DI
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // a10.2 tendon length + moment arms (mj_tendon + mju_wrap), one lane per tendon.
@@ -353,7 +365,7 @@ MYO_DI bool seg_intersect(const float* p1, const float* p2, const float* p3, con
 }
 // 2-D wrap around a circle (MuJoCo wrap_circle). Arc angle via atan2(|cross|, dot): same value as
 // MuJoCo's acos(dot) but well conditioned in fp32 for small arcs.
-MYO_PHASE float wrap_circle(float* pnt, const float* d, const float* sd, float rad) {
+MYO_HELPER float wrap_circle(float* pnt, const float* d, const float* sd, float rad) {
   const float sqlen0 = d[0] * d[0] + d[1] * d[1], sqlen1 = d[2] * d[2] + d[3] * d[3], sqrad = rad * rad;
   const float dif[2] = {d[2] - d[0], d[3] - d[1]};
   const float dd = dif[0] * dif[0] + dif[1] * dif[1];
@@ -395,7 +407,7 @@ MYO_PHASE float wrap_circle(float* pnt, const float* d, const float* sd, float r
   return rad * angle;
 }
 // returns curved length (>= 0) and two world points in wpnt[0..5]; -1 no wrap; -2 unsupported (inside wrap)
-MYO_PHASE float wrap_geom(float* wpnt, const float* x0, const float* x1, const float* gpos, const float* gmat, float radius,
+MYO_HELPER float wrap_geom(float* wpnt, const float* x0, const float* x1, const float* gpos, const float* gmat, float radius,
                            int type, const float* side) {
   float p0[3], p1[3], dif[3], axis0[3], axis1[3], normal[3];
   sub3(dif, x0, gpos); mulmatTvec3(p0, gmat, dif);
@@ -464,7 +476,7 @@ MYO_DI int common_prefix(const DevModel& m, int ba, int bb) {
 // for the dofs on either body's chain past their common prefix (- on the pa side, + on the pb side). The dof list of the
 // (body, body) pair is precomputed (myo_pack.cpp seg_list): header n | rootA << 8 | rootB << 20, entries
 // dof | slot << 8 | end << 16, slot = position in the tendon's dof list = position in the segment's result row.
-MYO_PHASE void segment_moment(int mslot, int soff, int list, const float* pa, const float* pb, float inv_div, float* out) {
+MYO_HELPER void segment_moment(int mslot, int soff, int list, const float* pa, const float* pb, float inv_div, float* out) {
   MYO_M
   if (list < 0) return;
   const float* s = MYO_SMEM_WORDS + soff;
@@ -491,8 +503,8 @@ MYO_PHASE void segment_moment(int mslot, int soff, int list, const float* pa, co
 // One lane per path segment (results to scratch: length and moment-arm slots), then one lane per tendon adds its
 // segments in path order: ten_length, ten_J (KT slots over the tendon's dof list) and ten_velocity = J . qvel.
 // The per-segment results live in the Newton Hessian's scratch (free outside the constraint solve).
-template <int G>
-MYO_PHASE void phase_tendon(int mslot, Ctx<G>& c, int* status) {
+template <int G, int V>
+MYO_PHASE void phase_tendon(int mslot, Ctx<G, V> c, int* status) {
   MYO_M
   float* res = SF(o_H);
   for (int sg = c.lane; sg < m.nseg; sg += G) {
@@ -569,8 +581,8 @@ MYO_DI float muscle_FL(float L, float lmin, float lmax) {
   x = (lmax - L) / fmaxf(kMinVal, lmax - b);
   return 0.5f * x * x;
 }
-template <int G>
-MYO_PHASE void phase_actuation(int mslot, Ctx<G>& c) {
+template <int G, int V>
+MYO_PHASE void phase_actuation(int mslot, Ctx<G, V> c) {
   MYO_M
   const float* ctrl = SF(o_ctrl); const float* act = SF(o_act);
   for (int i = c.lane; i < m.nu; i += G) {
@@ -598,13 +610,13 @@ MYO_PHASE void phase_actuation(int mslot, Ctx<G>& c) {
       if (F0 < 0.f) F0 = gp[3] / fmaxf(kMinVal, acc0);
       const float L0 = (lr1 - lr0) / fmaxf(kMinVal, gp[1] - gp[0]);
       const float L = gp[0] + (len - lr0) / fmaxf(kMinVal, L0);
-      const float V = vel / fmaxf(kMinVal, L0 * gp[6]);
+      const float Vn = vel / fmaxf(kMinVal, L0 * gp[6]);
       const float FL = muscle_FL(L, gp[4], gp[5]);
       const float y = gp[8] - 1.f;
       float FV;
-      if (V <= -1.f) FV = 0.f;
-      else if (V <= 0.f) FV = (V + 1.f) * (V + 1.f);
-      else if (V <= y) FV = gp[8] - (y - V) * (y - V) / fmaxf(kMinVal, y);
+      if (Vn <= -1.f) FV = 0.f;
+      else if (Vn <= 0.f) FV = (Vn + 1.f) * (Vn + 1.f);
+      else if (Vn <= y) FV = gp[8] - (y - Vn) * (y - Vn) / fmaxf(kMinVal, y);
       else FV = gp[8];
       gain = -F0 * FL * FV;
     } else gain = gp[0];
@@ -786,8 +798,8 @@ MYO_PHASE bool capsule_box(int sub, float margin, const float* pc, const float* 
   return true;
 }
 
-template <int G>
-MYO_PHASE void phase_collision(int mslot, Ctx<G>& c, int* status) {
+template <int G, int V>
+MYO_PHASE void phase_collision(int mslot, Ctx<G, V> c, int* status) {
   MYO_M
   int* misc = SI(o_misc);
   int ncon = 0;
@@ -883,7 +895,7 @@ MYO_PHASE void phase_collision(int mslot, Ctx<G>& c, int* status) {
 }
 
 // impedance, regularisation and reference-acceleration coefficients of one row (mj_makeImpedance)
-MYO_PHASE void row_params(int mslot, const float* solref, const float* solimp, float pos, float margin, float diag,
+MYO_HELPER void row_params(int mslot, const float* solref, const float* solimp, float pos, float margin, float diag,
                        float* R, float* K, float* B, float* imp) {
   MYO_M
   const float s0 = clipf(solimp[0], 0.0001f, 0.9999f), s1 = clipf(solimp[1], 0.0001f, 0.9999f);
@@ -918,8 +930,8 @@ MYO_PHASE void row_params(int mslot, const float* solref, const float* solimp, f
 // 2*(condim-1) pyramid rows each. Rows keep (D, aref); Jacobians stay factored per block:
 // a limit has one basis vector over <= KT dofs, a contact has (normal, tangent1, tangent2) over
 // the <= KS dofs in chain(body1) xor chain(body2).
-template <int G>
-MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
+template <int G, int V>
+MYO_PHASE void phase_constraints(int mslot, Ctx<G, V> c, int* status) {
   MYO_M
   int* misc = SI(o_misc);
   const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel);
@@ -1110,8 +1122,8 @@ MYO_PHASE void phase_constraints(int mslot, Ctx<G>& c, int* status) {
 
 // ------------------------------------------------------------------------------------------------
 // row helper: J_r . x for every row -> rows[r][field]; optionally subtract aref (jar = J a - aref)
-template <int G>
-MYO_PHASE void rows_dot(int mslot, Ctx<G>& c, int ox, int field, bool sub_aref, bool sync = true) {
+template <int G, int V>
+MYO_PHASE void rows_dot(int mslot, Ctx<G, V> c, int ox, int field, bool sub_aref, bool sync = true) {
   MYO_M
   const float* x = SO(ox);
   const int* misc = SI(o_misc);
@@ -1159,8 +1171,8 @@ MYO_PHASE void rows_dot(int mslot, Ctx<G>& c, int ox, int field, bool sub_aref, 
 // Joint-limit rows touch one dof each and come joint-major (lower side, then upper side), so a lane per row can apply
 // them without write conflicts: the lane of a joint's first row also applies the second row if both sides are present.
 // fn(r) -> contribution weight of row r; apply(dof, sign * weight)
-template <int G, class W, class A>
-MYO_DI void for_joint_limit_rows(const DevModel& m, const Ctx<G>& c, int nlim, W weight, A apply) {
+template <int G, int V, class W, class A>
+MYO_DI void for_joint_limit_rows(const DevModel& m, const Ctx<G, V> c, int nlim, W weight, A apply) {
   for (int r = c.lane; r < nlim; r += G) {
     const float* lr = MYO_SMEM_WORDS + c.soff + m.o_lim + r * LIM_WORDS; const int* li = reinterpret_cast<const int*>(lr);
     if (li[L_KIND] != EFC_LIMIT_JOINT) continue;
@@ -1174,8 +1186,8 @@ MYO_DI void for_joint_limit_rows(const DevModel& m, const Ctx<G>& c, int nlim, W
 // out[dof] += sum_r J_r[dof] * w_r  with w_r = (jar_r < 0 ? -D_r jar_r : 0) * scale  (forces)
 // joint-limit rows in parallel (above); tendon-limit rows and contacts one after the other, lanes across the block's
 // support: no atomics, fixed order.
-template <int G>
-MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
+template <int G, int V>
+MYO_PHASE void rows_JT_force(int mslot, Ctx<G, V> c, int oout, float scale) {
   MYO_M
   float* out = SO(oout);
   const int* misc = SI(o_misc);
@@ -1223,8 +1235,8 @@ MYO_PHASE void rows_JT_force(int mslot, Ctx<G>& c, int oout, float scale) {
 //   H    = M + sum_{active rows} D_r J_r' J_r,  right-hand side = -grad
 // One walk over the constraint blocks feeds both: joint-limit rows lane-parallel (disjoint dofs), tendon-limit rows and
 // contacts one after the other, lanes across the block's support / support pairs (no atomics, fixed order).
-template <int G>
-MYO_PHASE void newton_system(int mslot, Ctx<G>& c) {
+template <int G, int V>
+MYO_PHASE void newton_system(int mslot, Ctx<G, V> c) {
   MYO_M
   float* H = SF(o_H); const float* M = SF(o_M); float* grad = SF(o_grad);
   const float* Ma = SF(o_Ma); const float* fs = SF(o_smooth);
@@ -1336,8 +1348,8 @@ MYO_PHASE void newton_system(int mslot, Ctx<G>& c) {
 // 1 / L_jj. n4 = n rounded up to 4 (rows n..n4-1 are identity rows written by build_hessian).
 // Then the back substitution L' x = y, column oriented, with y held in registers (lane i owns y_i, y_{i+G}, ...)
 // and each finished x_j broadcast by a shuffle; x goes to scratch at ox.
-template <int G>
-MYO_PHASE void chol_factor_solve(int mslot, Ctx<G>& c, int oH, int ox, int n) {
+template <int G, int V>
+MYO_PHASE void chol_factor_solve(int mslot, Ctx<G, V> c, int oH, int ox, int n) {
   MYO_M
   float* H = SO(oH); float* x = SO(ox);
   const int* roff = m.h_roff.ptr();
@@ -1441,8 +1453,8 @@ MYO_PHASE void chol_factor_solve(int mslot, Ctx<G>& c, int oH, int ox, int n) {
 // The coupled dofs [0, m.nd) go through the dense blocked Cholesky above (the Newton Hessian's scratch is free outside
 // the constraint solve); the simple dofs behind them (free bodies with diagonal inertia: dof_simplenum) divide by
 // their diagonal entry.
-template <int G>
-MYO_PHASE void solve_M_dense(int mslot, Ctx<G>& c, int ox, float hdamp) {
+template <int G, int V>
+MYO_PHASE void solve_M_dense(int mslot, Ctx<G, V> c, int ox, float hdamp) {
   MYO_M
   float* H = SF(o_H); const float* M = SF(o_M); float* x = SO(ox);
   const int nd = m.nd, n4 = (nd + 3) & ~3;
@@ -1520,8 +1532,8 @@ MYO_DI bool cta_any(bool v) {
   return __syncthreads_or(v ? 1 : 0) != 0;
 #endif
 }
-template <int G, int RMAX>
-MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
+template <int G, int RMAX, int V>
+MYO_PHASE void phase_solve(int mslot, Ctx<G, V> c, bool fast) {
   MYO_M
   int* misc = SI(o_misc);
   const int nv = m.nv, nefc = misc[MI_NEFC];
@@ -1667,8 +1679,8 @@ MYO_PHASE void phase_solve(int mslot, Ctx<G>& c, bool fast) {
 
 // ------------------------------------------------------------------------------------------------
 // a10.9 mj_Euler (implicit in joint damping) + mj_advance
-template <int G>
-MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
+template <int G, int V>
+MYO_PHASE void phase_integrate(int mslot, Ctx<G, V> c) {
   MYO_M
   const float h = m.timestep;
   float* qacc = SF(o_qacc); float* qvel = SF(o_qvel); float* qpos = SF(o_qpos); float* act = SF(o_act);
@@ -1709,8 +1721,8 @@ MYO_PHASE void phase_integrate(int mslot, Ctx<G>& c) {
 
 // one full mj_step on the world in scratch
 // SYNC: the CTA's tiles walk the phases in lock step (fast kernel); false where tiles run on their own (full-capacity passes)
-template <int G, int RMAX, bool SYNC>
-MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
+template <int G, int RMAX, bool SYNC, int V>
+MYO_PHASE void mj_forward_dev(int mslot, Ctx<G, V> c, int* status, bool fast) {
   MYO_M
   MYO_PH_BEGIN
   MYO_SYNC(0) phase_tree_forward<G>(mslot, c, true); MYO_PH(0)
@@ -1725,8 +1737,8 @@ MYO_PHASE void mj_forward_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
   MYO_PH(8)
   MYO_SYNC(6) phase_solve<G, RMAX>(mslot, c, fast); MYO_PH(9)
 }
-template <int G, int RMAX, bool SYNC>
-MYO_PHASE void mj_step_dev(int mslot, Ctx<G>& c, int* status, bool fast) {
+template <int G, int RMAX, bool SYNC, int V>
+MYO_PHASE void mj_step_dev(int mslot, Ctx<G, V> c, int* status, bool fast) {
   MYO_M
   mj_forward_dev<G, RMAX, SYNC>(mslot, c, status, fast);
   MYO_PH_BEGIN

@@ -10,15 +10,15 @@
 
 namespace myo {
 
-template <int G>
-MYO_PHASE void copy_words(Ctx<G>& c, float* dst, const float* src, int n4) {   // n4: multiple of 4 words
+template <int G, int V>
+MYO_PHASE void copy_words(Ctx<G, V> c, float* dst, const float* src, int n4) {   // n4: multiple of 4 words
   const float4* s4 = reinterpret_cast<const float4*>(src);
   float4* d4 = reinterpret_cast<float4*>(dst);
   for (int i = c.lane; i < n4 / 4; i += G) d4[i] = s4[i];
 }
 
-template <int G>
-MYO_PHASE void load_world(int mslot, Ctx<G>& c, const BatchPtrs& b, int w) {
+template <int G, int V>
+MYO_PHASE void load_world(int mslot, Ctx<G, V> c, const BatchPtrs& b, int w) {
   MYO_M
   copy_words<G>(c, SF(o_qpos), b.qpos + (size_t)w * m.nq4, m.nq4);
   copy_words<G>(c, SF(o_qvel), b.qvel + (size_t)w * m.nv4, m.nv4);
@@ -28,8 +28,8 @@ MYO_PHASE void load_world(int mslot, Ctx<G>& c, const BatchPtrs& b, int w) {
   if (c.lane == 0) SF(o_misc)[MI_ONE] = 1.f;
   c.tile.sync();
 }
-template <int G>
-MYO_PHASE void store_world(int mslot, Ctx<G>& c, const BatchPtrs& b, int w, bool params) {
+template <int G, int V>
+MYO_PHASE void store_world(int mslot, Ctx<G, V> c, const BatchPtrs& b, int w, bool params) {
   MYO_M
   c.tile.sync();
   copy_words<G>(c, b.qpos + (size_t)w * m.nq4, SF(o_qpos), m.nq4);
@@ -41,8 +41,8 @@ MYO_PHASE void store_world(int mslot, Ctx<G>& c, const BatchPtrs& b, int w, bool
 
 // BaseV0.step: muscle actuators with normalize_act get ctrl = 1/(1+exp(-5(a-0.5))); other actuators
 // are de-normalised linearly into ctrlrange (MyoSuite Robot.normalize_actions).
-template <int G>
-MYO_PHASE void task_action(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float* a) {      // a == nullptr: the zero action
+template <int G, int V>
+MYO_PHASE void task_action(int mslot, const myo_task_cfg& t, Ctx<G, V> c, const float* a) {      // a == nullptr: the zero action
   MYO_M
   float* ctrl = SF(o_ctrl);
   for (int i = c.lane; i < m.nu; i += G) {
@@ -60,8 +60,8 @@ MYO_PHASE void task_action(int mslot, const myo_task_cfg& t, Ctx<G>& c, const fl
 }
 
 // BaodingEnvV1.step: target sites follow goal[counter] = sign*2*pi*counter*dt/period (a6, a7)
-template <int G>
-MYO_PHASE void baoding_targets(int mslot, const myo_task_cfg& t, Ctx<G>& c, const int* ti, const float* tf) {
+template <int G, int V>
+MYO_PHASE void baoding_targets(int mslot, const myo_task_cfg& t, Ctx<G, V> c, const int* ti, const float* tf) {
   MYO_M
   if (c.lane == 0) {
     const int task = ti[TI_TASK], counter = ti[TI_ELAPSED] + (ti[TI_FLAGS] & 1);   // bit 0: RSI's in-reset step already advanced self.counter
@@ -87,8 +87,8 @@ MYO_PHASE void baoding_targets(int mslot, const myo_task_cfg& t, Ctx<G>& c, cons
 }
 
 // observation vector into scratch o_obs (kinematics must be current)
-template <int G>
-MYO_PHASE void task_obs(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float* pose_target) {
+template <int G, int V>
+MYO_PHASE void task_obs(int mslot, const myo_task_cfg& t, Ctx<G, V> c, const float* pose_target) {
   MYO_M
   float* obs = SF(o_obs);
   const float* qpos = SF(o_qpos); const float* qvel = SF(o_qvel); const float* act = SF(o_act);
@@ -140,8 +140,8 @@ MYO_PHASE void task_obs(int mslot, const myo_task_cfg& t, Ctx<G>& c, const float
 }
 
 // reward terms + dense reward + termination from the observation in scratch. info: MYO_INFO_TERMS floats.
-template <int G>
-MYO_PHASE void task_reward(int mslot, const myo_task_cfg& t, Ctx<G>& c, float* tf, float* info, float* reward, bool* done) {
+template <int G, int V>
+MYO_PHASE void task_reward(int mslot, const myo_task_cfg& t, Ctx<G, V> c, float* tf, float* info, float* reward, bool* done) {
   MYO_M
   const float* obs = SF(o_obs); const float* act = SF(o_act);
   float a2 = 0.f;
@@ -200,8 +200,8 @@ inline __host__ __device__ bool reset_needs_physics(const myo_task_cfg& t) { ret
 
 // env.reset(): sample the task's reset distribution with a counter-based RNG keyed by
 // (seed, world, episode) and write the initial state into scratch.
-template <int G, int RMAX, bool SOLO>
-MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G>& c, const BatchPtrs& b, int w, int* ti,
+template <int G, int RMAX, bool SOLO, int V>
+MYO_PHASE void task_reset(int mslot, const myo_task_cfg& t, Ctx<G, V> c, const BatchPtrs& b, int w, int* ti,
                            float* tf, float* pose_target) {
   MYO_M
   float* qpos = SF(o_qpos);
