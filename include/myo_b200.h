@@ -294,6 +294,11 @@ int myo_policy_set_obs_norm(myo_policy* p, const float* mean_dev, const float* v
 /* seed != 0: when noise_dev is NULL, myo_policy_forward samples the Gaussian action noise in-kernel from a
  * counter-based stream keyed by (seed, world, forward-call counter); seed 0 restores the deterministic mean. */
 int myo_policy_seed(myo_policy* p, uint64_t seed);
+/* 0 (default): bf16 operands, fp32 accumulation on the tensor cores (tcgen05) - the rollout path. 1: plain fp32 arithmetic
+ * (library SGEMMs + elementwise kernels), the precision sb3-contrib's torch policy runs at: for evaluating trained reference
+ * checkpoints (/root/reference/src/main_eval.py:60-120) without the bf16 rounding of the action mean. Same arguments, same
+ * sampling stream. */
+int myo_policy_set_precision(myo_policy* p, int precision);
 int64_t myo_policy_launch_count(const myo_policy* p);
 /* latent_dev: float[max_batch][latent_dim] (latent_dim = last mlp_extractor policy width) that every following
  * myo_policy_forward fills with latent_pi, the input of action_net; NULL stops it. Without policy MLP layers latent_pi is

@@ -120,6 +120,7 @@ SIGNATURES = {
     "myo_policy_forward": (_i, [_vp, _i, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "myo_policy_set_obs_norm": (_i, [_vp, _fp, _fp, C.c_float, C.c_float, _vp]),
     "myo_policy_seed": (_i, [_vp, C.c_uint64]),
+    "myo_policy_set_precision": (_i, [_vp, _i]),
     "myo_policy_launch_count": (C.c_int64, [_vp]),
     "myo_policy_set_latent_out": (_i, [_vp, _fp]),
     "myo_sde_reset_noise": (_i, [_vp, _fp, _fp, _i, _i, _i, C.c_uint64, C.c_uint32, _vp]),

@@ -12,6 +12,7 @@
 // streams them from L2 with one cp.async.bulk (TMA engine, mbarrier complete_tx) per chunk into a 4-deep ring.
 // Warp roles: warps 0-3 = loader / epilogue (one world per thread, TMEM lane = thread), warp 4 = weight
 // producer, warp 5 = TMEM allocator + the single MMA-issuing thread.
+#include <cublas_v2.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -528,6 +529,11 @@ struct myo_policy {
   int swap_lbo_sbo = 0;
   int64_t launches = 0;
   float* latent_out = nullptr;   // caller-owned [max_batch][latent_dim], see myo_policy_set_latent_out
+  // fp32 mode (myo_policy_set_precision): plain SGEMMs on the fp32 weights + elementwise kernels, for evaluating trained
+  // checkpoints at the reference's own precision; scratch allocated on first use
+  int precision = 0;
+  cublasHandle_t blas = nullptr;
+  float* f32_scratch = nullptr;
 };
 
 namespace {
@@ -630,6 +636,136 @@ int pack_weights(myo_policy* p, cudaStream_t st) {
   return MYO_OK;
 }
 
+// ---- fp32 mode: the same function, plain fp32 arithmetic (library SGEMMs; this is the evaluation path, not the hot path) ----
+__global__ void f32_prepare_kernel(float* xn, float* hm, const float* obs, const float* h, const uint8_t* start, const float* mean,
+                                   const float* inv_std, float clip, int n, int O, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)n * O) {
+    const int k = (int)(i % O);
+    float v = obs[i];
+    if (mean) v = fminf(fmaxf((v - mean[k]) * inv_std[k], -clip), clip);
+    xn[i] = v;
+  }
+  if (i < (long long)n * H) hm[i] = start[i / H] ? 0.f : h[i];
+}
+__global__ void f32_cell_kernel(const float* gates, const float* b_ih, const float* b_hh, float* h, float* c, const uint8_t* start, int n, int H) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * H) return;
+  const int w = (int)(i / H), u = (int)(i % H);
+  const float* g = gates + (size_t)w * 4 * H;
+  const float gi = g[u] + b_ih[u] + b_hh[u], gf = g[H + u] + b_ih[H + u] + b_hh[H + u];
+  const float gg = g[2 * H + u] + b_ih[2 * H + u] + b_hh[2 * H + u], go = g[3 * H + u] + b_ih[3 * H + u] + b_hh[3 * H + u];
+  const float cp = start[w] ? 0.f : c[i];
+  const float cn = (1.f / (1.f + expf(-gf))) * cp + (1.f / (1.f + expf(-gi))) * tanhf(gg);
+  c[i] = cn;
+  h[i] = (1.f / (1.f + expf(-go))) * tanhf(cn);
+}
+__global__ void f32_bias_act_kernel(float* y, const float* b, int n, int N, int relu) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n * N) return;
+  const float v = y[i] + b[i % N];
+  y[i] = relu ? fmaxf(v, 0.f) : v;
+}
+__global__ void f32_gauss_kernel(const float* mean, const float* log_std, const float* noise, unsigned long long seed, unsigned long long step,
+                                 float* actions, float* logp, int n, int A) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  float lp = 0.f;
+  for (int j = 0; j < A; j += 2) {
+    float z0 = 0.f, z1 = 0.f;
+    if (noise) { z0 = noise[(size_t)w * A + j]; if (j + 1 < A) z1 = noise[(size_t)w * A + j + 1]; }
+    else if (seed) philox_normal2(seed, (uint32_t)w, (uint32_t)step, (uint32_t)j, &z0, &z1);
+    actions[(size_t)w * A + j] = mean[(size_t)w * A + j] + expf(log_std[j]) * z0;
+    lp += -0.5f * z0 * z0 - log_std[j] - 0.9189385332046727f;
+    if (j + 1 < A) {
+      actions[(size_t)w * A + j + 1] = mean[(size_t)w * A + j + 1] + expf(log_std[j + 1]) * z1;
+      lp += -0.5f * z1 * z1 - log_std[j + 1] - 0.9189385332046727f;
+    }
+  }
+  if (logp) logp[w] = lp;
+}
+
+// Y[n][N] (row major) = X[n][K] W[N][K]' (+ Y if accumulate)
+int f32_gemm(myo_policy* p, const float* X, const float* W, float* Y, int n, int N, int K, bool accumulate) {
+  const float one = 1.f, beta = accumulate ? 1.f : 0.f;
+  if (cublasSgemm(p->blas, CUBLAS_OP_T, CUBLAS_OP_N, N, n, K, &one, W, K, X, K, &beta, Y, N) != CUBLAS_STATUS_SUCCESS) {
+    myo::set_error("cublasSgemm failed in the fp32 policy forward");
+    return MYO_E_CUDA;
+  }
+  return MYO_OK;
+}
+
+int forward_fp32(myo_policy* p, int n, const float* obs, float* h, float* c, const uint8_t* start, const float* noise, float* actions,
+                 float* values, float* logp, cudaStream_t st) {
+  const myo_policy_cfg& cf = p->cfg;
+  const int H = cf.lstm_hidden, O = cf.obs_dim, A = cf.act_dim, W = 256;
+  if (!p->blas) {
+    if (cublasCreate(&p->blas) != CUBLAS_STATUS_SUCCESS) { myo::set_error("cublasCreate failed"); return MYO_E_CUDA; }
+    cublasSetMathMode(p->blas, CUBLAS_PEDANTIC_MATH);      // true fp32: no TF32, no reduced-precision accumulation
+  }
+  cublasSetStream(p->blas, st);
+  const size_t per = (size_t)O + H + 4 * H + 2 * W + A;      // xn | hm | gates | two activation buffers | mean
+  if (!p->f32_scratch) PCK(cudaMalloc(&p->f32_scratch, sizeof(float) * per * p->max_batch));
+  float* xn = p->f32_scratch;
+  float* hm = xn + (size_t)p->max_batch * O;
+  float* gates = hm + (size_t)p->max_batch * H;
+  float* act[2] = {gates + (size_t)p->max_batch * 4 * H, gates + (size_t)p->max_batch * (4 * H + W)};
+  float* mean = act[1] + (size_t)p->max_batch * W;
+  auto blocks = [](long long total) { return (unsigned)((total + 255) / 256); };
+  int rc;
+  for (int net = 0; net < 2; net++) {
+    const std::string lstm = net == 0 ? "lstm_actor." : "lstm_critic.";
+    const float* w_ih = find_w(p, lstm + "weight_ih_l0", (int64_t)4 * H * O);
+    const float* w_hh = find_w(p, lstm + "weight_hh_l0", (int64_t)4 * H * H);
+    const float* b_ih = find_w(p, lstm + "bias_ih_l0", 4 * H);
+    const float* b_hh = find_w(p, lstm + "bias_hh_l0", 4 * H);
+    if (!w_ih || !w_hh || !b_ih || !b_hh) return MYO_E_ARG;
+    float* hn = h + (size_t)net * n * H;
+    float* cn = c + (size_t)net * n * H;
+    f32_prepare_kernel<<<blocks((long long)n * std::max(O, H)), 256, 0, st>>>(xn, hm, obs, hn, start, p->has_norm ? p->obs_mean : nullptr,
+                                                                           p->obs_inv_std, p->clip_obs, n, O, H);
+    if ((rc = f32_gemm(p, xn, w_ih, gates, n, 4 * H, O, false)) || (rc = f32_gemm(p, hm, w_hh, gates, n, 4 * H, H, true))) return rc;
+    f32_cell_kernel<<<blocks((long long)n * H), 256, 0, st>>>(gates, b_ih, b_hh, hn, cn, start, n, H);
+    p->launches += 4;
+    const int nl = net == 0 ? cf.n_pi_layers : cf.n_vf_layers;
+    const int* widths = net == 0 ? cf.pi_layers : cf.vf_layers;
+    const float* x = hn;
+    int in_dim = H;
+    for (int l = 0; l < nl; l++) {
+      const std::string base = std::string("mlp_extractor.") + (net == 0 ? "policy_net." : "value_net.") + std::to_string(2 * l);
+      const float* w = find_w(p, base + ".weight", (int64_t)widths[l] * in_dim);
+      const float* b = find_w(p, base + ".bias", widths[l]);
+      if (!w || !b) return MYO_E_ARG;
+      float* y = act[l & 1];
+      if ((rc = f32_gemm(p, x, w, y, n, widths[l], in_dim, false))) return rc;
+      f32_bias_act_kernel<<<blocks((long long)n * widths[l]), 256, 0, st>>>(y, b, n, widths[l], 1);
+      p->launches += 2;
+      x = y; in_dim = widths[l];
+    }
+    if (net == 0) {
+      const float* w = find_w(p, "action_net.weight", (int64_t)A * in_dim);
+      const float* b = find_w(p, "action_net.bias", A);
+      const float* ls = find_w(p, "log_std", A);
+      if (!w || !b || !ls) return MYO_E_ARG;
+      if (p->latent_out && nl > 0) PCK(cudaMemcpyAsync(p->latent_out, x, sizeof(float) * (size_t)n * in_dim, cudaMemcpyDeviceToDevice, st));
+      if ((rc = f32_gemm(p, x, w, mean, n, A, in_dim, false))) return rc;
+      f32_bias_act_kernel<<<blocks((long long)n * A), 256, 0, st>>>(mean, b, n, A, 0);
+      f32_gauss_kernel<<<blocks(n), 256, 0, st>>>(mean, ls, noise, p->seed, p->step, actions, logp, n, A);
+      p->launches += 3;
+    } else if (values) {
+      const float* w = find_w(p, "value_net.weight", in_dim);
+      const float* b = find_w(p, "value_net.bias", 1);
+      if (!w || !b) return MYO_E_ARG;
+      if ((rc = f32_gemm(p, x, w, values, n, 1, in_dim, false))) return rc;
+      f32_bias_act_kernel<<<blocks(n), 256, 0, st>>>(values, b, n, 1, 0);
+      p->launches += 2;
+    }
+  }
+  p->step++;
+  PCK(cudaGetLastError());
+  return MYO_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -681,6 +817,8 @@ void myo_policy_destroy(myo_policy* p) {
   for (auto& kv : p->weights) cudaFree(kv.second);
   for (int net = 0; net < 2; net++) { cudaFree(p->wpack[net]); cudaFree(p->bias[net]); }
   cudaFree(p->log_std); cudaFree(p->obs_mean); cudaFree(p->obs_inv_std);
+  cudaFree(p->f32_scratch);
+  if (p->blas) cublasDestroy(p->blas);
   delete p;
 }
 
@@ -717,6 +855,12 @@ int myo_policy_set_latent_out(myo_policy* p, float* latent_dev) {
   return MYO_OK;
 }
 
+int myo_policy_set_precision(myo_policy* p, int precision) {
+  if (!p || (precision != 0 && precision != 1)) { myo::set_error("precision: 0 (bf16 operands on the tensor cores) or 1 (fp32)"); return MYO_E_ARG; }
+  p->precision = precision;
+  return MYO_OK;
+}
+
 int myo_policy_seed(myo_policy* p, uint64_t seed) {
   if (!p) { myo::set_error("null policy"); return MYO_E_ARG; }
   p->seed = seed; p->step = 0;
@@ -729,6 +873,7 @@ int myo_policy_forward(myo_policy* p, int n, const float* obs_dev, float* h_dev,
   if (n > p->max_batch) { myo::set_error("batch exceeds max_batch given to myo_policy_create"); return MYO_E_ARG; }
   PCK(cudaSetDevice(p->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->precision == 1) return forward_fp32(p, n, obs_dev, h_dev, c_dev, episode_start_dev, noise_dev, actions_dev, values_dev, logp_dev, st);
   if (p->dirty) { int rc = pack_weights(p, st); if (rc) return rc; }
   FwdArgs a{};
   a.n = n; a.obs_dim = p->cfg.obs_dim; a.obs_pad = p->obs_pad; a.H = p->cfg.lstm_hidden; a.act_dim = p->cfg.act_dim;

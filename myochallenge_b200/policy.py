@@ -31,7 +31,8 @@ class RecurrentPolicy:
     ``action_net`` + state-independent ``log_std`` (DiagGaussian) and ``value_net``."""
 
     def __init__(self, obs_dim: int, act_dim: int, lstm_hidden: int = 256, pi: Sequence[int] = (256, 256),
-                 vf: Sequence[int] = (256, 256), max_batch: int = 32768, device="cuda:0", lib=None, use_sde: bool = False):
+                 vf: Sequence[int] = (256, 256), max_batch: int = 32768, device="cuda:0", lib=None, use_sde: bool = False,
+                 precision: str = "bf16"):
         self._L = lib if lib is not None else _capi.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda" or not torch.cuda.is_available():
@@ -52,6 +53,7 @@ class RecurrentPolicy:
         check(self._L, self._L.myo_policy_create(C.byref(cfg), int(max_batch), self.device.index or 0, C.byref(h)))
         self._h = h
         self.max_batch = int(max_batch)
+        self.set_precision(precision)
         self._state: Dict[str, torch.Tensor] = {}
         # generalised state-dependent exploration (use_sde=True): the kernel produces the mean and latent_pi; the noise
         # latent_pi . E[w] with one exploration matrix per world and the log-prob come from myo_sde_sample
@@ -156,6 +158,14 @@ class RecurrentPolicy:
                                                    C.c_uint64(self._sde_seed), C.c_uint32(self._noise_epoch), self._stream()))
 
     # -- forward ------------------------------------------------------------------------------
+    def set_precision(self, precision: str):
+        """"bf16": bf16 operands with fp32 accumulation on the tensor cores (the rollout path). "fp32": plain fp32 arithmetic,
+        the precision sb3-contrib's torch policy runs at - for evaluating trained reference checkpoints (src/main_eval.py)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        check(self._L, self._L.myo_policy_set_precision(self._h, 1 if precision == "fp32" else 0))
+        self.precision = precision
+
     def initial_state(self, n: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """(h, c), each ``[2, n, H]`` (0 = actor LSTM, 1 = critic LSTM), zero-initialised."""
         z = torch.zeros(2, n, self.lstm_hidden, dtype=torch.float32, device=self.device)
