@@ -263,12 +263,10 @@ __global__ void __launch_bounds__(kThreads) world_kernel(int mslot, int mslot_fu
             exhausted = true;
             continue;
           }
-          if (!b.redo_list) break;
-          if (ld_volatile(&b.sched[1]) >= ngroups) {      // every group has finished: the list cannot grow any more
-            if (ld_volatile(&b.sched[2]) >= ld_volatile(b.redo_count)) break;
-            continue;
-          }
-          __nanosleep(1000);
+          // Queue empty and no redo entry waiting: done. Nothing can be orphaned - an entry is pushed by a CTA while it works on
+          // a group, and that CTA comes back here afterwards, where the entry is either already taken by someone or taken now -
+          // so nobody has to wait for the other CTAs, and a kernel queued behind this one can start on the freed SMs.
+          break;
         }
         s_pick[0] = kind; s_pick[1] = idx; s_pick[2] = cnt;
       }
@@ -279,8 +277,6 @@ __global__ void __launch_bounds__(kThreads) world_kernel(int mslot, int mslot_fu
       if (kind == 0) {
         const int slot = idx * wpc + tid;
         run_world<G, RMAX, false>(mslot, t, b, a, c, b.order ? b.order[slot] : slot, 0);
-        __syncthreads();
-        if (threadIdx.x == 0) { __threadfence(); atomicAdd(&b.sched[1], 1); }
       } else if (tid < cnt) {
         int e;
         while ((e = ld_volatile(b.redo_list + idx + tid)) < 0) __nanosleep(200);      // reserved but not written yet
