@@ -162,3 +162,81 @@ class EvalCallback(BaseCallback):
         if self.callback_after_eval is not None:
             ok = self.callback_after_eval.on_rollout_end(0, self.locals.get("log", {})) and ok
         return ok
+
+
+class EvaluateLSTM(BaseCallback):
+    """/root/reference/src/metrics/custom_callbacks.py:7-48: every ``eval_freq`` timesteps play ``num_episodes`` deterministic
+    episodes on ``eval_env`` with the TRAINING model, observations normalised by the TRAINING env's moments, and record the mean
+    cumulative reward under ``name``. Batched: the episodes are spread over the worlds of ``eval_env`` (a ``MyoVecEnv``)."""
+
+    def __init__(self, eval_freq: int, eval_env, name: str, num_episodes: int = 20, verbose: int = 0):
+        super().__init__(verbose)
+        self.eval_freq, self.eval_env, self.name, self.num_episodes = int(eval_freq), eval_env, name, int(num_episodes)
+
+    def _on_step(self) -> bool:
+        if not self._crossed(self.eval_freq):
+            return True
+        from .evaluate import evaluate_policy
+        from .rollout import DeviceVecNormalize
+
+        norm = self.model.env if isinstance(self.model.env, DeviceVecNormalize) else None
+        out = evaluate_policy(self.model.policy, getattr(self.eval_env, "venv", self.eval_env), self.num_episodes, True, norm)
+        if norm is not None:
+            norm._push_obs_norm()
+        self.model.logs[-1][self.name] = out["mean_reward"]
+        if self.verbose:
+            print(f"{self.name}: {out['mean_reward']:.3f} over {out['episodes']} episodes")
+        return True
+
+
+class EnvDumpCallback(BaseCallback):
+    """/root/reference/src/metrics/custom_callbacks.py:51-61: ``training_env.save(save_path/training_env.pkl)`` when triggered
+    (the reference hangs it on ``EvalCallback(callback_on_new_best=...)``, /root/reference/src/main_baoding.py:84-95)."""
+
+    def __init__(self, save_path: str, verbose: int = 0):
+        super().__init__(verbose)
+        self.save_path = save_path
+
+    def _on_step(self) -> bool:
+        env_path = os.path.join(self.save_path, "training_env.pkl")
+        if self.verbose > 0:
+            print("Saving the training environment to path ", env_path)
+        os.makedirs(self.save_path, exist_ok=True)
+        self.model.env.save(env_path)
+        return True
+
+
+class TensorboardCallback(BaseCallback):
+    """/root/reference/src/metrics/custom_callbacks.py:64-81: the mean over a rollout of ``info[key]`` for every key in
+    ``info_keywords``, recorded as ``rollout/<key>``. The device rollout keeps the per-step reward terms in its buffer
+    (``RecurrentRolloutBuffer.infos`` [T, n, MYO_INFO_TERMS]); the means are taken there, no per-step host round trip. The scalars
+    land in ``model.logs[-1]`` and, when ``log_dir`` is given, in ``<log_dir>/progress.csv`` (one row per rollout; there is no
+    TensorBoard writer in this image, the CSV has the columns SB3's csv logger writes)."""
+
+    def __init__(self, info_keywords, verbose: int = 0, log_dir: Optional[str] = None):
+        super().__init__(verbose)
+        self.info_keywords = tuple(info_keywords)
+        self.rollout_info: Dict[str, float] = {}
+        self.log_dir = log_dir
+        self._columns = None
+
+    def _on_step(self) -> bool:
+        env = getattr(self.model.env, "venv", self.model.env)
+        keys = list(env.info_keys)
+        means = self.model.buffer.info_means()           # [MYO_INFO_TERMS] on the host
+        self.rollout_info = {}
+        for key in self.info_keywords:
+            if key not in keys:
+                raise KeyError(f"info keyword {key!r} is not one of {keys}")
+            self.rollout_info[key] = float(means[keys.index(key)])
+            self.model.logs[-1]["rollout/" + key] = self.rollout_info[key]
+        if self.log_dir:
+            os.makedirs(self.log_dir, exist_ok=True)
+            row = {k: v for k, v in self.model.logs[-1].items() if isinstance(v, (int, float))}
+            path = os.path.join(self.log_dir, "progress.csv")
+            with open(path, "a") as fh:
+                if self._columns is None:           # columns are fixed by the first row; later rows fill them by name
+                    self._columns = list(row.keys())
+                    fh.write(",".join(self._columns) + "\n")
+                fh.write(",".join(repr(row[k]) if k in row else "" for k in self._columns) + "\n")
+        return True

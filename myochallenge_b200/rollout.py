@@ -247,9 +247,22 @@ class RecurrentRolloutBuffer:
         self.pos, self.full = 0, False
         self._L = _capi.lib()
         self.launch_count = 0
+        # reward terms (the env's ``info`` dict entries) summed over the rollout, for TensorboardCallback-style logging
+        self.info_sum = torch.zeros(_capi.MYO_INFO_TERMS, dtype=torch.float64, device=dev)
+        self.info_count = 0
 
     def reset(self):
         self.pos, self.full = 0, False
+        self.info_sum.zero_(); self.info_count = 0
+
+    def add_info(self, info: torch.Tensor) -> None:
+        """``info`` [n, MYO_INFO_TERMS]: the reward terms of this env step (``BatchSim.info``)."""
+        self.info_sum += info.sum(0, dtype=torch.float64)
+        self.info_count += info.shape[0]
+
+    def info_means(self):
+        """Mean of every info term over the steps and worlds of the rollout (host numpy array)."""
+        return (self.info_sum / max(self.info_count, 1)).cpu().numpy()
 
     def put_obs(self, obs, obs_norm=None):
         """Store the observation of the current step. ``obs_norm``: a ``DeviceVecNormalize`` whose CURRENT moments (the
@@ -308,6 +321,9 @@ def collect_rollouts(env, policy, buffer: RecurrentRolloutBuffer, state, obs, ep
             tv = policy.predict_values(env.terminal_obs.index_select(0, idx), (h.index_select(1, idx), c.index_select(1, idx)))
             rewards.index_add_(0, idx, buffer.gamma * tv)
         buffer.add(None, actions, rewards, episode_starts, values, logp)
+        sim = getattr(getattr(env, "venv", env), "sim", None)
+        if sim is not None:
+            buffer.add_info(sim.info)
         obs, episode_starts = new_obs.clone(), dones.clone()
     last_values = policy.predict_values(obs, (h.clone(), c.clone()), episode_starts)
     buffer.compute_returns_and_advantage(last_values, episode_starts)

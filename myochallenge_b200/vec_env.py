@@ -88,6 +88,7 @@ class MyoVecEnv:
         self.observation_space = Box(-10.0, 10.0, (self.sim.nobs,), np.float32)
         self.action_space = Box(-1.0, 1.0, (self.sim.nu,), np.float32)
         self._keys = {_capi.TASK_BAODING: BAODING_KEYS, _capi.TASK_REORIENT: REORIENT_KEYS}.get(cfg.kind, POSE_KEYS)
+        self.info_keys = tuple(self._keys)      # names of the columns of ``sim.info`` (the reward terms ``infos[i]`` carries)
         n, pin = self.num_envs, self.device.type == "cuda"
         self._h_act = torch.zeros(n, self.sim.nu, dtype=torch.float32, pin_memory=pin)
         self._h_obs = torch.zeros(n, self.sim.nobs, dtype=torch.float32, pin_memory=pin)
