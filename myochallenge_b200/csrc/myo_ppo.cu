@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -29,6 +30,7 @@
 #include <vector>
 
 #include "../../include/myo_b200.h"
+#include "myo_lstm_seq.hpp"
 
 namespace myo { void set_error(const std::string& msg); }
 
@@ -494,6 +496,8 @@ struct NetBufs {
   float *G = nullptr, *Cs = nullptr, *C0 = nullptr, *T1 = nullptr, *head_out = nullptr, *dh_carry = nullptr, *dc_carry = nullptr, *cpart = nullptr;
   cublasHandle_t blas = nullptr;
   void* workspace = nullptr;
+  uint8_t* seq_wpack = nullptr;      // persistent recurrent kernels (myo_lstm_seq.cu): packed W_hh images, combined bias
+  float* seq_bias = nullptr;
 };
 
 struct GradKey {      // everything a captured graph bakes in
@@ -527,6 +531,8 @@ struct myo_ppo {
   cudaStream_t side = nullptr, main = nullptr;     // main: the graph's origin stream (the caller's may be the legacy default stream, which cannot be captured)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_in = nullptr, ev_out = nullptr;
   bool use_graph = true, have_graph = false;
+  long long* seq_prof = nullptr;     // MYO_PPO_SEQ_PROF=1: cycle counters of the forward cluster kernel (development)
+  bool use_seq = false;              // bf16 mode with a supported hidden size: the recurrence runs in the persistent cluster kernels
   cudaGraphExec_t exec = nullptr;
   GradKey key{};
   int64_t graph_launches = 0;
@@ -672,6 +678,11 @@ int net_chain(myo_ppo* p, const GradArgs& a, int k, cudaStream_t st) {
   gather_state_kernel<T><<<(B * H + 255) / 256, 256, 0, st>>>(B, H, p->idx, a.h0 + (int64_t)k * a.n * H, a.c0 + (int64_t)k * a.n * H, p->keep, HP, nb.C0);
   p->launches++;
   RCK(gemm_nt(p, blas, M, 4 * H, Op, X, Op, wop + n.op_wih, Op, 0.f, nb.G, 4 * H));
+  if (p->use_seq) {
+    myo::LstmSeqFwd f{Tn, B, H, a.params + n.whh, a.params + n.bih, a.params + n.bhh, nb.seq_wpack, nb.seq_bias, nb.G, p->keep, nb.C0, nb.Cs, Hs, HP, k == 0 ? p->seq_prof : nullptr};
+    RCK(myo::lstm_seq_forward(f, st));
+    p->launches += 2;
+  } else
   for (int t = 0; t < Tn; t++) {
     RCK(gemm_nt(p, blas, B, 4 * H, H, HP + (int64_t)t * B * H, H, wop + n.op_whh, H, 1.f, nb.G + (int64_t)t * B * 4 * H, 4 * H));
     lstm_cell_fwd_kernel<T><<<cell_blocks, 256, 0, st>>>(t, Tn, B, H, nb.G, a.params + n.bih, a.params + n.bhh, p->keep, nb.C0, nb.Cs, Hs, HP);
@@ -864,7 +875,11 @@ int myo_ppo_create(const myo_policy_cfg* cfg, int max_steps, int max_worlds, int
     A_(&nb.dh_carry, sizeof(float) * B * H); A_(&nb.dc_carry, sizeof(float) * B * H);
     A_(&nb.cpart, sizeof(float) * cpart_words);
     A_(&nb.workspace, kBlasWorkspace);
+    if (precision && myo::lstm_seq_supported((int)H)) { A_(&nb.seq_wpack, 2 * myo::lstm_seq_wpack_bytes((int)H)); A_(&nb.seq_bias, sizeof(float) * 4 * H); }
   }
+  p->use_seq = precision && myo::lstm_seq_supported((int)H);
+  if (const char* e = getenv("MYO_PPO_SEQ")) p->use_seq = p->use_seq && atoi(e) != 0;
+  if (const char* e = getenv("MYO_PPO_SEQ_PROF")) if (atoi(e)) { A_(&p->seq_prof, sizeof(long long) * 8); if (!rc) cudaMemset(p->seq_prof, 0, 64); }
   A_(&p->act, sizeof(float) * M * p->A); A_(&p->keep, sizeof(float) * M); A_(&p->ov, sizeof(float) * M); A_(&p->ol, sizeof(float) * M);
   A_(&p->ad, sizeof(float) * M); A_(&p->rt, sizeof(float) * M); A_(&p->adv_stats, sizeof(float) * 2);
   A_(&p->ppart, sizeof(float) * kLossBlocks * (kStatSlots + p->A)); A_(&p->vpart, sizeof(float) * kLossBlocks);
@@ -897,6 +912,13 @@ int myo_ppo_create(const myo_policy_cfg* cfg, int max_steps, int max_worlds, int
 void myo_ppo_destroy(myo_ppo* p) {
   if (!p) return;
   cudaSetDevice(p->device);
+  if (p->seq_prof) {
+    long long h[8];
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h, p->seq_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess)
+      fprintf(stderr, "lstm_seq_fwd cycles (last launch, one thread): mma+wait %lld | epilogue math+global %lld | cluster wait #1 %lld | remote stores %lld | fences %lld | barrier #2 %lld\n",
+              h[0], h[1], h[2], h[3], h[4], h[5]);
+  }
   if (p->exec) cudaGraphExecDestroy(p->exec);
   for (int k = 0; k < 2; k++) if (p->nb[k].blas) cublasDestroy(p->nb[k].blas);
   if (p->side) cudaStreamDestroy(p->side);

@@ -95,6 +95,32 @@ def test_gradient_matches_oracle_bf16_winning_architecture(product_lib):
         assert cos >= 0.98 and 0.9 <= float(gk.norm() / rk.norm()) <= 1.1, (k, cos, float(gk.norm() / rk.norm()))
 
 
+@pytest.mark.parametrize("H,B,T", [(64, 7, 12), (128, 150, 9), (256, 33, 6), (256, 260, 5)])
+def test_persistent_recurrent_kernels_match_the_launch_chain(product_lib, monkeypatch, H, B, T):
+    """bf16 mode runs the LSTM recurrence in the persistent tcgen05 cluster kernels (csrc/myo_lstm_seq.cu); MYO_PPO_SEQ=0 keeps round
+    1's chain of cuBLAS GEMM + cell launches. Same operands (bf16-rounded W_hh and h, fp32 accumulation), so both must give the
+    same loss and gradients up to accumulation order, the fast exp of the fused cell and the bf16 roundings those flip: loss terms
+    to 2e-3 relative, every gradient tensor to 1 % in the L2 norm and 3 % of its max entrywise (the oracle bars - cosine >= 0.98 -
+    hold for both and are far looser)."""
+    O, A, pi, vf = 30, 6, (64,), (64,)
+    hyper = dict(clip_range=0.2, ent_coef=0.01, vf_coef=0.7, normalize_advantage=True)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MYO_PPO_SEQ", mode)
+        pol, upd, buf, idx, sd64, batch = _setup(O, A, H, pi, vf, T, B, B + 5, 11, "bf16", **hyper)
+        stats = upd.minibatch_grad(buf, idx).cpu().numpy().copy()
+        grads = {k: v.cpu().double().clone() for k, v in upd.grad_dict().items()}
+        out[mode] = (stats, grads, upd.launch_count)
+    (s0, g0, l0), (s1, g1, l1) = out["0"], out["1"]
+    assert l1 < l0 - T, (l0, l1)                       # the recurrent chain no longer launches per step
+    for i in range(6):
+        assert abs(s0[i] - s1[i]) <= 2e-3 * abs(s0[i]) + 2e-4, (STAT_NAMES[i], s0[i], s1[i])
+    for k in g0:
+        err = float((g0[k] - g1[k]).abs().max()); ref = float(g0[k].abs().max())
+        l2 = float((g0[k] - g1[k]).norm() / (g0[k].norm() + 1e-30))
+        assert err <= 3e-2 * ref + 1e-7 and l2 <= 1e-2, (k, err, ref, l2)
+
+
 def test_value_clipping_and_raw_advantages_fp32(product_lib):
     hyper = dict(clip_range=0.1, clip_range_vf=0.05, ent_coef=0.0, vf_coef=1.0, normalize_advantage=False)
     pol, upd, buf, idx, sd64, batch = _setup(17, 5, 64, (), (32,), 10, 9, 12, 5, "fp32", **hyper)
