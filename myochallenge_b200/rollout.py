@@ -328,3 +328,72 @@ def collect_rollouts(env, policy, buffer: RecurrentRolloutBuffer, state, obs, ep
     last_values = policy.predict_values(obs, (h.clone(), c.clone()), episode_starts)
     buffer.compute_returns_and_advantage(last_values, episode_starts)
     return obs, episode_starts
+
+
+class PipelinedStepper:
+    """Device-resident stepping of the worlds as ``k`` sub-batches on ``k`` CUDA streams. The rollout's two kernels have opposite
+    shapes - the world kernel is one long persistent launch that owns every SM, the policy forward a short tensor-core launch - and
+    with one stream they alternate, the policy waiting for the world kernel's last wave. With two sub-batches the policy forward
+    of one half (and the head of its next world launch) runs on the SMs the other half's world kernel frees as it drains, so the
+    policy's time and the drain tail disappear from the step. Worlds are independent, so the results of a sub-batch do not depend
+    on the split (``envs[i]`` is an ordinary ``MyoVecEnv``); the policy handle is shared (read-only weights, per-call state).
+
+    ``step()`` enqueues one env step of every sub-batch and returns without synchronising; ``obs[i]``, ``rewards[i]``,
+    ``dones[i]`` hold the latest results of sub-batch ``i`` (valid on ``streams[i]``; ``join()`` makes the current stream wait)."""
+
+    def __init__(self, envs, policy, deterministic: bool = False, clip_actions: bool = True):
+        self.envs, self.policy = list(envs), policy
+        dev = self.envs[0].device
+        self.device = dev
+        self.streams = [torch.cuda.Stream(dev) for _ in self.envs]
+        self.states = [policy.initial_state(e.num_envs) for e in self.envs]
+        self.starts = [torch.ones(e.num_envs, dtype=torch.uint8, device=dev) for e in self.envs]
+        self.out = [(torch.empty(e.num_envs, e.sim.nu, device=dev), torch.empty(e.num_envs, device=dev), torch.empty(e.num_envs, device=dev))
+                    for e in self.envs]
+        self.obs = [None] * len(self.envs)
+        self.rewards = [None] * len(self.envs)
+        self.dones = [None] * len(self.envs)
+        self.deterministic, self.clip_actions = deterministic, clip_actions
+        self.num_envs = sum(e.num_envs for e in self.envs)
+
+    def reset(self):
+        cur = torch.cuda.current_stream(self.device)
+        for i, e in enumerate(self.envs):
+            self.streams[i].wait_stream(cur)
+            with torch.cuda.stream(self.streams[i]):
+                self.obs[i] = e.reset_device()
+                self.starts[i].fill_(1)
+        return self.obs
+
+    def step(self):
+        for i, e in enumerate(self.envs):
+            with torch.cuda.stream(self.streams[i]):
+                a, _, _, _ = self.policy.forward(self.obs[i], self.states[i], self.starts[i], deterministic=self.deterministic, out=self.out[i])
+                if self.clip_actions:
+                    a = a.clamp_(-1.0, 1.0)
+                self.obs[i], self.rewards[i], d, _ = e.step_device(a)
+                self.dones[i] = d
+                self.starts[i] = d
+        return self.obs, self.rewards, self.dones
+
+    def spin_up(self, steps: int):
+        """Untimed steps to the steady state of the workload with the episode phases of the worlds staggered uniformly over the
+        horizon (world w of a sub-batch is reset once more at step ``w mod horizon``); see bench.py."""
+        horizon = int(self.envs[0].cfg.max_episode_steps)
+        for t in range(steps):
+            if horizon > 0 and t < horizon:
+                for i, e in enumerate(self.envs):
+                    with torch.cuda.stream(self.streams[i]):
+                        mask = (torch.arange(e.num_envs, device=self.device) % horizon) == t
+                        e.sim.reset(mask)
+                        self.starts[i] = torch.maximum(self.starts[i], mask.to(torch.uint8))
+            self.step()
+
+    def join(self):
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def synchronize(self):
+        for s in self.streams:
+            s.synchronize()

@@ -106,3 +106,34 @@ def test_collect_rollouts_on_baoding(product_lib):
     lv = pol.predict_values(obs, (h, c), starts).cpu().numpy()
     adv, _ = ro.gae(buf.rewards.cpu().numpy(), buf.values.cpu().numpy(), es, lv, starts.cpu().numpy(), 0.99, 0.95)
     np.testing.assert_allclose(buf.advantages.cpu().numpy(), adv, rtol=1e-4, atol=1e-4)
+
+
+def test_pipelined_stepper_equals_plain_stepping(product_lib):
+    """``rollout.PipelinedStepper`` (sub-batches on their own streams, one shared policy handle) changes the schedule, not the
+    results: every sub-batch ends bit-identical to the same env stepped alone on the default stream."""
+    from myochallenge_b200.envs import make_vec_env
+    from myochallenge_b200.policy import RecurrentPolicy
+    from myochallenge_b200.rollout import PipelinedStepper
+
+    dev, n, T = "cuda:0", 96, 12
+    mk = lambda seed: make_vec_env("CustomMyoChallengeBaodingP2-v1", n, device=dev, seed=seed, clip_actions=True, max_episode_steps=7)
+    pol = RecurrentPolicy(86, 39, lstm_hidden=64, pi=(64,), vf=(64,), max_batch=n, device=dev)
+    pol.init_random(seed=3, log_std_init=-1.0)
+    st = PipelinedStepper([mk(5), mk(6)], pol, deterministic=True)
+    st.reset()
+    for _ in range(T):
+        st.step()
+    st.join()
+    torch.cuda.synchronize()
+    for i, seed in enumerate((5, 6)):
+        env = mk(seed)
+        obs = env.reset_device()
+        state = pol.initial_state(n)
+        starts = torch.ones(n, dtype=torch.uint8, device=dev)
+        for _ in range(T):
+            a, _, _, _ = pol.forward(obs, state, starts, deterministic=True)
+            obs, rew, done, _ = env.step_device(a.clamp(-1.0, 1.0))
+            starts = done
+        torch.cuda.synchronize()
+        assert torch.equal(obs, st.obs[i]) and torch.equal(rew, st.rewards[i]) and torch.equal(done, st.dones[i])
+        assert torch.equal(state[0], st.states[i][0]) and torch.equal(state[1], st.states[i][1])
