@@ -1206,6 +1206,76 @@ MYO_PHASE void rows_JT_force(int mslot, Ctx<G, V> c, int oout, float scale) {
       if (f != 0.f) for (int e = c.lane; e < li[L_NSUP]; e += G) out[lim_idx(li, e)] += lim_J(c.sp(), lr, li, e) * f;
       c.tile.sync();
     }
+  if constexpr (G >= 2 * KS) {
+    // two contacts per pass, half a tile each (support <= KS): the Jacobian entries - the expensive part - are computed for both at
+    // once; the two halves then add one after the other (their supports overlap on the dofs of a shared body)
+    const int hf = c.lane / KS, sub = c.lane % KS;
+    for (int k0 = 0; k0 < ncon; k0 += 2) {
+      const int k = k0 + hf;
+      const bool has = k < ncon;
+      const float* cr = SF(o_con) + (has ? k : k0) * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+      const int row0 = has ? ci[C_ROW0] : -1;
+      float fn = 0.f, ft1 = 0.f, ft2 = 0.f;
+      if (row0 >= 0) {
+        const int nr = ci[C_DIM] == 1 ? 1 : 4;
+        const float mu = cr[C_MU];
+        for (int q = 0; q < nr; q++) {
+          const float* row = rows + (row0 + q) * ROW_WORDS;
+          const float f = row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] * scale : 0.f;
+          fn += f;
+          if (nr == 4) { const float t = ((q & 1) ? -mu : mu) * f; if (q < 2) ft1 += t; else ft2 += t; }
+        }
+      }
+      const bool on = fn != 0.f && sub < ci[C_NSUP];
+      float v = 0.f;
+      int dof = 0;
+      if (on) {
+        float jn, jt1, jt2;
+        dof = contact_entry(m, c.sp(), cr, ci, sub, &jn, &jt1, &jt2);
+        v = jn * fn + jt1 * ft1 + jt2 * ft2;
+      }
+      if (on && hf == 0) out[dof] += v;
+      c.tile.sync();
+      if (on && hf == 1) out[dof] += v;
+      c.tile.sync();
+    }
+  } else
+  if constexpr (G >= KS && G > 1) {
+    // support <= KS <= G: lane e holds entry e; the entries of contact k + 1 are computed under the update of contact k (see newton_system)
+    auto load_entry = [&](int k, float& e_jn, float& e_jt1, float& e_jt2, int& e_dof) {
+      e_jn = 0.f; e_jt1 = 0.f; e_jt2 = 0.f; e_dof = 0;
+      if (k < ncon) {
+        const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+        if (ci[C_ROW0] >= 0 && c.lane < ci[C_NSUP]) e_dof = contact_entry(m, c.sp(), cr, ci, c.lane, &e_jn, &e_jt1, &e_jt2);
+      }
+    };
+    float jn, jt1, jt2;
+    int dof;
+    load_entry(0, jn, jt1, jt2, dof);
+    for (int k = 0; k < ncon; k++) {
+      float njn, njt1, njt2;
+      int ndof;
+      load_entry(k + 1, njn, njt1, njt2, ndof);
+      const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+      const int row0 = ci[C_ROW0];
+      if (row0 >= 0) {
+        const int nr = ci[C_DIM] == 1 ? 1 : 4;
+        const float mu = cr[C_MU];
+        float fn = 0.f, ft1 = 0.f, ft2 = 0.f;
+        for (int q = 0; q < nr; q++) {
+          const float* row = rows + (row0 + q) * ROW_WORDS;
+          const float f = row[R_JAR] < 0.f ? -row[R_D] * row[R_JAR] * scale : 0.f;
+          fn += f;
+          if (nr == 4) { const float t = ((q & 1) ? -mu : mu) * f; if (q < 2) ft1 += t; else ft2 += t; }
+        }
+        if (fn != 0.f) {
+          if (c.lane < ci[C_NSUP]) out[dof] += jn * fn + jt1 * ft1 + jt2 * ft2;
+          c.tile.sync();
+        }
+      }
+      jn = njn; jt1 = njt1; jt2 = njt2; dof = ndof;
+    }
+  } else
   for (int k = 0; k < ncon; k++) {
     const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
     const int row0 = ci[C_ROW0];
