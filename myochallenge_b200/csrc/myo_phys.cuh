@@ -1355,6 +1355,74 @@ MYO_PHASE void newton_system(int mslot, Ctx<G, V> c) {
       }
       c.tile.sync();
     }
+  if constexpr (G >= 2 * KS) {
+    // Two contacts per pass: half h of the tile holds the Jacobian entries of contact k0 + h (support <= KS), computed for both at
+    // once and - software-pipelined by hand - one pass ahead of the pair updates that consume them by shuffle; two batches of pairs
+    // are in flight at a time (loads, arithmetic, stores: the pairs of one contact are distinct entries of H). With 3.5 warps per
+    // scheduler the kernel lives on the independent instructions each warp brings itself.
+    const int hf = c.lane / KS, sub = c.lane % KS;
+    auto load_entry = [&](int k0, float& e_jn, float& e_jt1, float& e_jt2, int& e_dof) {
+      e_jn = 0.f; e_jt1 = 0.f; e_jt2 = 0.f; e_dof = 0;
+      const int k = k0 + hf;
+      if (k < ncon) {
+        const float* cr = SF(o_con) + k * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+        if (ci[C_ROW0] >= 0 && sub < ci[C_NSUP]) e_dof = contact_entry(m, c.sp(), cr, ci, sub, &e_jn, &e_jt1, &e_jt2);
+      }
+    };
+    float jn, jt1, jt2;
+    int dof;
+    load_entry(0, jn, jt1, jt2, dof);
+    for (int k0 = 0; k0 < ncon; k0 += 2) {
+      float njn, njt1, njt2;
+      int ndof;
+      load_entry(k0 + 2, njn, njt1, njt2, ndof);
+      for (int h = 0; h < 2 && k0 + h < ncon; h++) {
+        const float* cr = SF(o_con) + (k0 + h) * CON_WORDS; const int* ci = reinterpret_cast<const int*>(cr);
+        const int row0 = ci[C_ROW0];
+        if (row0 < 0) continue;
+        const int nr = ci[C_DIM] == 1 ? 1 : 4, ns = ci[C_NSUP];
+        const float mu = cr[C_MU];
+        // W = sum_active D c c', c = (1, +-mu, 0) / (1, 0, +-mu); (gn, g1, g2) = -(force in the contact frame)
+        float w00 = 0.f, w01 = 0.f, w02 = 0.f, w11 = 0.f, w22 = 0.f, gn = 0.f, g1 = 0.f, g2 = 0.f;
+        for (int q = 0; q < nr; q++) {
+          const float4 row = *reinterpret_cast<const float4*>(rows + (row0 + q) * ROW_WORDS);     // D, aref, jar, jp
+          if (row.z < 0.f) {
+            const float D = row.x, nf = D * row.z;
+            w00 += D; gn += nf;
+            if (nr == 4) {
+              const float s = (q & 1) ? -mu : mu;
+              if (q < 2) { w01 += D * s; w11 += D * s * s; g1 += nf * s; } else { w02 += D * s; w22 += D * s * s; g2 += nf * s; }
+            }
+          }
+        }
+        if (w00 == 0.f) continue;
+        const int base = h * KS;
+        if (hf == h && sub < ns) grad[dof] += jn * gn + jt1 * g1 + jt2 * g2;
+        // every unordered pair (a >= b) of the support once: e = a (a + 1) / 2 + b
+        const int npair = ns * (ns + 1) / 2;
+        for (int e0 = 0; e0 < npair; e0 += 2 * G) {
+          const int eA = e0 + c.lane, eB = e0 + G + c.lane;
+          const bool onA = eA < npair, onB = eB < npair;
+          const int abA = m.pair_ab[onA ? eA : 0], abB = m.pair_ab[onB ? eB : 0];
+          const int aA = base + (abA & 255), bA = base + (abA >> 8), aB = base + (abB & 255), bB = base + (abB >> 8);
+          const int iaA = c.tile.shfl(dof, aA), ibA = c.tile.shfl(dof, bA), iaB = c.tile.shfl(dof, aB), ibB = c.tile.shfl(dof, bB);
+          const float naA = c.tile.shfl(jn, aA), taA = c.tile.shfl(jt1, aA), uaA = c.tile.shfl(jt2, aA);
+          const float nbA = c.tile.shfl(jn, bA), tbA = c.tile.shfl(jt1, bA), ubA = c.tile.shfl(jt2, bA);
+          const float naB = c.tile.shfl(jn, aB), taB = c.tile.shfl(jt1, aB), uaB = c.tile.shfl(jt2, aB);
+          const float nbB = c.tile.shfl(jn, bB), tbB = c.tile.shfl(jt1, bB), ubB = c.tile.shfl(jt2, bB);
+          float* hA = H + roff[max(iaA, ibA)] + min(iaA, ibA);
+          float* hB = H + roff[max(iaB, ibB)] + min(iaB, ibB);
+          const float oA = onA ? *hA : 0.f, oB = onB ? *hB : 0.f;
+          const float vA = w00 * naA * nbA + w01 * (naA * tbA + taA * nbA) + w02 * (naA * ubA + uaA * nbA) + w11 * taA * tbA + w22 * uaA * ubA;
+          const float vB = w00 * naB * nbB + w01 * (naB * tbB + taB * nbB) + w02 * (naB * ubB + uaB * nbB) + w11 * taB * tbB + w22 * uaB * ubB;
+          if (onA) *hA = oA + vA;
+          if (onB) *hB = oB + vB;
+        }
+        c.tile.sync();
+      }
+      jn = njn; jt1 = njt1; jt2 = njt2; dof = ndof;
+    }
+  } else
   if constexpr (G >= KS && G > 1) {
     // A contact block fits the tile (support <= KS <= G): lane e holds entry e and pairs fetch both entries by shuffle. The walk is
     // software-pipelined by hand - the entries of contact k + 1 (a chain of dependent shared-memory loads) are computed before
