@@ -364,9 +364,25 @@ def run_b200(args):
     h2d = env.h2d_bytes_per_step + n * sim.nobs * 4 + n
     d2h = env.d2h_bytes_per_step + n * sim.nu * 4
 
-    strm = stepper.streams
-    hb = [dict(h_obs=torch.zeros(nh, sim.nobs, **pin), h_act=torch.zeros(nh, sim.nu, **pin), d_obs=torch.zeros(nh, sim.nobs, device=dev),
-               out=stepper.out[k], state=stepper.states[k], starts=stepper.starts[k].clone()) for k in range(2)]
+    # K sub-batches, each with its own stream and pinned buffers (K = 2 reuses the halves of the device-resident loop). More parts
+    # than two keep a world kernel queued on the GPU while the host handles one part's copies, at the price of shorter launches.
+    K = max(2, args.e2e_parts)
+    if K == 2:
+        parts, strm, nk = halves, stepper.streams, nh
+        pstate, pstarts, pout = stepper.states, [x.clone() for x in stepper.starts], stepper.out
+        pobs = stepper.obs
+    else:
+        del halves
+        nk = n // K
+        parts = [make_vec_env(ENV_ID, nk, device=dev, seed=rank_seed(args.seed + 211 + k, rank), weighted_reward_keys=RWD, clip_actions=True)
+                 for k in range(K)]
+        pst = PipelinedStepper(parts, pol)
+        pst.reset()
+        pst.spin_up(args.spinup)
+        pst.synchronize()
+        strm, pstate, pstarts, pout, pobs = pst.streams, pst.states, [x.clone() for x in pst.starts], pst.out, pst.obs
+    hb = [dict(h_obs=torch.zeros(nk, sim.nobs, **pin), h_act=torch.zeros(nk, sim.nu, **pin), d_obs=torch.zeros(nk, sim.nobs, device=dev),
+               out=pout[k], state=pstate[k], starts=pstarts[k]) for k in range(K)]
 
     def issue(k):
         b = hb[k]
@@ -375,35 +391,37 @@ def run_b200(args):
             actions, _, _, _ = pol.forward(b["d_obs"], b["state"], b["starts"], out=b["out"])
             b["h_act"].copy_(actions, non_blocking=True)
             strm[k].synchronize()
-            halves[k].step_async(np.clip(b["h_act"].numpy(), -1.0, 1.0))
+            parts[k].step_async(np.clip(b["h_act"].numpy(), -1.0, 1.0))
 
     def collect(k):
         b = hb[k]
         with torch.cuda.stream(strm[k]):
-            ob, rw, dn, _ = halves[k].step_wait(with_infos=False)
+            ob, rw, dn, _ = parts[k].step_wait(with_infos=False)
             b["h_obs"].copy_(torch.from_numpy(ob))
             b["starts"] = torch.from_numpy(dn.astype(np.uint8)).to(dev, non_blocking=True)
 
-    for k in range(2):                                                     # the halves are at the steady state already
+    for k in range(K):                                                     # the parts are at the steady state already
         with torch.cuda.stream(strm[k]):
-            hb[k]["h_obs"].copy_(stepper.obs[k])
+            hb[k]["h_obs"].copy_(pobs[k])
             strm[k].synchronize()
-    for _ in range(2):                                                     # warm both halves
-        for k in range(2):
+    for _ in range(2):                                                     # warm the host path of every part
+        for k in range(K):
             issue(k)
-        for k in range(2):
+        for k in range(K):
             collect(k)
     barrier()
     t0 = time.perf_counter()
-    issue(0); issue(1)
+    for k in range(K):
+        issue(k)
     for _ in range(e2e_steps - 1):
-        for k in range(2):
+        for k in range(K):
             collect(k)
             issue(k)
-    collect(0); collect(1)
+    for k in range(K):
+        collect(k)
     barrier()
     e2e_s = time.perf_counter() - t0
-    e2e_launches = sum(hv.sim.launch_count for hv in halves)
+    e2e_launches = sum(hv.sim.launch_count for hv in parts)
 
     # ---- whole PPO iteration (BASELINE configs[4]: "... with PPO training"): rollout of n_steps + RecurrentPPO.train ------
     ppo = None
@@ -411,7 +429,11 @@ def run_b200(args):
         from myochallenge_b200.ppo import RecurrentPPO
         from myochallenge_b200.rollout import DeviceVecNormalize, collect_rollouts
 
-        del halves, hb, stepper
+        del parts, hb, stepper
+        if K == 2:
+            del halves
+        else:
+            del pst
         torch.cuda.empty_cache()
         vn = DeviceVecNormalize(env, gamma=0.99)
         bw = min(n, args.ppo_batch_worlds)
@@ -457,7 +479,7 @@ def run_b200(args):
     ms_per_step = pipe_ms / args.steps
     value = world * 2 * nh * args.steps / (pipe_ms * 1e-3)
     single_value = world * n * args.steps / (total_ms * 1e-3)
-    e2e_value = world * 2 * nh * e2e_steps / e2e_s
+    e2e_value = world * K * nk * e2e_steps / e2e_s
     seq_value = world * n * e2e_steps / seq_s
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------------------
@@ -511,8 +533,9 @@ def run_b200(args):
                    "policy_ms": policy_ms, "world_kernel_ms": world_ms, "status_flags": status},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "sequential": seq_value,
-                "api": "MyoVecEnv.step_async/step_wait with numpy arrays + RecurrentPolicy.forward on H2D-copied observations; two half-size "
-                       "envs stepped alternately on two streams (`sequential`: one env, every copy on the critical path)"},
+                "parts": K,
+                "api": f"MyoVecEnv.step_async/step_wait with numpy arrays + RecurrentPolicy.forward on H2D-copied observations; {K} envs of {nk} worlds "
+                       "stepped in turn on their own streams (`sequential`: one env, every copy on the critical path)"},
         "gpu_launches": int(pipe_launches), "clocks": clocks, "roofline": roofline, "compute_roofline": compute, "ppo_iteration": ppo,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -539,6 +562,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-parts", type=int, default=2, help="sub-batches of the end-to-end loop (each with its own stream and pinned buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spinup", type=int, default=200, help="untimed env steps before warm-up (one horizon: steady-state episode phases)")
     ap.add_argument("--use-sde", action="store_true", help="generalised state-dependent exploration (the reference's winning runs train with use_sde=True)")

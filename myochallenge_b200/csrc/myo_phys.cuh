@@ -490,14 +490,25 @@ MYO_HELPER void segment_moment(int mslot, int soff, int list, const float* pa, c
   cross3(ta, oa, dir);
   cross3(tb, ob, dir);
   const float* cdof = s + m.o_cdof;
-  for (int k = 1; k <= n; k++) {
-    const int e = L[k];
+  auto term = [&](int e) {
     const float* cd = cdof + 6 * (e & 255);
     const bool end = (e >> 16) & 1;
     const float* t = end ? tb : ta;
     const float v = cd[0] * t[0] + cd[1] * t[1] + cd[2] * t[2] + cd[3] * dir[0] + cd[4] * dir[1] + cd[5] * dir[2];
-    out[1 + ((e >> 8) & 255)] += end ? v * inv_div : -v * inv_div;
+    return end ? v * inv_div : -v * inv_div;
+  };
+  // two entries at a time, loads before stores: the entries of one list are distinct dofs, hence distinct slots of `out`
+  int k = 1;
+  for (; k + 1 <= n; k += 2) {
+    const int e0 = L[k], e1 = L[k + 1];
+    float* o0 = out + 1 + ((e0 >> 8) & 255);
+    float* o1 = out + 1 + ((e1 >> 8) & 255);
+    const float a0 = *o0, a1 = *o1;
+    const float v0 = term(e0), v1 = term(e1);
+    *o0 = a0 + v0;
+    *o1 = a1 + v1;
   }
+  if (k <= n) { const int e = L[k]; out[1 + ((e >> 8) & 255)] += term(e); }
 }
 
 // One lane per path segment (results to scratch: length and moment-arm slots), then one lane per tendon adds its
