@@ -1583,12 +1583,22 @@ MYO_PHASE void chol_factor_solve(int mslot, Ctx<G, V> c, int oH, int ox, int n) 
     const float* P0 = H + roff[J];     // pivot rows J..J+3
     const float* P1 = H + roff[J + 1]; const float* P2 = H + roff[J + 2]; const float* P3 = H + roff[J + 3];
     float l10 = 0.f, l20 = 0.f, l21 = 0.f, l30 = 0.f, l31 = 0.f, l32 = 0.f, inv0 = 0.f, inv1 = 0.f, inv2 = 0.f, inv3 = 0.f;
+    // Late blocks have few rows left (n4 + 1 - J) and the longest dot products: when the rows fit half a tile, two lanes share a
+    // row - lane and lane + G/2 each take half of the column chunks, one shuffle adds the halves - so the idle lanes shorten the
+    // longest dependent stretch of the factorisation (the result differs from the one-lane sum in the last bits only).
+    const bool split = G >= 8 && J >= 8 && n4 + 1 - J <= G / 2;
     for (int i0 = J; i0 <= n4; i0 += G) {
-      const int i = i0 + c.lane;
+      const int hlf = split ? c.lane / (G / 2) : 0;
+      const int i = i0 + (split ? c.lane % (G / 2) : c.lane);
       const bool on = i <= n4;
       float* Li = H + roff[on ? i : J];
       float4 acc = *reinterpret_cast<const float4*>(Li + J);
-      for (int k = 0; k < J; k += 4) {
+      int k0 = 0, k1 = J;
+      if (split) {
+        const int mid = ((J / 4 + 1) / 2) * 4;
+        if (hlf) { k0 = mid; acc = make_float4(0.f, 0.f, 0.f, 0.f); } else k1 = mid;
+      }
+      for (int k = k0; k < k1; k += 4) {
         const float4 a = *reinterpret_cast<const float4*>(Li + k);
         const float4 b0 = *reinterpret_cast<const float4*>(P0 + k);
         const float4 b1 = *reinterpret_cast<const float4*>(P1 + k);
@@ -1598,6 +1608,10 @@ MYO_PHASE void chol_factor_solve(int mslot, Ctx<G, V> c, int oH, int ox, int n) 
         acc.y -= a.x * b1.x; acc.y -= a.y * b1.y; acc.y -= a.z * b1.z; acc.y -= a.w * b1.w;
         acc.z -= a.x * b2.x; acc.z -= a.y * b2.y; acc.z -= a.z * b2.z; acc.z -= a.w * b2.w;
         acc.w -= a.x * b3.x; acc.w -= a.y * b3.y; acc.w -= a.z * b3.z; acc.w -= a.w * b3.w;
+      }
+      if (split) {
+        acc.x += c.tile.shfl_xor(acc.x, G / 2); acc.y += c.tile.shfl_xor(acc.y, G / 2);
+        acc.z += c.tile.shfl_xor(acc.z, G / 2); acc.w += c.tile.shfl_xor(acc.w, G / 2);
       }
       if (i0 == J) {   // first pass: lanes 0..3 hold the diagonal block
         const float d00 = c.tile.shfl(acc.x, 0);
