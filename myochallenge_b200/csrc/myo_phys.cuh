@@ -33,6 +33,18 @@ struct Ctx {
 #define SI(field) (reinterpret_cast<int*>(MYO_SMEM_WORDS + c.soff + m.field))
 #define SO(off) (MYO_SMEM_WORDS + c.soff + (off))   // scratch word offset -> pointer (noinline phases take offsets, not pointers)
 
+// optional per-phase cycle counters (development builds: -DMYO_PROFILE)
+#ifdef MYO_PROFILE
+__device__ unsigned long long g_prof[16];
+#define MYO_PH_BEGIN long long ph_t0 = clock64();
+#define MYO_PH_RESTART ph_t0 = clock64();
+#define MYO_PH(i) { long long ph_t = clock64(); if (c.lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(ph_t - ph_t0)); ph_t0 = clock64(); }
+#else
+#define MYO_PH_BEGIN
+#define MYO_PH_RESTART
+#define MYO_PH(i)
+#endif
+
 template <int G, int V> MYO_DI float tile_sum(const Ctx<G, V> c, float v) {
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) v += c.tile.shfl_xor(v, o);
@@ -1409,6 +1421,8 @@ MYO_PHASE void newton_system(int mslot, Ctx<G, V> c) {
         if (w00 == 0.f) continue;
         const int base = h * KS;
         if (hf == h && sub < ns) grad[dof] += jn * gn + jt1 * g1 + jt2 * g2;
+        // (W J) of the lane's own entry once, so that a pair costs three products: (W J_a) . J_b
+        const float un = w00 * jn + w01 * jt1 + w02 * jt2, ut = w01 * jn + w11 * jt1, uu = w02 * jn + w22 * jt2;
         // every unordered pair (a >= b) of the support once: e = a (a + 1) / 2 + b
         const int npair = ns * (ns + 1) / 2;
         for (int e0 = 0; e0 < npair; e0 += 2 * G) {
@@ -1417,15 +1431,15 @@ MYO_PHASE void newton_system(int mslot, Ctx<G, V> c) {
           const int abA = m.pair_ab[onA ? eA : 0], abB = m.pair_ab[onB ? eB : 0];
           const int aA = base + (abA & 255), bA = base + (abA >> 8), aB = base + (abB & 255), bB = base + (abB >> 8);
           const int iaA = c.tile.shfl(dof, aA), ibA = c.tile.shfl(dof, bA), iaB = c.tile.shfl(dof, aB), ibB = c.tile.shfl(dof, bB);
-          const float naA = c.tile.shfl(jn, aA), taA = c.tile.shfl(jt1, aA), uaA = c.tile.shfl(jt2, aA);
+          const float naA = c.tile.shfl(un, aA), taA = c.tile.shfl(ut, aA), uaA = c.tile.shfl(uu, aA);
           const float nbA = c.tile.shfl(jn, bA), tbA = c.tile.shfl(jt1, bA), ubA = c.tile.shfl(jt2, bA);
-          const float naB = c.tile.shfl(jn, aB), taB = c.tile.shfl(jt1, aB), uaB = c.tile.shfl(jt2, aB);
+          const float naB = c.tile.shfl(un, aB), taB = c.tile.shfl(ut, aB), uaB = c.tile.shfl(uu, aB);
           const float nbB = c.tile.shfl(jn, bB), tbB = c.tile.shfl(jt1, bB), ubB = c.tile.shfl(jt2, bB);
           float* hA = H + roff[max(iaA, ibA)] + min(iaA, ibA);
           float* hB = H + roff[max(iaB, ibB)] + min(iaB, ibB);
           const float oA = onA ? *hA : 0.f, oB = onB ? *hB : 0.f;
-          const float vA = w00 * naA * nbA + w01 * (naA * tbA + taA * nbA) + w02 * (naA * ubA + uaA * nbA) + w11 * taA * tbA + w22 * uaA * ubA;
-          const float vB = w00 * naB * nbB + w01 * (naB * tbB + taB * nbB) + w02 * (naB * ubB + uaB * nbB) + w11 * taB * tbB + w22 * uaB * ubB;
+          const float vA = naA * nbA + taA * tbA + uaA * ubA;
+          const float vB = naB * nbB + taB * tbB + uaB * ubB;
           if (onA) *hA = oA + vA;
           if (onB) *hB = oB + vB;
         }
@@ -1705,17 +1719,6 @@ MYO_PHASE void solve_M_dense(int mslot, Ctx<G, V> c, int ox, float hdamp) {
   if (nd > 0) chol_factor_solve<G>(mslot, c, m.o_H, ox, nd);
 }
 
-// optional per-phase cycle counters (development builds: -DMYO_PROFILE)
-#ifdef MYO_PROFILE
-__device__ unsigned long long g_prof[16];
-#define MYO_PH_BEGIN long long ph_t0 = clock64();
-#define MYO_PH_RESTART ph_t0 = clock64();
-#define MYO_PH(i) { long long ph_t = clock64(); if (c.lane == 0) atomicAdd(&g_prof[i], (unsigned long long)(ph_t - ph_t0)); ph_t0 = clock64(); }
-#else
-#define MYO_PH_BEGIN
-#define MYO_PH_RESTART
-#define MYO_PH(i)
-#endif
 
 // a10.8 constraint solve: primal Newton with exact line search on
 //   cost(a) = 1/2 (a - a_s)' M (a - a_s) + sum_r 1/2 D_r min(0, J_r a - aref_r)^2
