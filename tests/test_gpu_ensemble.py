@@ -92,3 +92,35 @@ def test_reference_custom_callbacks(product_lib, tmp_path):
     collect_rollouts(vn, agent.policy, agent.buffer, state, o, st)
     m = agent.buffer.info_means()
     assert agent.buffer.info_count == n * T and m.shape[0] == env.sim.info.shape[1] and np.isfinite(m).all()
+
+
+def test_ensemble_loads_sb3_zips_and_vecnormalize_pickles(product_lib, tmp_path):
+    """``Ensemble.load(PATH_TO_*_NET, PATH_TO_NORMALIZED_*_ENV)``: the files the reference lists are SB3 zips and VecNormalize pickles.
+    Two are written here from the reference's phase-1 weights (golden fixture) with different normalisers; the loaded ensemble must
+    act like the two policies evaluated by hand at fp32 with their own moments."""
+    from myochallenge_b200 import checkpoint
+
+    g = np.load(os.path.join(GOLDEN, "policy_phase1.npz"))
+    sd = {k[2:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("w:")}
+    rng = np.random.default_rng(5)
+    zips, pkls, norms = [], [], []
+    for i in range(2):
+        sdi = {k: (v + 0.01 * i * torch.randn(v.shape, generator=torch.Generator().manual_seed(i))) for k, v in sd.items()}
+        zp, pp = str(tmp_path / f"rl_model_{i}.zip"), str(tmp_path / f"rl_model_vecnormalize_{i}.pkl")
+        checkpoint.save_sb3_zip(zp, sdi)
+        st = dict(obs_mean=rng.normal(0, 0.2, 86), obs_var=rng.uniform(0.5, 1.5, 86), obs_count=1e6, ret_mean=0.0, ret_var=1.0, ret_count=1e4,
+                  clip_obs=10.0, clip_reward=10.0, gamma=0.99, epsilon=1e-8, training=False, norm_obs=True, norm_reward=False)
+        checkpoint.save_vecnormalize(pp, st, num_envs=1, act_dim=39)
+        zips.append(zp); pkls.append(pp); norms.append((sdi, st))
+    n = 64
+    ens = ensemble.Ensemble.load(zips, pkls, device=DEV, max_batch=n, precision="fp32")
+    obs = torch.from_numpy(g["obs"][:n]).to(DEV)
+    starts = torch.ones(n, dtype=torch.uint8, device=DEV)
+    got = ens.act(obs, starts)
+    want = 0
+    for sdi, st in norms:
+        p = RecurrentPolicy(86, 39, lstm_hidden=128, pi=(), vf=(), max_batch=n, device=DEV, precision="fp32")
+        p.load_state_dict(sdi)
+        p.set_obs_norm(st["obs_mean"], st["obs_var"], 1e-8, 10.0)
+        want = want + p.forward(obs, p.initial_state(n), starts, deterministic=True)[0]
+    assert torch.allclose(got, want / 2, atol=1e-5)
